@@ -1,0 +1,221 @@
+/*
+ * b200det.h -- C ABI of libb200det.so: the B200 (sm_100a) implementation of SimpleAICV's
+ * dense-detection loss + decode hot path.
+ *
+ * Nothing like this exists in the reference (the path is pure torch / NumPy there); every
+ * entry point names the reference code it replaces (paths relative to the reference repo).
+ * The Python classes in `b200det.losses` / `b200det.decode` bind these with ctypes and keep
+ * the reference's constructor / __call__ signatures.
+ *
+ * Conventions
+ *  - plain C: POD structs, raw device pointers, sizes; no torch / C++ types.
+ *  - the caller owns every buffer (including `workspace`); the library allocates nothing
+ *    on the device and keeps no mutable global state except a launch counter.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *    and never synchronises the host.
+ *  - return value: 0 = ok, negative = B200DET_E* argument error, positive = cudaError_t of
+ *    the failed launch.  Nothing throws or aborts.
+ *  - head outputs are channels-last, one contiguous allocation per pyramid level, exactly
+ *    as the reference heads emit them (models/retinanet.py:72-83, models/fcos.py:71-80):
+ *      Retina: cls[l] float32 [B,H,W,A,C] probabilities, reg[l] [B,H,W,A,4]
+ *      FCOS  : cls[l] float32 [B,H,W,C] probabilities, reg[l] [B,H,W,4], ctr[l] [B,H,W,1]
+ *    `reg` may be float32, float16 or bfloat16 (autocast); it is upcast on load.
+ *  - "rows": one row = one anchor (Retina) or point (FCOS).  Per image there are
+ *    N = sum_l H_l*W_l*per_loc rows.  Per-row device arrays produced/consumed by this
+ *    library (labels, matched, keys, classes, targets) are LEVEL-MAJOR: level l occupies
+ *    rows [B*off_l, B*off_{l+1}) laid out [B, n_l], off_l = rows of one image before level l
+ *    (i.e. the same order as the head tensors themselves, so streaming kernels index them
+ *    without division).  b200det_rows_to_image_major() converts to the reference's [B,N].
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DET_ABI_VERSION 1
+#define B200DET_MAX_LEVELS 8
+#define B200DET_MAX_PER_LOC 16
+#define B200DET_MAX_GT 2048   /* annotation rows per image staged in shared memory */
+#define B200DET_MAX_TOPN 2048
+
+/* error codes (negative) */
+#define B200DET_EINVAL (-1)    /* null pointer / bad enum / bad size */
+#define B200DET_ERANGE (-2)    /* a size exceeds a compiled limit (levels, GT rows, topn, 2^31 rows) */
+#define B200DET_EWORKSPACE (-3) /* workspace too small */
+#define B200DET_EALIGN (-4)    /* pointer not aligned as required */
+
+/* dtype of the regression head */
+#define B200DET_F32 0
+#define B200DET_F16 1
+#define B200DET_BF16 2
+
+/* box loss: RetinaLoss box_loss_type (losses.py:139-148) / FCOSLoss box_loss_iou_type (:443-448) */
+#define B200DET_BOX_NONE 0 /* assignment only */
+#define B200DET_BOX_SMOOTHL1 1
+#define B200DET_BOX_IOU 2
+#define B200DET_BOX_GIOU 3
+#define B200DET_BOX_DIOU 4
+#define B200DET_BOX_CIOU 5
+#define B200DET_BOX_EIOU 6
+
+/* DetNMSMethod nms_type (decode.py:28-32) */
+#define B200DET_NMS_PYTHON 0
+#define B200DET_NMS_DIOU_PYTHON 1
+#define B200DET_NMS_TORCH 2
+
+/*
+ * Pyramid geometry shared by every call.  Replaces what the reference re-derives on the host
+ * every step: RetinaAnchors.__call__ (models/anchor.py:18-86), FCOSPositions.__call__ (:94-130)
+ * and the per-point mi / stride tables of FCOSLoss (losses.py:623-632).  Anchors / points are
+ * generated in registers from this table; they are never materialised in memory.
+ */
+typedef struct b200det_geometry {
+    int32_t n_levels;                 /* 1..B200DET_MAX_LEVELS */
+    int32_t batch;                    /* B (images held by this rank) */
+    int32_t per_loc;                  /* anchors per location: 9 (Retina), 1 (FCOS) */
+    int32_t num_classes;              /* C */
+    int32_t height[B200DET_MAX_LEVELS];
+    int32_t width[B200DET_MAX_LEVELS];
+    float stride[B200DET_MAX_LEVELS];
+    /* Retina: float32 base anchors [level][a] = (x1,y1,x2,y2) centred on 0 (anchor.py:35-57) */
+    float base_anchors[B200DET_MAX_LEVELS][B200DET_MAX_PER_LOC][4];
+    /* FCOS: regress range (mi) per level, and stride*center_sample_radius (losses.py:690) */
+    float mi_lo[B200DET_MAX_LEVELS];
+    float mi_hi[B200DET_MAX_LEVELS];
+    float radius[B200DET_MAX_LEVELS];
+} b200det_geometry;
+
+/* ---- library info ------------------------------------------------------------------- */
+int b200det_abi_version(void);
+const char *b200det_error_string(int code);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+unsigned long long b200det_launch_count(void);
+/* rows per image (N) for a geometry; negative on error */
+long long b200det_rows_per_image(const b200det_geometry *geo);
+
+/* ---- loss --------------------------------------------------------------------------- */
+/* bytes of scratch the loss calls need (block partials); same buffer for all three calls */
+size_t b200det_loss_workspace_bytes(const b200det_geometry *geo);
+
+/*
+ * Anchor<->GT IoU assignment + box loss of RetinaLoss.
+ * Replaces RetinaLoss.get_batch_anchors_annotations (losses.py:322-388), IoUMethod
+ * (losses.py:33-70), snap_annotations_to_txtytwth (:390-409), snap_txtytwth_to_xyxy (:411-429),
+ * compute_batch_box_loss / compute_batch_smoothl1_loss (:263-320).
+ *   annotations : device float32 [B, max_gt, 5] = x1,y1,x2,y2,class ; rows with class < 0 ignored
+ *   reg         : host array of n_levels device pointers (may be NULL iff box_loss == NONE)
+ *   labels      : device int32 [B*N] level-major, out: -1 ignore, 0 background, k = class k-1
+ *   matched     : device int32 [B*N] level-major or NULL, out: arg-max GT index in the image's
+ *                 filtered GT list (first maximum on ties), -1 if the image has no GT
+ *   reg_grad    : NULL, or host array of n_levels device float32 buffers shaped like reg[l];
+ *                 receives d(sum of box loss)/d(reg) (NOT yet divided by the positive count)
+ *   workspace   : per-block {positives, box-loss sum} partials for b200det_loss_finalize
+ */
+int b200det_retina_assign(const b200det_geometry *geo, const float *annotations, int max_gt,
+                          const void *const *reg, int reg_dtype, int box_loss, float beta,
+                          int32_t *labels, int32_t *matched, void *const *reg_grad,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Point<->GT assignment with centre sampling + IoU loss + centre-ness loss of FCOSLoss.
+ * Replaces FCOSLoss.get_batch_position_annotations (losses.py:612-833),
+ * compute_batch_iou_loss (:550-586), compute_batch_centerness_loss (:588-610).
+ *   targets : device float32 [B*N, 6] level-major or NULL, out: l,t,r,b,label,centre-ness
+ *   ctr     : host array of n_levels device float32 pointers (probabilities), NULL iff
+ *             box_loss == NONE
+ *   reg_grad / ctr_grad : NULL or per-level float32 buffers (un-normalised gradients)
+ */
+int b200det_fcos_assign(const b200det_geometry *geo, const float *annotations, int max_gt,
+                        const void *const *reg, int reg_dtype, const void *const *ctr,
+                        int box_loss, int use_center_sample, int32_t *labels, int32_t *matched,
+                        float *targets, void *const *reg_grad, void *const *ctr_grad,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Focal loss over the classification head: one streaming pass over cls (4*N*C bytes/image).
+ * Replaces torch.cat + clamp (losses.py:183-198 / :488-494) and compute_batch_focal_loss
+ * (losses.py:220-261 / :513-548).  Rows with label < 0 contribute nothing.
+ *   cls_grad   : NULL (forward only) or host array of n_levels device float32 buffers; receives
+ *                d(cls_loss)/d(cls) already multiplied by grad_scale / sums[0]
+ *   sums       : device double[4] written by b200det_loss_reduce: {positives, cls, box, ctr};
+ *                only read when cls_grad != NULL (element 0 = positive count, possibly
+ *                all-reduced across ranks by the caller)
+ */
+int b200det_focal_loss(const b200det_geometry *geo, const void *const *cls,
+                       const int32_t *labels, float alpha, float gamma, void *const *cls_grad,
+                       const double *sums, float grad_scale, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/*
+ * Deterministic (fixed-order, fp64) reduction of the block partials.
+ *   which : bit 0 = assignment partials (positives, box, ctr), bit 1 = focal partials
+ *   sums  : device double[4] {positives, cls_sum, box_sum, ctr_sum}; only selected fields written
+ * Replaces the `.sum()` / `positive_anchors_num` bookkeeping of losses.py:231-259, :277-293.
+ */
+int b200det_loss_reduce(const b200det_geometry *geo, int which, const void *workspace,
+                        size_t workspace_bytes, double *sums, void *stream);
+
+/*
+ * losses[i] = weights[i] * sums[1+i] / sums[0]  (0 when sums[0] == 0), i = 0..2, float32.
+ * Replaces the final divisions and weightings of losses.py:210-211, :259, :293, :318, :501-503.
+ */
+int b200det_loss_finish(const double *sums, float w_cls, float w_box, float w_ctr,
+                        float *losses, void *stream);
+
+/* x[i] *= *scale for n float32 values unless *scale == 1 (autograd backward helper) */
+int b200det_scale_f32(float *x, long long n, const float *scale_dev, void *stream);
+
+/* ---- decode ------------------------------------------------------------------------- */
+size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, int topn);
+
+/*
+ * Per-row class arg-max / score / threshold: one streaming pass over cls.
+ * Replaces np.concatenate + np.argmax + score gather (decode.py:208-238 / :300-338, incl. the
+ * FCOS sqrt(cls*centerness)) and the `score > min_score_threshold` filter (decode.py:133-138).
+ *   ctr     : NULL for Retina; per-level centre-ness pointers for FCOS
+ *   keys    : device uint32 [B*N] level-major: 0 for rows at or below the threshold, else an
+ *             order-preserving transform of the float32 score bits
+ *   classes : device int32 [B*N] level-major arg-max class (first maximum)
+ */
+int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
+                         const void *const *ctr, float min_score, uint32_t *keys,
+                         int32_t *classes, void *stream);
+
+/*
+ * Global top-n per image (radix select + bitonic sort), box decode, NMS, max_object_num cap.
+ * Replaces DecodeMethod.__call__ (decode.py:121-172), DetNMSMethod.__call__ (:34-104),
+ * RetinaDecoder.snap_txtytwth_to_x1y1x2y2 (:251-271) / FCOSDecoder.snap_ltrb_to_x1y1x2y2
+ * (:350-364) incl. NumPy's float32 exp and the int32 truncation.
+ *   is_fcos       : 0 = anchor (tx,ty,tw,th) decoding, 1 = point (l,t,r,b) decoding
+ *   out           : device float32 [6*B*max_out]: scores [B,max_out] (pad -1), classes
+ *                   [B,max_out] (pad -1), boxes [B,max_out,4] (pad 0), back to back
+ *   order / keep  : NULL or device int32 [B,topn] (pad -1): image-major row index of the sorted
+ *                   top-n, and the positions in that list surviving NMS (full list, no cap)
+ *   counts        : NULL or device int32 [B,3]: candidates, selected (<= topn), kept by NMS
+ *                   (the NMS count stops at max_out unless `keep` is given)
+ */
+int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
+                              const int32_t *classes, const void *const *reg, int reg_dtype,
+                              int is_fcos, int topn, int max_out, int nms_type,
+                              double nms_threshold, float *out, int32_t *order, int32_t *keep,
+                              int32_t *counts, void *workspace, size_t workspace_bytes,
+                              void *stream);
+
+/* ---- utilities (tests / parity outputs) ---------------------------------------------- */
+/* dst[b*N + off_l + i] = src[B*off_l + b*n_l + i] for `width` int32/float32 words per row */
+int b200det_rows_to_image_major(const b200det_geometry *geo, const void *src, void *dst,
+                                int width, void *stream);
+/* materialise the anchors (per_loc > 1, [N,4]) or points ([N,2]) the kernels generate */
+int b200det_generate_rows(const b200det_geometry *geo, int is_fcos, float *out, void *stream);
+/* y[i] = exp(x[i]) with the NumPy float32 algorithm used by the decoders (test hook) */
+int b200det_npexp_f32(const float *x, float *y, long long n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

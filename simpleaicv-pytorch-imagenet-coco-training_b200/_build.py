@@ -1,0 +1,65 @@
+"""Builds libb200det.so (hand-written CUDA, sm_100a only) in-tree with nvcc.
+
+    python -m b200det._build          # or __graft_entry__.build()
+
+The library is a plain C-ABI shared object (include/b200det.h); it links only cudart.
+assign.cu / decode.cu are compiled with -fmad=false because their float32 arithmetic must be
+bit-identical to the reference's op-by-op torch / NumPy arithmetic; focal.cu may contract.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, 'csrc')
+LIB_PATH = os.path.join(PKG_DIR, 'libb200det.so')
+
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+COMMON = ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC']
+SOURCES = {
+    'assign.cu': ['-fmad=false'],
+    'decode.cu': ['-fmad=false'],
+    'focal.cu': [],
+}
+
+
+def _nvcc():
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: libb200det.so cannot be built')
+    return nvcc
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(PKG_DIR, '..', 'include', 'b200det.h'))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compiles every CUDA source for sm_100a and links libb200det.so. Returns its path."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    obj_dir = os.path.join(PKG_DIR, 'csrc', '_obj')
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    for src, extra in SOURCES.items():
+        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + ARCH + COMMON + extra + ['-c', os.path.join(CSRC, src), '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+            print(' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    cmd = [nvcc] + ARCH + ['-shared', '-o', LIB_PATH] + objs
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

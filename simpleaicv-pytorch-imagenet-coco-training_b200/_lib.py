@@ -1,0 +1,131 @@
+"""ctypes binding of libb200det.so (C ABI declared in include/b200det.h).
+
+There is NO CPU fallback: if the library is missing, or a tensor is not on a CUDA device, the
+callers raise.  Build the library with `python -m b200det._build` / `__graft_entry__.build()`.
+"""
+import ctypes
+import os
+
+from . import _build
+
+MAX_LEVELS = 8
+MAX_PER_LOC = 16
+MAX_GT = 2048
+MAX_TOPN = 2048
+
+F32, F16, BF16 = 0, 1, 2
+BOX_NONE, BOX_SMOOTHL1, BOX_IOU, BOX_GIOU, BOX_DIOU, BOX_CIOU, BOX_EIOU = range(7)
+NMS_PYTHON, NMS_DIOU_PYTHON, NMS_TORCH = range(3)
+
+BOX_LOSS_CODES = {
+    'SmoothL1': BOX_SMOOTHL1,
+    'IoU': BOX_IOU,
+    'GIoU': BOX_GIOU,
+    'DIoU': BOX_DIOU,
+    'CIoU': BOX_CIOU,
+    'EIoU': BOX_EIOU,
+}
+NMS_CODES = {'python_nms': NMS_PYTHON, 'diou_python_nms': NMS_DIOU_PYTHON, 'torch_nms': NMS_TORCH}
+
+
+class Geometry(ctypes.Structure):
+    """Mirror of `b200det_geometry`."""
+    _fields_ = [
+        ('n_levels', ctypes.c_int32),
+        ('batch', ctypes.c_int32),
+        ('per_loc', ctypes.c_int32),
+        ('num_classes', ctypes.c_int32),
+        ('height', ctypes.c_int32 * MAX_LEVELS),
+        ('width', ctypes.c_int32 * MAX_LEVELS),
+        ('stride', ctypes.c_float * MAX_LEVELS),
+        ('base_anchors', ((ctypes.c_float * 4) * MAX_PER_LOC) * MAX_LEVELS),
+        ('mi_lo', ctypes.c_float * MAX_LEVELS),
+        ('mi_hi', ctypes.c_float * MAX_LEVELS),
+        ('radius', ctypes.c_float * MAX_LEVELS),
+    ]
+
+
+_vp = ctypes.c_void_p
+_vpp = ctypes.POINTER(ctypes.c_void_p)
+_geo = ctypes.POINTER(Geometry)
+
+# name -> (restype, argtypes); every symbol include/b200det.h declares
+SIGNATURES = {
+    'b200det_abi_version': (ctypes.c_int, []),
+    'b200det_error_string': (ctypes.c_char_p, [ctypes.c_int]),
+    'b200det_launch_count': (ctypes.c_ulonglong, []),
+    'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
+    'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),
+    'b200det_retina_assign': (ctypes.c_int, [
+        _geo, _vp, ctypes.c_int, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_float, _vp, _vp, _vpp,
+        _vp, ctypes.c_size_t, _vp
+    ]),
+    'b200det_fcos_assign': (ctypes.c_int, [
+        _geo, _vp, ctypes.c_int, _vpp, ctypes.c_int, _vpp, ctypes.c_int, ctypes.c_int, _vp, _vp,
+        _vp, _vpp, _vpp, _vp, ctypes.c_size_t, _vp
+    ]),
+    'b200det_focal_loss': (ctypes.c_int, [
+        _geo, _vpp, _vp, ctypes.c_float, ctypes.c_float, _vpp, _vp, ctypes.c_float, _vp,
+        ctypes.c_size_t, _vp
+    ]),
+    'b200det_loss_reduce': (ctypes.c_int, [_geo, ctypes.c_int, _vp, ctypes.c_size_t, _vp, _vp]),
+    'b200det_loss_finish': (ctypes.c_int,
+                            [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp]),
+    'b200det_scale_f32': (ctypes.c_int, [_vp, ctypes.c_longlong, _vp, _vp]),
+    'b200det_decode_workspace_bytes': (ctypes.c_size_t, [_geo, ctypes.c_int]),
+    'b200det_score_argmax': (ctypes.c_int, [_geo, _vpp, _vpp, ctypes.c_float, _vp, _vp, _vp]),
+    'b200det_select_decode_nms': (ctypes.c_int, [
+        _geo, _vp, _vp, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
+    ]),
+    'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
+    'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),
+    'b200det_npexp_f32': (ctypes.c_int, [_vp, _vp, ctypes.c_longlong, _vp]),
+}
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Returns the loaded library; raises RuntimeError (loudly) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f'{path} is missing: the b200det CUDA library has not been built. Run '
+            '`python -m b200det._build` (needs nvcc; targets sm_100a). There is no CPU fallback.')
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.b200det_abi_version() != 1:
+        raise RuntimeError('libb200det.so ABI version mismatch; rebuild it')
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().b200det_error_string(rc).decode()
+        raise RuntimeError(f'{what} failed: {msg} (code {rc})')
+
+
+def ptr_array(tensors):
+    """ctypes void*[n] of device pointers (None -> NULL array)."""
+    if tensors is None:
+        return None
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def launch_count():
+    return int(load().b200det_launch_count())

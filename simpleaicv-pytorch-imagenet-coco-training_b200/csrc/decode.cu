@@ -1,0 +1,615 @@
+// decode.cu -- RetinaDecoder / FCOSDecoder on the GPU (the reference does this in NumPy on the
+// host after a D2H copy of every head output, decode.py:208-219).
+//
+//  score_argmax_kernel   one streaming pass over cls (4*C bytes/row, 128-bit loads, HBM-bound):
+//                        first-maximum class, score (FCOS: sqrt(cls*centerness)), strict
+//                        threshold; writes an order-preserving uint32 key + class per row.
+//  select_nms_kernel     one CTA per image (the keys of one image are <= 0.5 MB and L2-resident):
+//                        adaptive-range radix select of the top-n keys (2048-bin shared-memory
+//                        histograms), bitonic sort of the <= 2048 survivors by (score desc,
+//                        row asc), box decode with NumPy's exp + x86 int32 truncation, greedy
+//                        NMS driven by warp ballots into a removed-bitmask, max_object_num cap.
+// Compiled with -fmad=false: box / IoU arithmetic is one IEEE float32 op per reference op.
+#include "common.cuh"
+
+namespace b200det {
+
+// order-preserving float32 -> uint32 (larger float <=> larger key); never 0 for a non-NaN
+__device__ __forceinline__ uint32_t flip_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unflip_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---------------------------------------------------------------------------------------
+// score / arg-max sweep
+// ---------------------------------------------------------------------------------------
+constexpr int kArgThreads = 256;
+constexpr int kArgMaxPerLane = 8;
+
+struct ArgmaxArgs {
+    PtrTab cls, ctr;
+    long long row_base[kMaxLevels];   // level-major row base (B*off_l)
+    long long rows[kMaxLevels];       // B*rows_l
+    int block_off[kMaxLevels + 1];
+    int n_levels;
+    int C;
+    int group;        // lanes cooperating on one row (power of two <= 32)
+    int group_shift;
+    float min_score;
+    int has_ctr;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kArgThreads)
+    score_argmax_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
+    const int rows_per_block = kArgThreads >> a.group_shift;
+    const long long row = (long long)(blockIdx.x - a.block_off[l]) * rows_per_block +
+                          (threadIdx.x >> a.group_shift);
+    const int j = threadIdx.x & (a.group - 1);
+    const bool active = row < a.rows[l];
+    const int units = a.C / VEC;  // float4s (or floats) per row
+    const float *src = static_cast<const float *>(a.cls.p[l]) + (active ? row : 0) * a.C;
+
+    float best = -__int_as_float(0x7f800000);
+    int best_c = 0x7fffffff;
+    for (int i0 = 0; i0 < units; i0 += a.group * kArgMaxPerLane) {
+        float v[kArgMaxPerLane][VEC];
+#pragma unroll
+        for (int i = 0; i < kArgMaxPerLane; ++i) {
+            const int u = i0 + j + i * a.group;
+            if (active && u < units) {
+                if (VEC == 4) {
+                    const float4 t = __ldcs(reinterpret_cast<const float4 *>(src) + u);
+                    v[i][0] = t.x;
+                    v[i][1 % VEC] = t.y;
+                    v[i][2 % VEC] = t.z;
+                    v[i][3 % VEC] = t.w;
+                } else {
+                    v[i][0] = __ldcs(src + u);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[i][e] = -__int_as_float(0x7f800000);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kArgMaxPerLane; ++i) {
+            const int c0 = (i0 + j + i * a.group) * VEC;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (v[i][e] > best) {  // strict: first maximum in class order (np.argmax)
+                    best = v[i][e];
+                    best_c = c0 + e;
+                }
+            }
+        }
+    }
+    // combine the group's lanes: larger value wins, equal values -> lower class index
+    for (int o = a.group >> 1; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        if (ov > best || (ov == best && oc < best_c)) {
+            best = ov;
+            best_c = oc;
+        }
+    }
+    if (active && j == 0) {
+        float score = best;
+        if (a.has_ctr) {
+            // np.sqrt(cls_scores * center_preds)  (decode.py:338): one mul, one IEEE sqrt
+            const float c = __ldg(static_cast<const float *>(a.ctr.p[l]) + row);
+            score = __fsqrt_rn(__fmul_rn(best, c));
+        }
+        const long long lm = a.row_base[l] + row;
+        keys[lm] = (score > a.min_score) ? flip_key(score) : 0u;  // strict '>' (decode.py:133-138)
+        classes[lm] = best_c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-image select + decode + NMS
+// ---------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kBins = 2048;
+
+struct SelectArgs {
+    Geo g;
+    BaseAnchors ba;
+    PtrTab reg;
+    int reg_dtype, is_fcos, topn, pad_n /* pow2 >= topn */, max_out, nms_type;
+    float nms_thr_f;
+    double nms_thr_d;
+};
+
+// block-wide sums; result broadcast to all threads.  `scratch` holds kSelWarps values.
+__device__ __forceinline__ int block_sum_int(int v, int *scratch) {
+    v = warp_sum_int(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = scratch[threadIdx.x & 31];
+    t = warp_sum_int(t);
+    return t;
+}
+__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t *scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = scratch[threadIdx.x & 31];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
+__device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t *scratch) {
+    return ~block_max_u32(~v, scratch);
+}
+
+// visit every (key, image-major row) of image b; F(key, row)
+template <typename F>
+__device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t *__restrict__ keys,
+                                             F f) {
+    for (int l = 0; l < g.n_levels; ++l) {
+        const uint32_t *p = keys + lm_index(g, b, l, 0);
+        const int n = g.rows[l], off = g.off[l];
+        for (int j = threadIdx.x; j < n; j += kSelThreads) f(__ldg(p + j), off + j);
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+    select_nms_kernel(SelectArgs a, const uint32_t *__restrict__ keys,
+                      const int *__restrict__ classes, float *__restrict__ out,
+                      int *__restrict__ order_out, int *__restrict__ keep_out,
+                      int *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // carve: hist | key64 | box | cls | keep | removed
+    int *hist = reinterpret_cast<int *>(smem);                                // kBins
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(hist + kBins);  // pad_n
+    float4 *sbox = reinterpret_cast<float4 *>(skey + a.pad_n);                // pad_n
+    int *scls = reinterpret_cast<int *>(sbox + a.pad_n);                      // pad_n
+    int *skeep = scls + a.pad_n;                                              // pad_n
+    uint32_t *srem = reinterpret_cast<uint32_t *>(skeep + a.pad_n);           // pad_n/32
+    __shared__ int scratch[kSelWarps];
+    __shared__ int s_digit, s_above, s_count;
+
+    const Geo &g = a.g;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = g.off[g.n_levels];
+    const int B = g.batch;
+
+    // ---- pass 0: candidates, key range ----
+    int ncand_t = 0;
+    uint32_t kmax_t = 0u, kmin_t = 0xffffffffu;
+    for_each_key(g, b, keys, [&](uint32_t k, int) {
+        if (k) {
+            ++ncand_t;
+            kmax_t = max(kmax_t, k);
+            kmin_t = min(kmin_t, k);
+        }
+    });
+    const int ncand = block_sum_int(ncand_t, scratch);
+    const uint32_t kmax = block_max_u32(kmax_t, reinterpret_cast<uint32_t *>(scratch));
+    const uint32_t kmin = block_min_u32(kmin_t, reinterpret_cast<uint32_t *>(scratch));
+    const int k_sel = min(a.topn, ncand);
+
+    float *out_scores = out + (size_t)b * a.max_out;
+    float *out_classes = out + (size_t)B * a.max_out + (size_t)b * a.max_out;
+    float *out_boxes = out + (size_t)2 * B * a.max_out + (size_t)b * a.max_out * 4;
+
+    // ---- radix select: threshold key T and how many of the keys == T to take ----
+    uint32_t T = 1u;          // select keys >= T ...
+    int tie_take = -1;        // ... or, if >= 0: keys > T plus the first `tie_take` keys == T
+    if (ncand > a.topn) {
+        uint32_t lo = kmin, hi = kmax;
+        int need = k_sel;
+        while (true) {
+            const unsigned long long span = (unsigned long long)hi - lo + 1ull;
+            int shift = 0;
+            while ((span - 1ull) >> shift >= (unsigned long long)kBins) ++shift;
+            for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
+            __syncthreads();
+            for_each_key(g, b, keys, [&](uint32_t k, int) {
+                if (k >= lo && k <= hi) atomicAdd(&hist[(k - lo) >> shift], 1);
+            });
+            __syncthreads();
+            // suffix scan over bins (thread t owns bins 2t, 2t+1), find the bin where the
+            // count from the top crosses `need`
+            const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+            const int mine = h0 + h1;
+            // inclusive suffix sum within the warp (higher lanes = higher bins)
+            int suf = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            if (lane == 0) scratch[warp] = suf;  // warp total
+            __syncthreads();
+            int above_warps = 0;
+            for (int w = warp + 1; w < kSelWarps; ++w) above_warps += scratch[w];
+            const int above_excl = above_warps + suf - mine;  // keys in bins above my two bins
+            if (above_excl < need && need <= above_excl + mine) {
+                if (need <= above_excl + h1) {
+                    s_digit = 2 * tid + 1;
+                    s_above = above_excl;
+                    s_count = h1;
+                } else {
+                    s_digit = 2 * tid;
+                    s_above = above_excl + h1;
+                    s_count = h0;
+                }
+            }
+            __syncthreads();
+            const int digit = s_digit, cnt = s_count;
+            need -= s_above;
+            const uint32_t lo2 = lo + ((uint32_t)digit << shift);
+            const unsigned long long hi2 = (unsigned long long)lo2 + ((1ull << shift) - 1ull);
+            lo = lo2;
+            if (hi2 < hi) hi = (uint32_t)hi2;
+            __syncthreads();  // everyone has read s_* before the next round overwrites them
+            if (cnt == need) {  // take the whole bucket
+                T = lo;
+                break;
+            }
+            if (shift == 0) {   // a single key value with more copies than needed: ties
+                T = lo;
+                tie_take = need;
+                break;
+            }
+        }
+    }
+
+    // ---- collect the selected (key,row) pairs ----
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (k_sel > 0) {
+        for_each_key(g, b, keys, [&](uint32_t k, int row) {
+            const bool take = tie_take < 0 ? (k >= T && k != 0u) : (k > T);
+            if (take) {
+                const int slot = atomicAdd(&s_count, 1);
+                skey[slot] = ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
+            }
+        });
+        if (tie_take >= 0) {
+            // ties at the cut: lowest rows first (deterministic; the reference's argsort order
+            // is unspecified here).  Ordered block scan over the image's rows.
+            __syncthreads();
+            int running = 0;  // ties accepted so far (uniform)
+            for (int l = 0; l < g.n_levels && running < tie_take; ++l) {
+                const uint32_t *p = keys + lm_index(g, b, l, 0);
+                const int n = g.rows[l];
+                for (int j0 = 0; j0 < n && running < tie_take; j0 += kSelThreads) {
+                    const int j = j0 + tid;
+                    const bool is_tie = j < n && __ldg(p + j) == T;
+                    const unsigned bal = __ballot_sync(0xffffffffu, is_tie);
+                    __syncthreads();
+                    if (lane == 0) scratch[warp] = __popc(bal);
+                    __syncthreads();
+                    int before = 0, total = 0;
+                    for (int w = 0; w < kSelWarps; ++w) {
+                        const int c = scratch[w];
+                        if (w < warp) before += c;
+                        total += c;
+                    }
+                    const int rank = running + before + __popc(bal & ((1u << lane) - 1u));
+                    if (is_tie && rank < tie_take) {
+                        const int slot = atomicAdd(&s_count, 1);
+                        skey[slot] =
+                            ((unsigned long long)T << 32) | (0xffffffffu - (uint32_t)(g.off[l] + j));
+                    }
+                    running += total;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_sel = s_count;  // == k_sel
+    int sort_n = 1;
+    while (sort_n < n_sel) sort_n <<= 1;
+    for (int i = n_sel + tid; i < sort_n; i += kSelThreads) skey[i] = 0ull;
+    __syncthreads();
+
+    // ---- bitonic sort, descending (score desc, then row asc) ----
+    for (int size = 2; size <= sort_n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (sort_n >> 1); t += kSelThreads) {
+                const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const int p = i | stride;
+                const bool desc = (i & size) == 0;
+                const unsigned long long x = skey[i], y = skey[p];
+                if ((x < y) == desc) {
+                    skey[i] = y;
+                    skey[p] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- decode the selected rows (reference op order, NumPy exp, x86 int32 truncation) ----
+    for (int i = tid; i < n_sel; i += kSelThreads) {
+        const unsigned long long kk = skey[i];
+        const int row = (int)(0xffffffffu - (uint32_t)(kk & 0xffffffffull));
+        const int l = level_of_row(g, row);
+        const int local = row - g.off[l];
+        scls[i] = __ldg(classes + lm_index(g, b, l, local));
+        const float4 t = load_reg4(a.reg.p[l], a.reg_dtype, (long long)b * g.rows[l] + local);
+        float x1, y1, x2, y2;
+        if (a.is_fcos) {
+            // decode.py:356-361
+            const float2 p = point_of(g, l, local);
+            x1 = __fsub_rn(p.x, npexp(t.x));
+            y1 = __fsub_rn(p.y, npexp(t.y));
+            x2 = __fadd_rn(p.x, npexp(t.z));
+            y2 = __fadd_rn(p.y, npexp(t.w));
+        } else {
+            // decode.py:257-268
+            const float4 an = anchor_of(g, a.ba, l, local);
+            const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
+            const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw));
+            const float acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
+            const float bw = __fmul_rn(npexp(t.z), aw), bh = __fmul_rn(npexp(t.w), ah);
+            const float cx = __fadd_rn(__fmul_rn(t.x, aw), acx);
+            const float cy = __fadd_rn(__fmul_rn(t.y, ah), acy);
+            const float hw = __fmul_rn(0.5f, bw), hh = __fmul_rn(0.5f, bh);
+            x1 = __fsub_rn(cx, hw);
+            y1 = __fsub_rn(cy, hh);
+            x2 = __fadd_rn(cx, hw);
+            y2 = __fadd_rn(cy, hh);
+        }
+        sbox[i] = make_float4(__int2float_rn(x86_f2i(x1)), __int2float_rn(x86_f2i(y1)),
+                              __int2float_rn(x86_f2i(x2)), __int2float_rn(x86_f2i(y2)));
+        if (order_out) order_out[(size_t)b * a.topn + i] = row;
+    }
+    if (order_out)
+        for (int i = n_sel + tid; i < a.topn; i += kSelThreads) order_out[(size_t)b * a.topn + i] = -1;
+    const int n_words = (n_sel + 31) >> 5;
+    for (int i = tid; i < (a.pad_n >> 5); i += kSelThreads) srem[i] = 0u;
+    __syncthreads();
+
+    // ---- greedy NMS (decode.py:45-100): ballots build the removed-bitmask ----
+    const int limit = keep_out ? n_sel : min(a.max_out, n_sel);
+    int n_keep = 0, cur = 0;
+    while (n_keep < limit) {
+        // every warp finds the first alive index >= cur (identical result in all warps)
+        int found = -1;
+        for (int w0 = cur >> 5; w0 < n_words && found < 0; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t alive = 0u;
+            if (w < n_words) {
+                alive = ~srem[w];
+                if (w == (cur >> 5)) alive &= ~((1u << (cur & 31)) - 1u);
+                if (w == n_words - 1 && (n_sel & 31)) alive &= (1u << (n_sel & 31)) - 1u;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, alive != 0u);
+            if (bal) {
+                const int src_lane = __ffs(bal) - 1;
+                const uint32_t word = __shfl_sync(0xffffffffu, alive, src_lane);
+                found = ((w0 + src_lane) << 5) + (__ffs(word) - 1);
+            }
+        }
+        if (found < 0) break;
+        if (tid == 0) skeep[n_keep] = found;
+        ++n_keep;
+        if (n_keep >= limit) break;
+        const float4 kb = sbox[found];
+        const float kw = __fsub_rn(kb.z, kb.x), kh = __fsub_rn(kb.w, kb.y);
+        const float karea_raw = __fmul_rn(kw, kh);
+        const float karea = a.nms_type == B200DET_NMS_TORCH ? karea_raw : fmaxf(karea_raw, 0.f);
+        __syncthreads();  // all warps have read srem for `found` before it is updated
+        for (int j0 = (found + 1) & ~31; j0 < n_sel; j0 += kSelThreads) {
+            const int j = j0 + tid;
+            bool suppress = false;
+            if (j > found && j < n_sel) {
+                const float4 ob = sbox[j];
+                const float oarea_raw = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
+                const float iw = fmaxf(__fsub_rn(fminf(kb.z, ob.z), fmaxf(kb.x, ob.x)), 0.f);
+                const float ih = fmaxf(__fsub_rn(fminf(kb.w, ob.w), fmaxf(kb.y, ob.y)), 0.f);
+                const float inter = __fmul_rn(iw, ih);
+                if (a.nms_type == B200DET_NMS_TORCH) {
+                    // torchvision.ops.nms (CPU kernel): unclamped areas, no union clamp,
+                    // suppress when iou > threshold with the threshold kept in double
+                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(karea, oarea_raw), inter));
+                    suppress = (double)iou > a.nms_thr_d;
+                } else {
+                    const float oarea = fmaxf(oarea_raw, 0.f);
+                    const float uni = fmaxf(__fsub_rn(__fadd_rn(karea, oarea), inter), 1e-4f);
+                    float iou = __fdiv_rn(inter, uni);
+                    if (a.nms_type == B200DET_NMS_DIOU_PYTHON) {
+                        // decode.py:78-97
+                        const float ew = fmaxf(__fsub_rn(fmaxf(kb.z, ob.z), fminf(kb.x, ob.x)), 0.f);
+                        const float eh = fmaxf(__fsub_rn(fmaxf(kb.w, ob.w), fminf(kb.y, ob.y)), 0.f);
+                        const float c2 = fmaxf(__fadd_rn(__fmul_rn(ew, ew), __fmul_rn(eh, eh)), 1e-4f);
+                        const float dx = __fsub_rn(__fdiv_rn(__fadd_rn(kb.z, kb.x), 2.f),
+                                                   __fdiv_rn(__fadd_rn(ob.z, ob.x), 2.f));
+                        const float dy = __fsub_rn(__fdiv_rn(__fadd_rn(kb.w, kb.y), 2.f),
+                                                   __fdiv_rn(__fadd_rn(ob.w, ob.y), 2.f));
+                        const float p2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                        iou = __fsub_rn(iou, __fdiv_rn(p2, c2));
+                    }
+                    suppress = !(iou < a.nms_thr_f);  // survivors are `ious < thr` (decode.py:99)
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, suppress);
+            if (lane == 0 && bal) srem[j >> 5] |= bal;  // each word is owned by one warp
+        }
+        cur = found + 1;
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- outputs (decode.py:123-128, :158-167) ----
+    const int n_out = min(n_keep, a.max_out);
+    for (int i = tid; i < a.max_out; i += kSelThreads) {
+        float s = -1.f, c = -1.f;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n_out) {
+            const int k = skeep[i];
+            s = unflip_key((uint32_t)(skey[k] >> 32));
+            c = (float)scls[k];
+            bx = sbox[k];
+        }
+        out_scores[i] = s;
+        out_classes[i] = c;
+        reinterpret_cast<float4 *>(out_boxes)[i] = bx;
+    }
+    if (keep_out) {
+        for (int i = tid; i < a.topn; i += kSelThreads)
+            keep_out[(size_t)b * a.topn + i] = i < n_keep ? skeep[i] : -1;
+    }
+    if (counts && tid == 0) {
+        counts[b * 3 + 0] = ncand;
+        counts[b * 3 + 1] = n_sel;
+        counts[b * 3 + 2] = n_keep;
+    }
+}
+
+__global__ void npexp_kernel(const float *__restrict__ x, float *__restrict__ y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = npexp(x[i]);
+}
+
+static size_t select_smem_bytes(int pad_n) {
+    return (size_t)kBins * 4 + (size_t)pad_n * (8 + 16 + 4 + 4) + (size_t)(pad_n / 32) * 4 + 16;
+}
+
+}  // namespace b200det
+
+using namespace b200det;
+
+extern "C" size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, int topn) {
+    (void)geo;
+    (void)topn;
+    return 256;  // the select kernel works entirely in shared memory; kept for ABI stability
+}
+
+extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
+                                    const void *const *ctr, float min_score, uint32_t *keys,
+                                    int32_t *classes, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!cls || !keys || !classes) return B200DET_EINVAL;
+    ArgmaxArgs a;
+    const int vec = (g.num_classes % 4 == 0) ? 4 : 1;
+    const uintptr_t amask = vec == 4 ? 15 : 3;
+    a.n_levels = g.n_levels;
+    a.C = g.num_classes;
+    a.min_score = min_score;
+    a.has_ctr = ctr != nullptr;
+    // lanes per row: smallest power of two that leaves <= kArgMaxPerLane units per lane
+    const int units = g.num_classes / vec;
+    int group = 1, shift = 0;
+    while (group < 32 && units > group * kArgMaxPerLane) {
+        group <<= 1;
+        ++shift;
+    }
+    if (vec == 4 && units >= 16 && group < 4) {  // keep >= 64 B contiguous per row and instruction
+        group = 4;
+        shift = 2;
+    }
+    a.group = group;
+    a.group_shift = shift;
+    const int rows_per_block = kArgThreads / group;
+    int blocks = 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        a.cls.p[l] = a.ctr.p[l] = nullptr;
+        a.row_base[l] = a.rows[l] = 0;
+    }
+    for (int l = 0; l < g.n_levels; ++l) {
+        if (!cls[l] || (ctr && !ctr[l])) return B200DET_EINVAL;
+        if (reinterpret_cast<uintptr_t>(cls[l]) & amask) return B200DET_EALIGN;
+        if (ctr && (reinterpret_cast<uintptr_t>(ctr[l]) & 3)) return B200DET_EALIGN;
+        a.cls.p[l] = cls[l];
+        a.ctr.p[l] = ctr ? ctr[l] : nullptr;
+        a.row_base[l] = (long long)g.batch * g.off[l];
+        a.rows[l] = (long long)g.batch * g.rows[l];
+        a.block_off[l] = blocks;
+        blocks += (int)((a.rows[l] + rows_per_block - 1) / rows_per_block);
+    }
+    for (int l = g.n_levels; l <= kMaxLevels; ++l) a.block_off[l] = blocks;
+    if (vec == 4)
+        score_argmax_kernel<4><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+    else
+        score_argmax_kernel<1><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
+                                         const int32_t *classes, const void *const *reg,
+                                         int reg_dtype, int is_fcos, int topn, int max_out,
+                                         int nms_type, double nms_threshold, float *out,
+                                         int32_t *order, int32_t *keep, int32_t *counts,
+                                         void *workspace, size_t workspace_bytes, void *stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!keys || !classes || !reg || !out) return B200DET_EINVAL;
+    if (topn < 1 || topn > B200DET_MAX_TOPN || max_out < 1) return B200DET_ERANGE;
+    if (nms_type < B200DET_NMS_PYTHON || nms_type > B200DET_NMS_TORCH) return B200DET_EINVAL;
+    if (reg_dtype != B200DET_F32 && reg_dtype != B200DET_F16 && reg_dtype != B200DET_BF16)
+        return B200DET_EINVAL;
+    if (reinterpret_cast<uintptr_t>(out) & 15) return B200DET_EALIGN;
+    // the boxes block starts at out + 2*B*max_out floats and is written as float4
+    if (((size_t)2 * g.batch * max_out) & 3) return B200DET_EALIGN;
+    SelectArgs a;
+    a.g = g;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        a.reg.p[l] = nullptr;
+        for (int q = 0; q < kMaxPerLoc; ++q)
+            for (int k = 0; k < 4; ++k) a.ba.v[l][q][k] = geo->base_anchors[l][q][k];
+    }
+    const uintptr_t rmask = reg_dtype == B200DET_F32 ? 15 : 7;
+    for (int l = 0; l < g.n_levels; ++l) {
+        if (!reg[l]) return B200DET_EINVAL;
+        if (reinterpret_cast<uintptr_t>(reg[l]) & rmask) return B200DET_EALIGN;
+        a.reg.p[l] = reg[l];
+    }
+    a.reg_dtype = reg_dtype;
+    a.is_fcos = is_fcos;
+    a.topn = topn;
+    int pad_n = 32;
+    while (pad_n < topn) pad_n <<= 1;
+    a.pad_n = pad_n;
+    a.max_out = max_out;
+    a.nms_type = nms_type;
+    a.nms_thr_f = (float)nms_threshold;
+    a.nms_thr_d = nms_threshold;
+    const size_t smem = select_smem_bytes(pad_n);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(select_nms_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)select_smem_bytes(B200DET_MAX_TOPN));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    select_nms_kernel<<<g.batch, kSelThreads, smem, (cudaStream_t)stream>>>(a, keys, classes, out,
+                                                                           order, keep, counts);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200det_npexp_f32(const float *x, float *y, long long n, void *stream) {
+    if (!x || !y || n < 0) return B200DET_EINVAL;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    npexp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,186 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on seeded
+synthetic inputs.  Run in the development container only:
+
+    python tests/golden/make_golden.py
+
+Each fixture stores the exact inputs (so no RNG has to be reproduced elsewhere) and what the
+reference's own classes returned for them:
+  * RetinaLoss / FCOSLoss: loss dict values for every box-loss type, plus the labels the
+    reference's assignment method produced (get_batch_anchors_annotations /
+    get_batch_position_annotations) and FCOS regression/centre-ness targets;
+  * RetinaDecoder / FCOSDecoder: the three returned arrays for python_nms, diou_python_nms and
+    torch_nms, default and small (topn, max_object_num) settings;
+  * RetinaAnchors / FCOSPositions tables; np.exp samples.
+numpy / torch / torchvision versions used are recorded in the fixture.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import refload  # noqa: E402
+from b200det import synth  # noqa: E402
+
+IOU_TYPES = ['IoU', 'GIoU', 'DIoU', 'CIoU', 'EIoU']
+
+
+def versions():
+    import torchvision
+    return np.array([f'numpy {np.__version__}', f'torch {torch.__version__}',
+                     f'torchvision {torchvision.__version__}'])
+
+
+def edge_annotations(ann, size):
+    """Adds the edge cases the domain has: an image without GT, duplicated GT boxes (IoU ties ->
+    first maximum), a degenerate zero-area box, a box touching the image border, interleaved
+    invalid rows (already produced by synth)."""
+    ann = ann.clone()
+    ann[1, :, :] = -1                       # image 1: no annotations at all
+    valid = (ann[0, :, 4] >= 0).nonzero().flatten()
+    free = (ann[0, :, 4] < 0).nonzero().flatten()
+    if len(valid) and len(free) >= 2:
+        ann[0, free[0]] = ann[0, valid[0]]      # exact duplicate, different class
+        ann[0, free[0], 4] = (ann[0, valid[0], 4] + 1) % 3
+        ann[0, free[1]] = torch.tensor([10., 10., 10., 30., 2.])  # zero width
+    ann[2, 0] = torch.tensor([0., 0., float(size), float(size), 1.])  # whole image
+    return ann
+
+
+def make_retina(path):
+    L, D, _ = refload.load()
+    size, C, B, G = 128, 8, 3, 12
+    preds = synth.make_retina_preds(B, size, C, seed=0)
+    preds = synth.make_tie_free(preds)
+    ann = edge_annotations(synth.make_annotations(B, G, size, C, seed=1), size)
+    # plant confident, well-localised predictions so positives exist with sensible box losses
+    out = {'versions': versions(), 'size': size, 'annotations': ann.numpy()}
+    for i, (c, r) in enumerate(zip(*preds)):
+        out[f'cls{i}'] = c.numpy()
+        out[f'reg{i}'] = r.numpy()
+    for box_type in ['SmoothL1'] + IOU_TYPES:
+        crit = L.RetinaLoss(**synth.RETINA_KW, box_loss_type=box_type)
+        with torch.no_grad():
+            d = crit(preds, ann)
+        out[f'loss_{box_type}'] = np.array([d['cls_loss'].item(), d['reg_loss'].item()],
+                                           dtype=np.float32)
+        if box_type in ('SmoothL1', 'GIoU'):
+            anchors = crit.anchors([[c.shape[2], c.shape[1]] for c in preds[0]])
+            flat = torch.cat([torch.tensor(a).view(-1, 4) for a in anchors], dim=0)
+            t = crit.get_batch_anchors_annotations(flat.unsqueeze(0).repeat(B, 1, 1), ann)
+            out[f'assign_{box_type}'] = t.numpy()
+            out['anchors'] = flat.numpy()
+    # gradients of the reference (autograd) for SmoothL1 and GIoU
+    for box_type in ['SmoothL1', 'GIoU', 'CIoU']:
+        crit = L.RetinaLoss(**synth.RETINA_KW, box_loss_type=box_type)
+        p = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+        d = crit(p, ann)
+        (d['cls_loss'] + 2.0 * d['reg_loss']).backward()
+        for i in range(len(p[0])):
+            out[f'gcls_{box_type}_{i}'] = p[0][i].grad.numpy()
+            out[f'greg_{box_type}_{i}'] = p[1][i].grad.numpy()
+    for nms in ['python_nms', 'diou_python_nms', 'torch_nms']:
+        for tag, kw in [('default', {}), ('small', dict(topn=300, max_object_num=20))]:
+            dec = D.RetinaDecoder(**synth.RETINA_KW, nms_type=nms, **kw)
+            s, c, b = dec(preds)
+            out[f'dec_{nms}_{tag}_scores'] = s
+            out[f'dec_{nms}_{tag}_classes'] = c
+            out[f'dec_{nms}_{tag}_boxes'] = b
+    np.savez_compressed(path, **out)
+
+
+def make_fcos(path):
+    L, D, _ = refload.load()
+    size, C, B, G = 256, 8, 3, 12
+    preds = synth.make_fcos_preds(B, size, C, seed=2)
+    preds = synth.make_tie_free(preds)
+    ann = edge_annotations(synth.make_annotations(B, G, size, C, seed=3), size)
+    out = {'versions': versions(), 'size': size, 'annotations': ann.numpy()}
+    for i, (c, r, t) in enumerate(zip(*preds)):
+        out[f'cls{i}'] = c.numpy()
+        out[f'reg{i}'] = r.numpy()
+        out[f'ctr{i}'] = t.numpy()
+    for iou_type in IOU_TYPES:
+        crit = L.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, box_loss_iou_type=iou_type)
+        with torch.no_grad():
+            d = crit(preds, ann)
+        out[f'loss_{iou_type}'] = np.array(
+            [d['cls_loss'].item(), d['reg_loss'].item(), d['center_ness_loss'].item()],
+            dtype=np.float32)
+    for tag, kw in [('center', dict(use_center_sample=True)),
+                    ('nocenter', dict(use_center_sample=False))]:
+        crit = L.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, **kw)
+        with torch.no_grad():
+            d = crit(preds, ann)
+            out[f'loss_{tag}'] = np.array(
+                [d['cls_loss'].item(), d['reg_loss'].item(), d['center_ness_loss'].item()],
+                dtype=np.float32)
+            positions = crit.positions([[c.shape[2], c.shape[1]] for c in preds[0]])
+            batch_positions = [torch.tensor(p).unsqueeze(0).repeat(B, 1, 1, 1) for p in positions]
+            t = crit.get_batch_position_annotations(preds[0], preds[1], preds[2], batch_positions,
+                                                    ann, use_center_sample=kw['use_center_sample'])
+            out[f'targets_{tag}'] = t[3].numpy()
+    for iou_type in ['GIoU', 'EIoU']:
+        crit = L.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, box_loss_iou_type=iou_type)
+        p = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+        d = crit(p, ann)
+        (d['cls_loss'] + 2.0 * d['reg_loss'] + 3.0 * d['center_ness_loss']).backward()
+        for i in range(len(p[0])):
+            out[f'gcls_{iou_type}_{i}'] = p[0][i].grad.numpy()
+            out[f'greg_{iou_type}_{i}'] = p[1][i].grad.numpy()
+            out[f'gctr_{iou_type}_{i}'] = p[2][i].grad.numpy()
+    for nms in ['python_nms', 'diou_python_nms', 'torch_nms']:
+        for tag, kw in [('default', {}), ('small', dict(topn=300, max_object_num=20))]:
+            dec = D.FCOSDecoder(strides=synth.STRIDES, nms_type=nms, **kw)
+            s, c, b = dec(preds)
+            out[f'dec_{nms}_{tag}_scores'] = s
+            out[f'dec_{nms}_{tag}_classes'] = c
+            out[f'dec_{nms}_{tag}_boxes'] = b
+    np.savez_compressed(path, **out)
+
+
+def make_tables(path):
+    _, _, A = refload.load()
+    out = {'versions': versions()}
+    anchors = A.RetinaAnchors(**synth.RETINA_KW)
+    for size in (800, 1024):
+        p = synth.pyramid_sizes(size)
+        levels = anchors([[q, q] for q in p])
+        flat = np.concatenate([a.reshape(-1, 4) for a in levels], axis=0)
+        # full tables are ~2 MB each: store the base anchors, two rows per level and a checksum
+        out[f'anchors_{size}_sum'] = flat.astype(np.float64).sum(axis=0)
+        out[f'anchors_{size}_head'] = np.stack([a.reshape(-1, 4)[:18] for a in levels])
+        out[f'anchors_{size}_tail'] = np.stack([a.reshape(-1, 4)[-9:] for a in levels])
+        pos = A.FCOSPositions(strides=synth.STRIDES)([[q, q] for q in p])
+        out[f'positions_{size}_sum'] = np.concatenate([q.reshape(-1, 2) for q in pos]).astype(
+            np.float64).sum(axis=0)
+    out['base_anchors'] = np.stack(
+        [anchors.generate_base_anchors(a, anchors.scales, anchors.ratios) for a in anchors.areas])
+    # non-square map and odd strides
+    odd = A.RetinaAnchors(areas=[[24, 40], [48, 80]], ratios=[0.5, 1, 2], scales=[1, 1.5],
+                          strides=[6, 12])
+    lv = odd([[7, 5], [4, 3]])
+    out['odd_anchors0'] = lv[0]
+    out['odd_anchors1'] = lv[1]
+    rng = np.random.RandomState(7)
+    x = np.concatenate([rng.normal(0, 2, 4096), rng.uniform(-104, 89, 4096),
+                        np.array([0., -0., 1e-30, -1e-30, 88.7228, 88.7229, -103.97, -103.98,
+                                  np.inf, -np.inf, np.nan])]).astype(np.float32)
+    out['exp_x'] = x
+    with np.errstate(all='ignore'):
+        out['exp_y'] = np.exp(x)
+    np.savez_compressed(path, **out)
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    make_retina(os.path.join(HERE, 'retina_small.npz'))
+    make_fcos(os.path.join(HERE, 'fcos_small.npz'))
+    make_tables(os.path.join(HERE, 'tables.npz'))
+    for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
