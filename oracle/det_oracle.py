@@ -217,12 +217,13 @@ def retina_assign(anchors, annotations, box_loss_type='SmoothL1'):
     Returns (targets [B,A,5], labels [B,A] int64, matched [B,A] int64).  `matched` indexes the
     image's FILTERED GT list (rows with class >= 0); -1 for images without GT."""
     num_anchors = anchors.shape[0]
+    device = annotations.device
     all_targets, all_labels, all_matched = [], [], []
     for annots in annotations:
         annots = annots[annots[:, 4] >= 0]
         if annots.shape[0] == 0:
-            targets = torch.ones([num_anchors, 5], dtype=torch.float32) * (-1)
-            matched = torch.full([num_anchors], -1, dtype=torch.int64)
+            targets = torch.ones([num_anchors, 5], dtype=torch.float32, device=device) * (-1)
+            matched = torch.full([num_anchors], -1, dtype=torch.int64, device=device)
         else:
             gt_boxes, gt_cls = annots[:, 0:4], annots[:, 4]
             ious = box_iou(anchors.unsqueeze(1), gt_boxes.unsqueeze(0), 'IoU')
@@ -248,7 +249,8 @@ def retina_loss(preds, annotations, areas, ratios, scales, strides, alpha=0.25, 
     cls_levels, reg_levels = preds
     batch = annotations.shape[0]
     level_anchors = retina_anchors(feature_sizes_of(cls_levels), areas, ratios, scales, strides)
-    anchors = torch.cat([torch.tensor(a).view(-1, 4) for a in level_anchors], dim=0)
+    device = annotations.device
+    anchors = torch.cat([torch.tensor(a).view(-1, 4) for a in level_anchors], dim=0).to(device)
     targets, labels, matched = retina_assign(anchors, annotations, box_loss_type)
 
     cls = torch.cat([c.view(c.shape[0], -1, c.shape[-1]) for c in cls_levels], dim=1)
@@ -266,7 +268,7 @@ def retina_loss(preds, annotations, areas, ratios, scales, strides, alpha=0.25, 
     num_pos = int((flat_used[:, 4] > 0).sum())
     out['num_pos'] = num_pos
     if num_pos == 0:
-        cls_loss = torch.tensor(0.)
+        cls_loss = torch.tensor(0.).to(device)
         out['cls_sum'] = torch.tensor(0.)
     else:
         cls_sum = _focal_sum(cls_used, flat_used[:, 4], alpha, gamma)
@@ -276,7 +278,7 @@ def retina_loss(preds, annotations, areas, ratios, scales, strides, alpha=0.25, 
     pos = flat[:, 4] > 0
     reg_pos, anc_pos, flat_pos = reg[pos], batch_anchors[pos], flat[pos]
     if flat_pos.shape[0] == 0:
-        reg_loss = torch.tensor(0.)
+        reg_loss = torch.tensor(0.).to(device)
         out['reg_sum'] = torch.tensor(0.)
     elif box_loss_type == 'SmoothL1':
         x = torch.abs(reg_pos - flat_pos[:, 0:4])
@@ -305,15 +307,17 @@ def fcos_assign(points, point_mi, point_stride, annotations, center_sample_radiu
     Returns (targets [B,P,6] = l,t,r,b,label,centerness ; labels [B,P] int64 ;
     matched [B,P] int64 = index in the filtered GT list, -1 for background)."""
     num_points = points.shape[0]
+    device = annotations.device
     all_targets, all_matched = [], []
     for annots in annotations:
         annots = annots[annots[:, 4] >= 0]
-        targets = torch.zeros([num_points, 6], dtype=torch.float32)
-        matched = torch.full([num_points], -1, dtype=torch.int64)
+        targets = torch.zeros([num_points, 6], dtype=torch.float32, device=device)
+        matched = torch.full([num_points], -1, dtype=torch.int64, device=device)
         if annots.shape[0] > 0:
             num_gt = annots.shape[0]
             gt = annots[:, 0:4]
-            cand = torch.zeros([num_points, num_gt, 4], dtype=torch.float32) + gt.unsqueeze(0)
+            cand = torch.zeros([num_points, num_gt, 4], dtype=torch.float32,
+                               device=device) + gt.unsqueeze(0)
             pts = points.unsqueeze(1).repeat(1, num_gt, 1)
             if use_center_sample:
                 gt_ctr = (cand[:, :, 2:4] + cand[:, :, 0:2]) / 2
@@ -336,7 +340,7 @@ def fcos_assign(points, point_mi, point_stride, annotations, center_sample_radiu
                 pos_cand = cand[pos_idx]
                 gt_cls = annots[:, 4]
                 if num_gt == 1:
-                    choice = torch.zeros([pos_cand.shape[0]], dtype=torch.int64)
+                    choice = torch.zeros([pos_cand.shape[0]], dtype=torch.int64, device=device)
                 else:
                     gt_wh = gt[:, 2:4] - gt[:, 0:2]
                     gt_area = (gt_wh[:, 0] * gt_wh[:, 1]).unsqueeze(0).repeat(
@@ -344,7 +348,7 @@ def fcos_assign(points, point_mi, point_stride, annotations, center_sample_radiu
                     big = torch.ones_like(gt_area) * 100000000
                     gt_area = torch.where(torch.eq(pos_cand.sum(axis=2), 0.), big, gt_area)
                     choice = gt_area.min(axis=1)[1]
-                rows = torch.arange(pos_cand.shape[0])
+                rows = torch.arange(pos_cand.shape[0], device=device)
                 targets[pos_idx, 0:4] = pos_cand[rows, choice, :]
                 targets[pos_idx, 4] = gt_cls[choice] + 1
                 l, t = targets[pos_idx, 0:1], targets[pos_idx, 1:2]
@@ -378,7 +382,9 @@ def fcos_loss(preds, annotations, strides, mi, alpha=0.25, gamma=2., cls_loss_we
     'num_pos' and the three un-normalised sums."""
     cls_levels, reg_levels, ctr_levels = preds
     batch = annotations.shape[0]
-    points, point_mi, point_stride = fcos_point_tables(reg_levels, strides, mi)
+    device = annotations.device
+    points, point_mi, point_stride = [
+        t.to(device) for t in fcos_point_tables(reg_levels, strides, mi)]
     targets, labels, matched = fcos_assign(points, point_mi, point_stride, annotations,
                                            center_sample_radius, use_center_sample)
     cls = torch.cat([c.view(c.shape[0], -1, c.shape[-1]) for c in cls_levels], dim=1)
@@ -396,7 +402,7 @@ def fcos_loss(preds, annotations, strides, mi, alpha=0.25, gamma=2., cls_loss_we
     pos = full[:, 4] > 0
     num_pos = int(pos.sum())
     out = {'labels': labels, 'matched': matched, 'targets': targets, 'num_pos': num_pos}
-    zero = torch.tensor(0.)
+    zero = torch.tensor(0.).to(device)
     if num_pos == 0:
         out.update(cls_sum=zero, reg_sum=zero, ctr_sum=zero, cls_loss=cls_loss_weight * zero,
                    reg_loss=box_loss_weight * zero,

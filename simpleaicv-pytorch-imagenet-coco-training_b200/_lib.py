@@ -129,3 +129,37 @@ def ptr_array(tensors):
 
 def launch_count():
     return int(load().b200det_launch_count())
+
+
+# Optional per-kernel timing (bench.py): when PROFILE is a dict, every C-ABI launch made by the
+# drop-in classes is bracketed by CUDA events on the launching stream; durations are read after
+# the caller synchronises.  None (default) = no events, no overhead.
+PROFILE = None
+
+
+class timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            import torch
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.stop = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.stop.record()
+            PROFILE.setdefault(self.name, []).append((self.start, self.stop))
+        return False
+
+
+def profile_summary():
+    """{kernel name: (launches, mean ms)} from the recorded events (call after a synchronize)."""
+    out = {}
+    for name, pairs in (PROFILE or {}).items():
+        ms = [a.elapsed_time(b) for a, b in pairs]
+        out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    return out

@@ -64,18 +64,22 @@ class _DecoderBase:
             keep = torch.empty(batch * self.topn, dtype=torch.int32, device=device)
             counts = torch.empty(batch * 3, dtype=torch.int32, device=device)
 
-        _lib.check(
-            lib.b200det_score_argmax(ctypes.byref(geo), _lib.ptr_array(cls), _lib.ptr_array(ctr),
-                                     float(np.float32(self.min_score_threshold)), keys.data_ptr(),
-                                     classes.data_ptr(), st), 'b200det_score_argmax')
-        _lib.check(
-            lib.b200det_select_decode_nms(
-                ctypes.byref(geo), keys.data_ptr(), classes.data_ptr(), _lib.ptr_array(reg),
-                reg_dtype, int(self._is_fcos), int(self.topn), m, self._nms_code,
-                float(self.nms_threshold), out.data_ptr(),
-                order.data_ptr() if details else None, keep.data_ptr() if details else None,
-                counts.data_ptr() if details else None, None, 0, st),
-            'b200det_select_decode_nms')
+        with _lib.timed('score_argmax'):
+            _lib.check(
+                lib.b200det_score_argmax(ctypes.byref(geo), _lib.ptr_array(cls),
+                                         _lib.ptr_array(ctr),
+                                         float(np.float32(self.min_score_threshold)),
+                                         keys.data_ptr(), classes.data_ptr(), st),
+                'b200det_score_argmax')
+        with _lib.timed('select_decode_nms'):
+            _lib.check(
+                lib.b200det_select_decode_nms(
+                    ctypes.byref(geo), keys.data_ptr(), classes.data_ptr(), _lib.ptr_array(reg),
+                    reg_dtype, int(self._is_fcos), int(self.topn), m, self._nms_code,
+                    float(self.nms_threshold), out.data_ptr(),
+                    order.data_ptr() if details else None, keep.data_ptr() if details else None,
+                    counts.data_ptr() if details else None, None, 0, st),
+                'b200det_select_decode_nms')
 
         host = out.cpu().numpy()  # the only D2H copy: 24*M bytes per image (synchronises)
         scores = host[0:batch * m].reshape(batch, m)

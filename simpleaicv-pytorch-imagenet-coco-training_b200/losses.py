@@ -136,20 +136,24 @@ class _DetLossFunction(torch.autograd.Function):
         cls_grad = [torch.empty_like(c) for c in cls] if want_grad else None
 
         if is_fcos:
-            _lib.check(
-                lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                        int(annotations.shape[1]), _lib.ptr_array(reg), reg_dtype,
-                                        _lib.ptr_array(ctr), owner._box_code,
-                                        int(owner.use_center_sample), labels.data_ptr(), None, None,
-                                        _lib.ptr_array(reg_grad), _lib.ptr_array(ctr_grad),
-                                        ws.data_ptr(), ws_bytes, st), 'b200det_fcos_assign')
+            with _lib.timed('fcos_assign'):
+                _lib.check(
+                    lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
+                                            int(annotations.shape[1]), _lib.ptr_array(reg),
+                                            reg_dtype, _lib.ptr_array(ctr), owner._box_code,
+                                            int(owner.use_center_sample), labels.data_ptr(), None,
+                                            None, _lib.ptr_array(reg_grad),
+                                            _lib.ptr_array(ctr_grad), ws.data_ptr(), ws_bytes, st),
+                    'b200det_fcos_assign')
         else:
-            _lib.check(
-                lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                          int(annotations.shape[1]), _lib.ptr_array(reg), reg_dtype,
-                                          owner._box_code, float(owner.beta), labels.data_ptr(),
-                                          None, _lib.ptr_array(reg_grad), ws.data_ptr(), ws_bytes,
-                                          st), 'b200det_retina_assign')
+            with _lib.timed('retina_assign'):
+                _lib.check(
+                    lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
+                                              int(annotations.shape[1]), _lib.ptr_array(reg),
+                                              reg_dtype, owner._box_code, float(owner.beta),
+                                              labels.data_ptr(), None, _lib.ptr_array(reg_grad),
+                                              ws.data_ptr(), ws_bytes, st),
+                    'b200det_retina_assign')
         sync, group = owner.sync_normalizer, owner.process_group
         if want_grad:
             # the focal gradient is written once, already divided by the (global) positive count
@@ -157,13 +161,14 @@ class _DetLossFunction(torch.autograd.Function):
                 lib.b200det_loss_reduce(ctypes.byref(geo), 1, ws.data_ptr(), ws_bytes,
                                         sums.data_ptr(), st), 'b200det_loss_reduce')
             _maybe_all_reduce(sums, sync, group)
-        _lib.check(
-            lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls), labels.data_ptr(),
-                                   float(owner.alpha), float(owner.gamma),
-                                   _lib.ptr_array(cls_grad),
-                                   sums.data_ptr() if want_grad else None,
-                                   float(owner.cls_loss_weight), ws.data_ptr(), ws_bytes, st),
-            'b200det_focal_loss')
+        with _lib.timed('focal_loss'):
+            _lib.check(
+                lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls), labels.data_ptr(),
+                                       float(owner.alpha), float(owner.gamma),
+                                       _lib.ptr_array(cls_grad),
+                                       sums.data_ptr() if want_grad else None,
+                                       float(owner.cls_loss_weight), ws.data_ptr(), ws_bytes, st),
+                'b200det_focal_loss')
         if want_grad:
             focal = torch.zeros(4, dtype=torch.float64, device=device)
             _lib.check(
@@ -172,9 +177,10 @@ class _DetLossFunction(torch.autograd.Function):
             _maybe_all_reduce(focal, sync, group)
             sums = sums + focal
         else:
-            _lib.check(
-                lib.b200det_loss_reduce(ctypes.byref(geo), 3, ws.data_ptr(), ws_bytes,
-                                        sums.data_ptr(), st), 'b200det_loss_reduce')
+            with _lib.timed('loss_reduce'):
+                _lib.check(
+                    lib.b200det_loss_reduce(ctypes.byref(geo), 3, ws.data_ptr(), ws_bytes,
+                                            sums.data_ptr(), st), 'b200det_loss_reduce')
             _maybe_all_reduce(sums, sync, group)
         _lib.check(
             lib.b200det_loss_finish(sums.data_ptr(), float(owner.cls_loss_weight),

@@ -1,0 +1,488 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in classes) against
+  (a) the golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+  (b) the oracle on seeded inputs at the BASELINE.json shapes.
+Bars: labels / matched indices / targets / top-n order / keep lists / decoded boxes / scores
+bit-exact; loss values within 1e-5 relative; gradients within 1e-4 relative (+1e-7 abs)."""
+import numpy as np
+import pytest
+import torch
+
+from b200det import synth, losses, decode
+from oracle import det_oracle as O
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5   # north_star: "loss values must agree within 1e-5 relative"
+GRAD_RTOL = 1e-4
+GRAD_ATOL = 1e-7
+
+
+def dev(preds):
+    return synth.to_device(preds, 'cuda')
+
+
+def loss_values(d, keys):
+    return np.array([d[k].item() for k in keys], dtype=np.float64)
+
+
+def assert_close(got, want, rtol, what):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
+    assert (err <= rtol).all(), f'{what}: got {got}, want {want}, rel err {err}'
+
+
+def assert_targets_equal(got, want, what):
+    """FCOS targets: l,t,r,b,label bit-exact.  Centre-ness is sqrt(...) (losses.py:822-824): the
+    kernel and torch-CUDA use the correctly rounded IEEE sqrt, but torch-CPU's float32 sqrt goes
+    through MKL VML and is off by one ulp for ~0.6 % of inputs (measured), so against CPU-made
+    truth the centre-ness may differ by exactly one ulp; test_fcos_targets_vs_oracle_on_cuda
+    checks it bit-exactly against the same oracle run on torch-CUDA."""
+    got = np.asarray(got)
+    want = np.asarray(want)
+    G.assert_bit_equal(got[..., 0:5], want[..., 0:5], what + ' l,t,r,b,label')
+    ulp = np.abs(G.bits(got[..., 5]).astype(np.int64) - G.bits(want[..., 5]).astype(np.int64))
+    assert ulp.max() <= 1, f'{what}: centre-ness differs by {ulp.max()} ulp'
+    assert (ulp != 0).mean() < 0.02
+
+
+def check_decode_details(info, extras, topn):
+    for b, e in enumerate(extras):
+        n = len(e['order'])
+        assert info['counts'][b, 1] == n
+        assert np.array_equal(info['order'][b, :n], e['order']), f'top-n order, image {b}'
+        assert (info['order'][b, n:] == -1).all()
+        k = len(e['keep'])
+        assert info['counts'][b, 2] == k
+        assert np.array_equal(info['keep'][b, :k], e['keep']), f'NMS keep list, image {b}'
+        assert (info['keep'][b, k:] == -1).all()
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors (reference outputs)
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def retina():
+    return G.load('retina_small.npz')
+
+
+@pytest.fixture(scope='module')
+def fcos():
+    return G.load('fcos_small.npz')
+
+
+@pytest.mark.parametrize('box_type', ['SmoothL1'] + G.IOU_TYPES)
+def test_retina_loss_golden(retina, box_type):
+    preds, ann = G.retina_inputs(retina)
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type=box_type).cuda()
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+    assert set(d.keys()) == {'cls_loss', 'reg_loss'}
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss']), retina[f'loss_{box_type}'], LOSS_RTOL,
+                 f'RetinaLoss {box_type}')
+
+
+def test_retina_assignment_golden(retina):
+    preds, ann = G.retina_inputs(retina)
+    crit = losses.RetinaLoss(**synth.RETINA_KW)
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    want = retina['assign_GIoU']
+    assert np.array_equal(got['labels'].cpu().numpy(), want[..., 4].astype(np.int32))
+    _, _, matched = O.retina_assign(torch.from_numpy(retina['anchors'].copy()), ann, 'GIoU')
+    assert np.array_equal(got['matched'].cpu().numpy(), matched.numpy().astype(np.int32))
+
+
+@pytest.mark.parametrize('box_type', ['SmoothL1', 'GIoU', 'CIoU'])
+def test_retina_gradients_golden(retina, box_type):
+    preds, ann = G.retina_inputs(retina)
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(preds)]
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type=box_type)
+    d = crit(p, ann.cuda())
+    (d['cls_loss'] + 2.0 * d['reg_loss']).backward()
+    for i in range(len(p[0])):
+        np.testing.assert_allclose(p[0][i].grad.cpu().numpy(), retina[f'gcls_{box_type}_{i}'],
+                                   rtol=GRAD_RTOL, atol=GRAD_ATOL)
+        np.testing.assert_allclose(p[1][i].grad.cpu().numpy(), retina[f'greg_{box_type}_{i}'],
+                                   rtol=GRAD_RTOL, atol=GRAD_ATOL)
+
+
+@pytest.mark.parametrize('nms', ['python_nms', 'diou_python_nms', 'torch_nms'])
+@pytest.mark.parametrize('tag,kw', [('default', {}), ('small', dict(topn=300, max_object_num=20))])
+def test_retina_decoder_golden(retina, nms, tag, kw):
+    preds, _ = G.retina_inputs(retina)
+    dec = decode.RetinaDecoder(**synth.RETINA_KW, nms_type=nms, **kw)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    assert s.dtype == np.float32 and c.dtype == np.float32 and b.dtype == np.float32
+    assert s.flags.writeable and b.flags.writeable
+    G.assert_bit_equal(s, retina[f'dec_{nms}_{tag}_scores'], 'scores')
+    G.assert_bit_equal(c, retina[f'dec_{nms}_{tag}_classes'], 'classes')
+    G.assert_bit_equal(b, retina[f'dec_{nms}_{tag}_boxes'], 'boxes')
+    _, extra = O.retina_decode(preds, **synth.RETINA_KW, nms_type=nms, **kw)
+    check_decode_details(info, extra['per_image'], dec.topn)
+    s2, c2, b2 = dec(dev(preds))   # the plain __call__ path (NMS stops at max_object_num)
+    G.assert_bit_equal(s2, s)
+    G.assert_bit_equal(c2, c)
+    G.assert_bit_equal(b2, b)
+
+
+@pytest.mark.parametrize('iou_type', G.IOU_TYPES)
+def test_fcos_loss_golden(fcos, iou_type):
+    preds, ann = G.fcos_inputs(fcos)
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, box_loss_iou_type=iou_type)
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+    assert set(d.keys()) == {'cls_loss', 'reg_loss', 'center_ness_loss'}
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                 fcos[f'loss_{iou_type}'], LOSS_RTOL, f'FCOSLoss {iou_type}')
+
+
+@pytest.mark.parametrize('tag,center', [('center', True), ('nocenter', False)])
+def test_fcos_assignment_golden(fcos, tag, center):
+    preds, ann = G.fcos_inputs(fcos)
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, use_center_sample=center)
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    want = fcos[f'targets_{tag}']
+    assert_targets_equal(got['targets'].cpu().numpy(), want[..., 0:6], 'golden targets')
+    assert np.array_equal(got['labels'].cpu().numpy(), want[..., 4].astype(np.int32))
+    with torch.no_grad():
+        ref = O.fcos_loss(preds, ann, synth.STRIDES, synth.MI, use_center_sample=center)
+        d = crit(dev(preds), ann.cuda())
+    assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                 fcos[f'loss_{tag}'], LOSS_RTOL, 'FCOSLoss')
+
+
+@pytest.mark.parametrize('iou_type', ['GIoU', 'EIoU'])
+def test_fcos_gradients_golden(fcos, iou_type):
+    preds, ann = G.fcos_inputs(fcos)
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(preds)]
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, box_loss_iou_type=iou_type)
+    d = crit(p, ann.cuda())
+    (d['cls_loss'] + 2.0 * d['reg_loss'] + 3.0 * d['center_ness_loss']).backward()
+    for i in range(len(p[0])):
+        np.testing.assert_allclose(p[0][i].grad.cpu().numpy(), fcos[f'gcls_{iou_type}_{i}'],
+                                   rtol=GRAD_RTOL, atol=GRAD_ATOL)
+        np.testing.assert_allclose(p[1][i].grad.cpu().numpy(), fcos[f'greg_{iou_type}_{i}'],
+                                   rtol=GRAD_RTOL, atol=GRAD_ATOL)
+        np.testing.assert_allclose(p[2][i].grad.cpu().numpy(), fcos[f'gctr_{iou_type}_{i}'],
+                                   rtol=GRAD_RTOL, atol=GRAD_ATOL)
+
+
+@pytest.mark.parametrize('nms', ['python_nms', 'diou_python_nms', 'torch_nms'])
+@pytest.mark.parametrize('tag,kw', [('default', {}), ('small', dict(topn=300, max_object_num=20))])
+def test_fcos_decoder_golden(fcos, nms, tag, kw):
+    preds, _ = G.fcos_inputs(fcos)
+    dec = decode.FCOSDecoder(strides=synth.STRIDES, nms_type=nms, **kw)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    G.assert_bit_equal(s, fcos[f'dec_{nms}_{tag}_scores'], 'scores')
+    G.assert_bit_equal(c, fcos[f'dec_{nms}_{tag}_classes'], 'classes')
+    G.assert_bit_equal(b, fcos[f'dec_{nms}_{tag}_boxes'], 'boxes')
+    _, extra = O.fcos_decode(preds, synth.STRIDES, nms_type=nms, **kw)
+    check_decode_details(info, extra['per_image'], dec.topn)
+
+
+def test_fcos_targets_vs_oracle_on_cuda(fcos):
+    """The oracle's torch ops run on CUDA tensors (how the reference runs in training): every
+    primitive is then a correctly rounded IEEE op and the whole target tensor is bit-exact."""
+    preds, ann = G.fcos_inputs(fcos)
+    for center in (True, False):
+        crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, use_center_sample=center)
+        got = crit.debug_assign(dev(preds), ann.cuda())
+        with torch.no_grad():
+            ref = O.fcos_loss(dev(preds), ann.cuda(), synth.STRIDES, synth.MI,
+                              use_center_sample=center)
+        G.assert_bit_equal(got['targets'].cpu().numpy(), ref['targets'].cpu().numpy(), 'targets')
+        assert np.array_equal(got['matched'].cpu().numpy(),
+                              ref['matched'].cpu().numpy().astype(np.int32))
+    preds, ann = G.retina_inputs(G.load('retina_small.npz'))
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    with torch.no_grad():
+        ref = O.retina_loss(dev(preds), ann.cuda(), **synth.RETINA_KW, box_loss_type='GIoU')
+    assert np.array_equal(got['labels'].cpu().numpy(), ref['labels'].cpu().numpy().astype(np.int32))
+    assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].cpu().numpy().astype(np.int32))
+
+
+# ------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------
+def test_npexp_kernel():
+    import ctypes
+    from b200det import _lib
+    lib = _lib.load()
+    t = G.load('tables.npz')
+    rng = np.random.RandomState(11)
+    x = np.concatenate([t['exp_x'], rng.uniform(-110, 90, 1 << 20).astype(np.float32),
+                        rng.normal(0, 1, 1 << 20).astype(np.float32)])
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    _lib.check(lib.b200det_npexp_f32(xd.data_ptr(), yd.data_ptr(), xd.numel(),
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               'npexp')
+    G.assert_bit_equal(yd.cpu().numpy(), O.np_exp_f32(x), 'device npexp vs oracle')
+    G.assert_bit_equal(yd.cpu().numpy()[:t['exp_y'].size], t['exp_y'], 'device npexp vs np.exp')
+
+
+@pytest.mark.parametrize('size', [800, 1024])
+def test_generated_rows(size):
+    import ctypes
+    from b200det import _lib, geometry
+    lib = _lib.load()
+    p = synth.pyramid_sizes(size)
+    shapes = [(q, q) for q in p]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    base = geometry.retina_base_anchors(synth.AREAS, synth.RATIOS, synth.SCALES)
+    geo = geometry.make_geometry(shapes, 1, 9, 80, synth.STRIDES, base_anchors=base)
+    n = geometry.rows_per_image(shapes, 9)
+    out = torch.empty(n * 4, dtype=torch.float32, device='cuda')
+    _lib.check(lib.b200det_generate_rows(ctypes.byref(geo), 0, out.data_ptr(), st), 'rows')
+    want = np.concatenate([a.reshape(-1, 4) for a in
+                           O.retina_anchors([[q, q] for q in p], **synth.RETINA_KW)])
+    G.assert_bit_equal(out.cpu().numpy().reshape(-1, 4), want, 'anchors')
+    geo = geometry.make_geometry(shapes, 1, 1, 80, synth.STRIDES)
+    n = geometry.rows_per_image(shapes, 1)
+    out = torch.empty(n * 2, dtype=torch.float32, device='cuda')
+    _lib.check(lib.b200det_generate_rows(ctypes.byref(geo), 1, out.data_ptr(), st), 'rows')
+    want = np.concatenate([a.reshape(-1, 2) for a in
+                           O.fcos_positions([[q, q] for q in p], synth.STRIDES)])
+    G.assert_bit_equal(out.cpu().numpy().reshape(-1, 2), want, 'positions')
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json shapes vs the oracle (sizes the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------
+def test_config1_retina_decode_800():
+    """configs[0]: RetinaDecoder + NMS, COCO 80 cls, 800x800, 9 anchors, batch 1."""
+    preds = synth.make_tie_free(synth.make_retina_preds(1, 800, 80, seed=0))
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **synth.RETINA_KW)
+    G.assert_bit_equal(s, s0, 'scores')
+    G.assert_bit_equal(c, c0, 'classes')
+    G.assert_bit_equal(b, b0, 'boxes')
+    check_decode_details(info, extra['per_image'], 1000)
+    assert info['counts'][0, 0] == int((extra['scores'][0] > np.float32(0.05)).sum())
+
+
+@pytest.mark.parametrize('box_type', ['SmoothL1', 'GIoU'])
+def test_config2_retina_loss_800(box_type):
+    """configs[1] at batch 4 (the oracle needs ~1 s per image): assignment + focal + box loss."""
+    B, G_ = 4, 100
+    preds = synth.make_retina_preds(B, 800, 80, seed=0)
+    ann = synth.make_annotations(B, G_, 800, 80, seed=1, empty_images=(2,))
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type=box_type)
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+        ref = O.retina_loss(preds, ann, **synth.RETINA_KW, box_loss_type=box_type)
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    assert np.array_equal(got['labels'].cpu().numpy(), ref['labels'].numpy().astype(np.int32))
+    assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+    assert int(crit.last_stats['sums'][0].item()) == ref['num_pos'] > 0
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
+                 [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, 'RetinaLoss')
+
+
+def test_config3_fcos_800():
+    """configs[2] at batch 4: FCOSLoss centre-sampling assignment + FCOSDecoder NMS."""
+    B, G_ = 4, 100
+    preds = synth.make_tie_free(synth.make_fcos_preds(B, 800, 80, seed=0))
+    ann = synth.make_annotations(B, G_, 800, 80, seed=1, empty_images=(1,))
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+        ref = O.fcos_loss(preds, ann, synth.STRIDES, synth.MI)
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    assert_targets_equal(got['targets'].cpu().numpy(), ref['targets'].numpy(), 'targets')
+    assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                 [ref['cls_loss'].item(), ref['reg_loss'].item(), ref['center_ness_loss'].item()],
+                 LOSS_RTOL, 'FCOSLoss')
+    dec = decode.FCOSDecoder(strides=synth.STRIDES)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.fcos_decode(preds, synth.STRIDES)
+    G.assert_bit_equal(s, s0, 'scores')
+    G.assert_bit_equal(c, c0, 'classes')
+    G.assert_bit_equal(b, b0, 'boxes')
+    check_decode_details(info, extra['per_image'], 1000)
+
+
+def test_config4_fcos_objects365_1024():
+    """configs[3] at batch 2: 365 classes (rows not 16-byte aligned -> scalar path), 1024x1024,
+    up to 200 GT per image."""
+    B, G_ = 2, 200
+    preds = synth.make_tie_free(synth.make_fcos_preds(B, 1024, 365, seed=4))
+    ann = synth.make_annotations(B, G_, 1024, 365, seed=5, min_gt=150)
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+        ref = O.fcos_loss(preds, ann, synth.STRIDES, synth.MI)
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    assert_targets_equal(got['targets'].cpu().numpy(), ref['targets'].numpy(), 'targets')
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                 [ref['cls_loss'].item(), ref['reg_loss'].item(), ref['center_ness_loss'].item()],
+                 LOSS_RTOL, 'FCOSLoss')
+    dec = decode.FCOSDecoder(strides=synth.STRIDES)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.fcos_decode(preds, synth.STRIDES)
+    G.assert_bit_equal(s, s0, 'scores')
+    G.assert_bit_equal(c, c0, 'classes')
+    G.assert_bit_equal(b, b0, 'boxes')
+    check_decode_details(info, extra['per_image'], 1000)
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------
+def test_no_annotations_anywhere():
+    preds = synth.make_retina_preds(2, 128, 8, seed=3)
+    ann = torch.full((2, 6, 5), -1.)
+    d = losses.RetinaLoss(**synth.RETINA_KW)(dev(preds), ann.cuda())
+    assert d['cls_loss'].item() == 0. and d['reg_loss'].item() == 0.   # losses.py:234-235
+    got = losses.RetinaLoss(**synth.RETINA_KW).debug_assign(dev(preds), ann.cuda())
+    assert (got['labels'] == -1).all() and (got['matched'] == -1).all()  # losses.py:341-345
+    fp = synth.make_fcos_preds(2, 128, 8, seed=3)
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    d = crit(dev(fp), ann.cuda())
+    assert all(v.item() == 0. for v in d.values())
+    got = crit.debug_assign(dev(fp), ann.cuda())
+    assert (got['labels'] == 0).all() and (got['targets'] == 0).all()     # losses.py:671-675
+    empty = torch.zeros((2, 0, 5))
+    d = crit(dev(fp), empty.cuda())
+    assert all(v.item() == 0. for v in d.values())
+
+
+def test_no_candidates_and_few_candidates():
+    preds = synth.make_retina_preds(2, 128, 8, seed=3)
+    for c in preds[0]:
+        c.mul_(0.01)                       # every score far below 0.05
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    s, c, b = dec(dev(preds))
+    assert (s == -1).all() and (c == -1).all() and (b == 0).all()
+    preds[0][0][1, 3, 4, 2, 5] = 0.9       # exactly one candidate in image 1
+    preds[0][2][1, 0, 1, 7, 0] = 0.05      # == threshold: strict '>' keeps it out
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **synth.RETINA_KW)
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0)
+    assert info['counts'][:, 0].tolist() == [0, 1]
+
+
+def test_heavy_score_ties_are_ordered_by_row():
+    """All-equal scores: the reference's argsort order is undefined; ours is ascending row index
+    (the oracle's stable sort), and the radix select must cut the tie bucket exactly."""
+    preds = synth.make_retina_preds(2, 128, 8, seed=3)
+    for c in preds[0]:
+        c.fill_(0.02)
+        c[..., 3] = 0.3
+    preds[0][1][0, 1, 1, 4, 6] = 0.7
+    dec = decode.RetinaDecoder(**synth.RETINA_KW, topn=500, max_object_num=50)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **synth.RETINA_KW, topn=500, max_object_num=50)
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0)
+    check_decode_details(info, extra['per_image'], 500)
+
+
+def test_extreme_regression_values_truncate_like_x86():
+    """exp overflow / huge boxes: NumPy's astype(int32) yields INT_MIN, CUDA would saturate."""
+    preds = synth.make_tie_free(synth.make_retina_preds(1, 128, 8, seed=5))
+    preds[1][0][0, :4, :, :, 2:] = 30.      # exp(30) * anchor >> 2^31
+    preds[1][0][0, 4:8, :, :, 2:] = 95.     # exp -> inf
+    preds[1][1][0, :, :, :, 0] = -1e9
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **synth.RETINA_KW)
+    G.assert_bit_equal(b, b0, 'boxes')
+    G.assert_bit_equal(s, s0, 'scores')
+    check_decode_details(info, extra['per_image'], 1000)
+
+
+def test_half_precision_regression_head():
+    """Under autocast the Retina reg head is fp16: accepted and upcast."""
+    preds = synth.make_tie_free(synth.make_retina_preds(2, 128, 8, seed=6))
+    ann = synth.make_annotations(2, 12, 128, 8, seed=7)
+    for dt in (torch.float16, torch.bfloat16):
+        half = [preds[0], [r.to(dt) for r in preds[1]]]
+        up = [preds[0], [r.float() for r in half[1]]]
+        crit = losses.RetinaLoss(**synth.RETINA_KW)
+        with torch.no_grad():
+            d = crit(dev(half), ann.cuda())
+            ref = O.retina_loss(up, ann, **synth.RETINA_KW)
+        assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
+                     [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, str(dt))
+        s, c, b = decode.RetinaDecoder(**synth.RETINA_KW)(dev(half))
+        (s0, c0, b0), _ = O.retina_decode(up, **synth.RETINA_KW)
+        G.assert_bit_equal(b, b0, 'boxes')
+
+
+def test_non_default_focal_parameters_and_weights():
+    preds = synth.make_retina_preds(2, 128, 8, seed=8)
+    ann = synth.make_annotations(2, 12, 128, 8, seed=9)
+    kw = dict(alpha=0.4, gamma=1.5, beta=0.3, cls_loss_weight=0.7, box_loss_weight=2.5)
+    crit = losses.RetinaLoss(**synth.RETINA_KW, **kw)
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+        ref = O.retina_loss(preds, ann, **synth.RETINA_KW, **kw)
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
+                 [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, 'RetinaLoss')
+
+
+def test_cpu_tensors_are_rejected():
+    preds = synth.make_retina_preds(1, 128, 8, seed=8)
+    ann = synth.make_annotations(1, 4, 128, 8, seed=9)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        losses.RetinaLoss(**synth.RETINA_KW)(preds, ann)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        decode.RetinaDecoder(**synth.RETINA_KW)(preds)
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at the benchmark shape
+# ------------------------------------------------------------------------------------------
+def test_sharding_linearity_full_size():
+    """Sums over an image-sharded batch add up to the unsharded sums (what the multi-GPU
+    all-reduce relies on); labels are per-image, so shard labels concatenate exactly."""
+    B = 8
+    preds = synth.make_retina_preds(B, 800, 80, seed=0, device='cuda')
+    ann = synth.make_annotations(B, 100, 800, 80, seed=1).cuda()
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+    with torch.no_grad():
+        crit(preds, ann)
+        full = crit.last_stats['sums'].cpu().numpy().copy()
+        full_labels = crit.debug_assign(preds, ann)['labels'].cpu().numpy()
+        parts, part_labels = [], []
+        for lo in (0, 3):
+            hi = 3 if lo == 0 else B
+            shard = [[t[lo:hi].contiguous() for t in grp] for grp in preds]
+            crit(shard, ann[lo:hi].contiguous())
+            parts.append(crit.last_stats['sums'].cpu().numpy().copy())
+            part_labels.append(crit.debug_assign(shard, ann[lo:hi].contiguous())['labels'].cpu().numpy())
+    assert parts[0][0] + parts[1][0] == full[0]
+    assert np.array_equal(np.concatenate(part_labels, axis=0), full_labels)
+    np.testing.assert_allclose(parts[0][1:] + parts[1][1:], full[1:], rtol=1e-6)
+
+
+def test_decoder_output_invariants_full_size():
+    B = 4
+    preds = synth.make_retina_preds(B, 800, 80, seed=3, device='cuda')
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    (s, c, b), info = dec.decode_with_details(preds)
+    assert s.shape == (B, 100) and c.shape == (B, 100) and b.shape == (B, 100, 4)
+    for i in range(B):
+        n = int((s[i] >= 0).sum())
+        assert (np.diff(s[i, :n]) <= 0).all()            # sorted by score
+        assert (s[i, :n] > np.float32(0.05)).all()
+        assert (s[i, n:] == -1).all() and (c[i, n:] == -1).all() and (b[i, n:] == 0).all()
+        assert (b[i, :n] == np.trunc(b[i, :n])).all()     # integer-valued coordinates
+        order = info['order'][i]
+        assert len(set(order[order >= 0].tolist())) == int((order >= 0).sum())
+        keep = info['keep'][i]
+        assert (np.diff(keep[keep >= 0]) > 0).all()
+    # idempotence: same inputs -> bit-identical outputs
+    s2, c2, b2 = dec(preds)
+    G.assert_bit_equal(s, s2)
+    G.assert_bit_equal(b, b2)
