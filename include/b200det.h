@@ -99,47 +99,69 @@ unsigned long long b200det_launch_count(void);
 long long b200det_rows_per_image(const b200det_geometry *geo);
 
 /* ---- loss --------------------------------------------------------------------------- */
-/* bytes of scratch the loss calls need (block partials); same buffer for all three calls */
+/* bytes of scratch the loss calls of one step share (per-CTA partials + the matched annotation
+ * row of every row, 2 bytes each); the same buffer must be passed to every call of the step */
 size_t b200det_loss_workspace_bytes(const b200det_geometry *geo);
 
 /*
- * Anchor<->GT IoU assignment + box loss of RetinaLoss.
- * Replaces RetinaLoss.get_batch_anchors_annotations (losses.py:322-388), IoUMethod
- * (losses.py:33-70), snap_annotations_to_txtytwth (:390-409), snap_txtytwth_to_xyxy (:411-429),
- * compute_batch_box_loss / compute_batch_smoothl1_loss (:263-320).
+ * Anchor<->GT IoU assignment of RetinaLoss: a pure ALU scan, no head tensor is touched.
+ * Replaces RetinaLoss.get_batch_anchors_annotations (losses.py:322-388) and the assignment use of
+ * IoUMethod (losses.py:33-70).
  *   annotations : device float32 [B, max_gt, 5] = x1,y1,x2,y2,class ; rows with class < 0 ignored
- *   reg         : host array of n_levels device pointers (may be NULL iff box_loss == NONE)
  *   labels      : device int32 [B*N] level-major, out: -1 ignore, 0 background, k = class k-1
  *   matched     : device int32 [B*N] level-major or NULL, out: arg-max GT index in the image's
  *                 filtered GT list (first maximum on ties), -1 if the image has no GT
- *   reg_grad    : NULL, or host array of n_levels device float32 buffers shaped like reg[l];
- *                 receives d(sum of box loss)/d(reg) (NOT yet divided by the positive count)
- *   workspace   : per-block {positives, box-loss sum} partials for b200det_loss_finalize
+ *   workspace   : receives the per-CTA positive counts and the work queues of positive rows
+ *                 (with their matched annotation row) and ignored rows consumed by
+ *                 b200det_sparse_losses.  The call enqueues one 8-byte cudaMemsetAsync.
+ * Environment: B200DET_ASSIGN_CTAS_PER_SM (default: no cap) limits the kernel's residency; only
+ * useful when the caller overlaps it with the HBM-bound sweep on another stream.
  */
 int b200det_retina_assign(const b200det_geometry *geo, const float *annotations, int max_gt,
-                          const void *const *reg, int reg_dtype, int box_loss, float beta,
-                          int32_t *labels, int32_t *matched, void *const *reg_grad,
-                          void *workspace, size_t workspace_bytes, void *stream);
+                          int32_t *labels, int32_t *matched, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 /*
- * Point<->GT assignment with centre sampling + IoU loss + centre-ness loss of FCOSLoss.
- * Replaces FCOSLoss.get_batch_position_annotations (losses.py:612-833),
- * compute_batch_iou_loss (:550-586), compute_batch_centerness_loss (:588-610).
+ * Point<->GT assignment with centre sampling of FCOSLoss.
+ * Replaces FCOSLoss.get_batch_position_annotations (losses.py:612-833).
  *   targets : device float32 [B*N, 6] level-major or NULL, out: l,t,r,b,label,centre-ness
- *   ctr     : host array of n_levels device float32 pointers (probabilities), NULL iff
- *             box_loss == NONE
- *   reg_grad / ctr_grad : NULL or per-level float32 buffers (un-normalised gradients)
  */
 int b200det_fcos_assign(const b200det_geometry *geo, const float *annotations, int max_gt,
-                        const void *const *reg, int reg_dtype, const void *const *ctr,
-                        int box_loss, int use_center_sample, int32_t *labels, int32_t *matched,
-                        float *targets, void *const *reg_grad, void *const *ctr_grad,
+                        int use_center_sample, int32_t *labels, int32_t *matched, float *targets,
                         void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Losses that only involve the positive (and ignored) rows; must follow the assign call on the
+ * same workspace.  Replaces RetinaLoss.compute_batch_box_loss / compute_batch_smoothl1_loss
+ * (losses.py:263-320) with snap_annotations_to_txtytwth (:390-409) and snap_txtytwth_to_xyxy
+ * (:411-429); FCOSLoss.compute_batch_iou_loss (:550-586) and compute_batch_centerness_loss
+ * (:588-610); IoUMethod for all five IoU types (:33-123).
+ *   reg       : host array of n_levels device pointers (NULL iff box_loss == NONE)
+ *   ctr       : FCOS: host array of n_levels device float32 centre-ness pointers
+ *   cls       : NULL, or host array of n_levels device float32 cls pointers.  When given, the
+ *               kernel also produces the focal-loss CORRECTIONS of the rows that are not plain
+ *               background (target class of positives, every class of ignored rows), so that
+ *               b200det_focal_loss can run label-free (labels == NULL) and concurrently on
+ *               another stream.  alpha / gamma are the focal parameters for those terms.
+ *   reg_grad / ctr_grad : NULL, or per-level device float32 buffers shaped like reg[l] / ctr[l],
+ *               ZEROED by the caller; the rows of the positives receive
+ *               d(sum of box / centre-ness loss)/d(input), NOT yet divided by the positive count
+ */
+int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos, const float *annotations,
+                          int max_gt, const int32_t *labels, const void *const *reg,
+                          int reg_dtype, const void *const *ctr, int box_loss, float beta,
+                          const void *const *cls, float alpha, float gamma,
+                          void *const *reg_grad, void *const *ctr_grad, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 /*
  * Focal loss over the classification head: one streaming pass over cls (4*N*C bytes/image).
  * Replaces torch.cat + clamp (losses.py:183-198 / :488-494) and compute_batch_focal_loss
  * (losses.py:220-261 / :513-548).  Rows with label < 0 contribute nothing.
+ *   labels     : level-major labels from the assign call, or NULL = label-free sweep: every
+ *                element is summed as background and b200det_sparse_losses (given `cls`)
+ *                supplies the corrections; the sweep is then independent of the assignment and
+ *                may overlap it on another stream.  Forward only (cls_grad must be NULL).
  *   cls_grad   : NULL (forward only) or host array of n_levels device float32 buffers; receives
  *                d(cls_loss)/d(cls) already multiplied by grad_scale / sums[0]
  *   sums       : device double[4] written by b200det_loss_reduce: {positives, cls, box, ctr};
@@ -153,7 +175,8 @@ int b200det_focal_loss(const b200det_geometry *geo, const void *const *cls,
 
 /*
  * Deterministic (fixed-order, fp64) reduction of the block partials.
- *   which : bit 0 = assignment partials (positives, box, ctr), bit 1 = focal partials
+ *   which : bit 0 = assignment + sparse partials (positives, box, ctr, focal corrections),
+ *           bit 1 = focal sweep partials
  *   sums  : device double[4] {positives, cls_sum, box_sum, ctr_sum}; only selected fields written
  * Replaces the `.sum()` / `positive_anchors_num` bookkeeping of losses.py:231-259, :277-293.
  */
@@ -192,6 +215,7 @@ int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
  * RetinaDecoder.snap_txtytwth_to_x1y1x2y2 (:251-271) / FCOSDecoder.snap_ltrb_to_x1y1x2y2
  * (:350-364) incl. NumPy's float32 exp and the int32 truncation.
  *   is_fcos       : 0 = anchor (tx,ty,tw,th) decoding, 1 = point (l,t,r,b) decoding
+ *   min_score     : the threshold given to b200det_score_argmax (sizes the selection histogram)
  *   out           : device float32 [6*B*max_out]: scores [B,max_out] (pad -1), classes
  *                   [B,max_out] (pad -1), boxes [B,max_out,4] (pad 0), back to back
  *   order / keep  : NULL or device int32 [B,topn] (pad -1): image-major row index of the sorted
@@ -201,7 +225,7 @@ int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
  */
 int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
                               const int32_t *classes, const void *const *reg, int reg_dtype,
-                              int is_fcos, int topn, int max_out, int nms_type,
+                              int is_fcos, float min_score, int topn, int max_out, int nms_type,
                               double nms_threshold, float *out, int32_t *order, int32_t *keep,
                               int32_t *counts, void *workspace, size_t workspace_bytes,
                               void *stream);

@@ -56,13 +56,14 @@ SIGNATURES = {
     'b200det_launch_count': (ctypes.c_ulonglong, []),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
     'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),
-    'b200det_retina_assign': (ctypes.c_int, [
-        _geo, _vp, ctypes.c_int, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_float, _vp, _vp, _vpp,
-        _vp, ctypes.c_size_t, _vp
-    ]),
+    'b200det_retina_assign': (ctypes.c_int,
+                              [_geo, _vp, ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     'b200det_fcos_assign': (ctypes.c_int, [
-        _geo, _vp, ctypes.c_int, _vpp, ctypes.c_int, _vpp, ctypes.c_int, ctypes.c_int, _vp, _vp,
-        _vp, _vpp, _vpp, _vp, ctypes.c_size_t, _vp
+        _geo, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
+    ]),
+    'b200det_sparse_losses': (ctypes.c_int, [
+        _geo, ctypes.c_int, _vp, ctypes.c_int, _vp, _vpp, ctypes.c_int, _vpp, ctypes.c_int,
+        ctypes.c_float, _vpp, ctypes.c_float, ctypes.c_float, _vpp, _vpp, _vp, ctypes.c_size_t, _vp
     ]),
     'b200det_focal_loss': (ctypes.c_int, [
         _geo, _vpp, _vp, ctypes.c_float, ctypes.c_float, _vpp, _vp, ctypes.c_float, _vp,
@@ -75,8 +76,8 @@ SIGNATURES = {
     'b200det_decode_workspace_bytes': (ctypes.c_size_t, [_geo, ctypes.c_int]),
     'b200det_score_argmax': (ctypes.c_int, [_geo, _vpp, _vpp, ctypes.c_float, _vp, _vp, _vp]),
     'b200det_select_decode_nms': (ctypes.c_int, [
-        _geo, _vp, _vp, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-        ctypes.c_int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
+        _geo, _vp, _vp, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+        ctypes.c_int, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
     ]),
     'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
     'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),

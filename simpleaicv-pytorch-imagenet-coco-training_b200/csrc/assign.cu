@@ -1,20 +1,39 @@
-// assign.cu -- target assignment + box / centre-ness losses (prediction-independent part of
-// RetinaLoss / FCOSLoss).  Compiled with -fmad=false: every float op below is one IEEE
-// float32 operation in the reference's order, so labels and matched
-// indices are bit-exact.
+// assign.cu -- target assignment of RetinaLoss / FCOSLoss and the sparse losses that depend on it.
+// Compiled with -fmad=false: every float op on the assignment path is one IEEE float32 operation
+// in the reference's order, so labels and matched indices are bit-exact.
 //
-// Layout / roofline: per image the kernels read G<=2048 annotation rows (20 B each, staged
-// once per CTA into shared memory with one cp.async.bulk + mbarrier), generate anchors / points
-// in registers, and write 4 (labels) [+4 matched, +24 targets] bytes per row; regression rows
-// are read only for positives.  The kernels are ALU/latency work that must hide under the
-// classification sweep (focal.cu); Retina culls GT boxes that cannot overlap the CTA's 256
-// anchors before the pair loop, and skips the IEEE divide when the overlap is empty.
+// Two kernels per loss call:
+//
+//  *_assign_kernel   pure ALU scan, no head tensors touched.  Per image it reads G <= 2048
+//      annotation rows (20 B each, staged once per CTA into shared memory with one cp.async.bulk +
+//      mbarrier), generates anchors / points in registers and writes 4 B (label) + 2 B (matched
+//      annotation row) per row.  Instruction count per (anchor, GT) pair is what matters:
+//        - a WARP owns an 8x4 patch of locations of one pyramid level, a THREAD one location; for
+//          RetinaNet's 9 anchors per location the 9 anchors live in registers, so a GT box read
+//          from shared memory is reused 9 times and level/x/y/shift arithmetic is paid once;
+//        - GT boxes that cannot overlap the CTA's patch row are culled once per CTA (ordered ballot
+//          compaction, so "first maximum / first minimum" survive), then per WARP with one ballot
+//          per 32 candidates; a culled GT has IoU exactly 0 with every anchor of the warp and can
+//          never beat best >= 0 under the reference's strict '>' scan;
+//        - the IEEE divide is skipped when the intersection is empty.
+//
+//  sparse_loss_kernel   driven by the labels: for the ~1 % positive rows it gathers the matched
+//      annotation, the regression row (and FCOS centre-ness) and evaluates the box / centre-ness
+//      loss and their gradients; when asked, it also produces the focal-loss CORRECTIONS (target
+//      class of positives, every class of ignored rows) that let the classification sweep in
+//      focal.cu run label-free and concurrently.  Sums are accumulated in 64-bit fixed point, so
+//      they do not depend on the order in which rows are visited (deterministic).
+#include <stdlib.h>
 #include "common.cuh"
 #include "dual.cuh"
+#include "focal_terms.cuh"
 
 namespace b200det {
 
-constexpr int kAssignThreads = 256;
+constexpr int kAssignThreads = 128;
+constexpr int kAssignWarps = kAssignThreads / 32;
+constexpr int kTileW = 8, kTileH = 4;   // locations per warp: 8 wide x 4 high
+constexpr int kSparseThreads = 256;
 
 // ---------------------------------------------------------------------------------------
 // GT staging: global [G,5] float rows -> shared memory, via TMA bulk copy when aligned.
@@ -70,7 +89,8 @@ struct GtSmem {
     float4 *box;   // [G]
     float *area;   // [G]
     int *label;    // [G]  class + 1
-    int *fidx;     // [G]  index in the filtered (class >= 0) list
+    short *fidx;   // [G]  index in the filtered (class >= 0) list
+    short *ridx;   // [G]  annotation row (unfiltered)
 };
 __device__ __forceinline__ GtSmem carve(unsigned char *base, int G) {
     GtSmem s;
@@ -79,23 +99,28 @@ __device__ __forceinline__ GtSmem carve(unsigned char *base, int G) {
     s.box = reinterpret_cast<float4 *>(s.raw + raw_floats);
     s.area = reinterpret_cast<float *>(s.box + G);
     s.label = reinterpret_cast<int *>(s.area + G);
-    s.fidx = s.label + G;
+    s.fidx = reinterpret_cast<short *>(s.label + G);
+    s.ridx = s.fidx + G;
     return s;
 }
 static size_t gt_smem_bytes(int G) {
     const int raw_floats = (G * 5 + 3) & ~3;
-    return (size_t)raw_floats * 4 + (size_t)G * (16 + 4 + 4 + 4);
+    return (size_t)raw_floats * 4 + (size_t)G * (16 + 4 + 4 + 2 + 2);
 }
 
+enum CullMode { kCullNone = 0, kCullOverlap = 1, kCullContain = 2 };
+
 // Ordered compaction of annotation rows: keeps rows with class >= 0 (filtered index = rank
-// among them, losses.py:338-339 / :667-668) and, if `cull`, only those whose box can overlap
-// the CTA's region [rx1,ry1,rx2,ry2].  Returns {#kept, #valid}.  Order is preserved, which
-// is what makes "first maximum / first minimum" tie rules exact.
-__device__ __forceinline__ int2 compact_gt(const GtSmem &s, int G, bool cull, float rx1,
-                                           float ry1, float rx2, float ry2, bool fcos_area,
-                                           int *warp_cnt /* [2*8] smem */) {
+// among them, losses.py:338-339 / :667-668) and, depending on `mode`, only those whose box can
+// matter for the CTA's region [rx1,ry1,rx2,ry2]:
+//   kCullOverlap : the box has a non-empty intersection with the region (Retina IoU > 0)
+//   kCullContain : the box can strictly contain a point of the region (FCOS min(l,t,r,b) > 0)
+// Returns {#kept, #valid}.  Order is preserved, which keeps the reference's "first maximum /
+// first minimum" tie rules exact.
+__device__ __forceinline__ int2 compact_gt(const GtSmem &s, int G, int mode, float rx1, float ry1,
+                                           float rx2, float ry2, bool fcos_area,
+                                           int *warp_cnt /* [2*kAssignWarps] smem */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarp = kAssignThreads / 32;
     int base_valid = 0, base_keep = 0;
     for (int j0 = 0; j0 < G; j0 += kAssignThreads) {
         const int j = j0 + threadIdx.x;
@@ -109,19 +134,21 @@ __device__ __forceinline__ int2 compact_gt(const GtSmem &s, int G, bool cull, fl
         }
         const bool valid = (j < G) && (c >= 0.f);
         bool keep = valid;
-        if (cull && valid)
+        if (valid && mode == kCullOverlap)
             keep = (fminf(rx2, x2) > fmaxf(rx1, x1)) && (fminf(ry2, y2) > fmaxf(ry1, y1));
+        if (valid && mode == kCullContain)
+            keep = (x1 < rx2) && (x2 > rx1) && (y1 < ry2) && (y2 > ry1);
         const unsigned bv = __ballot_sync(0xffffffffu, valid);
         const unsigned bk = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) {
             warp_cnt[warp] = __popc(bv);
-            warp_cnt[nwarp + warp] = __popc(bk);
+            warp_cnt[kAssignWarps + warp] = __popc(bk);
         }
         __syncthreads();
         int pv = base_valid, pk = base_keep, tv = 0, tk = 0;
 #pragma unroll
-        for (int w = 0; w < nwarp; ++w) {
-            const int cv = warp_cnt[w], ck = warp_cnt[nwarp + w];
+        for (int w = 0; w < kAssignWarps; ++w) {
+            const int cv = warp_cnt[w], ck = warp_cnt[kAssignWarps + w];
             if (w < warp) {
                 pv += cv;
                 pk += ck;
@@ -142,7 +169,8 @@ __device__ __forceinline__ int2 compact_gt(const GtSmem &s, int G, bool cull, fl
                 s.area[pk] = __fmul_rn(fmaxf(__fsub_rn(x2, x1), 0.f), fmaxf(__fsub_rn(y2, y1), 0.f));
             }
             s.label[pk] = (int)(c + 1.f);
-            s.fidx[pk] = pv;
+            s.fidx[pk] = (short)pv;
+            s.ridx[pk] = (short)j;
         }
         base_valid += tv;
         base_keep += tk;
@@ -151,276 +179,333 @@ __device__ __forceinline__ int2 compact_gt(const GtSmem &s, int G, bool cull, fl
     return make_int2(base_keep, base_valid);
 }
 
-__device__ __forceinline__ void block_partial(int npos, float box, float ctr,
-                                              AssignPartial *dst, float *red /* [3*8] smem */) {
+// CTA-wide min/max of a per-thread box -> region[4] in shared memory; also returns the WARP's box.
+__device__ __forceinline__ float4 reduce_region(bool active, float x1, float y1, float x2, float y2,
+                                                float *red /* [4*kAssignWarps] */,
+                                                float *region /* [4] */) {
+    const float big = 3.0e38f;
+    float mnx = active ? x1 : big, mny = active ? y1 : big;
+    float mxx = active ? x2 : -big, mxy = active ? y2 : -big;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarp = kAssignThreads / 32;
-    const int wn = warp_sum_int(npos);
-    const float wb = warp_sum(box), wc = warp_sum(ctr);
     if (lane == 0) {
-        red[warp] = __int_as_float(wn);
-        red[nwarp + warp] = wb;
-        red[2 * nwarp + warp] = wc;
+        red[warp * 4 + 0] = mnx;
+        red[warp * 4 + 1] = mny;
+        red[warp * 4 + 2] = mxx;
+        red[warp * 4 + 3] = mxy;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int n = 0;
-        float b = 0.f, c = 0.f;
-        for (int w = 0; w < nwarp; ++w) {
-            n += __float_as_int(red[w]);
-            b += red[nwarp + w];
-            c += red[2 * nwarp + w];
+        float a = red[0], b = red[1], c = red[2], d = red[3];
+        for (int w = 1; w < kAssignWarps; ++w) {
+            a = fminf(a, red[w * 4 + 0]);
+            b = fminf(b, red[w * 4 + 1]);
+            c = fmaxf(c, red[w * 4 + 2]);
+            d = fmaxf(d, red[w * 4 + 3]);
         }
-        AssignPartial p;
-        p.npos = n;
-        p.box = b;
-        p.ctr = c;
-        p.pad = 0.f;
-        *dst = p;
+        region[0] = a;
+        region[1] = b;
+        region[2] = c;
+        region[3] = d;
     }
+    return make_float4(mnx, mny, mxx, mxy);
+}
+
+// Location owned by this thread: warp -> 8x4 patch of one level, lane -> location in the patch.
+struct TileTab {
+    int tile_off[kMaxLevels + 1];   // patches of one image before level l
+    int tiles_x[kMaxLevels];
+};
+struct Loc {
+    bool active;
+    int l, x, y, loc;   // level, position, y*W + x
+};
+__device__ __forceinline__ Loc my_location(const Geo &g, const TileTab &tt) {
+    Loc r;
+    r.active = false;
+    r.l = r.x = r.y = r.loc = 0;
+    const int tile = blockIdx.x * kAssignWarps + (threadIdx.x >> 5);
+    if (tile >= tt.tile_off[g.n_levels]) return r;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < g.n_levels && tile >= tt.tile_off[i]) l = i;
+    const int tl = tile - tt.tile_off[l];
+    const int ty = tl / tt.tiles_x[l], tx = tl - ty * tt.tiles_x[l];
+    const int lane = threadIdx.x & 31;
+    r.l = l;
+    r.x = tx * kTileW + (lane & (kTileW - 1));
+    r.y = ty * kTileH + (lane / kTileW);
+    r.active = r.x < g.W[l] && r.y < g.H[l];
+    r.loc = r.y * g.W[l] + r.x;
+    return r;
+}
+
+// Work queues handed from the assignment kernels to sparse_loss_kernel (global memory, in the
+// caller's workspace).  Order inside the queues is arbitrary (atomics); every consumer
+// accumulates in fixed point, so results do not depend on it.
+struct Queues {
+    int *counters;   // [0] = positives queued, [1] = ignored rows queued
+    int2 *pos;       // (level-major row, annotation row)
+    int *ign;        // level-major row
+};
+
+// CTA-local queues in shared memory -> one global atomic per queue and CTA, coalesced copy-out.
+// Also stores the CTA's positive count (deterministic integer partial).
+__device__ __forceinline__ void flush_queues(const Queues &q, const int2 *pos_q, int n_pos,
+                                             const int *ign_q, int n_ign, int *npos_dst,
+                                             int *bases /* [2] smem */) {
+    if (threadIdx.x == 0) {
+        *npos_dst = n_pos;
+        bases[0] = n_pos ? atomicAdd(q.counters + 0, n_pos) : 0;
+        bases[1] = n_ign ? atomicAdd(q.counters + 1, n_ign) : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pos; i += kAssignThreads) q.pos[bases[0] + i] = pos_q[i];
+    for (int i = threadIdx.x; i < n_ign; i += kAssignThreads) q.ign[bases[1] + i] = ign_q[i];
 }
 
 // ---------------------------------------------------------------------------------------
-// Retina: anchor <-> GT IoU, max / arg-max, label, box loss
+// Retina: anchor <-> GT IoU, max / arg-max, label  (losses.py:322-388)
+//   PL > 0 : per_loc == PL anchors of the location held in registers (scan unrolled over them)
+//   PL == 0: any per_loc, anchors processed one after the other
 // ---------------------------------------------------------------------------------------
+template <int NA>
+__device__ __forceinline__ void scan_candidates(const GtSmem &s, int n_cand, const float4 wreg,
+                                                const float4 (&A)[NA], float (&best)[NA],
+                                                int (&best_slot)[NA]) {
+    float area_a[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+        area_a[a] = __fmul_rn(fmaxf(__fsub_rn(A[a].z, A[a].x), 0.f),
+                              fmaxf(__fsub_rn(A[a].w, A[a].y), 0.f));
+        best[a] = 0.f;
+        best_slot[a] = -1;
+    }
+    const int lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        // warp-level cull: one candidate per lane against the warp's anchor bounding box
+        bool hit = false;
+        if (c0 + lane < n_cand) {
+            const float4 gt = s.box[c0 + lane];
+            hit = (fminf(wreg.z, gt.z) > fmaxf(wreg.x, gt.x)) &&
+                  (fminf(wreg.w, gt.w) > fmaxf(wreg.y, gt.y));
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int k = c0 + __ffs(m) - 1;
+            m &= m - 1;
+            const float4 gt = s.box[k];
+            const float garea = s.area[k];
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                // IoU (losses.py:54-70); strict '>' in GT order == first maximum (:357)
+                const float mnx = fminf(A[a].z, gt.z), mxx = fmaxf(A[a].x, gt.x);
+                const float mny = fminf(A[a].w, gt.w), mxy = fmaxf(A[a].y, gt.y);
+                if (mnx > mxx && mny > mxy) {
+                    const float ov = __fmul_rn(__fsub_rn(mnx, mxx), __fsub_rn(mny, mxy));
+                    const float un = fmaxf(__fsub_rn(__fadd_rn(area_a[a], garea), ov), 1e-4f);
+                    const float iou = __fdiv_rn(ov, un);
+                    if (iou > best[a]) {
+                        best[a] = iou;
+                        best_slot[a] = k;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int PL>
 __global__ void __launch_bounds__(kAssignThreads)
-    retina_assign_kernel(Geo g, BaseAnchors ba, const float *__restrict__ annots, int G,
-                         PtrTab reg, int reg_dtype, int box_loss, float beta,
-                         int *__restrict__ labels, int *__restrict__ matched, MutPtrTab reg_grad,
-                         AssignPartial *__restrict__ partials) {
+    retina_assign_kernel(Geo g, BaseAnchors ba, TileTab tt, const float *__restrict__ annots, int G,
+                         int *__restrict__ labels, int *__restrict__ matched, Queues q,
+                         int *__restrict__ npos_partials) {
+    constexpr int NA = PL > 0 ? PL : 1;
+    constexpr int kQueue = kAssignThreads * (PL > 0 ? PL : kMaxPerLoc);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ float red[4 * (kAssignThreads / 32)];
-    __shared__ int warp_cnt[2 * (kAssignThreads / 32)];
+    __shared__ float red[4 * kAssignWarps];
+    __shared__ int warp_cnt[2 * kAssignWarps];
     __shared__ float region[4];
+    __shared__ int2 pos_q[kQueue];
+    __shared__ int ign_q[kQueue];
+    __shared__ int n_pos_s, n_ign_s, bases[2];
+    if (threadIdx.x == 0) {
+        n_pos_s = 0;
+        n_ign_s = 0;
+    }
 
     const int b = blockIdx.y;
-    const int N = g.off[g.n_levels];
-    const int row = blockIdx.x * kAssignThreads + threadIdx.x;
-    const bool active = row < N;
     const GtSmem s = carve(smem_raw, G);
-
     const float *src = annots + (size_t)b * G * 5;
     const bool bulk = (((G * 5 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     stage_rows_begin(s.raw, src, G * 5, &mbar, bulk);
 
-    // this thread's anchor, generated in registers (models/anchor.py:59-86)
-    int l = 0, local = 0;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        l = level_of_row(g, row);
-        local = row - g.off[l];
-        a = anchor_of(g, ba, l, local);
+    const Loc me = my_location(g, tt);
+    const int per_loc = PL > 0 ? PL : g.per_loc;
+    const float sx = shift_of(me.x, g.stride[me.l]), sy = shift_of(me.y, g.stride[me.l]);
+    // bounding box of this location's anchors (models/anchor.py:59-86: base + shift in float32)
+    float tx1 = 3.0e38f, ty1 = 3.0e38f, tx2 = -3.0e38f, ty2 = -3.0e38f;
+    for (int a = 0; a < per_loc; ++a) {
+        tx1 = fminf(tx1, __fadd_rn(ba.v[me.l][a][0], sx));
+        ty1 = fminf(ty1, __fadd_rn(ba.v[me.l][a][1], sy));
+        tx2 = fmaxf(tx2, __fadd_rn(ba.v[me.l][a][2], sx));
+        ty2 = fmaxf(ty2, __fadd_rn(ba.v[me.l][a][3], sy));
     }
-    // CTA region = bounding box of its anchors (for GT culling)
-    {
-        const float big = 3.0e38f;
-        float mnx = active ? a.x : big, mny = active ? a.y : big;
-        float mxx = active ? a.z : -big, mxy = active ? a.w : -big;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-        }
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) {
-            red[warp * 4 + 0] = mnx;
-            red[warp * 4 + 1] = mny;
-            red[warp * 4 + 2] = mxx;
-            red[warp * 4 + 3] = mxy;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < kAssignThreads / 32; ++w) {
-                mnx = fminf(mnx, red[w * 4 + 0]);
-                mny = fminf(mny, red[w * 4 + 1]);
-                mxx = fmaxf(mxx, red[w * 4 + 2]);
-                mxy = fmaxf(mxy, red[w * 4 + 3]);
-            }
-            region[0] = mnx;
-            region[1] = mny;
-            region[2] = mxx;
-            region[3] = mxy;
-        }
-    }
+    const float4 wreg = reduce_region(me.active, tx1, ty1, tx2, ty2, red, region);
     stage_rows_wait(&mbar, bulk);  // contains a __syncthreads(): region[] is visible too
-
-    const int2 cnt = compact_gt(s, G, true, region[0], region[1], region[2], region[3], false,
-                                warp_cnt);
+    const int2 cnt = compact_gt(s, G, kCullOverlap, region[0], region[1], region[2], region[3],
+                                false, warp_cnt);
     const int n_cand = cnt.x;
     const bool has_gt = cnt.y > 0;
 
-    // IoU scan (losses.py:54-70, :357): strict '>' in GT order == first maximum.
-    // Culled / non-overlapping GTs have IoU exactly 0 and can never beat best >= 0.
-    const float aw = fmaxf(__fsub_rn(a.z, a.x), 0.f), ah = fmaxf(__fsub_rn(a.w, a.y), 0.f);
-    const float area_a = __fmul_rn(aw, ah);
-    float best = 0.f;
-    int best_slot = -1;
-    for (int k = 0; k < n_cand; ++k) {
-        const float4 gt = s.box[k];
-        const float mnx = fminf(a.z, gt.z), mxx = fmaxf(a.x, gt.x);
-        const float mny = fminf(a.w, gt.w), mxy = fmaxf(a.y, gt.y);
-        if (mnx > mxx && mny > mxy) {
-            const float ov = __fmul_rn(__fsub_rn(mnx, mxx), __fsub_rn(mny, mxy));
-            const float un = fmaxf(__fsub_rn(__fadd_rn(area_a, s.area[k]), ov), 1e-4f);
-            const float iou = __fdiv_rn(ov, un);
-            if (iou > best) {
-                best = iou;
-                best_slot = k;
-            }
-        }
-    }
-
-    int label = -1, match = -1;
-    if (has_gt) {
-        match = best_slot >= 0 ? s.fidx[best_slot] : 0;
-        if (best < 0.4f) label = 0;
-        if (best >= 0.5f) label = s.label[best_slot];
-    }
-    long long lm = 0;
-    if (active) {
-        lm = lm_index(g, b, l, local);
-        labels[lm] = label;
-        if (matched) matched[lm] = match;
-    }
-
-    // box loss for positives (losses.py:263-320)
-    float box_term = 0.f;
-    const bool pos = active && label > 0;
-    if (box_loss != B200DET_BOX_NONE && active) {
-        const long long rrow = (long long)b * g.rows[l] + local;
-        float4 grad = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pos) {
-            const float4 t = load_reg4(reg.p[l], reg_dtype, rrow);
-            const float4 gt = s.box[best_slot];
-            const float awx = __fsub_rn(a.z, a.x), awy = __fsub_rn(a.w, a.y);
-            const float acx = __fadd_rn(a.x, __fmul_rn(0.5f, awx));
-            const float acy = __fadd_rn(a.y, __fmul_rn(0.5f, awy));
-            if (box_loss == B200DET_BOX_SMOOTHL1) {
-                // targets (losses.py:390-409)
-                const float gwx = fmaxf(__fsub_rn(gt.z, gt.x), 1e-4f);
-                const float gwy = fmaxf(__fsub_rn(gt.w, gt.y), 1e-4f);
-                const float gcx = __fadd_rn(gt.x, __fmul_rn(0.5f, gwx));
-                const float gcy = __fadd_rn(gt.y, __fmul_rn(0.5f, gwy));
-                const float tg[4] = {__fdiv_rn(__fsub_rn(gcx, acx), awx),
-                                     __fdiv_rn(__fsub_rn(gcy, acy), awy),
-                                     logf(__fdiv_rn(gwx, awx)), logf(__fdiv_rn(gwy, awy))};
-                const float pr[4] = {t.x, t.y, t.z, t.w};
-                float gr[4];
-                const float half_beta = 0.5f * beta;
+    const long long lm0 = lm_index(g, b, me.l, me.loc * per_loc);
+    for (int a0 = 0; a0 < per_loc; a0 += NA) {   // one trip when PL > 0
+        float4 A[NA];
+        float best[NA];
+        int best_slot[NA];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float d = __fsub_rn(pr[i], tg[i]);
-                    const float x = fabsf(d);
-                    if (x >= beta) {
-                        box_term += __fsub_rn(x, half_beta);
-                        gr[i] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-                    } else {
-                        box_term += __fdiv_rn(__fmul_rn(0.5f, __fmul_rn(x, x)), beta);
-                        gr[i] = d / beta;
-                    }
+        for (int a = 0; a < NA; ++a) {
+            A[a].x = __fadd_rn(ba.v[me.l][a0 + a][0], sx);
+            A[a].y = __fadd_rn(ba.v[me.l][a0 + a][1], sy);
+            A[a].z = __fadd_rn(ba.v[me.l][a0 + a][2], sx);
+            A[a].w = __fadd_rn(ba.v[me.l][a0 + a][3], sy);
+        }
+        scan_candidates<NA>(s, n_cand, wreg, A, best, best_slot);
+        // labels (losses.py:358-365)
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            int label = -1, match = -1, grow = -1;
+            if (has_gt) {
+                match = best_slot[a] >= 0 ? s.fidx[best_slot[a]] : 0;
+                if (best[a] < 0.4f) label = 0;
+                if (best[a] >= 0.5f) {
+                    label = s.label[best_slot[a]];
+                    grow = s.ridx[best_slot[a]];
                 }
-                grad = make_float4(gr[0], gr[1], gr[2], gr[3]);
-            } else {
-                // decode (losses.py:411-429) then 1 - IoU-family (losses.py:286-293)
-                const Dual tx = dvar(t.x, 0), ty = dvar(t.y, 1), tw = dvar(t.z, 2), th = dvar(t.w, 3);
-                const Dual bw = dexp(tw) * awx, bh = dexp(th) * awy;
-                const Dual cx = tx * awx + acx, cy = ty * awy + acy;
-                const Dual hw = bw * 0.5f, hh = bh * 0.5f;
-                const Dual p[4] = {cx - hw, cy - hh, cx + hw, cy + hh};
-                const float gg[4] = {gt.x, gt.y, gt.z, gt.w};
-                const Dual iou = iou_family(p, gg, box_loss);
-                box_term = __fsub_rn(1.f, iou.v);
-                grad = make_float4(-iou.d[0], -iou.d[1], -iou.d[2], -iou.d[3]);
+            }
+            if (me.active) {
+                const int row = (int)(lm0 + a0 + a);
+                labels[row] = label;
+                if (matched) matched[row] = match;
+                if (label > 0) pos_q[atomicAdd(&n_pos_s, 1)] = make_int2(row, grow);
+                if (label < 0) ign_q[atomicAdd(&n_ign_s, 1)] = row;
             }
         }
-        if (reg_grad.p[0] != nullptr)
-            reinterpret_cast<float4 *>(reg_grad.p[l])[rrow] = grad;
     }
-    block_partial(pos ? 1 : 0, box_term, 0.f,
-                  partials + (size_t)blockIdx.y * gridDim.x + blockIdx.x, red);
+    __syncthreads();
+    flush_queues(q, pos_q, n_pos_s, ign_q, n_ign_s,
+                 npos_partials + (size_t)blockIdx.y * gridDim.x + blockIdx.x, bases);
 }
 
 // ---------------------------------------------------------------------------------------
-// FCOS: point <-> GT with centre sampling, scale range, min-area; IoU + centre-ness losses
+// FCOS: point <-> GT with centre sampling, scale range, min-area  (losses.py:612-833)
 // ---------------------------------------------------------------------------------------
+struct FcosPick {
+    int slot;
+    float l, t, r, b;
+};
+
+// losses.py:688-735 (candidate tests) for one (point, GT) pair
+__device__ __forceinline__ bool fcos_candidate(const float2 pt, const float4 gt, float m0, float m1,
+                                               float rad, int use_center_sample, float &cl,
+                                               float &ct, float &cr, float &cb) {
+    cl = __fsub_rn(pt.x, gt.x);
+    ct = __fsub_rn(pt.y, gt.y);
+    cr = __fsub_rn(gt.z, pt.x);
+    cb = __fsub_rn(gt.w, pt.y);
+    const float mn = fminf(fminf(cl, ct), fminf(cr, cb));
+    bool ok = mn > 0.f;
+    if (ok && use_center_sample) {
+        const float cx = __fdiv_rn(__fadd_rn(gt.z, gt.x), 2.f);
+        const float cy = __fdiv_rn(__fadd_rn(gt.w, gt.y), 2.f);
+        const float dx = __fsub_rn(pt.x, cx), dy = __fsub_rn(pt.y, cy);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        ok = d < rad;
+    }
+    if (ok) {
+        const float mx = fmaxf(fmaxf(cl, ct), fmaxf(cr, cb));
+        ok = (mx > m0) && (mx < m1);
+    }
+    return ok;
+}
+
+// centre-ness target, losses.py:822-824
+__device__ __forceinline__ float fcos_centerness(float l, float t, float r, float b) {
+    return __fsqrt_rn(__fmul_rn(__fdiv_rn(fminf(l, r), fmaxf(l, r)),
+                                __fdiv_rn(fminf(t, b), fmaxf(t, b))));
+}
+
 __global__ void __launch_bounds__(kAssignThreads)
-    fcos_assign_kernel(Geo g, FcosTab ft, const float *__restrict__ annots, int G, PtrTab reg,
-                       int reg_dtype, PtrTab ctr, int box_loss, int use_center_sample,
-                       int *__restrict__ labels, int *__restrict__ matched,
-                       float *__restrict__ targets, MutPtrTab reg_grad, MutPtrTab ctr_grad,
-                       AssignPartial *__restrict__ partials) {
+    fcos_assign_kernel(Geo g, FcosTab ft, TileTab tt, const float *__restrict__ annots, int G,
+                       int use_center_sample, int *__restrict__ labels,
+                       int *__restrict__ matched, float *__restrict__ targets, Queues q,
+                       int *__restrict__ npos_partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ float red[4 * (kAssignThreads / 32)];
-    __shared__ int warp_cnt[2 * (kAssignThreads / 32)];
+    __shared__ float red[4 * kAssignWarps];
+    __shared__ int warp_cnt[2 * kAssignWarps];
+    __shared__ float region[4];
+    __shared__ int2 pos_q[kAssignThreads];
+    __shared__ int n_pos_s, bases[2];
+    if (threadIdx.x == 0) n_pos_s = 0;
 
     const int b = blockIdx.y;
-    const int N = g.off[g.n_levels];
-    const int row = blockIdx.x * kAssignThreads + threadIdx.x;
-    const bool active = row < N;
     const GtSmem s = carve(smem_raw, G);
-
     const float *src = annots + (size_t)b * G * 5;
     const bool bulk = (((G * 5 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     stage_rows_begin(s.raw, src, G * 5, &mbar, bulk);
 
-    int l = 0, local = 0;
-    float2 pt = make_float2(0.f, 0.f);
-    if (active) {
-        l = level_of_row(g, row);
-        local = row - g.off[l];
-        pt = point_of(g, l, local);
-    }
-    const float m0 = ft.mi_lo[l], m1 = ft.mi_hi[l], rad = ft.radius[l];
+    const Loc me = my_location(g, tt);
+    const float2 pt = make_float2(shift_of(me.x, g.stride[me.l]), shift_of(me.y, g.stride[me.l]));
+    const float m0 = ft.mi_lo[me.l], m1 = ft.mi_hi[me.l], rad = ft.radius[me.l];
+    const float4 wreg = reduce_region(me.active, pt.x, pt.y, pt.x, pt.y, red, region);
     stage_rows_wait(&mbar, bulk);
-    const int2 cnt = compact_gt(s, G, false, 0.f, 0.f, 0.f, 0.f, true, warp_cnt);
-    const int n_gt = cnt.x;
+    // only GT boxes that can strictly contain one of the CTA's points can be candidates
+    const int2 cnt = compact_gt(s, G, kCullContain, region[0], region[1], region[2], region[3],
+                                true, warp_cnt);
+    const int n_cand = cnt.x;
 
-    // losses.py:688-735 (candidate tests) and :785-808 (smallest area, first minimum)
+    // smallest area among the candidates, first minimum (losses.py:785-808)
     float best_area = __int_as_float(0x7f800000);
     int best = -1;
     float bl = 0.f, bt = 0.f, br = 0.f, bb = 0.f;
-    for (int k = 0; k < n_gt; ++k) {
-        const float4 gt = s.box[k];
-        const float cl = __fsub_rn(pt.x, gt.x), ct = __fsub_rn(pt.y, gt.y);
-        const float cr = __fsub_rn(gt.z, pt.x), cb = __fsub_rn(gt.w, pt.y);
-        const float mn = fminf(fminf(cl, ct), fminf(cr, cb));
-        bool ok = mn > 0.f;
-        if (ok && use_center_sample) {
-            const float cx = __fdiv_rn(__fadd_rn(gt.z, gt.x), 2.f);
-            const float cy = __fdiv_rn(__fadd_rn(gt.w, gt.y), 2.f);
-            const float dx = __fsub_rn(pt.x, cx), dy = __fsub_rn(pt.y, cy);
-            const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-            ok = d < rad;
+    const int lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        bool hit = false;
+        if (c0 + lane < n_cand) {
+            const float4 gt = s.box[c0 + lane];
+            hit = (gt.x < wreg.z) && (gt.z > wreg.x) && (gt.y < wreg.w) && (gt.w > wreg.y);
         }
-        if (ok) {
-            const float mx = fmaxf(fmaxf(cl, ct), fmaxf(cr, cb));
-            ok = (mx > m0) && (mx < m1);
-        }
-        if (ok && s.area[k] < best_area) {
-            best_area = s.area[k];
-            best = k;
-            bl = cl;
-            bt = ct;
-            br = cr;
-            bb = cb;
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int k = c0 + __ffs(m) - 1;
+            m &= m - 1;
+            float cl, ct, cr, cb;
+            const bool ok = fcos_candidate(pt, s.box[k], m0, m1, rad, use_center_sample, cl, ct, cr, cb);
+            if (ok && s.area[k] < best_area) {
+                best_area = s.area[k];
+                best = k;
+                bl = cl;
+                bt = ct;
+                br = cr;
+                bb = cb;
+            }
         }
     }
-    const bool pos = active && best >= 0;
-    int label = 0;
-    float ctr_t = 0.f;
-    if (pos) {
-        label = s.label[best];
-        // losses.py:822-824
-        ctr_t = __fsqrt_rn(__fmul_rn(__fdiv_rn(fminf(bl, br), fmaxf(bl, br)),
-                                     __fdiv_rn(fminf(bt, bb), fmaxf(bt, bb))));
-    }
-    if (active) {
-        const long long lm = lm_index(g, b, l, local);
+    const bool pos = me.active && best >= 0;
+    if (me.active) {
+        const long long lm = lm_index(g, b, me.l, me.loc);
+        const int label = pos ? s.label[best] : 0;
         labels[lm] = label;
+        if (pos) pos_q[atomicAdd(&n_pos_s, 1)] = make_int2((int)lm, s.ridx[best]);
         if (matched) matched[lm] = pos ? s.fidx[best] : -1;
         if (targets) {
             float *t = targets + lm * 6;
@@ -429,41 +514,216 @@ __global__ void __launch_bounds__(kAssignThreads)
             t[2] = br;
             t[3] = bb;
             t[4] = (float)label;
-            t[5] = ctr_t;
+            t[5] = pos ? fcos_centerness(bl, bt, br, bb) : 0.f;
+        }
+    }
+    __syncthreads();
+    flush_queues(q, pos_q, n_pos_s, nullptr, 0,
+                 npos_partials + (size_t)blockIdx.y * gridDim.x + blockIdx.x, bases);
+}
+
+// ---------------------------------------------------------------------------------------
+// sparse losses: box / centre-ness loss of the positives (+ gradients), focal corrections
+// ---------------------------------------------------------------------------------------
+// Box loss of one positive anchor (losses.py:263-320) and d(loss)/d(reg row).
+__device__ __forceinline__ float retina_box_term(const float4 a, const float4 gt, const float4 t,
+                                                 int box_loss, float beta, float4 &grad) {
+    const float awx = __fsub_rn(a.z, a.x), awy = __fsub_rn(a.w, a.y);
+    const float acx = __fadd_rn(a.x, __fmul_rn(0.5f, awx));
+    const float acy = __fadd_rn(a.y, __fmul_rn(0.5f, awy));
+    float term = 0.f;
+    if (box_loss == B200DET_BOX_SMOOTHL1) {
+        // targets (losses.py:390-409)
+        const float gwx = fmaxf(__fsub_rn(gt.z, gt.x), 1e-4f);
+        const float gwy = fmaxf(__fsub_rn(gt.w, gt.y), 1e-4f);
+        const float gcx = __fadd_rn(gt.x, __fmul_rn(0.5f, gwx));
+        const float gcy = __fadd_rn(gt.y, __fmul_rn(0.5f, gwy));
+        const float tg[4] = {__fdiv_rn(__fsub_rn(gcx, acx), awx), __fdiv_rn(__fsub_rn(gcy, acy), awy),
+                             logf(__fdiv_rn(gwx, awx)), logf(__fdiv_rn(gwy, awy))};
+        const float pr[4] = {t.x, t.y, t.z, t.w};
+        float gr[4];
+        const float half_beta = 0.5f * beta;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float d = __fsub_rn(pr[i], tg[i]);
+            const float x = fabsf(d);
+            if (x >= beta) {
+                term += __fsub_rn(x, half_beta);
+                gr[i] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+            } else {
+                term += __fdiv_rn(__fmul_rn(0.5f, __fmul_rn(x, x)), beta);
+                gr[i] = d / beta;
+            }
+        }
+        grad = make_float4(gr[0], gr[1], gr[2], gr[3]);
+    } else {
+        // decode (losses.py:411-429) then 1 - IoU-family (losses.py:286-293)
+        const Dual tx = dvar(t.x, 0), ty = dvar(t.y, 1), tw = dvar(t.z, 2), th = dvar(t.w, 3);
+        const Dual bw = dexp(tw) * awx, bh = dexp(th) * awy;
+        const Dual cx = tx * awx + acx, cy = ty * awy + acy;
+        const Dual hw = bw * 0.5f, hh = bh * 0.5f;
+        const Dual p[4] = {cx - hw, cy - hh, cx + hw, cy + hh};
+        const float gg[4] = {gt.x, gt.y, gt.z, gt.w};
+        const Dual iou = iou_family(p, gg, box_loss);
+        term = __fsub_rn(1.f, iou.v);
+        grad = make_float4(-iou.d[0], -iou.d[1], -iou.d[2], -iou.d[3]);
+    }
+    return term;
+}
+
+struct SparseArgs {
+    Geo g;
+    BaseAnchors ba;
+    PtrTab reg, ctr, cls;        // cls.p[0] == nullptr: no focal corrections
+    MutPtrTab reg_grad, ctr_grad;
+    int reg_dtype, box_loss, is_fcos, G, C;
+    float beta, alpha, gamma;
+};
+
+// 64-bit fixed point: integer adds commute, so the sums are independent of the visiting order
+constexpr double kFxBox = 4294967296.0;          // 2^32
+constexpr double kFxFocal = 1099511627776.0;     // 2^40
+__device__ __forceinline__ long long to_fx(float v, double scale) {
+    return __double2ll_rn((double)v * scale);
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// level-major row -> level and row inside that level's [B*rows_l] tensor
+__device__ __forceinline__ int split_row(const Geo &g, int i, long long &rrow) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxLevels; ++k)
+        if (k < g.n_levels && (long long)i >= (long long)g.batch * g.off[k]) l = k;
+    rrow = (long long)i - (long long)g.batch * g.off[l];
+    return l;
+}
+
+__global__ void __launch_bounds__(kSparseThreads)
+    sparse_loss_kernel(SparseArgs a, const float *__restrict__ annots,
+                       const int *__restrict__ labels, Queues q,
+                       SparsePartial *__restrict__ partials) {
+    const Geo &g = a.g;
+    const int lane = threadIdx.x & 31;
+    const bool want_fix = a.cls.p[0] != nullptr;
+    const bool want_loss = a.box_loss != B200DET_BOX_NONE;
+    const bool gamma2 = a.gamma == 2.f;
+    const int n_pos = q.counters[0], n_ign = q.counters[1];
+    const int gtid = blockIdx.x * kSparseThreads + threadIdx.x;
+    const int gsize = gridDim.x * kSparseThreads;
+    long long box_fx = 0, ctr_fx = 0, foc_fx = 0;
+
+    // ---- positives: one thread each ----
+    for (int k = gtid; k < n_pos; k += gsize) {
+        const int2 e = q.pos[k];
+        long long rrow;
+        const int l = split_row(g, e.x, rrow);
+        const int label = __ldg(labels + e.x);
+        if (want_loss) {
+            const int b = (int)(rrow / g.rows[l]);
+            const int local = (int)(rrow - (long long)b * g.rows[l]);
+            const float *gp = annots + ((size_t)b * a.G + e.y) * 5;
+            const float4 gt = make_float4(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3));
+            const float4 t = load_reg4(a.reg.p[l], a.reg_dtype, rrow);
+            float4 grad = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!a.is_fcos) {
+                const float4 an = anchor_of(g, a.ba, l, local);
+                box_fx += to_fx(retina_box_term(an, gt, t, a.box_loss, a.beta, grad), kFxBox);
+            } else {
+                // IoU loss, losses.py:550-586: boxes rebuilt around the point from l,t,r,b
+                const float2 pt = point_of(g, l, local);
+                const float bl = __fsub_rn(pt.x, gt.x), bt = __fsub_rn(pt.y, gt.y);
+                const float br = __fsub_rn(gt.z, pt.x), bb = __fsub_rn(gt.w, pt.y);
+                const float ctr_t = fcos_centerness(bl, bt, br, bb);
+                const Dual e0 = dexp(dvar(t.x, 0)), e1 = dexp(dvar(t.y, 1));
+                const Dual e2 = dexp(dvar(t.z, 2)), e3 = dexp(dvar(t.w, 3));
+                const Dual p[4] = {pt.x - e0, pt.y - e1, e2 + pt.x, e3 + pt.y};
+                const float gg[4] = {__fsub_rn(pt.x, bl), __fsub_rn(pt.y, bt), __fadd_rn(pt.x, br),
+                                     __fadd_rn(pt.y, bb)};
+                const Dual iou = iou_family(p, gg, a.box_loss);
+                box_fx += to_fx(__fmul_rn(__fsub_rn(1.f, iou.v), ctr_t), kFxBox);
+                grad = make_float4(-iou.d[0] * ctr_t, -iou.d[1] * ctr_t, -iou.d[2] * ctr_t,
+                                   -iou.d[3] * ctr_t);
+                // centre-ness BCE, losses.py:588-610 (prob clamped at losses.py:494)
+                const float craw = __ldg(static_cast<const float *>(a.ctr.p[l]) + rrow);
+                const float cp = fminf(fmaxf(craw, kClampLo), kClampHi);
+                const float one_m = __fsub_rn(1.f, cp), one_t = __fsub_rn(1.f, ctr_t);
+                ctr_fx += to_fx(-__fadd_rn(__fmul_rn(ctr_t, logf(cp)), __fmul_rn(one_t, logf(one_m))),
+                                kFxBox);
+                if (a.ctr_grad.p[0] != nullptr) {
+                    const float cgrad =
+                        (craw >= kClampLo && craw <= kClampHi) ? -(ctr_t / cp - one_t / one_m) : 0.f;
+                    static_cast<float *>(a.ctr_grad.p[l])[rrow] = cgrad;
+                }
+            }
+            if (a.reg_grad.p[0] != nullptr) reinterpret_cast<float4 *>(a.reg_grad.p[l])[rrow] = grad;
+        }
+        if (want_fix) {
+            // the sweep counted the target class as background: swap the term
+            const float p = __ldg(static_cast<const float *>(a.cls.p[l]) + rrow * a.C + (label - 1));
+            foc_fx += to_fx(a.alpha * pos_term(p, a.gamma, gamma2) -
+                                (1.f - a.alpha) * neg_term(p, a.gamma, gamma2),
+                            kFxFocal);
         }
     }
 
-    float box_term = 0.f, ctr_term = 0.f;
-    if (box_loss != B200DET_BOX_NONE && active) {
-        const long long rrow = (long long)b * g.rows[l] + local;
-        float4 grad = make_float4(0.f, 0.f, 0.f, 0.f);
-        float cgrad = 0.f;
-        if (pos) {
-            // IoU loss, losses.py:550-586: boxes rebuilt around the point from l,t,r,b
-            const float4 t = load_reg4(reg.p[l], reg_dtype, rrow);
-            const Dual e0 = dexp(dvar(t.x, 0)), e1 = dexp(dvar(t.y, 1));
-            const Dual e2 = dexp(dvar(t.z, 2)), e3 = dexp(dvar(t.w, 3));
-            const Dual p[4] = {pt.x - e0, pt.y - e1, e2 + pt.x, e3 + pt.y};
-            const float gg[4] = {__fsub_rn(pt.x, bl), __fsub_rn(pt.y, bt), __fadd_rn(pt.x, br),
-                                 __fadd_rn(pt.y, bb)};
-            const Dual iou = iou_family(p, gg, box_loss);
-            box_term = __fmul_rn(__fsub_rn(1.f, iou.v), ctr_t);
-            grad = make_float4(-iou.d[0] * ctr_t, -iou.d[1] * ctr_t, -iou.d[2] * ctr_t,
-                               -iou.d[3] * ctr_t);
-            // centre-ness BCE, losses.py:588-610 (prob clamped at losses.py:494)
-            const float craw = __ldg(reinterpret_cast<const float *>(ctr.p[l]) + rrow);
-            const float lo = 1e-4f, hi = 0.9999f;  // float32(1e-4), float32(1. - 1e-4)
-            const float cp = fminf(fmaxf(craw, lo), hi);
-            const float one_m = __fsub_rn(1.f, cp), one_t = __fsub_rn(1.f, ctr_t);
-            ctr_term = -__fadd_rn(__fmul_rn(ctr_t, logf(cp)), __fmul_rn(one_t, logf(one_m)));
-            if (craw >= lo && craw <= hi) cgrad = -(ctr_t / cp - one_t / one_m);
+    // ---- ignored rows (Retina: 0.4 <= IoU < 0.5, or image without GT) take no part in the focal
+    // loss (losses.py:228-230): remove what the label-free sweep added.  One warp per row, two rows
+    // in flight; a row's sum has a fixed order (lane-strided partials + xor tree) and is converted
+    // to fixed point once, so the result is independent of the queue order.
+    if (want_fix) {
+        const int gwarp = gtid >> 5, n_warps = gsize >> 5;
+        for (int r0 = gwarp; r0 < n_ign; r0 += 2 * n_warps) {
+            const int r1 = r0 + n_warps;
+            long long rr0, rr1 = 0;
+            const int l0 = split_row(g, q.ign[r0], rr0);
+            const bool two = r1 < n_ign;
+            const int l1 = two ? split_row(g, q.ign[r1], rr1) : l0;
+            const float *p0 = static_cast<const float *>(a.cls.p[l0]) + rr0 * a.C;
+            const float *p1 = static_cast<const float *>(a.cls.p[l1]) + rr1 * a.C;
+            float s0 = 0.f, s1 = 0.f;
+            for (int c = lane; c < a.C; c += 32) {
+                const float v0 = __ldg(p0 + c);
+                const float v1 = two ? __ldg(p1 + c) : 0.f;
+                s0 += neg_term(v0, a.gamma, gamma2);
+                if (two) s1 += neg_term(v1, a.gamma, gamma2);
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            if (lane == 0) {
+                foc_fx -= to_fx((1.f - a.alpha) * s0, kFxFocal);
+                if (two) foc_fx -= to_fx((1.f - a.alpha) * s1, kFxFocal);
+            }
         }
-        if (reg_grad.p[0] != nullptr)
-            reinterpret_cast<float4 *>(reg_grad.p[l])[rrow] = grad;
-        if (ctr_grad.p[0] != nullptr) reinterpret_cast<float *>(ctr_grad.p[l])[rrow] = cgrad;
     }
-    block_partial(pos ? 1 : 0, box_term, ctr_term,
-                  partials + (size_t)blockIdx.y * gridDim.x + blockIdx.x, red);
+
+    __shared__ long long red[3][kSparseThreads / 32];
+    const int warp = threadIdx.x >> 5;
+    box_fx = warp_sum_ll(box_fx);
+    ctr_fx = warp_sum_ll(ctr_fx);
+    foc_fx = warp_sum_ll(foc_fx);
+    if (lane == 0) {
+        red[0][warp] = box_fx;
+        red[1][warp] = ctr_fx;
+        red[2][warp] = foc_fx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long sb = 0, sc = 0, sf = 0;
+        for (int w = 0; w < kSparseThreads / 32; ++w) {
+            sb += red[0][w];
+            sc += red[1][w];
+            sf += red[2][w];
+        }
+        SparsePartial p;
+        p.box = (double)sb / kFxBox;
+        p.ctr = (double)sc / kFxBox;
+        p.focal = (double)sf / kFxFocal;
+        partials[blockIdx.x] = p;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -497,6 +757,60 @@ __global__ void rows_to_image_major_kernel(Geo g, const uint32_t *src, uint32_t 
     }
 }
 
+static TileTab make_tiles(const Geo &g) {
+    TileTab t;
+    int off = 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        t.tile_off[l] = off;
+        t.tiles_x[l] = 1;
+        if (l < g.n_levels) {
+            t.tiles_x[l] = (g.W[l] + kTileW - 1) / kTileW;
+            off += t.tiles_x[l] * ((g.H[l] + kTileH - 1) / kTileH);
+        }
+    }
+    for (int l = g.n_levels; l <= kMaxLevels; ++l) t.tile_off[l] = off;
+    return t;
+}
+
+static Queues queues_of(char *base, const LossWs &ws) {
+    Queues q;
+    q.counters = reinterpret_cast<int *>(base + ws.off_counters);
+    q.pos = reinterpret_cast<int2 *>(base + ws.off_pos_queue);
+    q.ign = reinterpret_cast<int *>(base + ws.off_ign_queue);
+    return q;
+}
+
+// Optional residency cap for the assignment kernels (B200DET_ASSIGN_CTAS_PER_SM, default: none).
+// When a caller overlaps them with the HBM-bound sweep on another stream, their register
+// footprint (up to 92 x 128 per CTA, five CTAs per SM) can lock the sweep out of the SMs; padding
+// the dynamic shared-memory request limits how many fit.  Measured on B200 (profiles/): running
+// the kernels back to back is faster than any overlap, so the default is no cap.
+constexpr size_t kAssignSmemBudget = 200 * 1024;
+static size_t assign_dyn_smem(int max_gt) {
+    static int ctas = 0;
+    if (ctas == 0) {
+        const char *e = getenv("B200DET_ASSIGN_CTAS_PER_SM");
+        ctas = e ? atoi(e) : 16;
+        if (ctas < 1) ctas = 1;
+        if (ctas > 16) ctas = 16;
+    }
+    const size_t need = gt_smem_bytes(max_gt);
+    const size_t pad = kAssignSmemBudget / (size_t)ctas;   // static smem (<= 26 KB) comes on top
+    return need > pad ? need : pad;
+}
+
+// CTAs per image of the assignment kernels / CTAs of the sparse kernel (workspace layout)
+int assign_blocks_per_image(const Geo &g) {
+    const TileTab t = make_tiles(g);
+    return (t.tile_off[g.n_levels] + kAssignWarps - 1) / kAssignWarps;
+}
+int sparse_blocks(const Geo &g) {
+    const long long total = (long long)g.batch * g.off[g.n_levels];
+    const long long want = (total + kSparseThreads - 1) / kSparseThreads;
+    const long long cap = 148 * 8;
+    return (int)(want < cap ? want : cap);
+}
+
 }  // namespace b200det
 
 using namespace b200det;
@@ -504,11 +818,12 @@ using namespace b200det;
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static int fill_ptrs(const void *const *src, int n, PtrTab *dst) {
+static int fill_ptrs(const void *const *src, int n, PtrTab *dst, uintptr_t align_mask) {
     for (int i = 0; i < kMaxLevels; ++i) dst->p[i] = nullptr;
     if (!src) return 0;
     for (int i = 0; i < n; ++i) {
         if (!src[i]) return B200DET_EINVAL;
+        if (reinterpret_cast<uintptr_t>(src[i]) & align_mask) return B200DET_EALIGN;
         dst->p[i] = src[i];
     }
     return 0;
@@ -523,81 +838,64 @@ static int fill_mut_ptrs(void *const *src, int n, MutPtrTab *dst, uintptr_t alig
     }
     return 0;
 }
-static int check_reg(const PtrTab &t, int n, int dtype) {
-    if (dtype != B200DET_F32 && dtype != B200DET_F16 && dtype != B200DET_BF16)
-        return B200DET_EINVAL;
-    const uintptr_t mask = dtype == B200DET_F32 ? 15 : 7;
-    for (int i = 0; i < n; ++i)
-        if (reinterpret_cast<uintptr_t>(t.p[i]) & mask) return B200DET_EALIGN;
+static void copy_base(const b200det_geometry *geo, BaseAnchors *ba) {
+    for (int l = 0; l < kMaxLevels; ++l)
+        for (int a = 0; a < kMaxPerLoc; ++a)
+            for (int k = 0; k < 4; ++k) ba->v[l][a][k] = geo->base_anchors[l][a][k];
+}
+template <typename K>
+static int raise_smem_limit(K kernel, bool *done) {
+    if (*done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kAssignSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    *done = true;
     return 0;
 }
 
 extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *annotations,
-                                     int max_gt, const void *const *reg, int reg_dtype,
-                                     int box_loss, float beta, int32_t *labels,
-                                     int32_t *matched, void *const *reg_grad, void *workspace,
-                                     size_t workspace_bytes, void *stream) {
+                                     int max_gt, int32_t *labels, int32_t *matched,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
     if (!annotations || !labels || !workspace) return B200DET_EINVAL;
     if (max_gt < 1 || max_gt > B200DET_MAX_GT) return B200DET_ERANGE;
-    if (box_loss < B200DET_BOX_NONE || box_loss > B200DET_BOX_EIOU) return B200DET_EINVAL;
-    if (box_loss != B200DET_BOX_NONE && !reg) return B200DET_EINVAL;
-    if (g.per_loc > kMaxPerLoc) return B200DET_ERANGE;
-    PtrTab regt;
-    MutPtrTab gradt;
-    if ((rc = fill_ptrs(box_loss != B200DET_BOX_NONE ? reg : nullptr, g.n_levels, &regt))) return rc;
-    if (box_loss != B200DET_BOX_NONE && (rc = check_reg(regt, g.n_levels, reg_dtype))) return rc;
-    if ((rc = fill_mut_ptrs(box_loss != B200DET_BOX_NONE ? reg_grad : nullptr, g.n_levels, &gradt, 15)))
-        return rc;
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     BaseAnchors ba;
-    for (int l = 0; l < kMaxLevels; ++l)
-        for (int a = 0; a < kMaxPerLoc; ++a)
-            for (int k = 0; k < 4; ++k) ba.v[l][a][k] = geo->base_anchors[l][a][k];
-
-    const size_t smem = gt_smem_bytes(max_gt);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(retina_assign_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)gt_smem_bytes(B200DET_MAX_GT));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    copy_base(geo, &ba);
+    const TileTab tt = make_tiles(g);
+    static bool a9 = false, a0 = false;
+    if ((rc = raise_smem_limit(retina_assign_kernel<9>, &a9))) return rc;
+    if ((rc = raise_smem_limit(retina_assign_kernel<0>, &a0))) return rc;
+    char *base = static_cast<char *>(workspace);
+    int *npos = reinterpret_cast<int *>(base + ws.off_assign);
+    const Queues q = queues_of(base, ws);
+    cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)g.batch);
-    retina_assign_kernel<<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
-        g, ba, annotations, max_gt, regt, reg_dtype, box_loss, beta, labels, matched, gradt,
-        reinterpret_cast<AssignPartial *>(static_cast<char *>(workspace) + ws.off_assign));
+    const size_t smem = assign_dyn_smem(max_gt);
+    if (g.per_loc == 9)
+        retina_assign_kernel<9><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
+            g, ba, tt, annotations, max_gt, labels, matched, q, npos);
+    else
+        retina_assign_kernel<0><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
+            g, ba, tt, annotations, max_gt, labels, matched, q, npos);
     count_launch();
     return (int)cudaGetLastError();
 }
 
 extern "C" int b200det_fcos_assign(const b200det_geometry *geo, const float *annotations,
-                                   int max_gt, const void *const *reg, int reg_dtype,
-                                   const void *const *ctr, int box_loss, int use_center_sample,
-                                   int32_t *labels, int32_t *matched, float *targets,
-                                   void *const *reg_grad, void *const *ctr_grad, void *workspace,
+                                   int max_gt, int use_center_sample, int32_t *labels,
+                                   int32_t *matched, float *targets, void *workspace,
                                    size_t workspace_bytes, void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
     if (!annotations || !labels || !workspace) return B200DET_EINVAL;
     if (max_gt < 1 || max_gt > B200DET_MAX_GT) return B200DET_ERANGE;
-    if (box_loss == B200DET_BOX_SMOOTHL1 || box_loss < B200DET_BOX_NONE || box_loss > B200DET_BOX_EIOU)
-        return B200DET_EINVAL;
     if (g.per_loc != 1) return B200DET_EINVAL;
-    const bool with_loss = box_loss != B200DET_BOX_NONE;
-    if (with_loss && (!reg || !ctr)) return B200DET_EINVAL;
-    PtrTab regt, ctrt;
-    MutPtrTab rgrad, cgrad;
-    if ((rc = fill_ptrs(with_loss ? reg : nullptr, g.n_levels, &regt))) return rc;
-    if ((rc = fill_ptrs(with_loss ? ctr : nullptr, g.n_levels, &ctrt))) return rc;
-    if (with_loss && (rc = check_reg(regt, g.n_levels, reg_dtype))) return rc;
-    if ((rc = fill_mut_ptrs(with_loss ? reg_grad : nullptr, g.n_levels, &rgrad, 15))) return rc;
-    if ((rc = fill_mut_ptrs(with_loss ? ctr_grad : nullptr, g.n_levels, &cgrad, 3))) return rc;
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     FcosTab ft;
@@ -606,20 +904,64 @@ extern "C" int b200det_fcos_assign(const b200det_geometry *geo, const float *ann
         ft.mi_hi[l] = geo->mi_hi[l];
         ft.radius[l] = geo->radius[l];
     }
-    const size_t smem = gt_smem_bytes(max_gt);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fcos_assign_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)gt_smem_bytes(B200DET_MAX_GT));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    const TileTab tt = make_tiles(g);
+    static bool done = false;
+    if ((rc = raise_smem_limit(fcos_assign_kernel, &done))) return rc;
+    char *base = static_cast<char *>(workspace);
+    const Queues q = queues_of(base, ws);
+    cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)g.batch);
-    fcos_assign_kernel<<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
-        g, ft, annotations, max_gt, regt, reg_dtype, ctrt, box_loss, use_center_sample, labels,
-        matched, targets, rgrad, cgrad,
-        reinterpret_cast<AssignPartial *>(static_cast<char *>(workspace) + ws.off_assign));
+    fcos_assign_kernel<<<grid, kAssignThreads, assign_dyn_smem(max_gt), (cudaStream_t)stream>>>(
+        g, ft, tt, annotations, max_gt, use_center_sample, labels, matched, targets, q,
+        reinterpret_cast<int *>(base + ws.off_assign));
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos,
+                                     const float *annotations, int max_gt, const int32_t *labels,
+                                     const void *const *reg, int reg_dtype,
+                                     const void *const *ctr, int box_loss, float beta,
+                                     const void *const *cls, float alpha, float gamma,
+                                     void *const *reg_grad, void *const *ctr_grad,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!annotations || !labels || !workspace) return B200DET_EINVAL;
+    if (max_gt < 1 || max_gt > B200DET_MAX_GT) return B200DET_ERANGE;
+    if (box_loss < B200DET_BOX_NONE || box_loss > B200DET_BOX_EIOU) return B200DET_EINVAL;
+    if (is_fcos && (box_loss == B200DET_BOX_SMOOTHL1 || g.per_loc != 1)) return B200DET_EINVAL;
+    const bool with_loss = box_loss != B200DET_BOX_NONE;
+    if (with_loss && (!reg || (is_fcos && !ctr))) return B200DET_EINVAL;
+    if (reg_dtype != B200DET_F32 && reg_dtype != B200DET_F16 && reg_dtype != B200DET_BF16)
+        return B200DET_EINVAL;
+    SparseArgs a;
+    a.g = g;
+    copy_base(geo, &a.ba);
+    if ((rc = fill_ptrs(with_loss ? reg : nullptr, g.n_levels, &a.reg,
+                        reg_dtype == B200DET_F32 ? 15 : 7)))
+        return rc;
+    if ((rc = fill_ptrs(with_loss && is_fcos ? ctr : nullptr, g.n_levels, &a.ctr, 3))) return rc;
+    if ((rc = fill_ptrs(cls, g.n_levels, &a.cls, 3))) return rc;
+    if ((rc = fill_mut_ptrs(with_loss ? reg_grad : nullptr, g.n_levels, &a.reg_grad, 15))) return rc;
+    if ((rc = fill_mut_ptrs(with_loss && is_fcos ? ctr_grad : nullptr, g.n_levels, &a.ctr_grad, 3)))
+        return rc;
+    a.reg_dtype = reg_dtype;
+    a.box_loss = box_loss;
+    a.is_fcos = is_fcos;
+    a.G = max_gt;
+    a.C = g.num_classes;
+    a.beta = beta;
+    a.alpha = alpha;
+    a.gamma = gamma;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    char *base = static_cast<char *>(workspace);
+    sparse_loss_kernel<<<(unsigned)ws.sparse_blocks, kSparseThreads, 0, (cudaStream_t)stream>>>(
+        a, annotations, labels, queues_of(base, ws),
+        reinterpret_cast<SparsePartial *>(base + ws.off_sparse));
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -631,9 +973,7 @@ extern "C" int b200det_generate_rows(const b200det_geometry *geo, int is_fcos, f
     if (rc) return rc;
     if (!out) return B200DET_EINVAL;
     BaseAnchors ba;
-    for (int l = 0; l < kMaxLevels; ++l)
-        for (int a = 0; a < kMaxPerLoc; ++a)
-            for (int k = 0; k < 4; ++k) ba.v[l][a][k] = geo->base_anchors[l][a][k];
+    copy_base(geo, &ba);
     const int N = g.off[g.n_levels];
     generate_rows_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, ba, is_fcos, out);
     count_launch();

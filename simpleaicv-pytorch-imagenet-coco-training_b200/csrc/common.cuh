@@ -44,18 +44,20 @@ int make_geo(const b200det_geometry *g, Geo *out);
 void count_launch();
 unsigned long long launches();
 
-// Loss workspace: per-CTA partials, reduced in fixed order by loss_reduce_kernel.
-struct AssignPartial {
-    int npos;
-    float box;
-    float ctr;
-    float pad;
+// Loss workspace (caller-owned scratch): per-CTA partials, reduced in fixed order by
+// loss_reduce_kernel, plus the matched annotation row of every row (assign -> sparse kernel).
+struct SparsePartial {
+    double box, ctr, focal;
 };
 struct LossWs {
-    size_t assign_blocks_per_image, assign_blocks, focal_chunks;
-    size_t off_assign, off_focal, total;
+    size_t assign_blocks_per_image, assign_blocks, sparse_blocks, focal_chunks;
+    size_t off_assign /* int npos [assign_blocks] */, off_sparse /* SparsePartial [sparse_blocks] */,
+        off_focal /* float [focal_chunks] */, off_counters /* int [2] */,
+        off_pos_queue /* int2 [B*N] */, off_ign_queue /* int [B*N] */, total;
 };
 LossWs loss_ws_layout(const Geo &g);
+int assign_blocks_per_image(const Geo &g);  // assign.cu
+int sparse_blocks(const Geo &g);            // assign.cu
 
 // ---------------------------------------------------------------------------------------
 // device helpers

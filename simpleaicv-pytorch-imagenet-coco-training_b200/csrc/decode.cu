@@ -10,6 +10,7 @@
 //                        row asc), box decode with NumPy's exp + x86 int32 truncation, greedy
 //                        NMS driven by warp ballots into a removed-bitmask, max_object_num cap.
 // Compiled with -fmad=false: box / IoU arithmetic is one IEEE float32 op per reference op.
+#include <string.h>
 #include "common.cuh"
 
 namespace b200det {
@@ -125,6 +126,8 @@ struct SelectArgs {
     BaseAnchors ba;
     PtrTab reg;
     int reg_dtype, is_fcos, topn, pad_n /* pow2 >= topn */, max_out, nms_type;
+    uint32_t key_lo;   // flipped key of the score threshold: every candidate key is > key_lo
+    int key_shift;     // pass-A bin = min((key - key_lo) >> key_shift, kBins - 1)
     float nms_thr_f;
     double nms_thr_d;
 };
@@ -161,6 +164,7 @@ __device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t
     for (int l = 0; l < g.n_levels; ++l) {
         const uint32_t *p = keys + lm_index(g, b, l, 0);
         const int n = g.rows[l], off = g.off[l];
+#pragma unroll 4
         for (int j = threadIdx.x; j < n; j += kSelThreads) f(__ldg(p + j), off + j);
     }
 }
@@ -173,13 +177,13 @@ __global__ void __launch_bounds__(kSelThreads)
     extern __shared__ __align__(16) unsigned char smem[];
     // carve: hist | key64 | box | cls | keep | removed
     int *hist = reinterpret_cast<int *>(smem);                                // kBins
-    unsigned long long *skey = reinterpret_cast<unsigned long long *>(hist + kBins);  // pad_n
-    float4 *sbox = reinterpret_cast<float4 *>(skey + a.pad_n);                // pad_n
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(hist + kBins);  // 2*pad_n
+    float4 *sbox = reinterpret_cast<float4 *>(skey + 2 * a.pad_n);            // pad_n
     int *scls = reinterpret_cast<int *>(sbox + a.pad_n);                      // pad_n
     int *skeep = scls + a.pad_n;                                              // pad_n
     uint32_t *srem = reinterpret_cast<uint32_t *>(skeep + a.pad_n);           // pad_n/32
     __shared__ int scratch[kSelWarps];
-    __shared__ int s_digit, s_above, s_count;
+    __shared__ int s_digit, s_above, s_count, s_total;
 
     const Geo &g = a.g;
     const int b = blockIdx.x;
@@ -187,92 +191,144 @@ __global__ void __launch_bounds__(kSelThreads)
     const int N = g.off[g.n_levels];
     const int B = g.batch;
 
-    // ---- pass 0: candidates, key range ----
-    int ncand_t = 0;
-    uint32_t kmax_t = 0u, kmin_t = 0xffffffffu;
-    for_each_key(g, b, keys, [&](uint32_t k, int) {
-        if (k) {
-            ++ncand_t;
-            kmax_t = max(kmax_t, k);
-            kmin_t = min(kmin_t, k);
-        }
-    });
-    const int ncand = block_sum_int(ncand_t, scratch);
-    const uint32_t kmax = block_max_u32(kmax_t, reinterpret_cast<uint32_t *>(scratch));
-    const uint32_t kmin = block_min_u32(kmin_t, reinterpret_cast<uint32_t *>(scratch));
-    const int k_sel = min(a.topn, ncand);
-
     float *out_scores = out + (size_t)b * a.max_out;
     float *out_classes = out + (size_t)B * a.max_out + (size_t)b * a.max_out;
     float *out_boxes = out + (size_t)2 * B * a.max_out + (size_t)b * a.max_out * 4;
 
-    // ---- radix select: threshold key T and how many of the keys == T to take ----
-    uint32_t T = 1u;          // select keys >= T ...
-    int tie_take = -1;        // ... or, if >= 0: keys > T plus the first `tie_take` keys == T
-    if (ncand > a.topn) {
-        uint32_t lo = kmin, hi = kmax;
-        int need = k_sel;
-        while (true) {
-            const unsigned long long span = (unsigned long long)hi - lo + 1ull;
-            int shift = 0;
-            while ((span - 1ull) >> shift >= (unsigned long long)kBins) ++shift;
-            for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
-            __syncthreads();
-            for_each_key(g, b, keys, [&](uint32_t k, int) {
-                if (k >= lo && k <= hi) atomicAdd(&hist[(k - lo) >> shift], 1);
-            });
-            __syncthreads();
-            // suffix scan over bins (thread t owns bins 2t, 2t+1), find the bin where the
-            // count from the top crosses `need`
-            const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
-            const int mine = h0 + h1;
-            // inclusive suffix sum within the warp (higher lanes = higher bins)
-            int suf = mine;
+    // ---- pass A: 2048-bin histogram of the keys over the expected score range ----
+    // Candidate keys are > key_lo (the flipped threshold); keys above key_hi (scores > 1, not
+    // produced by sigmoid heads) saturate into the top bin.  Bin D where the count from the top
+    // crosses topn bounds the selection: everything at or above D is collected and sorted.
+    const uint32_t lo = a.key_lo;
+    const int shift = a.key_shift;
+    for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    for_each_key(g, b, keys, [&](uint32_t k, int) {
+        if (k) atomicAdd(&hist[min((k - lo) >> shift, (uint32_t)(kBins - 1))], 1);
+    });
+    __syncthreads();
+    int cut_bin, above, in_bin;
+    {
+        const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+        const int mine = h0 + h1;
+        int suf = mine;  // inclusive suffix sum within the warp (higher lanes = higher bins)
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_down_sync(0xffffffffu, suf, o);
-                if (lane + o < 32) suf += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, suf, o);
+            if (lane + o < 32) suf += t;
+        }
+        if (lane == 0) scratch[warp] = suf;
+        __syncthreads();
+        int above_warps = 0, total = 0;
+        for (int w = 0; w < kSelWarps; ++w) {
+            const int c = scratch[w];
+            total += c;
+            if (w > warp) above_warps += c;
+        }
+        const int need = min(a.topn, total);
+        const int above_excl = above_warps + suf - mine;
+        if (tid == 0) {
+            s_digit = 0;      // fewer candidates than topn (or none): take everything
+            s_above = 0;
+            s_count = total;
+            s_total = total;
+        }
+        __syncthreads();
+        if (total > a.topn && above_excl < need && need <= above_excl + mine) {
+            if (need <= above_excl + h1) {
+                s_digit = 2 * tid + 1;
+                s_above = above_excl;
+                s_count = h1;
+            } else {
+                s_digit = 2 * tid;
+                s_above = above_excl + h1;
+                s_count = h0;
             }
-            if (lane == 0) scratch[warp] = suf;  // warp total
-            __syncthreads();
-            int above_warps = 0;
-            for (int w = warp + 1; w < kSelWarps; ++w) above_warps += scratch[w];
-            const int above_excl = above_warps + suf - mine;  // keys in bins above my two bins
-            if (above_excl < need && need <= above_excl + mine) {
-                if (need <= above_excl + h1) {
-                    s_digit = 2 * tid + 1;
-                    s_above = above_excl;
-                    s_count = h1;
-                } else {
-                    s_digit = 2 * tid;
-                    s_above = above_excl + h1;
-                    s_count = h0;
+        }
+        __syncthreads();
+        cut_bin = s_digit;
+        above = s_above;
+        in_bin = s_count;
+    }
+    const int ncand = s_total;
+    const int k_sel = min(a.topn, ncand);
+    const int cap = 2 * a.pad_n;  // capacity of skey
+    __syncthreads();
+
+    uint32_t T = 1u;      // collect keys >= T ...
+    int tie_take = -1;    // ... or, if >= 0: keys > T plus the first `tie_take` rows with key == T
+    int n_collect = ncand <= a.topn ? ncand : above + in_bin;
+    if (ncand > a.topn) {
+        T = lo + ((uint32_t)cut_bin << shift);
+        if (cut_bin == 0) T = 1u;
+        if (n_collect > cap) {
+            // The cut bin is too crowded to sort (heavy ties, or scores far outside (thr, 1]):
+            // refine inside it with an adaptive-range radix select until the bucket is exact.
+            uint32_t rlo = cut_bin == 0 ? 1u : T;
+            uint32_t rhi = cut_bin == kBins - 1
+                               ? 0xffffffffu
+                               : (uint32_t)((unsigned long long)lo + (((unsigned long long)cut_bin + 1ull) << shift) - 1ull);
+            int need = k_sel - above;
+            while (true) {
+                const unsigned long long span = (unsigned long long)rhi - rlo + 1ull;
+                int sh = 0;
+                while ((span - 1ull) >> sh >= (unsigned long long)kBins) ++sh;
+                for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
+                __syncthreads();
+                for_each_key(g, b, keys, [&](uint32_t k, int) {
+                    if (k >= rlo && k <= rhi) atomicAdd(&hist[(k - rlo) >> sh], 1);
+                });
+                __syncthreads();
+                const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+                const int mine = h0 + h1;
+                int suf = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + o < 32) suf += t;
+                }
+                if (lane == 0) scratch[warp] = suf;
+                __syncthreads();
+                int above_warps = 0;
+                for (int w = warp + 1; w < kSelWarps; ++w) above_warps += scratch[w];
+                const int above_excl = above_warps + suf - mine;
+                if (above_excl < need && need <= above_excl + mine) {
+                    if (need <= above_excl + h1) {
+                        s_digit = 2 * tid + 1;
+                        s_above = above_excl;
+                        s_count = h1;
+                    } else {
+                        s_digit = 2 * tid;
+                        s_above = above_excl + h1;
+                        s_count = h0;
+                    }
+                }
+                __syncthreads();
+                const int digit = s_digit, cnt = s_count;
+                need -= s_above;
+                const uint32_t lo2 = rlo + ((uint32_t)digit << sh);
+                const unsigned long long hi2 = (unsigned long long)lo2 + ((1ull << sh) - 1ull);
+                rlo = lo2;
+                if (hi2 < rhi) rhi = (uint32_t)hi2;
+                __syncthreads();
+                if (cnt == need) {  // the whole bucket is needed
+                    T = rlo;
+                    break;
+                }
+                if (sh == 0) {      // one key value with more copies than needed: ties
+                    T = rlo;
+                    tie_take = need;
+                    break;
                 }
             }
-            __syncthreads();
-            const int digit = s_digit, cnt = s_count;
-            need -= s_above;
-            const uint32_t lo2 = lo + ((uint32_t)digit << shift);
-            const unsigned long long hi2 = (unsigned long long)lo2 + ((1ull << shift) - 1ull);
-            lo = lo2;
-            if (hi2 < hi) hi = (uint32_t)hi2;
-            __syncthreads();  // everyone has read s_* before the next round overwrites them
-            if (cnt == need) {  // take the whole bucket
-                T = lo;
-                break;
-            }
-            if (shift == 0) {   // a single key value with more copies than needed: ties
-                T = lo;
-                tie_take = need;
-                break;
-            }
+            n_collect = k_sel;
         }
     }
 
     // ---- collect the selected (key,row) pairs ----
     if (tid == 0) s_count = 0;
     __syncthreads();
-    if (k_sel > 0) {
+    if (n_collect > 0) {
         for_each_key(g, b, keys, [&](uint32_t k, int row) {
             const bool take = tie_take < 0 ? (k >= T && k != 0u) : (k > T);
             if (take) {
@@ -313,10 +369,11 @@ __global__ void __launch_bounds__(kSelThreads)
         }
     }
     __syncthreads();
-    const int n_sel = s_count;  // == k_sel
+    const int n_got = s_count;  // == n_collect
+    const int n_sel = min(n_got, k_sel);  // after the sort only the first k_sel entries are used
     int sort_n = 1;
-    while (sort_n < n_sel) sort_n <<= 1;
-    for (int i = n_sel + tid; i < sort_n; i += kSelThreads) skey[i] = 0ull;
+    while (sort_n < n_got) sort_n <<= 1;
+    for (int i = n_got + tid; i < sort_n; i += kSelThreads) skey[i] = 0ull;
     __syncthreads();
 
     // ---- bitonic sort, descending (score desc, then row asc) ----
@@ -481,7 +538,7 @@ __global__ void npexp_kernel(const float *__restrict__ x, float *__restrict__ y,
 }
 
 static size_t select_smem_bytes(int pad_n) {
-    return (size_t)kBins * 4 + (size_t)pad_n * (8 + 16 + 4 + 4) + (size_t)(pad_n / 32) * 4 + 16;
+    return (size_t)kBins * 4 + (size_t)pad_n * (16 + 16 + 4 + 4) + (size_t)(pad_n / 32) * 4 + 16;
 }
 
 }  // namespace b200det
@@ -549,8 +606,9 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
 
 extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
                                          const int32_t *classes, const void *const *reg,
-                                         int reg_dtype, int is_fcos, int topn, int max_out,
-                                         int nms_type, double nms_threshold, float *out,
+                                         int reg_dtype, int is_fcos, float min_score, int topn,
+                                         int max_out, int nms_type, double nms_threshold,
+                                         float *out,
                                          int32_t *order, int32_t *keep, int32_t *counts,
                                          void *workspace, size_t workspace_bytes, void *stream) {
     (void)workspace;
@@ -589,6 +647,20 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
     a.nms_type = nms_type;
     a.nms_thr_f = (float)nms_threshold;
     a.nms_thr_d = nms_threshold;
+    {
+        // host copies of flip_key(): bins span (min_score, max(1, 2*min_score)] in key space
+        auto flip = [](float f) {
+            uint32_t bits;
+            memcpy(&bits, &f, 4);
+            return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+        };
+        const float top = min_score < 1.f ? 1.f : (min_score > 0.f ? 2.f * min_score : 1.f);
+        a.key_lo = flip(min_score);
+        const uint32_t span = flip(top) > a.key_lo ? flip(top) - a.key_lo : 1u;
+        int sh = 0;
+        while ((span >> sh) >= (uint32_t)(kBins - 1)) ++sh;
+        a.key_shift = sh;
+    }
     const size_t smem = select_smem_bytes(pad_n);
     static bool attr_set = false;
     if (!attr_set) {

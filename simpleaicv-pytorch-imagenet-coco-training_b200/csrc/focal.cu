@@ -15,6 +15,7 @@
 // gamma != 2 fall back to logf/powf.  Loss tolerance vs the reference: 1e-5 relative.
 #include <atomic>
 #include "common.cuh"
+#include "focal_terms.cuh"
 
 namespace b200det {
 
@@ -66,8 +67,9 @@ static inline int focal_vec(const Geo &g) { return (g.num_classes % 4 == 0) ? 4 
 LossWs loss_ws_layout(const Geo &g) {
     LossWs w;
     const long long N = g.off[g.n_levels];
-    w.assign_blocks_per_image = (size_t)((N + 255) / 256);
+    w.assign_blocks_per_image = (size_t)assign_blocks_per_image(g);
     w.assign_blocks = w.assign_blocks_per_image * (size_t)g.batch;
+    w.sparse_blocks = (size_t)sparse_blocks(g);
     // vector width is a pure function of C (float4 when C % 4 == 0; pointers must then be
     // 16-byte aligned), so the partial count is exact
     size_t chunks = 0;
@@ -76,22 +78,28 @@ LossWs loss_ws_layout(const Geo &g) {
         chunks += (size_t)((units + kChunkUnits - 1) / kChunkUnits);
     }
     w.focal_chunks = chunks;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     w.off_assign = 0;
-    w.off_focal = (w.assign_blocks * 16 + 255) & ~(size_t)255;
-    w.total = w.off_focal + ((chunks * 4 + 255) & ~(size_t)255);
+    w.off_sparse = up(w.assign_blocks * sizeof(int));
+    w.off_focal = w.off_sparse + up(w.sparse_blocks * sizeof(SparsePartial));
+    w.off_counters = w.off_focal + up(chunks * sizeof(float));
+    w.off_pos_queue = w.off_counters + 256;
+    w.off_ign_queue = w.off_pos_queue + up((size_t)g.batch * (size_t)N * sizeof(int2));
+    w.total = w.off_ign_queue + up((size_t)g.batch * (size_t)N * sizeof(int));
     return w;
 }
 
 // ---------------------------------------------------------------------------------------
-// focal kernel
+// focal kernels
 // ---------------------------------------------------------------------------------------
 struct FocalArgs {
     PtrTab cls;
     MutPtrTab grad;
-    long long units[kMaxLevels];          // units (float4 or float) per level
+    long long units[kMaxLevels];          // units (float4 or float) per level, < 2^31
     long long row_base[kMaxLevels];       // level-major row base of level l (= B*off_l)
     int chunk_off[kMaxLevels + 1];        // first chunk of level l
-    unsigned long long magic;             // ceil(2^64 / units_per_row); 0 when units_per_row == 1
+    unsigned magic;                       // row = umulhi(u, magic) >> magic_shift  (u < 2^31)
+    int magic_shift;                      // -1: units_per_row == 1 (row = u)
     int units_per_row;                    // C/4 or C
     int n_levels;
     float alpha, gamma;
@@ -99,22 +107,109 @@ struct FocalArgs {
     const double *sums;
 };
 
-// -log(1 - x) / x on [0, 0.25]; Chebyshev-node fit, max rel err 1.3e-7 in float32 Horner
-__device__ __forceinline__ float neg_log1m_over_x(float x) {
-    float s = 0.3386436402797699f;
-    s = fmaf(s, x, 0.14463114738464355f);
-    s = fmaf(s, x, 0.2576442062854767f);
-    s = fmaf(s, x, 0.33287033438682556f);
-    s = fmaf(s, x, 0.500010073184967f);
-    s = fmaf(s, x, 0.9999999403953552f);
-    return s;
+__device__ __forceinline__ int chunk_level(const FocalArgs &a) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.chunk_off[i]) l = i;
+    return l;
 }
 
-constexpr float kClampLo = 1e-4f;    // float32(1e-4)      (losses.py:196, :493)
-constexpr float kClampHi = 0.9999f;  // float32(1. - 1e-4)
-constexpr float kFastMax = 0.25f;
+template <int VEC>
+__device__ __forceinline__ void load_unit(const float *__restrict__ src, long long u, float (&v)[VEC]) {
+    if (VEC == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4 *>(src) + u);
+        v[0] = t.x;
+        v[1 % VEC] = t.y;
+        v[2 % VEC] = t.z;
+        v[3 % VEC] = t.w;
+    } else {
+        v[0] = __ldcs(src + u);
+    }
+}
 
-// exact-form element (reference op order, accurate log/pow): used off the fast path
+__device__ __forceinline__ void block_store_partial(float value, float *dst) {
+    __shared__ float red[kFocalThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float w = warp_sum(value);
+    if (lane == 0) red[warp] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kFocalThreads / 32; ++i) s += red[i];
+        *dst = s;
+    }
+}
+
+// Label-free sweep (forward only): every element is treated as background; the rows that are
+// not (positives' target class, ignored rows) are corrected by the assignment kernel, which
+// knows them.  No label traffic, no index arithmetic beyond the load address.
+template <int VEC, bool GAMMA2, bool FULL>
+__device__ __forceinline__ float focal_all_chunk(const float *__restrict__ src, long long chunk_start,
+                                                 long long n_units, float gamma) {
+    float acc = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int bt = 0; bt < kFocalBatches; ++bt) {
+        const long long u0 = chunk_start + (long long)bt * kFocalThreads * kFocalUnroll + threadIdx.x;
+        float v[kFocalUnroll][VEC];
+#pragma unroll
+        for (int k = 0; k < kFocalUnroll; ++k) {
+            const long long u = u0 + (long long)k * kFocalThreads;
+            if (FULL || u < n_units) {
+                load_unit<VEC>(src, u, v[k]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[k][e] = -1.f;  // marks "no element"
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kFocalUnroll; ++k) {
+            float x[VEC];
+            float mx = 0.f;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                x[e] = fmaxf(v[k][e], kClampLo);
+                mx = fmaxf(mx, x[e]);
+            }
+            if (!FULL && v[k][0] < 0.f) continue;
+            if (GAMMA2 && mx <= kFastMax) {
+                if (VEC == 4) {
+                    float2 xr, xs;
+                    const float2 x01 = make_float2(x[0], x[1 % VEC]);
+                    const float2 x23 = make_float2(x[2 % VEC], x[3 % VEC]);
+                    acc2 = neg_term_fast2_acc(x01, acc2, xr, xs);
+                    acc2 = neg_term_fast2_acc(x23, acc2, xr, xs);
+                } else {
+                    float xr, xs;
+                    acc += neg_term_fast(x[0], xr, xs);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc += neg_term_slow(v[k][e], gamma, GAMMA2);
+            }
+        }
+    }
+    return acc + (acc2.x + acc2.y);
+}
+
+template <int VEC, bool GAMMA2>
+__global__ void __launch_bounds__(kFocalThreads)
+    focal_all_kernel(FocalArgs a, float *__restrict__ partials) {
+    const int l = chunk_level(a);
+    const long long chunk_start = (long long)(blockIdx.x - a.chunk_off[l]) * kChunkUnits;
+    const long long n_units = a.units[l];
+    const float *__restrict__ src = static_cast<const float *>(a.cls.p[l]);
+    float acc;
+    if (chunk_start + kChunkUnits <= n_units)
+        acc = focal_all_chunk<VEC, GAMMA2, true>(src, chunk_start, n_units, a.gamma);
+    else
+        acc = focal_all_chunk<VEC, GAMMA2, false>(src, chunk_start, n_units, a.gamma);
+    block_store_partial((1.f - a.alpha) * acc, partials + blockIdx.x);
+}
+
+// exact-form element with gradient (reference op order, accurate log/pow)
 template <bool GRAD>
 __device__ __forceinline__ void slow_element(float p, bool is_target, float alpha, float gamma,
                                              bool gamma2, float &acc_pos, float &acc_neg,
@@ -145,14 +240,13 @@ __device__ __forceinline__ void slow_element(float p, bool is_target, float alph
     }
 }
 
+// Label-aware sweep: used when gradients are requested (one read of cls, one write of its
+// gradient already scaled by weight / positives), or when the caller did not let the
+// assignment kernel apply the corrections.
 template <int VEC, bool GRAD, bool GAMMA2>
 __global__ void __launch_bounds__(kFocalThreads)
     focal_kernel(FocalArgs a, const int *__restrict__ labels, float *__restrict__ partials) {
-    // which level does this chunk belong to?
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < kMaxLevels; ++i)
-        if (i < a.n_levels && (int)blockIdx.x >= a.chunk_off[i]) l = i;
+    const int l = chunk_level(a);
     const long long chunk_start = (long long)(blockIdx.x - a.chunk_off[l]) * kChunkUnits;
     const long long n_units = a.units[l];
     const float *__restrict__ src = static_cast<const float *>(a.cls.p[l]);
@@ -173,7 +267,6 @@ __global__ void __launch_bounds__(kFocalThreads)
         float v[kFocalUnroll][VEC];
         int lab[kFocalUnroll];
         int tgt[kFocalUnroll];
-        // ---- issue all loads of the batch first ----
 #pragma unroll
         for (int k = 0; k < kFocalUnroll; ++k) {
             const long long u = u0 + (long long)k * kFocalThreads;
@@ -182,24 +275,16 @@ __global__ void __launch_bounds__(kFocalThreads)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) v[k][e] = 0.f;
             if (u < n_units) {
-                const unsigned long long row =
-                    a.magic ? __umul64hi((unsigned long long)u, a.magic) : (unsigned long long)u;
-                const int c0 = (int)(u - (long long)row * a.units_per_row) * VEC;
-                if (VEC == 4) {
-                    const float4 t = __ldcs(reinterpret_cast<const float4 *>(src) + u);
-                    v[k][0] = t.x;
-                    v[k][1 % VEC] = t.y;
-                    v[k][2 % VEC] = t.z;
-                    v[k][3 % VEC] = t.w;
-                } else {
-                    v[k][0] = __ldcs(src + u);
-                }
+                const unsigned uu = (unsigned)u;
+                const unsigned row =
+                    a.magic_shift < 0 ? uu : (__umulhi(uu, a.magic) >> a.magic_shift);
+                const int c0 = (int)(uu - row * (unsigned)a.units_per_row) * VEC;
+                load_unit<VEC>(src, u, v[k]);
                 const int lb = __ldg(lab_l + row);
                 lab[k] = lb;
                 tgt[k] = lb - 1 - c0;  // position of the target class inside this unit
             }
         }
-        // ---- compute ----
 #pragma unroll
         for (int k = 0; k < kFocalUnroll; ++k) {
             const long long u = u0 + (long long)k * kFocalThreads;
@@ -218,14 +303,11 @@ __global__ void __launch_bounds__(kFocalThreads)
                 if (GAMMA2 && !has_target && mx <= kFastMax) {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
-                        const float q = 1.f - x[e];
-                        const float xr = 1.f - q;  // the reference's (1 - pt)
-                        const float s = neg_log1m_over_x(xr);
-                        const float xs = xr * s;   // -log(1 - xr)
-                        acc_neg = fmaf(xr * xr, xs, acc_neg);
+                        float xr, xs;
+                        acc_neg += neg_term_fast(x[e], xr, xs);
                         if (GRAD) {
                             // (1-a) * x * (2*(-log q) + x/q), zero below the clamp
-                            const float t = fmaf(2.f, xs, __fdividef(xr, q));
+                            const float t = fmaf(2.f, xs, __fdividef(xr, 1.f - xr));
                             g[e] = v[k][e] >= kClampLo ? one_m_alpha * xr * t : 0.f;
                         }
                     }
@@ -246,48 +328,42 @@ __global__ void __launch_bounds__(kFocalThreads)
             }
         }
     }
-
-    // block partial = alpha * sum_pos + (1 - alpha) * sum_neg
-    __shared__ float red[2 * (kFocalThreads / 32)];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float wn = warp_sum(acc_neg), wp = warp_sum(acc_pos);
-    if (lane == 0) {
-        red[warp] = wn;
-        red[kFocalThreads / 32 + warp] = wp;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float sn = 0.f, sp = 0.f;
-#pragma unroll
-        for (int w = 0; w < kFocalThreads / 32; ++w) {
-            sn += red[w];
-            sp += red[kFocalThreads / 32 + w];
-        }
-        partials[blockIdx.x] = a.alpha * sp + one_m_alpha * sn;
-    }
+    block_store_partial(a.alpha * acc_pos + one_m_alpha * acc_neg, partials + blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------
 // deterministic reduction of block partials (fixed order, fp64)
 // ---------------------------------------------------------------------------------------
-typedef AssignPartial AssignPartialRO;
-
 __global__ void __launch_bounds__(1024)
-    loss_reduce_kernel(const AssignPartialRO *__restrict__ ap, long long n_assign,
+    loss_reduce_kernel(const int *__restrict__ npos, long long n_assign,
+                       const SparsePartial *__restrict__ sp, long long n_sparse,
                        const float *__restrict__ fp, long long n_focal, int which,
                        double *__restrict__ sums) {
     __shared__ double red[4][32];
     double s_pos = 0.0, s_cls = 0.0, s_box = 0.0, s_ctr = 0.0;
     if (which & 1) {
-        for (long long i = threadIdx.x; i < n_assign; i += blockDim.x) {
-            const AssignPartialRO p = ap[i];
-            s_pos += (double)p.npos;
-            s_box += (double)p.box;
-            s_ctr += (double)p.ctr;
+        for (long long i = threadIdx.x; i < n_assign; i += blockDim.x) s_pos += (double)npos[i];
+        for (long long i = threadIdx.x; i < n_sparse; i += blockDim.x) {
+            const SparsePartial p = sp[i];
+            s_box += p.box;
+            s_ctr += p.ctr;
+            s_cls += p.focal;  // focal corrections (zero unless the sweep ran label-free)
         }
     }
     if (which & 2) {
-        for (long long i = threadIdx.x; i < n_focal; i += blockDim.x) s_cls += (double)fp[i];
+        // four independent accumulators (fixed assignment of partials to them): the loop is
+        // latency-bound otherwise
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        long long i = threadIdx.x;
+        const long long step = blockDim.x;
+        for (; i + 3 * step < n_focal; i += 4 * step) {
+            c0 += (double)fp[i];
+            c1 += (double)fp[i + step];
+            c2 += (double)fp[i + 2 * step];
+            c3 += (double)fp[i + 3 * step];
+        }
+        for (; i < n_focal; i += step) c0 += (double)fp[i];
+        s_cls += (c0 + c1) + (c2 + c3);
     }
     // fixed-order tree: xor-shuffle inside the warp, then warp 0 over the 32 warp sums
 #pragma unroll
@@ -320,7 +396,7 @@ __global__ void __launch_bounds__(1024)
                 sums[2] = c;
                 sums[3] = d;
             }
-            if (which & 2) sums[1] = b;
+            sums[1] = b;  // focal partials (bit 1) + the sparse kernel's corrections (bit 0)
         }
     }
 }
@@ -404,8 +480,8 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
-    if (!cls || !labels || !workspace) return B200DET_EINVAL;
-    if (cls_grad && !sums) return B200DET_EINVAL;
+    if (!cls || !workspace) return B200DET_EINVAL;
+    if (cls_grad && (!sums || !labels)) return B200DET_EINVAL;
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
 
@@ -429,8 +505,17 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
         }
     }
     a.units_per_row = g.num_classes / vec;
-    // ceil(2^64 / d) == floor((2^64 - 1) / d) + 1 for every d >= 2; exact quotient for u < 2^64/d
-    a.magic = a.units_per_row == 1 ? 0ull : (~0ull / (unsigned long long)a.units_per_row) + 1ull;
+    // row = u / d for u < 2^31 by multiply-high: s = ceil(log2 d), m = floor(2^(31+s)/d) + 1,
+    // row = umulhi(u, m) >> (s - 1)   (Granlund-Montgomery, 31-bit dividends)
+    if (a.units_per_row == 1) {
+        a.magic = 0;
+        a.magic_shift = -1;
+    } else {
+        int sft = 0;
+        while ((1u << sft) < (unsigned)a.units_per_row) ++sft;
+        a.magic = (unsigned)(((1ull << (31 + sft)) / (unsigned long long)a.units_per_row) + 1ull);
+        a.magic_shift = sft - 1;
+    }
     a.n_levels = g.n_levels;
     a.alpha = alpha;
     a.gamma = gamma;
@@ -439,6 +524,7 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     int chunks = 0;
     for (int l = 0; l < g.n_levels; ++l) {
         a.units[l] = (long long)g.batch * g.rows[l] * a.units_per_row;
+        if (a.units[l] >= (1ll << 31)) return B200DET_ERANGE;
         a.row_base[l] = (long long)g.batch * g.off[l];
         a.chunk_off[l] = chunks;
         chunks += (int)((a.units[l] + kChunkUnits - 1) / kChunkUnits);
@@ -448,10 +534,23 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
 
     float *partials = reinterpret_cast<float *>(static_cast<char *>(workspace) + ws.off_focal);
     const bool gamma2 = gamma == 2.f;
-    cudaError_t e = vec == 4 ? launch_focal<4>(a, chunks, cls_grad != nullptr, gamma2, labels,
-                                               partials, (cudaStream_t)stream)
-                             : launch_focal<1>(a, chunks, cls_grad != nullptr, gamma2, labels,
-                                               partials, (cudaStream_t)stream);
+    cudaError_t e;
+    if (labels == nullptr) {
+        cudaStream_t st = (cudaStream_t)stream;
+        if (vec == 4) {
+            if (gamma2) focal_all_kernel<4, true><<<chunks, kFocalThreads, 0, st>>>(a, partials);
+            else focal_all_kernel<4, false><<<chunks, kFocalThreads, 0, st>>>(a, partials);
+        } else {
+            if (gamma2) focal_all_kernel<1, true><<<chunks, kFocalThreads, 0, st>>>(a, partials);
+            else focal_all_kernel<1, false><<<chunks, kFocalThreads, 0, st>>>(a, partials);
+        }
+        e = cudaGetLastError();
+    } else {
+        e = vec == 4 ? launch_focal<4>(a, chunks, cls_grad != nullptr, gamma2, labels, partials,
+                                       (cudaStream_t)stream)
+                     : launch_focal<1>(a, chunks, cls_grad != nullptr, gamma2, labels, partials,
+                                       (cudaStream_t)stream);
+    }
     count_launch();
     return (int)e;
 }
@@ -466,9 +565,10 @@ extern "C" int b200det_loss_reduce(const b200det_geometry *geo, int which, const
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     const char *base = static_cast<const char *>(workspace);
     loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const AssignPartialRO *>(base + ws.off_assign),
-        (long long)ws.assign_blocks, reinterpret_cast<const float *>(base + ws.off_focal),
-        (long long)ws.focal_chunks, which, sums);
+        reinterpret_cast<const int *>(base + ws.off_assign), (long long)ws.assign_blocks,
+        reinterpret_cast<const SparsePartial *>(base + ws.off_sparse), (long long)ws.sparse_blocks,
+        reinterpret_cast<const float *>(base + ws.off_focal), (long long)ws.focal_chunks, which,
+        sums);
     count_launch();
     return (int)cudaGetLastError();
 }

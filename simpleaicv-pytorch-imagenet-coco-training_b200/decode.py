@@ -75,7 +75,8 @@ class _DecoderBase:
             _lib.check(
                 lib.b200det_select_decode_nms(
                     ctypes.byref(geo), keys.data_ptr(), classes.data_ptr(), _lib.ptr_array(reg),
-                    reg_dtype, int(self._is_fcos), int(self.topn), m, self._nms_code,
+                    reg_dtype, int(self._is_fcos), float(np.float32(self.min_score_threshold)),
+                    int(self.topn), m, self._nms_code,
                     float(self.nms_threshold), out.data_ptr(),
                     order.data_ptr() if details else None, keep.data_ptr() if details else None,
                     counts.data_ptr() if details else None, None, 0, st),

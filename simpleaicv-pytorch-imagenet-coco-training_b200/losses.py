@@ -7,7 +7,8 @@ config picks them up with `from b200det import losses` in place of
 
 What runs where: nothing numeric runs in Python or torch.  forward() fills a geometry struct,
 collects the per-level device pointers (no torch.cat) and launches
-    b200det_retina_assign / b200det_fcos_assign   assignment + box (+centre-ness) loss
+    b200det_retina_assign / b200det_fcos_assign   assignment (pure ALU scan)
+    b200det_sparse_losses                         box (+centre-ness) loss of the positives
     b200det_focal_loss                            one streaming pass over cls (+ its gradient)
     b200det_loss_reduce / b200det_loss_finish     deterministic fp64 reduction, normalisation
 on the current CUDA stream without any host synchronisation.  There is no CPU path: CPU
@@ -19,6 +20,7 @@ Extra, keyword-only constructor arguments (defaults keep reference behaviour):
         (SURVEY.md section 8e).  Default False = the reference's per-rank normalisation.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -88,6 +90,24 @@ def _prep_annotations(annotations):
     return annotations
 
 
+_SIDE_STREAMS = {}
+# B200DET_OVERLAP=1 runs assignment + sparse losses on a second (high-priority) stream beside the
+# classification sweep.  Measured on B200 this is slower than running them back to back (the
+# sweep already saturates HBM and loses more than the overlap gains), so the default is one stream.
+_OVERLAP = os.environ.get('B200DET_OVERLAP', '0') == '1'
+
+
+def _side_stream(device):
+    """One extra stream per device for the kernels that can overlap (forked from and joined back
+    into the caller's current stream inside every call, so callers see plain stream semantics)."""
+    key = (device.type, device.index)
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device, priority=-1)
+        _SIDE_STREAMS[key] = s
+    return s
+
+
 def _maybe_all_reduce(t, sync, group):
     if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
@@ -130,46 +150,58 @@ class _DetLossFunction(torch.autograd.Function):
         sums = torch.zeros(4, dtype=torch.float64, device=device)
         losses = torch.empty(3, dtype=torch.float32, device=device)
 
-        reg_grad = [torch.empty(r.shape, dtype=torch.float32, device=device) for r in reg] \
+        # the sparse kernel writes gradients of the positive rows only
+        reg_grad = [torch.zeros(r.shape, dtype=torch.float32, device=device) for r in reg] \
             if want_grad else None
-        ctr_grad = [torch.empty_like(c) for c in ctr] if (want_grad and is_fcos) else None
+        ctr_grad = [torch.zeros_like(c) for c in ctr] if (want_grad and is_fcos) else None
         cls_grad = [torch.empty_like(c) for c in cls] if want_grad else None
 
-        if is_fcos:
-            with _lib.timed('fcos_assign'):
-                _lib.check(
-                    lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                            int(annotations.shape[1]), _lib.ptr_array(reg),
-                                            reg_dtype, _lib.ptr_array(ctr), owner._box_code,
-                                            int(owner.use_center_sample), labels.data_ptr(), None,
-                                            None, _lib.ptr_array(reg_grad),
-                                            _lib.ptr_array(ctr_grad), ws.data_ptr(), ws_bytes, st),
-                    'b200det_fcos_assign')
-        else:
-            with _lib.timed('retina_assign'):
-                _lib.check(
-                    lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                              int(annotations.shape[1]), _lib.ptr_array(reg),
-                                              reg_dtype, owner._box_code, float(owner.beta),
-                                              labels.data_ptr(), None, _lib.ptr_array(reg_grad),
-                                              ws.data_ptr(), ws_bytes, st),
-                    'b200det_retina_assign')
         sync, group = owner.sync_normalizer, owner.process_group
+        alpha, gamma = float(owner.alpha), float(owner.gamma)
+
+        def launch_assign(fix_cls, stream):
+            """assignment scan, then the sparse (positive / ignored rows) losses"""
+            name = 'fcos_assign' if is_fcos else 'retina_assign'
+            with _lib.timed(name):
+                if is_fcos:
+                    _lib.check(
+                        lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
+                                                int(annotations.shape[1]),
+                                                int(owner.use_center_sample), labels.data_ptr(),
+                                                None, None, ws.data_ptr(), ws_bytes, stream),
+                        'b200det_fcos_assign')
+                else:
+                    _lib.check(
+                        lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
+                                                  int(annotations.shape[1]), labels.data_ptr(),
+                                                  None, ws.data_ptr(), ws_bytes, stream),
+                        'b200det_retina_assign')
+            with _lib.timed('sparse_losses'):
+                _lib.check(
+                    lib.b200det_sparse_losses(ctypes.byref(geo), int(is_fcos),
+                                              annotations.data_ptr(), int(annotations.shape[1]),
+                                              labels.data_ptr(), _lib.ptr_array(reg), reg_dtype,
+                                              _lib.ptr_array(ctr), owner._box_code,
+                                              float(owner.beta), _lib.ptr_array(fix_cls), alpha,
+                                              gamma, _lib.ptr_array(reg_grad),
+                                              _lib.ptr_array(ctr_grad), ws.data_ptr(), ws_bytes,
+                                              stream), 'b200det_sparse_losses')
+
         if want_grad:
-            # the focal gradient is written once, already divided by the (global) positive count
+            # training: label-aware sweep; the focal gradient is written once, already divided
+            # by the (global) positive count, so the count must exist before the sweep
+            launch_assign(None, st)
             _lib.check(
                 lib.b200det_loss_reduce(ctypes.byref(geo), 1, ws.data_ptr(), ws_bytes,
                                         sums.data_ptr(), st), 'b200det_loss_reduce')
             _maybe_all_reduce(sums, sync, group)
-        with _lib.timed('focal_loss'):
-            _lib.check(
-                lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls), labels.data_ptr(),
-                                       float(owner.alpha), float(owner.gamma),
-                                       _lib.ptr_array(cls_grad),
-                                       sums.data_ptr() if want_grad else None,
-                                       float(owner.cls_loss_weight), ws.data_ptr(), ws_bytes, st),
-                'b200det_focal_loss')
-        if want_grad:
+            with _lib.timed('focal_loss'):
+                _lib.check(
+                    lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls),
+                                           labels.data_ptr(), alpha, gamma,
+                                           _lib.ptr_array(cls_grad), sums.data_ptr(),
+                                           float(owner.cls_loss_weight), ws.data_ptr(), ws_bytes,
+                                           st), 'b200det_focal_loss')
             focal = torch.zeros(4, dtype=torch.float64, device=device)
             _lib.check(
                 lib.b200det_loss_reduce(ctypes.byref(geo), 2, ws.data_ptr(), ws_bytes,
@@ -177,6 +209,25 @@ class _DetLossFunction(torch.autograd.Function):
             _maybe_all_reduce(focal, sync, group)
             sums = sums + focal
         else:
+            # forward only: label-free classification sweep; assignment + sparse losses supply the
+            # corrections and are independent of it
+            cur = torch.cuda.current_stream(device)
+            overlap = _OVERLAP
+            side = _side_stream(device) if overlap else cur
+            if overlap:
+                side.wait_stream(cur)
+            # the HBM-bound sweep stays on the caller's stream; the ALU-bound assignment + sparse
+            # kernels run beside it on a high-priority stream (their residency is capped inside
+            # the library so they cannot lock the sweep out of the SMs)
+            with torch.cuda.stream(side):
+                launch_assign(cls, ctypes.c_void_p(side.cuda_stream))
+            with _lib.timed('focal_loss'):
+                _lib.check(
+                    lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls), None, alpha,
+                                           gamma, None, None, 0., ws.data_ptr(), ws_bytes, st),
+                    'b200det_focal_loss')
+            if overlap:
+                cur.wait_stream(side)
             with _lib.timed('loss_reduce'):
                 _lib.check(
                     lib.b200det_loss_reduce(ctypes.byref(geo), 3, ws.data_ptr(), ws_bytes,
@@ -258,17 +309,16 @@ def _debug_assign(owner, preds, annotations):
         targets = torch.empty(batch * n_rows * 6, dtype=torch.float32, device=device)
         _lib.check(
             lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                    int(annotations.shape[1]), None, _lib.F32, None,
-                                    _lib.BOX_NONE, int(owner.use_center_sample),
+                                    int(annotations.shape[1]), int(owner.use_center_sample),
                                     labels.data_ptr(), matched.data_ptr(), targets.data_ptr(),
-                                    None, None, ws.data_ptr(), ws_bytes, st),
+                                    ws.data_ptr(), ws_bytes, st),
             'b200det_fcos_assign')
     else:
         _lib.check(
             lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                      int(annotations.shape[1]), None, _lib.F32, _lib.BOX_NONE,
-                                      0., labels.data_ptr(), matched.data_ptr(), None,
-                                      ws.data_ptr(), ws_bytes, st), 'b200det_retina_assign')
+                                      int(annotations.shape[1]), labels.data_ptr(),
+                                      matched.data_ptr(), ws.data_ptr(), ws_bytes, st),
+            'b200det_retina_assign')
 
     def to_image_major(t, width):
         out = torch.empty_like(t)
