@@ -27,8 +27,15 @@ __device__ __forceinline__ float unflip_key(uint32_t k) {
 // ---------------------------------------------------------------------------------------
 // score / arg-max sweep
 // ---------------------------------------------------------------------------------------
+// A CTA takes R consecutive rows (R*C floats, contiguous in memory because rows are) and reads
+// them as one flat, fully coalesced stream of 128-bit units (<= kArgLoads per thread, all issued
+// before any use).  Each unit is reduced to (max, first arg-max) in registers and parked in
+// shared memory at [row][unit]; a second phase scans each row's units in class order with the
+// strict '>' rule (np.argmax: first maximum).  Row pitch is padded to an odd number of words so
+// that "one thread per row" reads are bank-conflict free.
 constexpr int kArgThreads = 256;
-constexpr int kArgMaxPerLane = 8;
+constexpr int kArgLoadsVec = 5;      // 128-bit loads per thread (C % 4 == 0)
+constexpr int kArgLoadsScalar = 8;   // 32-bit loads per thread
 
 struct ArgmaxArgs {
     PtrTab cls, ctr;
@@ -37,8 +44,11 @@ struct ArgmaxArgs {
     int block_off[kMaxLevels + 1];
     int n_levels;
     int C;
-    int group;        // lanes cooperating on one row (power of two <= 32)
-    int group_shift;
+    int units_per_row;   // C/4 (VEC = 4) or C (VEC = 1)
+    int rows_per_block;  // R
+    int pitch;           // smem words per row (odd, >= units_per_row)
+    unsigned magic;      // unit -> row: (u * magic) >> 24, valid for u < R * units_per_row
+    int t2, t2_shift;    // threads cooperating on one row in phase 2 (power of two <= 32)
     float min_score;
     int has_ctr;
 };
@@ -46,71 +56,93 @@ struct ArgmaxArgs {
 template <int VEC>
 __global__ void __launch_bounds__(kArgThreads)
     score_argmax_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
+    constexpr int kArgLoads = VEC == 4 ? kArgLoadsVec : kArgLoadsScalar;
+    extern __shared__ __align__(16) unsigned char arg_smem[];
     int l = 0;
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i)
         if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
-    const int rows_per_block = kArgThreads >> a.group_shift;
-    const long long row = (long long)(blockIdx.x - a.block_off[l]) * rows_per_block +
-                          (threadIdx.x >> a.group_shift);
-    const int j = threadIdx.x & (a.group - 1);
-    const bool active = row < a.rows[l];
-    const int units = a.C / VEC;  // float4s (or floats) per row
-    const float *src = static_cast<const float *>(a.cls.p[l]) + (active ? row : 0) * a.C;
+    const long long row0 = (long long)(blockIdx.x - a.block_off[l]) * a.rows_per_block;
+    const int n_rows = (int)min((long long)a.rows_per_block, a.rows[l] - row0);
+    const int n_units = n_rows * a.units_per_row;
+    const float *src = static_cast<const float *>(a.cls.p[l]) + row0 * a.C;
+    float *sval = reinterpret_cast<float *>(arg_smem);
+    int *sidx = reinterpret_cast<int *>(arg_smem) + a.rows_per_block * a.pitch;
 
-    float best = -__int_as_float(0x7f800000);
-    int best_c = 0x7fffffff;
-    for (int i0 = 0; i0 < units; i0 += a.group * kArgMaxPerLane) {
-        float v[kArgMaxPerLane][VEC];
+    // ---- phase 1: flat coalesced loads, per-unit (max, first arg-max) ----
+    float v[kArgLoads][VEC];
 #pragma unroll
-        for (int i = 0; i < kArgMaxPerLane; ++i) {
-            const int u = i0 + j + i * a.group;
-            if (active && u < units) {
-                if (VEC == 4) {
-                    const float4 t = __ldcs(reinterpret_cast<const float4 *>(src) + u);
-                    v[i][0] = t.x;
-                    v[i][1 % VEC] = t.y;
-                    v[i][2 % VEC] = t.z;
-                    v[i][3 % VEC] = t.w;
-                } else {
-                    v[i][0] = __ldcs(src + u);
-                }
+    for (int k = 0; k < kArgLoads; ++k) {
+        const int u = k * kArgThreads + threadIdx.x;
+        if (u < n_units) {
+            if (VEC == 4) {
+                const float4 t = __ldcs(reinterpret_cast<const float4 *>(src) + u);
+                v[k][0] = t.x;
+                v[k][1 % VEC] = t.y;
+                v[k][2 % VEC] = t.z;
+                v[k][3 % VEC] = t.w;
             } else {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) v[i][e] = -__int_as_float(0x7f800000);
+                v[k][0] = __ldcs(src + u);
             }
         }
+    }
 #pragma unroll
-        for (int i = 0; i < kArgMaxPerLane; ++i) {
-            const int c0 = (i0 + j + i * a.group) * VEC;
+    for (int k = 0; k < kArgLoads; ++k) {
+        const int u = k * kArgThreads + threadIdx.x;
+        if (u < n_units) {
+            float best = v[k][0];
+            int bi = 0;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                if (v[i][e] > best) {  // strict: first maximum in class order (np.argmax)
-                    best = v[i][e];
-                    best_c = c0 + e;
+            for (int e = 1; e < VEC; ++e) {
+                if (v[k][e] > best) {
+                    best = v[k][e];
+                    bi = e;
+                }
+            }
+            const int row = (int)(((unsigned)u * a.magic) >> 24);
+            const int col = u - row * a.units_per_row;
+            sval[row * a.pitch + col] = best;
+            sidx[row * a.pitch + col] = col * VEC + bi;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: t2 threads per row scan the units in class order ----
+    const int j = threadIdx.x & (a.t2 - 1);
+    for (int r = threadIdx.x >> a.t2_shift; r < a.rows_per_block; r += kArgThreads >> a.t2_shift) {
+        const bool live = r < n_rows;
+        float best = -__int_as_float(0x7f800000);
+        int best_c = 0x7fffffff;
+        if (live) {
+            for (int c = j; c < a.units_per_row; c += a.t2) {
+                const float x = sval[r * a.pitch + c];
+                if (x > best) {  // strict: first maximum in class order (np.argmax)
+                    best = x;
+                    best_c = sidx[r * a.pitch + c];
                 }
             }
         }
-    }
-    // combine the group's lanes: larger value wins, equal values -> lower class index
-    for (int o = a.group >> 1; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-        if (ov > best || (ov == best && oc < best_c)) {
-            best = ov;
-            best_c = oc;
+        // combine the row's lanes: larger value wins, equal values -> lower class index
+        for (int o = a.t2 >> 1; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ov > best || (ov == best && oc < best_c)) {
+                best = ov;
+                best_c = oc;
+            }
         }
-    }
-    if (active && j == 0) {
-        float score = best;
-        if (a.has_ctr) {
-            // np.sqrt(cls_scores * center_preds)  (decode.py:338): one mul, one IEEE sqrt
-            const float c = __ldg(static_cast<const float *>(a.ctr.p[l]) + row);
-            score = __fsqrt_rn(__fmul_rn(best, c));
+        if (live && j == 0) {
+            const long long row = row0 + r;
+            float score = best;
+            if (a.has_ctr) {
+                // np.sqrt(cls_scores * center_preds)  (decode.py:338): one mul, one IEEE sqrt
+                const float c = __ldg(static_cast<const float *>(a.ctr.p[l]) + row);
+                score = __fsqrt_rn(__fmul_rn(best, c));
+            }
+            const long long lm = a.row_base[l] + row;
+            keys[lm] = (score > a.min_score) ? flip_key(score) : 0u;  // strict '>' (decode.py:133-138)
+            classes[lm] = best_c;
         }
-        const long long lm = a.row_base[l] + row;
-        keys[lm] = (score > a.min_score) ? flip_key(score) : 0u;  // strict '>' (decode.py:133-138)
-        classes[lm] = best_c;
     }
 }
 
@@ -565,20 +597,24 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
     a.C = g.num_classes;
     a.min_score = min_score;
     a.has_ctr = ctr != nullptr;
-    // lanes per row: smallest power of two that leaves <= kArgMaxPerLane units per lane
     const int units = g.num_classes / vec;
-    int group = 1, shift = 0;
-    while (group < 32 && units > group * kArgMaxPerLane) {
-        group <<= 1;
-        ++shift;
+    a.units_per_row = units;
+    // rows per CTA: 5 (vector) / <= 8 (scalar) loads per thread, all in flight at once
+    const int budget = kArgThreads * (vec == 4 ? kArgLoadsVec : kArgLoadsScalar);
+    int R = budget / units;
+    if (R < 1) R = 1;
+    if (R > kArgThreads) R = kArgThreads;
+    if (R * units > budget) return B200DET_ERANGE;  // more than 5120 (vector) / 2048 classes
+    a.rows_per_block = R;
+    a.pitch = units | 1;
+    a.magic = (unsigned)(((1u << 24) + units - 1) / units);
+    int t2 = 1, t2s = 0;
+    while (t2 < 32 && (units + t2 - 1) / t2 > 32) {
+        t2 <<= 1;
+        ++t2s;
     }
-    if (vec == 4 && units >= 16 && group < 4) {  // keep >= 64 B contiguous per row and instruction
-        group = 4;
-        shift = 2;
-    }
-    a.group = group;
-    a.group_shift = shift;
-    const int rows_per_block = kArgThreads / group;
+    a.t2 = t2;
+    a.t2_shift = t2s;
     int blocks = 0;
     for (int l = 0; l < kMaxLevels; ++l) {
         a.cls.p[l] = a.ctr.p[l] = nullptr;
@@ -593,13 +629,15 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
         a.row_base[l] = (long long)g.batch * g.off[l];
         a.rows[l] = (long long)g.batch * g.rows[l];
         a.block_off[l] = blocks;
-        blocks += (int)((a.rows[l] + rows_per_block - 1) / rows_per_block);
+        blocks += (int)((a.rows[l] + R - 1) / R);
     }
     for (int l = g.n_levels; l <= kMaxLevels; ++l) a.block_off[l] = blocks;
+    const size_t smem = (size_t)R * a.pitch * 8;
+    if (smem > 48 * 1024) return B200DET_ERANGE;
     if (vec == 4)
-        score_argmax_kernel<4><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+        score_argmax_kernel<4><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else
-        score_argmax_kernel<1><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+        score_argmax_kernel<1><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     count_launch();
     return (int)cudaGetLastError();
 }
