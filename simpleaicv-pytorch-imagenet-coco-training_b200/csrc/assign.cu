@@ -671,31 +671,37 @@ __global__ void __launch_bounds__(kSparseThreads)
     }
 
     // ---- ignored rows (Retina: 0.4 <= IoU < 0.5, or image without GT) take no part in the focal
-    // loss (losses.py:228-230): remove what the label-free sweep added.  One warp per row, two rows
+    // loss (losses.py:228-230): remove what the label-free sweep added.  One warp per row, four rows
     // in flight; a row's sum has a fixed order (lane-strided partials + xor tree) and is converted
     // to fixed point once, so the result is independent of the queue order.
     if (want_fix) {
+        constexpr int kRowsInFlight = 4;
         const int gwarp = gtid >> 5, n_warps = gsize >> 5;
-        for (int r0 = gwarp; r0 < n_ign; r0 += 2 * n_warps) {
-            const int r1 = r0 + n_warps;
-            long long rr0, rr1 = 0;
-            const int l0 = split_row(g, q.ign[r0], rr0);
-            const bool two = r1 < n_ign;
-            const int l1 = two ? split_row(g, q.ign[r1], rr1) : l0;
-            const float *p0 = static_cast<const float *>(a.cls.p[l0]) + rr0 * a.C;
-            const float *p1 = static_cast<const float *>(a.cls.p[l1]) + rr1 * a.C;
-            float s0 = 0.f, s1 = 0.f;
-            for (int c = lane; c < a.C; c += 32) {
-                const float v0 = __ldg(p0 + c);
-                const float v1 = two ? __ldg(p1 + c) : 0.f;
-                s0 += neg_term(v0, a.gamma, gamma2);
-                if (two) s1 += neg_term(v1, a.gamma, gamma2);
+        for (int r0 = gwarp; r0 < n_ign; r0 += kRowsInFlight * n_warps) {
+            const float *p[kRowsInFlight];
+            bool live[kRowsInFlight];
+#pragma unroll
+            for (int t = 0; t < kRowsInFlight; ++t) {
+                const int r = r0 + t * n_warps;
+                live[t] = r < n_ign;
+                long long rr;
+                const int l = split_row(g, q.ign[live[t] ? r : r0], rr);
+                p[t] = static_cast<const float *>(a.cls.p[l]) + rr * a.C;
             }
-            s0 = warp_sum(s0);
-            s1 = warp_sum(s1);
-            if (lane == 0) {
-                foc_fx -= to_fx((1.f - a.alpha) * s0, kFxFocal);
-                if (two) foc_fx -= to_fx((1.f - a.alpha) * s1, kFxFocal);
+            float sum[kRowsInFlight];
+#pragma unroll
+            for (int t = 0; t < kRowsInFlight; ++t) sum[t] = 0.f;
+            for (int c = lane; c < a.C; c += 32) {
+                float v[kRowsInFlight];
+#pragma unroll
+                for (int t = 0; t < kRowsInFlight; ++t) v[t] = __ldg(p[t] + c);
+#pragma unroll
+                for (int t = 0; t < kRowsInFlight; ++t) sum[t] += neg_term(v[t], a.gamma, gamma2);
+            }
+#pragma unroll
+            for (int t = 0; t < kRowsInFlight; ++t) {
+                const float s = warp_sum(sum[t]);
+                if (lane == 0 && live[t]) foc_fx -= to_fx((1.f - a.alpha) * s, kFxFocal);
             }
         }
     }

@@ -201,6 +201,41 @@ __device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t
     }
 }
 
+constexpr int kNmsWindow = 256;
+
+// does kept box kb suppress the later box ob?  (decode.py:45-100 / torchvision CPU nms)
+__device__ __forceinline__ bool nms_suppresses(const float4 kb, const float4 ob, int nms_type,
+                                               float thr_f, double thr_d) {
+    const float karea_raw = __fmul_rn(__fsub_rn(kb.z, kb.x), __fsub_rn(kb.w, kb.y));
+    const float oarea_raw = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
+    const float iw = fmaxf(__fsub_rn(fminf(kb.z, ob.z), fmaxf(kb.x, ob.x)), 0.f);
+    const float ih = fmaxf(__fsub_rn(fminf(kb.w, ob.w), fmaxf(kb.y, ob.y)), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    if (nms_type == B200DET_NMS_TORCH) {
+        // torchvision.ops.nms (CPU kernel): unclamped areas, no union clamp, suppress when
+        // iou > threshold with the threshold kept in double
+        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(karea_raw, oarea_raw), inter));
+        return (double)iou > thr_d;
+    }
+    // areas: np.maximum(w*h, 0) (decode.py:45-48); union clamped at 1e-4 (:73-76)
+    const float karea = fmaxf(karea_raw, 0.f), oarea = fmaxf(oarea_raw, 0.f);
+    const float uni = fmaxf(__fsub_rn(__fadd_rn(karea, oarea), inter), 1e-4f);
+    float iou = __fdiv_rn(inter, uni);
+    if (nms_type == B200DET_NMS_DIOU_PYTHON) {
+        // decode.py:78-97
+        const float ew = fmaxf(__fsub_rn(fmaxf(kb.z, ob.z), fminf(kb.x, ob.x)), 0.f);
+        const float eh = fmaxf(__fsub_rn(fmaxf(kb.w, ob.w), fminf(kb.y, ob.y)), 0.f);
+        const float c2 = fmaxf(__fadd_rn(__fmul_rn(ew, ew), __fmul_rn(eh, eh)), 1e-4f);
+        const float dx = __fsub_rn(__fdiv_rn(__fadd_rn(kb.z, kb.x), 2.f),
+                                   __fdiv_rn(__fadd_rn(ob.z, ob.x), 2.f));
+        const float dy = __fsub_rn(__fdiv_rn(__fadd_rn(kb.w, kb.y), 2.f),
+                                   __fdiv_rn(__fadd_rn(ob.w, ob.y), 2.f));
+        const float p2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        iou = __fsub_rn(iou, __fdiv_rn(p2, c2));
+    }
+    return !(iou < thr_f);  // survivors are `ious < thr` (decode.py:99)
+}
+
 __global__ void __launch_bounds__(kSelThreads)
     select_nms_kernel(SelectArgs a, const uint32_t *__restrict__ keys,
                       const int *__restrict__ classes, float *__restrict__ out,
@@ -467,70 +502,70 @@ __global__ void __launch_bounds__(kSelThreads)
     __syncthreads();
 
     // ---- greedy NMS (decode.py:45-100): ballots build the removed-bitmask ----
+    // Only the first max_object_num survivors are returned, and they almost always come from the
+    // head of the sorted list, so the scan works on a window of kNmsWindow candidates: inside
+    // the window it is the plain greedy loop (pick the first alive box, let every later box of
+    // the window test itself against it); when the window is exhausted the next kNmsWindow
+    // candidates first test themselves against ALL boxes kept so far, then the loop resumes.
+    // The keep list is identical to the full greedy scan.
     const int limit = keep_out ? n_sel : min(a.max_out, n_sel);
     int n_keep = 0, cur = 0;
+    int win_end = min(n_sel, kNmsWindow);
     while (n_keep < limit) {
-        // every warp finds the first alive index >= cur (identical result in all warps)
-        int found = -1;
-        for (int w0 = cur >> 5; w0 < n_words && found < 0; w0 += 32) {
-            const int w = w0 + lane;
-            uint32_t alive = 0u;
-            if (w < n_words) {
-                alive = ~srem[w];
-                if (w == (cur >> 5)) alive &= ~((1u << (cur & 31)) - 1u);
-                if (w == n_words - 1 && (n_sel & 31)) alive &= (1u << (n_sel & 31)) - 1u;
+        if (warp == 0) {
+            // first alive index in [cur, win_end)
+            int found = -1;
+            const int win_words = (win_end + 31) >> 5;
+            for (int w0 = cur >> 5; w0 < win_words && found < 0; w0 += 32) {
+                const int w = w0 + lane;
+                uint32_t alive = 0u;
+                if (w < win_words) {
+                    alive = ~srem[w];
+                    if (w == (cur >> 5)) alive &= ~((1u << (cur & 31)) - 1u);
+                    if (w == win_words - 1 && (win_end & 31)) alive &= (1u << (win_end & 31)) - 1u;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, alive != 0u);
+                if (bal) {
+                    const int src_lane = __ffs(bal) - 1;
+                    const uint32_t word = __shfl_sync(0xffffffffu, alive, src_lane);
+                    found = ((w0 + src_lane) << 5) + (__ffs(word) - 1);
+                }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, alive != 0u);
-            if (bal) {
-                const int src_lane = __ffs(bal) - 1;
-                const uint32_t word = __shfl_sync(0xffffffffu, alive, src_lane);
-                found = ((w0 + src_lane) << 5) + (__ffs(word) - 1);
-            }
+            if (lane == 0) s_digit = found;
         }
-        if (found < 0) break;
+        __syncthreads();
+        const int found = s_digit;
+        if (found < 0) {
+            if (win_end >= n_sel) break;
+            // slide the window: new candidates against everything kept so far
+            const int new_end = min(n_sel, win_end + kNmsWindow);
+            for (int j0 = win_end; j0 < new_end; j0 += kSelThreads) {
+                const int j = j0 + tid;
+                bool suppress = false;
+                if (j < new_end) {
+                    const float4 ob = sbox[j];
+                    for (int k = 0; k < n_keep && !suppress; ++k)
+                        suppress = nms_suppresses(sbox[skeep[k]], ob, a.nms_type, a.nms_thr_f, a.nms_thr_d);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, suppress);
+                if (lane == 0 && bal) srem[j >> 5] |= bal;  // each word is owned by one warp
+            }
+            cur = win_end;
+            win_end = new_end;
+            __syncthreads();
+            continue;
+        }
         if (tid == 0) skeep[n_keep] = found;
         ++n_keep;
         if (n_keep >= limit) break;
         const float4 kb = sbox[found];
-        const float kw = __fsub_rn(kb.z, kb.x), kh = __fsub_rn(kb.w, kb.y);
-        const float karea_raw = __fmul_rn(kw, kh);
-        const float karea = a.nms_type == B200DET_NMS_TORCH ? karea_raw : fmaxf(karea_raw, 0.f);
-        __syncthreads();  // all warps have read srem for `found` before it is updated
-        for (int j0 = (found + 1) & ~31; j0 < n_sel; j0 += kSelThreads) {
+        for (int j0 = (found + 1) & ~31; j0 < win_end; j0 += kSelThreads) {
             const int j = j0 + tid;
             bool suppress = false;
-            if (j > found && j < n_sel) {
-                const float4 ob = sbox[j];
-                const float oarea_raw = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
-                const float iw = fmaxf(__fsub_rn(fminf(kb.z, ob.z), fmaxf(kb.x, ob.x)), 0.f);
-                const float ih = fmaxf(__fsub_rn(fminf(kb.w, ob.w), fmaxf(kb.y, ob.y)), 0.f);
-                const float inter = __fmul_rn(iw, ih);
-                if (a.nms_type == B200DET_NMS_TORCH) {
-                    // torchvision.ops.nms (CPU kernel): unclamped areas, no union clamp,
-                    // suppress when iou > threshold with the threshold kept in double
-                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(karea, oarea_raw), inter));
-                    suppress = (double)iou > a.nms_thr_d;
-                } else {
-                    const float oarea = fmaxf(oarea_raw, 0.f);
-                    const float uni = fmaxf(__fsub_rn(__fadd_rn(karea, oarea), inter), 1e-4f);
-                    float iou = __fdiv_rn(inter, uni);
-                    if (a.nms_type == B200DET_NMS_DIOU_PYTHON) {
-                        // decode.py:78-97
-                        const float ew = fmaxf(__fsub_rn(fmaxf(kb.z, ob.z), fminf(kb.x, ob.x)), 0.f);
-                        const float eh = fmaxf(__fsub_rn(fmaxf(kb.w, ob.w), fminf(kb.y, ob.y)), 0.f);
-                        const float c2 = fmaxf(__fadd_rn(__fmul_rn(ew, ew), __fmul_rn(eh, eh)), 1e-4f);
-                        const float dx = __fsub_rn(__fdiv_rn(__fadd_rn(kb.z, kb.x), 2.f),
-                                                   __fdiv_rn(__fadd_rn(ob.z, ob.x), 2.f));
-                        const float dy = __fsub_rn(__fdiv_rn(__fadd_rn(kb.w, kb.y), 2.f),
-                                                   __fdiv_rn(__fadd_rn(ob.w, ob.y), 2.f));
-                        const float p2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                        iou = __fsub_rn(iou, __fdiv_rn(p2, c2));
-                    }
-                    suppress = !(iou < a.nms_thr_f);  // survivors are `ious < thr` (decode.py:99)
-                }
-            }
+            if (j > found && j < win_end)
+                suppress = nms_suppresses(kb, sbox[j], a.nms_type, a.nms_thr_f, a.nms_thr_d);
             const unsigned bal = __ballot_sync(0xffffffffu, suppress);
-            if (lane == 0 && bal) srem[j >> 5] |= bal;  // each word is owned by one warp
+            if (lane == 0 && bal) srem[j >> 5] |= bal;
         }
         cur = found + 1;
         __syncthreads();

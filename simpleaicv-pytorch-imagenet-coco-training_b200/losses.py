@@ -144,7 +144,10 @@ class _DetLossFunction(torch.autograd.Function):
         n_rows = _geom.rows_per_image(shapes, geo.per_loc)
         st = _stream()
 
-        ws_bytes = lib.b200det_loss_workspace_bytes(ctypes.byref(geo))
+        ws_bytes = getattr(geo, '_ws_bytes', None)
+        if ws_bytes is None:
+            ws_bytes = lib.b200det_loss_workspace_bytes(ctypes.byref(geo))
+            geo._ws_bytes = ws_bytes
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         labels = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
         sums = torch.zeros(4, dtype=torch.float64, device=device)
@@ -211,21 +214,20 @@ class _DetLossFunction(torch.autograd.Function):
         else:
             # forward only: label-free classification sweep; assignment + sparse losses supply the
             # corrections and are independent of it
+            # The sweep is enqueued first: it is the long kernel, so the host-side preparation of
+            # the remaining launches overlaps with it.
             cur = torch.cuda.current_stream(device)
             overlap = _OVERLAP
             side = _side_stream(device) if overlap else cur
             if overlap:
                 side.wait_stream(cur)
-            # the HBM-bound sweep stays on the caller's stream; the ALU-bound assignment + sparse
-            # kernels run beside it on a high-priority stream (their residency is capped inside
-            # the library so they cannot lock the sweep out of the SMs)
-            with torch.cuda.stream(side):
-                launch_assign(cls, ctypes.c_void_p(side.cuda_stream))
             with _lib.timed('focal_loss'):
                 _lib.check(
                     lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls), None, alpha,
                                            gamma, None, None, 0., ws.data_ptr(), ws_bytes, st),
                     'b200det_focal_loss')
+            with torch.cuda.stream(side):
+                launch_assign(cls, ctypes.c_void_p(side.cuda_stream))
             if overlap:
                 cur.wait_stream(side)
             with _lib.timed('loss_reduce'):
