@@ -138,12 +138,12 @@ def cpu_step(preds, ann):
     return out, res
 
 
-def time_cpu(images_per_step, steps, warmup, seed=0):
+def time_cpu(images_per_step, steps, warmup, seed=0, size=SIZE):
     import torch
     from b200det import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    preds = synth.make_retina_preds(images_per_step, SIZE, NUM_CLASSES, seed=seed)
-    ann = synth.make_annotations(images_per_step, MAX_GT, SIZE, NUM_CLASSES, seed=seed + 1)
+    preds = synth.make_retina_preds(images_per_step, size, NUM_CLASSES, seed=seed)
+    ann = synth.make_annotations(images_per_step, MAX_GT, size, NUM_CLASSES, seed=seed + 1)
     for _ in range(warmup):
         cpu_step(preds, ann)
     t0 = time.perf_counter()
@@ -161,7 +161,7 @@ def run_reference(args):
     if rank != 0:
         return
     per_step = 2
-    value, dt, threads = time_cpu(per_step, args.steps, min(args.warmup, 1))
+    value, dt, threads = time_cpu(per_step, args.steps, min(args.warmup, 1), size=args.ref_size)
     loss_b, dec_b = algorithmic_bytes_per_image()
     line = {
         'impl': 'reference',
@@ -416,6 +416,8 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-steps', type=int, default=20)
+    ap.add_argument('--ref-size', type=int, default=SIZE,
+                    help='image size of the --impl reference sample (tests use a small one)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
