@@ -70,7 +70,7 @@ def ncu_traffic():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -153,7 +153,7 @@ def time_cpu(images_per_step, steps, warmup, seed=0, size=SIZE):
     return images_per_step * steps / dt, dt, torch.get_num_threads()
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's own CPU implementation of the path (oracle port: the
     reference is pure Python and cannot travel to the GPU box), all host threads, bounded sample
     per step.  Under torchrun only rank 0 works."""
@@ -190,7 +190,7 @@ def run_reference(args):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 def workload_config(batch_per_gpu, n_gpus):
@@ -210,7 +210,7 @@ def workload_config(batch_per_gpu, n_gpus):
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
-def run_b200(args):
+def run_b200(args, out):
     import torch
     import torch.distributed as dist
     import b200det
@@ -346,7 +346,7 @@ def run_b200(args):
                       f'({dt:.1f} s); torch-CPU loss on all threads, NumPy decode single-threaded',
         }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
 
@@ -406,10 +406,31 @@ def run_e2e(args, preds, ann, crit, dec, dev, distributed, world):
     }
 
 
+class StdoutToStderr:
+    """Everything a library prints to fd 1 during the run (NCCL's version banner, ...) goes to
+    stderr, so that stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + '\n').encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200det', choices=['b200det', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
@@ -421,10 +442,11 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_b200(args)
+    with StdoutToStderr() as out:
+        if args.impl == 'reference':
+            run_reference(args, out)
+        else:
+            run_b200(args, out)
 
 
 if __name__ == '__main__':

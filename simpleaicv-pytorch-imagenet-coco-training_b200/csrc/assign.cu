@@ -276,15 +276,23 @@ __device__ __forceinline__ void flush_queues(const Queues &q, const int2 *pos_q,
 //   PL > 0 : per_loc == PL anchors of the location held in registers (scan unrolled over them)
 //   PL == 0: any per_loc, anchors processed one after the other
 // ---------------------------------------------------------------------------------------
-template <int NA>
+// EXACT = false (production: the arg-max index of non-positive rows is not an output): a pair
+// whose IoU cannot reach the 0.4 "background" threshold can change neither a label nor a
+// positive's matched box, so it is dropped early with conservative float32 bounds
+// (IoU <= min(area)/max(area), and ov < 0.38*union) and the IEEE divide only runs for the few
+// pairs above 0.38.  EXACT = true reproduces the reference's max/arg-max for every row.
+constexpr float kIouFloor = 0.38f;
+
+template <int NA, bool EXACT>
 __device__ __forceinline__ void scan_candidates(const GtSmem &s, int n_cand, const float4 wreg,
                                                 const float4 (&A)[NA], float (&best)[NA],
                                                 int (&best_slot)[NA]) {
-    float area_a[NA];
+    float area_a[NA], area_lo[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
         area_a[a] = __fmul_rn(fmaxf(__fsub_rn(A[a].z, A[a].x), 0.f),
                               fmaxf(__fsub_rn(A[a].w, A[a].y), 0.f));
+        area_lo[a] = kIouFloor * area_a[a];
         best[a] = 0.f;
         best_slot[a] = -1;
     }
@@ -303,14 +311,17 @@ __device__ __forceinline__ void scan_candidates(const GtSmem &s, int n_cand, con
             m &= m - 1;
             const float4 gt = s.box[k];
             const float garea = s.area[k];
+            const float garea_lo = kIouFloor * garea;
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
+                if (!EXACT && (garea < area_lo[a] || garea_lo > area_a[a])) continue;
                 // IoU (losses.py:54-70); strict '>' in GT order == first maximum (:357)
                 const float mnx = fminf(A[a].z, gt.z), mxx = fmaxf(A[a].x, gt.x);
                 const float mny = fminf(A[a].w, gt.w), mxy = fmaxf(A[a].y, gt.y);
                 if (mnx > mxx && mny > mxy) {
                     const float ov = __fmul_rn(__fsub_rn(mnx, mxx), __fsub_rn(mny, mxy));
                     const float un = fmaxf(__fsub_rn(__fadd_rn(area_a[a], garea), ov), 1e-4f);
+                    if (!EXACT && ov < kIouFloor * un) continue;
                     const float iou = __fdiv_rn(ov, un);
                     if (iou > best[a]) {
                         best[a] = iou;
@@ -378,7 +389,10 @@ __global__ void __launch_bounds__(kAssignThreads)
             A[a].z = __fadd_rn(ba.v[me.l][a0 + a][2], sx);
             A[a].w = __fadd_rn(ba.v[me.l][a0 + a][3], sy);
         }
-        scan_candidates<NA>(s, n_cand, wreg, A, best, best_slot);
+        if (matched)
+            scan_candidates<NA, true>(s, n_cand, wreg, A, best, best_slot);
+        else
+            scan_candidates<NA, false>(s, n_cand, wreg, A, best, best_slot);
         // labels (losses.py:358-365)
 #pragma unroll
         for (int a = 0; a < NA; ++a) {

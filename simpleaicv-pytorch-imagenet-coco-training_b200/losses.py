@@ -288,10 +288,12 @@ class _DetLossFunction(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
-def _debug_assign(owner, preds, annotations):
+def _debug_assign(owner, preds, annotations, exact=True):
     """Parity hook (tests / smoke): runs only the assignment kernel and returns the reference's
     intermediate truth in IMAGE-major order: labels [B,N] int32, matched [B,N] int32 (index in
-    the image's filtered GT list; -1 = none) and, for FCOS, targets [B,N,6] float32."""
+    the image's filtered GT list; -1 = none) and, for FCOS, targets [B,N,6] float32.
+    exact=False runs the production scan (no `matched` output: pairs that cannot reach IoU 0.38
+    are dropped early) and returns the labels only."""
     lib = _lib.load()
     is_fcos = owner._is_fcos
     cls = _prep_f32(preds[0], 'cls_preds')
@@ -305,21 +307,22 @@ def _debug_assign(owner, preds, annotations):
     ws_bytes = lib.b200det_loss_workspace_bytes(ctypes.byref(geo))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     labels = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
-    matched = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
+    matched = torch.empty(batch * n_rows, dtype=torch.int32, device=device) if exact else None
+    matched_ptr = matched.data_ptr() if exact else None
     targets = None
     if is_fcos:
         targets = torch.empty(batch * n_rows * 6, dtype=torch.float32, device=device)
         _lib.check(
             lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
                                     int(annotations.shape[1]), int(owner.use_center_sample),
-                                    labels.data_ptr(), matched.data_ptr(), targets.data_ptr(),
+                                    labels.data_ptr(), matched_ptr, targets.data_ptr(),
                                     ws.data_ptr(), ws_bytes, st),
             'b200det_fcos_assign')
     else:
         _lib.check(
             lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
                                       int(annotations.shape[1]), labels.data_ptr(),
-                                      matched.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                                      matched_ptr, ws.data_ptr(), ws_bytes, st),
             'b200det_retina_assign')
 
     def to_image_major(t, width):
@@ -329,10 +332,9 @@ def _debug_assign(owner, preds, annotations):
                                             width, st), 'b200det_rows_to_image_major')
         return out
 
-    res = {
-        'labels': to_image_major(labels, 1).view(batch, n_rows),
-        'matched': to_image_major(matched, 1).view(batch, n_rows),
-    }
+    res = {'labels': to_image_major(labels, 1).view(batch, n_rows)}
+    if exact:
+        res['matched'] = to_image_major(matched, 1).view(batch, n_rows)
     if targets is not None:
         res['targets'] = to_image_major(targets, 6).view(batch, n_rows, 6)
     return res
@@ -395,8 +397,8 @@ class RetinaLoss(nn.Module):
             self._geo_cache = {key: geo}
         return geo
 
-    def debug_assign(self, preds, annotations):
-        return _debug_assign(self, preds, annotations)
+    def debug_assign(self, preds, annotations, exact=True):
+        return _debug_assign(self, preds, annotations, exact)
 
     def forward(self, preds, annotations):
         '''
@@ -462,8 +464,8 @@ class FCOSLoss(nn.Module):
             self._geo_cache = {key: geo}
         return geo
 
-    def debug_assign(self, preds, annotations):
-        return _debug_assign(self, preds, annotations)
+    def debug_assign(self, preds, annotations, exact=True):
+        return _debug_assign(self, preds, annotations, exact)
 
     def forward(self, preds, annotations):
         '''

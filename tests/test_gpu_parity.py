@@ -90,6 +90,8 @@ def test_retina_assignment_golden(retina):
     got = crit.debug_assign(dev(preds), ann.cuda())
     want = retina['assign_GIoU']
     assert np.array_equal(got['labels'].cpu().numpy(), want[..., 4].astype(np.int32))
+    fast = crit.debug_assign(dev(preds), ann.cuda(), exact=False)
+    assert np.array_equal(fast['labels'].cpu().numpy(), want[..., 4].astype(np.int32))
     _, _, matched = O.retina_assign(torch.from_numpy(retina['anchors'].copy()), ann, 'GIoU')
     assert np.array_equal(got['matched'].cpu().numpy(), matched.numpy().astype(np.int32))
 
@@ -279,6 +281,9 @@ def test_config2_retina_loss_800(box_type):
     got = crit.debug_assign(dev(preds), ann.cuda())
     assert np.array_equal(got['labels'].cpu().numpy(), ref['labels'].numpy().astype(np.int32))
     assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+    # the production scan (what forward() runs: early rejection below IoU 0.38) gives the same labels
+    fast = crit.debug_assign(dev(preds), ann.cuda(), exact=False)
+    assert np.array_equal(fast['labels'].cpu().numpy(), ref['labels'].numpy().astype(np.int32))
     assert int(crit.last_stats['sums'][0].item()) == ref['num_pos'] > 0
     assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
                  [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, 'RetinaLoss')
