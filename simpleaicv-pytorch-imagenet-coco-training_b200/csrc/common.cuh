@@ -52,7 +52,7 @@ struct SparsePartial {
 struct LossWs {
     size_t assign_blocks_per_image, assign_blocks, sparse_blocks, focal_chunks;
     size_t off_assign /* int npos [assign_blocks] */, off_sparse /* SparsePartial [sparse_blocks] */,
-        off_focal /* float [focal_chunks] */, off_counters /* int [2] */,
+        off_focal /* int64 fixed-point [1024] */, off_counters /* int [2] */,
         off_pos_queue /* int2 [B*N] */, off_ign_queue /* int [B*N] */, total;
 };
 LossWs loss_ws_layout(const Geo &g);

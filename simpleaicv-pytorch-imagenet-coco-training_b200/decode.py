@@ -35,6 +35,12 @@ class _DecoderBase:
         self.nms_threshold = nms_threshold
         self._nms_code = _lib.NMS_CODES[nms_type]
         self._geo_cache = {}
+        self._pinned = None
+
+    def _staging(self, numel):
+        if self._pinned is None or self._pinned.numel() != numel:
+            self._pinned = torch.empty(numel, dtype=torch.float32, pin_memory=True)
+        return self._pinned
 
     def _run(self, preds, details=False):
         lib = _lib.load()
@@ -82,7 +88,12 @@ class _DecoderBase:
                     counts.data_ptr() if details else None, None, 0, st),
                 'b200det_select_decode_nms')
 
-        host = out.cpu().numpy()  # the only D2H copy: 24*M bytes per image (synchronises)
+        # the only D2H copy: 24*M bytes per image, through a cached pinned staging buffer; the
+        # caller gets fresh, writable arrays (tools/scripts.py:742-758 mutates them in place)
+        staging = self._staging(out.numel())
+        staging.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        host = staging.numpy().copy()
         scores = host[0:batch * m].reshape(batch, m)
         out_classes = host[batch * m:2 * batch * m].reshape(batch, m)
         boxes = host[2 * batch * m:].reshape(batch, m, 4)
