@@ -254,7 +254,7 @@ def run_b200(args, out):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    _lib.PROFILE = {}
+    _lib.profile_start()
     launches0 = _lib.launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -265,8 +265,7 @@ def run_b200(args, out):
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     launches = _lib.launch_count() - launches0
-    kernels = _lib.profile_summary()
-    _lib.PROFILE = None
+    kernels = _lib.profile_stop()
     clocks = sampler.stop()
 
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -287,7 +286,7 @@ def run_b200(args, out):
     alg = {
         'focal_loss': B * 4 * n * c,
         'score_argmax': B * 4 * n * c,
-        'retina_assign': B * (16 * n + 20 * MAX_GT),
+        'assign': B * (16 * n + 20 * MAX_GT),
         'select_decode_nms': B * (8 * n + 16 * 1000 + 2400),
     }
     dom = max((k for k in kernels if k in ('focal_loss', 'score_argmax')),

@@ -95,6 +95,16 @@ int b200det_abi_version(void);
 const char *b200det_error_string(int code);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 unsigned long long b200det_launch_count(void);
+/*
+ * Optional per-kernel timing: while enabled, every kernel launched by the library is bracketed
+ * by CUDA events on its stream.  b200det_profile(1) clears and starts, b200det_profile(0) stops;
+ * b200det_profile_read() waits for the recorded events and returns the summed device time and the
+ * number of launches of one kernel id (0 focal_loss, 1 assign, 2 sparse_losses, 3 loss_reduce,
+ * 4 loss_finish, 5 score_argmax, 6 select_decode_nms; see b200det_kernel_name).
+ */
+int b200det_profile(int enable);
+int b200det_profile_read(int kernel_id, double *total_ms, int *launches);
+const char *b200det_kernel_name(int kernel_id);
 /* rows per image (N) for a geometry; negative on error */
 long long b200det_rows_per_image(const b200det_geometry *geo);
 
@@ -229,6 +239,44 @@ int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
                               double nms_threshold, float *out, int32_t *order, int32_t *keep,
                               int32_t *counts, void *workspace, size_t workspace_bytes,
                               void *stream);
+
+/* ---- fused host entries (one C call per loss forward / per decode) -------------------- */
+typedef struct b200det_loss_params {
+    int32_t is_fcos;            /* 0 RetinaLoss, 1 FCOSLoss */
+    int32_t box_loss;           /* B200DET_BOX_* */
+    int32_t reg_dtype;          /* B200DET_F32 / F16 / BF16 */
+    int32_t use_center_sample;  /* FCOS */
+    float alpha, gamma, beta;
+    float w_cls, w_box, w_ctr;  /* cls_loss_weight, box_loss_weight, center_ness_loss_weight */
+} b200det_loss_params;
+
+typedef struct b200det_decode_params {
+    int32_t is_fcos, reg_dtype, topn, max_out, nms_type;
+    float min_score;
+    double nms_threshold;
+} b200det_decode_params;
+
+/*
+ * Whole forward pass of RetinaLoss.forward / FCOSLoss.forward (losses.py:161-218, :462-511) in one
+ * call: label-free focal sweep, assignment, sparse losses, reduction and (if `losses` != NULL)
+ * normalisation.  Equivalent to calling b200det_focal_loss(labels = NULL), b200det_*_assign,
+ * b200det_sparse_losses(cls given), b200det_loss_reduce(3), b200det_loss_finish in that order,
+ * with a single memset.  Pass losses = NULL to all-reduce `sums` across ranks first.
+ */
+int b200det_loss_forward(const b200det_geometry *geo, const b200det_loss_params *params,
+                         const float *annotations, int max_gt, const void *const *cls,
+                         const void *const *reg, const void *const *ctr, int32_t *labels,
+                         void *workspace, size_t workspace_bytes, double *sums, float *losses,
+                         void *stream);
+
+/*
+ * Whole RetinaDecoder.__call__ / FCOSDecoder.__call__ (decode.py:201-249, :293-348) up to the
+ * device-side result: b200det_score_argmax followed by b200det_select_decode_nms.
+ */
+int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *params,
+                   const void *const *cls, const void *const *ctr, const void *const *reg,
+                   uint32_t *keys, int32_t *classes, float *out, int32_t *order, int32_t *keep,
+                   int32_t *counts, void *stream);
 
 /* ---- utilities (tests / parity outputs) ---------------------------------------------- */
 /* dst[b*N + off_l + i] = src[B*off_l + b*n_l + i] for `width` int32/float32 words per row */

@@ -21,6 +21,7 @@ SOURCES = {
     'assign.cu': ['-fmad=false'],
     'decode.cu': ['-fmad=false'],
     'focal.cu': [],
+    'api.cu': [],
 }
 
 

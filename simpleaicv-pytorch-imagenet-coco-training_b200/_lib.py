@@ -45,6 +45,35 @@ class Geometry(ctypes.Structure):
     ]
 
 
+class LossParams(ctypes.Structure):
+    """Mirror of `b200det_loss_params`."""
+    _fields_ = [
+        ('is_fcos', ctypes.c_int32),
+        ('box_loss', ctypes.c_int32),
+        ('reg_dtype', ctypes.c_int32),
+        ('use_center_sample', ctypes.c_int32),
+        ('alpha', ctypes.c_float),
+        ('gamma', ctypes.c_float),
+        ('beta', ctypes.c_float),
+        ('w_cls', ctypes.c_float),
+        ('w_box', ctypes.c_float),
+        ('w_ctr', ctypes.c_float),
+    ]
+
+
+class DecodeParams(ctypes.Structure):
+    """Mirror of `b200det_decode_params`."""
+    _fields_ = [
+        ('is_fcos', ctypes.c_int32),
+        ('reg_dtype', ctypes.c_int32),
+        ('topn', ctypes.c_int32),
+        ('max_out', ctypes.c_int32),
+        ('nms_type', ctypes.c_int32),
+        ('min_score', ctypes.c_float),
+        ('nms_threshold', ctypes.c_double),
+    ]
+
+
 _vp = ctypes.c_void_p
 _vpp = ctypes.POINTER(ctypes.c_void_p)
 _geo = ctypes.POINTER(Geometry)
@@ -54,6 +83,17 @@ SIGNATURES = {
     'b200det_abi_version': (ctypes.c_int, []),
     'b200det_error_string': (ctypes.c_char_p, [ctypes.c_int]),
     'b200det_launch_count': (ctypes.c_ulonglong, []),
+    'b200det_profile': (ctypes.c_int, [ctypes.c_int]),
+    'b200det_profile_read': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_int)]),
+    'b200det_kernel_name': (ctypes.c_char_p, [ctypes.c_int]),
+    'b200det_loss_forward': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vp,
+        ctypes.c_size_t, _vp, _vp, _vp
+    ]),
+    'b200det_decode': (ctypes.c_int, [
+        _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp
+    ]),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
     'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),
     'b200det_retina_assign': (ctypes.c_int,
@@ -132,35 +172,20 @@ def launch_count():
     return int(load().b200det_launch_count())
 
 
-# Optional per-kernel timing (bench.py): when PROFILE is a dict, every C-ABI launch made by the
-# drop-in classes is bracketed by CUDA events on the launching stream; durations are read after
-# the caller synchronises.  None (default) = no events, no overhead.
-PROFILE = None
+def profile_start():
+    """Per-kernel CUDA-event timing inside the library (b200det_profile)."""
+    load().b200det_profile(1)
 
 
-class timed:
-    def __init__(self, name):
-        self.name = name
-
-    def __enter__(self):
-        if PROFILE is not None:
-            import torch
-            self.start = torch.cuda.Event(enable_timing=True)
-            self.stop = torch.cuda.Event(enable_timing=True)
-            self.start.record()
-        return self
-
-    def __exit__(self, *exc):
-        if PROFILE is not None:
-            self.stop.record()
-            PROFILE.setdefault(self.name, []).append((self.start, self.stop))
-        return False
-
-
-def profile_summary():
-    """{kernel name: (launches, mean ms)} from the recorded events (call after a synchronize)."""
+def profile_stop():
+    """Stops the timing and returns {kernel name: (launches, mean ms)}; synchronises the events."""
+    lib = load()
+    lib.b200det_profile(0)
     out = {}
-    for name, pairs in (PROFILE or {}).items():
-        ms = [a.elapsed_time(b) for a, b in pairs]
-        out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    for kid in range(8):
+        ms = ctypes.c_double(0.0)
+        n = ctypes.c_int(0)
+        check(lib.b200det_profile_read(kid, ctypes.byref(ms), ctypes.byref(n)), 'profile_read')
+        if n.value:
+            out[lib.b200det_kernel_name(kid).decode()] = (n.value, ms.value / n.value)
     return out

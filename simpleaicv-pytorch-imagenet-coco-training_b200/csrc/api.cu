@@ -1,0 +1,61 @@
+// api.cu -- fused host entry points: one C call per loss forward / decode.
+// For small and medium batches the step time is dominated by host work (argument marshalling,
+// one FFI call and one stream operation per kernel); these entries enqueue the whole sequence
+// with a single call and a single memset.  They only compose the public per-kernel entry points.
+#include "common.cuh"
+
+using namespace b200det;
+
+extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_loss_params *p,
+                                    const float *annotations, int max_gt, const void *const *cls,
+                                    const void *const *reg, const void *const *ctr,
+                                    int32_t *labels, void *workspace, size_t workspace_bytes,
+                                    double *sums, float *losses, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!p || !annotations || !cls || !labels || !workspace || !sums) return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    // sweep accumulators and queue counters are adjacent in the workspace: one memset
+    char *base = static_cast<char *>(workspace);
+    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
+                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
+                                    (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    g_skip_memset = true;
+    // the long HBM-bound sweep first: the host prepares the remaining launches behind it
+    rc = b200det_focal_loss(geo, cls, nullptr, p->alpha, p->gamma, nullptr, nullptr, 0.f,
+                            workspace, workspace_bytes, stream);
+    if (!rc) {
+        rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample,
+                                              labels, nullptr, nullptr, workspace,
+                                              workspace_bytes, stream)
+                        : b200det_retina_assign(geo, annotations, max_gt, labels, nullptr,
+                                                workspace, workspace_bytes, stream);
+    }
+    if (!rc)
+        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
+                                   ctr, p->box_loss, p->beta, cls, p->alpha, p->gamma, nullptr,
+                                   nullptr, workspace, workspace_bytes, stream);
+    g_skip_memset = false;
+    if (!rc) rc = b200det_loss_reduce(geo, 3, workspace, workspace_bytes, sums, stream);
+    if (!rc && losses) rc = b200det_loss_finish(sums, p->w_cls, p->w_box, p->w_ctr, losses, stream);
+    return rc;
+}
+
+extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *p,
+                              const void *const *cls, const void *const *ctr,
+                              const void *const *reg, uint32_t *keys, int32_t *classes,
+                              float *out, int32_t *order, int32_t *keep, int32_t *counts,
+                              void *stream) {
+    if (!p) return B200DET_EINVAL;
+    int rc = b200det_score_argmax(geo, cls, p->is_fcos ? ctr : nullptr, p->min_score, keys,
+                                  classes, stream);
+    if (!rc)
+        rc = b200det_select_decode_nms(geo, keys, classes, reg, p->reg_dtype, p->is_fcos,
+                                       p->min_score, p->topn, p->max_out, p->nms_type,
+                                       p->nms_threshold, out, order, keep, counts, nullptr, 0,
+                                       stream);
+    return rc;
+}

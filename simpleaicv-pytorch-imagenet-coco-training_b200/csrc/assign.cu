@@ -892,10 +892,13 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
     char *base = static_cast<char *>(workspace);
     int *npos = reinterpret_cast<int *>(base + ws.off_assign);
     const Queues q = queues_of(base, ws);
-    cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
+    if (!g_skip_memset) {
+        cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)g.batch);
     const size_t smem = assign_dyn_smem(max_gt);
+    ProfScope prof(kKernAssign, stream);
     if (g.per_loc == 9)
         retina_assign_kernel<9><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
             g, ba, tt, annotations, max_gt, labels, matched, q, npos);
@@ -929,9 +932,12 @@ extern "C" int b200det_fcos_assign(const b200det_geometry *geo, const float *ann
     if ((rc = raise_smem_limit(fcos_assign_kernel, &done))) return rc;
     char *base = static_cast<char *>(workspace);
     const Queues q = queues_of(base, ws);
-    cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
+    if (!g_skip_memset) {
+        cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)g.batch);
+    ProfScope prof(kKernAssign, stream);
     fcos_assign_kernel<<<grid, kAssignThreads, assign_dyn_smem(max_gt), (cudaStream_t)stream>>>(
         g, ft, tt, annotations, max_gt, use_center_sample, labels, matched, targets, q,
         reinterpret_cast<int *>(base + ws.off_assign));
@@ -979,6 +985,7 @@ extern "C" int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos,
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     char *base = static_cast<char *>(workspace);
+    ProfScope prof(kKernSparse, stream);
     sparse_loss_kernel<<<(unsigned)ws.sparse_blocks, kSparseThreads, 0, (cudaStream_t)stream>>>(
         a, annotations, labels, queues_of(base, ws),
         reinterpret_cast<SparsePartial *>(base + ws.off_sparse));

@@ -44,6 +44,26 @@ int make_geo(const b200det_geometry *g, Geo *out);
 void count_launch();
 unsigned long long launches();
 
+// Optional per-kernel timing with CUDA events on the launching stream (b200det_profile_*):
+// bench.py reads the dominant kernel's average duration from the same launches it times.
+enum KernelId {
+    kKernFocal = 0,
+    kKernAssign,
+    kKernSparse,
+    kKernReduce,
+    kKernFinish,
+    kKernArgmax,
+    kKernSelect,
+    kKernOther,
+    kKernCount
+};
+struct ProfScope {   // records start on construction, stop on destruction (no-op when disabled)
+    int slot;
+    cudaStream_t st;
+    ProfScope(int kernel_id, void *stream);
+    ~ProfScope();
+};
+
 // Loss workspace (caller-owned scratch): per-CTA partials, reduced in fixed order by
 // loss_reduce_kernel, plus the matched annotation row of every row (assign -> sparse kernel).
 struct SparsePartial {
@@ -56,6 +76,8 @@ struct LossWs {
         off_pos_queue /* int2 [B*N] */, off_ign_queue /* int [B*N] */, total;
 };
 LossWs loss_ws_layout(const Geo &g);
+// set by the fused entry points after they have cleared all accumulators with ONE memset
+extern thread_local bool g_skip_memset;
 int assign_blocks_per_image(const Geo &g);  // assign.cu
 int sparse_blocks(const Geo &g);            // assign.cu
 

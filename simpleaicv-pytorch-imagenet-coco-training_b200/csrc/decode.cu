@@ -669,6 +669,7 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
     for (int l = g.n_levels; l <= kMaxLevels; ++l) a.block_off[l] = blocks;
     const size_t smem = (size_t)R * a.pitch * 8;
     if (smem > 48 * 1024) return B200DET_ERANGE;
+    ProfScope prof(kKernArgmax, stream);
     if (vec == 4)
         score_argmax_kernel<4><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else
@@ -743,6 +744,7 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
+    ProfScope prof(kKernSelect, stream);
     select_nms_kernel<<<g.batch, kSelThreads, smem, (cudaStream_t)stream>>>(a, keys, classes, out,
                                                                            order, keep, counts);
     count_launch();

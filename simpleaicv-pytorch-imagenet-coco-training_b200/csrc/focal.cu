@@ -14,6 +14,8 @@
 // (~12 instructions, no MUFU); elements with p > 1/4, the target class of positive rows and
 // gamma != 2 fall back to logf/powf.  Loss tolerance vs the reference: 1e-5 relative.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "focal_terms.cuh"
 
@@ -23,6 +25,32 @@ namespace b200det {
 // host-side geometry + bookkeeping
 // ---------------------------------------------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
+thread_local bool g_skip_memset = false;
+
+// ---- per-kernel event profiler -------------------------------------------------------------
+struct ProfRec {
+    int id;
+    cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(int kernel_id, void *stream) : slot(-1), st((cudaStream_t)stream) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.id = kernel_id;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].b, st);
+}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
@@ -441,6 +469,45 @@ extern "C" const char *b200det_error_string(int code) {
 
 extern "C" unsigned long long b200det_launch_count(void) { return launches(); }
 
+extern "C" int b200det_profile(int enable) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (enable) {
+        for (auto &r : g_prof) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        g_prof.clear();
+    }
+    g_prof_on = enable != 0;
+    return 0;
+}
+
+extern "C" int b200det_profile_read(int kernel_id, double *total_ms, int *n_launches) {
+    if (kernel_id < 0 || kernel_id >= kKernCount || !total_ms || !n_launches) return B200DET_EINVAL;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double t = 0.0;
+    int n = 0;
+    for (auto &r : g_prof) {
+        if (r.id != kernel_id) continue;
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+        if (e != cudaSuccess) return (int)e;
+        t += ms;
+        ++n;
+    }
+    *total_ms = t;
+    *n_launches = n;
+    return 0;
+}
+
+extern "C" const char *b200det_kernel_name(int kernel_id) {
+    static const char *names[kKernCount] = {"focal_loss",  "assign",       "sparse_losses",
+                                            "loss_reduce", "loss_finish",  "score_argmax",
+                                            "select_decode_nms", "other"};
+    return (kernel_id >= 0 && kernel_id < kKernCount) ? names[kernel_id] : "?";
+}
+
 extern "C" long long b200det_rows_per_image(const b200det_geometry *geo) {
     Geo g;
     const int rc = make_geo(geo, &g);
@@ -532,13 +599,14 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
 
     long long *partials =
         reinterpret_cast<long long *>(static_cast<char *>(workspace) + ws.off_focal);
-    {
+    if (!g_skip_memset) {
         cudaError_t me = cudaMemsetAsync(partials, 0, kSweepSlots * sizeof(long long),
                                          (cudaStream_t)stream);
         if (me != cudaSuccess) return (int)me;
     }
     const bool gamma2 = gamma == 2.f;
     cudaError_t e;
+    ProfScope prof(kKernFocal, stream);
     if (labels == nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
         if (vec == 4) {
@@ -568,6 +636,7 @@ extern "C" int b200det_loss_reduce(const b200det_geometry *geo, int which, const
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     const char *base = static_cast<const char *>(workspace);
+    ProfScope prof(kKernReduce, stream);
     loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const int *>(base + ws.off_assign), (long long)ws.assign_blocks,
         reinterpret_cast<const SparsePartial *>(base + ws.off_sparse), (long long)ws.sparse_blocks,
@@ -580,6 +649,7 @@ extern "C" int b200det_loss_reduce(const b200det_geometry *geo, int which, const
 extern "C" int b200det_loss_finish(const double *sums, float w_cls, float w_box, float w_ctr,
                                    float *losses, void *stream) {
     if (!sums || !losses) return B200DET_EINVAL;
+    ProfScope prof(kKernFinish, stream);
     loss_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, w_cls, w_box, w_ctr, losses);
     count_launch();
     return (int)cudaGetLastError();

@@ -4,7 +4,7 @@ Same class names, constructor kwargs, __call__(preds) signature and return value
 three writable float32 NumPy arrays: scores [B,M] padded with -1, classes [B,M] padded with -1,
 boxes [B,M,4] padded with 0) as simpleAICV/detection/decode.py:175-271 (RetinaDecoder) and
 :274-364 (FCOSDecoder).  The reference copies every head output to the host and decodes in NumPy;
-here the head outputs stay in HBM, two kernels run
+here the head outputs stay in HBM, one C call (b200det_decode) enqueues two kernels
     b200det_score_argmax        arg-max / score / threshold: one streaming pass over cls
     b200det_select_decode_nms   per-image top-n, box decode, NMS, max_object_num cap
 and only the [B, M, 6] result (2.4 KB per image) crosses PCIe.  There is no CPU path.
@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from . import geometry as _geom
-from .losses import _prep_f32, _prep_reg, _stream
+from .losses import _prep_f32, _prep_reg
 
 __all__ = ['RetinaDecoder', 'FCOSDecoder']
 
@@ -36,6 +36,15 @@ class _DecoderBase:
         self._nms_code = _lib.NMS_CODES[nms_type]
         self._geo_cache = {}
         self._pinned = None
+        p = _lib.DecodeParams()
+        p.is_fcos = int(self._is_fcos)
+        p.reg_dtype = _lib.F32
+        p.topn = int(topn)
+        p.max_out = int(max_object_num)
+        p.nms_type = self._nms_code
+        p.min_score = float(np.float32(min_score_threshold))
+        p.nms_threshold = float(nms_threshold)
+        self._params = p
 
     def _staging(self, numel):
         if self._pinned is None or self._pinned.numel() != numel:
@@ -54,39 +63,38 @@ class _DecoderBase:
         ctr = _prep_f32([t.detach() for t in center_preds], 'center_preds') \
             if center_preds is not None else None
         device = cls[0].device
-        batch = int(cls[0].shape[0])
-        shapes = _geom.level_shapes(cls)
-        geo = self._geometry(shapes, batch, int(cls[0].shape[-1]))
-        n_rows = _geom.rows_per_image(shapes, geo.per_loc)
+        shape0 = cls[0].shape
+        key = (tuple(t.shape[1:3] for t in cls), shape0[0], shape0[-1])
+        plan = self._geo_cache.get(key)
+        if plan is None:
+            shapes = _geom.level_shapes(cls)
+            geo = self._geometry(shapes, int(shape0[0]), int(shape0[-1]))
+            plan = (geo, ctypes.byref(geo), int(shape0[0]),
+                    _geom.rows_per_image(shapes, geo.per_loc))
+            self._geo_cache = {key: plan}
+        _, geo_ref, batch, n_rows = plan
         m = int(self.max_object_num)
-        st = _stream()
 
-        keys = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
-        classes = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
+        # scratch = keys | classes (int32 each) ; out = scores | classes | boxes
+        scratch = torch.empty(2 * batch * n_rows, dtype=torch.int32, device=device)
         out = torch.empty(6 * batch * m, dtype=torch.float32, device=device)
         order = keep = counts = None
         if details:
             order = torch.empty(batch * self.topn, dtype=torch.int32, device=device)
             keep = torch.empty(batch * self.topn, dtype=torch.int32, device=device)
             counts = torch.empty(batch * 3, dtype=torch.int32, device=device)
-
-        with _lib.timed('score_argmax'):
-            _lib.check(
-                lib.b200det_score_argmax(ctypes.byref(geo), _lib.ptr_array(cls),
-                                         _lib.ptr_array(ctr),
-                                         float(np.float32(self.min_score_threshold)),
-                                         keys.data_ptr(), classes.data_ptr(), st),
-                'b200det_score_argmax')
-        with _lib.timed('select_decode_nms'):
-            _lib.check(
-                lib.b200det_select_decode_nms(
-                    ctypes.byref(geo), keys.data_ptr(), classes.data_ptr(), _lib.ptr_array(reg),
-                    reg_dtype, int(self._is_fcos), float(np.float32(self.min_score_threshold)),
-                    int(self.topn), m, self._nms_code,
-                    float(self.nms_threshold), out.data_ptr(),
-                    order.data_ptr() if details else None, keep.data_ptr() if details else None,
-                    counts.data_ptr() if details else None, None, 0, st),
-                'b200det_select_decode_nms')
+        params = self._params
+        params.reg_dtype = reg_dtype
+        keys_ptr = scratch.data_ptr()
+        _lib.check(
+            lib.b200det_decode(geo_ref, ctypes.byref(params), _lib.ptr_array(cls),
+                               _lib.ptr_array(ctr), _lib.ptr_array(reg), keys_ptr,
+                               keys_ptr + 4 * batch * n_rows, out.data_ptr(),
+                               order.data_ptr() if details else None,
+                               keep.data_ptr() if details else None,
+                               counts.data_ptr() if details else None,
+                               ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+            'b200det_decode')
 
         # the only D2H copy: 24*M bytes per image, through a cached pinned staging buffer; the
         # caller gets fresh, writable arrays (tools/scripts.py:742-758 mutates them in place)
@@ -140,15 +148,10 @@ class RetinaDecoder(_DecoderBase):
         self._base = _geom.retina_base_anchors(areas, ratios, scales)
 
     def _geometry(self, shapes, batch, num_classes):
-        key = (tuple(shapes), batch, num_classes)
-        geo = self._geo_cache.get(key)
-        if geo is None:
-            if len(shapes) > len(self.areas):
-                raise ValueError('more pyramid levels than anchor areas')
-            geo = _geom.make_geometry(shapes, batch, self._per_loc, num_classes, self.strides,
-                                      base_anchors=self._base)
-            self._geo_cache = {key: geo}
-        return geo
+        if len(shapes) > len(self.areas):
+            raise ValueError('more pyramid levels than anchor areas')
+        return _geom.make_geometry(shapes, batch, self._per_loc, num_classes, self.strides,
+                                   base_anchors=self._base)
 
 
 class FCOSDecoder(_DecoderBase):
@@ -167,9 +170,4 @@ class FCOSDecoder(_DecoderBase):
         self.strides = strides
 
     def _geometry(self, shapes, batch, num_classes):
-        key = (tuple(shapes), batch, num_classes)
-        geo = self._geo_cache.get(key)
-        if geo is None:
-            geo = _geom.make_geometry(shapes, batch, 1, num_classes, self.strides)
-            self._geo_cache = {key: geo}
-        return geo
+        return _geom.make_geometry(shapes, batch, 1, num_classes, self.strides)

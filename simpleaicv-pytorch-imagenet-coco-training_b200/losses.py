@@ -6,13 +6,14 @@ config picks them up with `from b200det import losses` in place of
 `from simpleAICV.detection import losses` (3.detection_training/*/train_config.py:37-63).
 
 What runs where: nothing numeric runs in Python or torch.  forward() fills a geometry struct,
-collects the per-level device pointers (no torch.cat) and launches
-    b200det_retina_assign / b200det_fcos_assign   assignment (pure ALU scan)
-    b200det_sparse_losses                         box (+centre-ness) loss of the positives
-    b200det_focal_loss                            one streaming pass over cls (+ its gradient)
-    b200det_loss_reduce / b200det_loss_finish     deterministic fp64 reduction, normalisation
-on the current CUDA stream without any host synchronisation.  There is no CPU path: CPU
-tensors raise.
+collects the per-level device pointers (no torch.cat) and enqueues, on the current CUDA stream and
+without any host synchronisation,
+  * evaluation / no_grad (tools/scripts.py:733): ONE C call, b200det_loss_forward =
+        focal sweep (label-free) -> assignment -> sparse losses -> reduce -> finish;
+  * training (inputs require grad, tools/scripts.py:893-945): assignment -> sparse losses (+ box /
+    centre-ness gradients) -> reduce -> label-aware focal sweep writing d(cls) in the same pass ->
+    reduce -> finish; backward() only multiplies the stored gradients by the upstream scalars.
+There is no CPU path: CPU tensors raise.
 
 Extra, keyword-only constructor arguments (defaults keep reference behaviour):
     sync_normalizer / process_group : all-reduce {positives, loss sums} over the process
@@ -20,7 +21,6 @@ Extra, keyword-only constructor arguments (defaults keep reference behaviour):
         (SURVEY.md section 8e).  Default False = the reference's per-rank normalisation.
 """
 import ctypes
-import os
 
 import torch
 import torch.nn as nn
@@ -47,28 +47,30 @@ def _prep_f32(levels, what):
     """float32, contiguous, 16-byte aligned per-level tensors (the heads already emit these)."""
     out = []
     for t in levels:
-        _require_cuda(t, what)
+        if not t.is_cuda:
+            _require_cuda(t, what)
         if t.dtype != torch.float32:
             t = t.float()
         if not t.is_contiguous():
             t = t.contiguous()
-        if t.data_ptr() % 16:
+        if t.data_ptr() & 15:
             t = t.clone()
         out.append(t)
     return out
 
 
 def _prep_reg(levels):
-    out = []
     dtype = levels[0].dtype
     if dtype not in _DTYPES or any(t.dtype != dtype for t in levels):
         levels = [t.float() for t in levels]
         dtype = torch.float32
+    out = []
     for t in levels:
-        _require_cuda(t, 'reg_preds')
+        if not t.is_cuda:
+            _require_cuda(t, 'reg_preds')
         if not t.is_contiguous():
             t = t.contiguous()
-        if t.data_ptr() % 16:
+        if t.data_ptr() & 15:
             t = t.clone()
         out.append(t)
     return out, _DTYPES[dtype]
@@ -90,169 +92,179 @@ def _prep_annotations(annotations):
     return annotations
 
 
-_SIDE_STREAMS = {}
-# B200DET_OVERLAP=1 runs assignment + sparse losses on a second (high-priority) stream beside the
-# classification sweep.  Measured on B200 this is slower than running them back to back (the
-# sweep already saturates HBM and loses more than the overlap gains), so the default is one stream.
-_OVERLAP = os.environ.get('B200DET_OVERLAP', '0') == '1'
-
-
-def _side_stream(device):
-    """One extra stream per device for the kernels that can overlap (forked from and joined back
-    into the caller's current stream inside every call, so callers see plain stream semantics)."""
-    key = (device.type, device.index)
-    s = _SIDE_STREAMS.get(key)
-    if s is None:
-        s = torch.cuda.Stream(device=device, priority=-1)
-        _SIDE_STREAMS[key] = s
-    return s
-
-
 def _maybe_all_reduce(t, sync, group):
     if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
 
 
+def _wants_grad(tensors):
+    if not torch.is_grad_enabled():
+        return False
+    for t in tensors:
+        if t.requires_grad:
+            return True
+    return False
+
+
+class _Plan:
+    """Everything about one (pyramid shapes, batch, classes) combination that does not change
+    between calls: geometry struct, workspace size, row count."""
+
+    __slots__ = ('geo', 'geo_ref', 'ws_bytes', 'n_rows', 'batch')
+
+    def __init__(self, geo, batch, n_rows):
+        self.geo = geo
+        self.geo_ref = ctypes.byref(geo)
+        self.batch = batch
+        self.n_rows = n_rows
+        self.ws_bytes = int(_lib.load().b200det_loss_workspace_bytes(self.geo_ref))
+
+
+def _plan_for(owner, cls):
+    shape0 = cls[0].shape
+    key = (tuple(t.shape[1:3] for t in cls), shape0[0], shape0[-1])
+    plan = owner._plans.get(key)
+    if plan is None:
+        shapes = _geom.level_shapes(cls)
+        batch, num_classes = int(shape0[0]), int(shape0[-1])
+        geo = owner._geometry(shapes, batch, num_classes)
+        plan = _Plan(geo, batch, _geom.rows_per_image(shapes, geo.per_loc))
+        owner._plans = {key: plan}
+    return plan
+
+
+def _loss_params(owner, reg_dtype):
+    p = _lib.LossParams()
+    p.is_fcos = int(owner._is_fcos)
+    p.box_loss = owner._box_code
+    p.reg_dtype = reg_dtype
+    p.use_center_sample = int(getattr(owner, 'use_center_sample', 0))
+    p.alpha = float(owner.alpha)
+    p.gamma = float(owner.gamma)
+    p.beta = float(owner.beta)
+    p.w_cls = float(owner.cls_loss_weight)
+    p.w_box = float(owner.box_loss_weight)
+    p.w_ctr = float(getattr(owner, 'center_ness_loss_weight', 0.))
+    return p
+
+
+def _forward_eval(owner, annotations, cls_in, reg_in, ctr_in):
+    """No-grad forward: one C call (b200det_loss_forward)."""
+    lib = _lib.load()
+    cls = _prep_f32(cls_in, 'cls_preds')
+    reg, reg_dtype = _prep_reg(reg_in)
+    ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
+    annotations = _prep_annotations(annotations)
+    plan = _plan_for(owner, cls)
+    if annotations.shape[0] != plan.batch:
+        raise ValueError('annotations and predictions disagree on the batch size')
+    device = cls[0].device
+    # scratch = workspace | labels ; out = sums (4 doubles) | losses (3 floats, 8 reserved)
+    scratch = torch.empty(plan.ws_bytes + 4 * plan.batch * plan.n_rows, dtype=torch.uint8,
+                          device=device)
+    out = torch.empty(8, dtype=torch.float64, device=device)
+    ws_ptr = scratch.data_ptr()
+    sums_ptr = out.data_ptr()
+    sync = owner.sync_normalizer and torch.distributed.is_available() \
+        and torch.distributed.is_initialized()
+    st = _stream()
+    params = _loss_params(owner, reg_dtype)
+    _lib.check(
+        lib.b200det_loss_forward(plan.geo_ref, ctypes.byref(params), annotations.data_ptr(),
+                                 int(annotations.shape[1]), _lib.ptr_array(cls),
+                                 _lib.ptr_array(reg), _lib.ptr_array(ctr),
+                                 ws_ptr + plan.ws_bytes, ws_ptr, plan.ws_bytes, sums_ptr,
+                                 None if sync else sums_ptr + 32, st), 'b200det_loss_forward')
+    if sync:
+        _maybe_all_reduce(out[0:4], True, owner.process_group)
+        _lib.check(
+            lib.b200det_loss_finish(sums_ptr, params.w_cls, params.w_box, params.w_ctr,
+                                    sums_ptr + 32, st), 'b200det_loss_finish')
+    owner.last_stats = {'sums': out[0:4]}
+    return out[4:8].view(torch.float32)
+
+
 class _DetLossFunction(torch.autograd.Function):
-    """One autograd node per loss call.  Gradients are produced by the forward kernels (scaled by
-    weight / positives) and only multiplied by the upstream scalars in backward."""
+    """Training path: one autograd node per loss call.  Gradients are produced by the forward
+    kernels (the focal gradient already scaled by weight / positives) and only multiplied by the
+    upstream scalars in backward.  backward() may be called once (the stored gradients are
+    scaled in place)."""
 
     @staticmethod
     def forward(ctx, owner, annotations, n_levels, *heads):
         lib = _lib.load()
         is_fcos = owner._is_fcos
-        cls_in = heads[0:n_levels]
-        reg_in = heads[n_levels:2 * n_levels]
-        ctr_in = heads[2 * n_levels:3 * n_levels] if is_fcos else ()
+        cls = _prep_f32(heads[0:n_levels], 'cls_preds')
+        reg, reg_dtype = _prep_reg(heads[n_levels:2 * n_levels])
+        ctr = _prep_f32(heads[2 * n_levels:3 * n_levels], 'center_preds') if is_fcos else None
         need = ctx.needs_input_grad[3:]
-        want_cls = any(need[0:n_levels])
-        want_reg = any(need[n_levels:2 * n_levels])
-        want_ctr = is_fcos and any(need[2 * n_levels:3 * n_levels])
-        want_grad = want_cls or want_reg or want_ctr
-
-        cls = _prep_f32(cls_in, 'cls_preds')
-        reg, reg_dtype = _prep_reg(reg_in)
-        ctr = _prep_f32(ctr_in, 'center_preds') if is_fcos else None
         annotations = _prep_annotations(annotations)
-        device = cls[0].device
-        batch = int(cls[0].shape[0])
-        if annotations.shape[0] != batch:
+        plan = _plan_for(owner, cls)
+        if annotations.shape[0] != plan.batch:
             raise ValueError('annotations and predictions disagree on the batch size')
-        shapes = _geom.level_shapes(cls)
-        num_classes = int(cls[0].shape[-1])
-        geo = owner._geometry(shapes, batch, num_classes)
-        n_rows = _geom.rows_per_image(shapes, geo.per_loc)
+        device = cls[0].device
+        geo, ws_bytes = plan.geo_ref, plan.ws_bytes
         st = _stream()
-
-        ws_bytes = getattr(geo, '_ws_bytes', None)
-        if ws_bytes is None:
-            ws_bytes = lib.b200det_loss_workspace_bytes(ctypes.byref(geo))
-            geo._ws_bytes = ws_bytes
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-        labels = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
-        sums = torch.zeros(4, dtype=torch.float64, device=device)
-        losses = torch.empty(3, dtype=torch.float32, device=device)
-
-        # the sparse kernel writes gradients of the positive rows only
-        reg_grad = [torch.zeros(r.shape, dtype=torch.float32, device=device) for r in reg] \
-            if want_grad else None
-        ctr_grad = [torch.zeros_like(c) for c in ctr] if (want_grad and is_fcos) else None
-        cls_grad = [torch.empty_like(c) for c in cls] if want_grad else None
-
-        sync, group = owner.sync_normalizer, owner.process_group
+        max_gt = int(annotations.shape[1])
         alpha, gamma = float(owner.alpha), float(owner.gamma)
+        w_cls = float(owner.cls_loss_weight)
+        w_box = float(owner.box_loss_weight)
+        w_ctr = float(getattr(owner, 'center_ness_loss_weight', 0.))
 
-        def launch_assign(fix_cls, stream):
-            """assignment scan, then the sparse (positive / ignored rows) losses"""
-            name = 'fcos_assign' if is_fcos else 'retina_assign'
-            with _lib.timed(name):
-                if is_fcos:
-                    _lib.check(
-                        lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                                int(annotations.shape[1]),
-                                                int(owner.use_center_sample), labels.data_ptr(),
-                                                None, None, ws.data_ptr(), ws_bytes, stream),
-                        'b200det_fcos_assign')
-                else:
-                    _lib.check(
-                        lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                                  int(annotations.shape[1]), labels.data_ptr(),
-                                                  None, ws.data_ptr(), ws_bytes, stream),
-                        'b200det_retina_assign')
-            with _lib.timed('sparse_losses'):
-                _lib.check(
-                    lib.b200det_sparse_losses(ctypes.byref(geo), int(is_fcos),
-                                              annotations.data_ptr(), int(annotations.shape[1]),
-                                              labels.data_ptr(), _lib.ptr_array(reg), reg_dtype,
-                                              _lib.ptr_array(ctr), owner._box_code,
-                                              float(owner.beta), _lib.ptr_array(fix_cls), alpha,
-                                              gamma, _lib.ptr_array(reg_grad),
-                                              _lib.ptr_array(ctr_grad), ws.data_ptr(), ws_bytes,
-                                              stream), 'b200det_sparse_losses')
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        labels = torch.empty(plan.batch * plan.n_rows, dtype=torch.int32, device=device)
+        out = torch.zeros(12, dtype=torch.float64, device=device)   # sums | focal sums | losses
+        sums, focal = out[0:4], out[4:8]
+        losses = out[8:12].view(torch.float32)
+        # the sparse kernel writes the rows of the positives only
+        reg_grad = [torch.zeros(r.shape, dtype=torch.float32, device=device) for r in reg]
+        ctr_grad = [torch.zeros_like(c) for c in ctr] if is_fcos else None
+        cls_grad = [torch.empty_like(c) for c in cls]
 
-        if want_grad:
-            # training: label-aware sweep; the focal gradient is written once, already divided
-            # by the (global) positive count, so the count must exist before the sweep
-            launch_assign(None, st)
+        if is_fcos:
             _lib.check(
-                lib.b200det_loss_reduce(ctypes.byref(geo), 1, ws.data_ptr(), ws_bytes,
-                                        sums.data_ptr(), st), 'b200det_loss_reduce')
-            _maybe_all_reduce(sums, sync, group)
-            with _lib.timed('focal_loss'):
-                _lib.check(
-                    lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls),
-                                           labels.data_ptr(), alpha, gamma,
-                                           _lib.ptr_array(cls_grad), sums.data_ptr(),
-                                           float(owner.cls_loss_weight), ws.data_ptr(), ws_bytes,
-                                           st), 'b200det_focal_loss')
-            focal = torch.zeros(4, dtype=torch.float64, device=device)
-            _lib.check(
-                lib.b200det_loss_reduce(ctypes.byref(geo), 2, ws.data_ptr(), ws_bytes,
-                                        focal.data_ptr(), st), 'b200det_loss_reduce')
-            _maybe_all_reduce(focal, sync, group)
-            sums = sums + focal
+                lib.b200det_fcos_assign(geo, annotations.data_ptr(), max_gt,
+                                        int(owner.use_center_sample), labels.data_ptr(), None,
+                                        None, ws.data_ptr(), ws_bytes, st), 'b200det_fcos_assign')
         else:
-            # forward only: label-free classification sweep; assignment + sparse losses supply the
-            # corrections and are independent of it
-            # The sweep is enqueued first: it is the long kernel, so the host-side preparation of
-            # the remaining launches overlaps with it.
-            cur = torch.cuda.current_stream(device)
-            overlap = _OVERLAP
-            side = _side_stream(device) if overlap else cur
-            if overlap:
-                side.wait_stream(cur)
-            with _lib.timed('focal_loss'):
-                _lib.check(
-                    lib.b200det_focal_loss(ctypes.byref(geo), _lib.ptr_array(cls), None, alpha,
-                                           gamma, None, None, 0., ws.data_ptr(), ws_bytes, st),
-                    'b200det_focal_loss')
-            with torch.cuda.stream(side):
-                launch_assign(cls, ctypes.c_void_p(side.cuda_stream))
-            if overlap:
-                cur.wait_stream(side)
-            with _lib.timed('loss_reduce'):
-                _lib.check(
-                    lib.b200det_loss_reduce(ctypes.byref(geo), 3, ws.data_ptr(), ws_bytes,
-                                            sums.data_ptr(), st), 'b200det_loss_reduce')
-            _maybe_all_reduce(sums, sync, group)
+            _lib.check(
+                lib.b200det_retina_assign(geo, annotations.data_ptr(), max_gt, labels.data_ptr(),
+                                          None, ws.data_ptr(), ws_bytes, st),
+                'b200det_retina_assign')
         _lib.check(
-            lib.b200det_loss_finish(sums.data_ptr(), float(owner.cls_loss_weight),
-                                    float(owner.box_loss_weight),
-                                    float(getattr(owner, 'center_ness_loss_weight', 0.)),
-                                    losses.data_ptr(), st), 'b200det_loss_finish')
+            lib.b200det_sparse_losses(geo, int(is_fcos), annotations.data_ptr(), max_gt,
+                                      labels.data_ptr(), _lib.ptr_array(reg), reg_dtype,
+                                      _lib.ptr_array(ctr), owner._box_code, float(owner.beta),
+                                      None, alpha, gamma, _lib.ptr_array(reg_grad),
+                                      _lib.ptr_array(ctr_grad), ws.data_ptr(), ws_bytes, st),
+            'b200det_sparse_losses')
+        # the focal gradient is written once, already divided by the (global) positive count, so
+        # the count has to exist before the sweep
+        _lib.check(lib.b200det_loss_reduce(geo, 1, ws.data_ptr(), ws_bytes, sums.data_ptr(), st),
+                   'b200det_loss_reduce')
+        sync, group = owner.sync_normalizer, owner.process_group
+        _maybe_all_reduce(sums, sync, group)
+        _lib.check(
+            lib.b200det_focal_loss(geo, _lib.ptr_array(cls), labels.data_ptr(), alpha, gamma,
+                                   _lib.ptr_array(cls_grad), sums.data_ptr(), w_cls,
+                                   ws.data_ptr(), ws_bytes, st), 'b200det_focal_loss')
+        _lib.check(lib.b200det_loss_reduce(geo, 2, ws.data_ptr(), ws_bytes, focal.data_ptr(), st),
+                   'b200det_loss_reduce')
+        _maybe_all_reduce(focal, sync, group)
+        sums.add_(focal)
+        _lib.check(lib.b200det_loss_finish(sums.data_ptr(), w_cls, w_box, w_ctr,
+                                           losses.data_ptr(), st), 'b200det_loss_finish')
 
         ctx.n_levels = n_levels
         ctx.is_fcos = is_fcos
         ctx.in_dtypes = [h.dtype for h in heads]
         ctx.in_shapes = [h.shape for h in heads]
-        ctx.want = (want_cls, want_reg, want_ctr)
-        ctx.weights = (float(owner.box_loss_weight),
-                       float(getattr(owner, 'center_ness_loss_weight', 0.)))
-        if want_grad:
-            ctx.save_for_backward(sums, *cls_grad, *reg_grad, *(ctr_grad or []))
-        owner.last_stats = {'sums': sums, 'labels': labels, 'geometry': geo}
-        outs = (losses[0], losses[1], losses[2]) if is_fcos else (losses[0], losses[1])
-        return outs
+        ctx.want = (any(need[0:n_levels]), any(need[n_levels:2 * n_levels]),
+                    is_fcos and any(need[2 * n_levels:3 * n_levels]))
+        ctx.weights = (w_box, w_ctr)
+        ctx.save_for_backward(sums, *cls_grad, *reg_grad, *(ctr_grad or []))
+        owner.last_stats = {'sums': sums}
+        return (losses[0], losses[1], losses[2]) if is_fcos else (losses[0], losses[1])
 
     @staticmethod
     def backward(ctx, *grad_out):
@@ -298,13 +310,10 @@ def _debug_assign(owner, preds, annotations, exact=True):
     is_fcos = owner._is_fcos
     cls = _prep_f32(preds[0], 'cls_preds')
     annotations = _prep_annotations(annotations)
+    plan = _plan_for(owner, cls)
     device = cls[0].device
-    batch = int(cls[0].shape[0])
-    shapes = _geom.level_shapes(cls)
-    geo = owner._geometry(shapes, batch, int(cls[0].shape[-1]))
-    n_rows = _geom.rows_per_image(shapes, geo.per_loc)
+    batch, n_rows, geo, ws_bytes = plan.batch, plan.n_rows, plan.geo_ref, plan.ws_bytes
     st = _stream()
-    ws_bytes = lib.b200det_loss_workspace_bytes(ctypes.byref(geo))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     labels = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
     matched = torch.empty(batch * n_rows, dtype=torch.int32, device=device) if exact else None
@@ -313,23 +322,21 @@ def _debug_assign(owner, preds, annotations, exact=True):
     if is_fcos:
         targets = torch.empty(batch * n_rows * 6, dtype=torch.float32, device=device)
         _lib.check(
-            lib.b200det_fcos_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                    int(annotations.shape[1]), int(owner.use_center_sample),
-                                    labels.data_ptr(), matched_ptr, targets.data_ptr(),
-                                    ws.data_ptr(), ws_bytes, st),
+            lib.b200det_fcos_assign(geo, annotations.data_ptr(), int(annotations.shape[1]),
+                                    int(owner.use_center_sample), labels.data_ptr(), matched_ptr,
+                                    targets.data_ptr(), ws.data_ptr(), ws_bytes, st),
             'b200det_fcos_assign')
     else:
         _lib.check(
-            lib.b200det_retina_assign(ctypes.byref(geo), annotations.data_ptr(),
-                                      int(annotations.shape[1]), labels.data_ptr(),
-                                      matched_ptr, ws.data_ptr(), ws_bytes, st),
-            'b200det_retina_assign')
+            lib.b200det_retina_assign(geo, annotations.data_ptr(), int(annotations.shape[1]),
+                                      labels.data_ptr(), matched_ptr, ws.data_ptr(), ws_bytes,
+                                      st), 'b200det_retina_assign')
 
     def to_image_major(t, width):
         out = torch.empty_like(t)
         _lib.check(
-            lib.b200det_rows_to_image_major(ctypes.byref(geo), t.data_ptr(), out.data_ptr(),
-                                            width, st), 'b200det_rows_to_image_major')
+            lib.b200det_rows_to_image_major(geo, t.data_ptr(), out.data_ptr(), width, st),
+            'b200det_rows_to_image_major')
         return out
 
     res = {'labels': to_image_major(labels, 1).view(batch, n_rows)}
@@ -383,19 +390,14 @@ class RetinaLoss(nn.Module):
         self._box_code = _lib.BOX_LOSS_CODES[box_loss_type]
         self._per_loc = len(ratios) * len(scales)
         self._base = _geom.retina_base_anchors(areas, ratios, scales)
-        self._geo_cache = {}
+        self._plans = {}
         self.last_stats = None
 
     def _geometry(self, shapes, batch, num_classes):
-        key = (tuple(shapes), batch, num_classes)
-        geo = self._geo_cache.get(key)
-        if geo is None:
-            if len(shapes) > len(self.areas):
-                raise ValueError('more pyramid levels than anchor areas')
-            geo = _geom.make_geometry(shapes, batch, self._per_loc, num_classes, self.strides,
-                                      base_anchors=self._base)
-            self._geo_cache = {key: geo}
-        return geo
+        if len(shapes) > len(self.areas):
+            raise ValueError('more pyramid levels than anchor areas')
+        return _geom.make_geometry(shapes, batch, self._per_loc, num_classes, self.strides,
+                                   base_anchors=self._base)
 
     def debug_assign(self, preds, annotations, exact=True):
         return _debug_assign(self, preds, annotations, exact)
@@ -407,7 +409,12 @@ class RetinaLoss(nn.Module):
         cls_preds, reg_preds = preds
         n = len(cls_preds)
         assert len(reg_preds) == n
-        cls_loss, reg_loss = _DetLossFunction.apply(self, annotations, n, *cls_preds, *reg_preds)
+        if _wants_grad(cls_preds) or _wants_grad(reg_preds):
+            cls_loss, reg_loss = _DetLossFunction.apply(self, annotations, n, *cls_preds,
+                                                        *reg_preds)
+        else:
+            losses = _forward_eval(self, annotations, cls_preds, reg_preds, None)
+            cls_loss, reg_loss = losses[0], losses[1]
         loss_dict = {
             'cls_loss': cls_loss,
             'reg_loss': reg_loss,
@@ -450,19 +457,14 @@ class FCOSLoss(nn.Module):
         self.process_group = process_group
         self.beta = 0.
         self._box_code = _lib.BOX_LOSS_CODES[box_loss_iou_type]
-        self._geo_cache = {}
+        self._plans = {}
         self.last_stats = None
 
     def _geometry(self, shapes, batch, num_classes):
-        key = (tuple(shapes), batch, num_classes)
-        geo = self._geo_cache.get(key)
-        if geo is None:
-            if len(shapes) > len(self.mi):
-                raise ValueError('more pyramid levels than mi ranges')
-            geo = _geom.make_geometry(shapes, batch, 1, num_classes, self.strides, mi=self.mi,
-                                      center_sample_radius=self.center_sample_radius)
-            self._geo_cache = {key: geo}
-        return geo
+        if len(shapes) > len(self.mi):
+            raise ValueError('more pyramid levels than mi ranges')
+        return _geom.make_geometry(shapes, batch, 1, num_classes, self.strides, mi=self.mi,
+                                   center_sample_radius=self.center_sample_radius)
 
     def debug_assign(self, preds, annotations, exact=True):
         return _debug_assign(self, preds, annotations, exact)
@@ -474,8 +476,12 @@ class FCOSLoss(nn.Module):
         cls_preds, reg_preds, center_preds = preds
         n = len(cls_preds)
         assert len(reg_preds) == n and len(center_preds) == n
-        cls_loss, reg_loss, center_ness_loss = _DetLossFunction.apply(
-            self, annotations, n, *cls_preds, *reg_preds, *center_preds)
+        if _wants_grad(cls_preds) or _wants_grad(reg_preds) or _wants_grad(center_preds):
+            cls_loss, reg_loss, center_ness_loss = _DetLossFunction.apply(
+                self, annotations, n, *cls_preds, *reg_preds, *center_preds)
+        else:
+            losses = _forward_eval(self, annotations, cls_preds, reg_preds, center_preds)
+            cls_loss, reg_loss, center_ness_loss = losses[0], losses[1], losses[2]
         loss_dict = {
             'cls_loss': cls_loss,
             'reg_loss': reg_loss,
