@@ -200,6 +200,10 @@ int b200det_loss_reduce(const b200det_geometry *geo, int which, const void *work
 int b200det_loss_finish(const double *sums, float w_cls, float w_box, float w_ctr,
                         float *losses, void *stream);
 
+/* x[l][i] *= *g * (sums ? weight / sums[0] : 1) for n_levels float32 buffers in one launch
+ * (autograd backward: upstream scalar, loss weight, positive count); no-op when the factor is 1 */
+int b200det_scale_levels(void *const *ptrs, const long long *counts, int n_levels,
+                         const float *g_dev, const double *sums, float weight, void *stream);
 /* x[i] *= *scale for n float32 values unless *scale == 1 (autograd backward helper) */
 int b200det_scale_f32(float *x, long long n, const float *scale_dev, void *stream);
 
@@ -226,6 +230,10 @@ int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
  * (:350-364) incl. NumPy's float32 exp and the int32 truncation.
  *   is_fcos       : 0 = anchor (tx,ty,tw,th) decoding, 1 = point (l,t,r,b) decoding
  *   min_score     : the threshold given to b200det_score_argmax (sizes the selection histogram)
+ *   scales/sizes/to_xywh : optional evaluation glue of the reference's test loop, fused into the
+ *                   epilogue (tools/scripts.py:742-757): scales = device float32 [B] -> boxes /=
+ *                   scale; sizes = device float32 [B,2] (h,w) -> clip x1,y1 >= 0, x2 <= w, y2 <= h
+ *                   and, if to_xywh, x2,y2 -> w,h.  NULL = the decoder's plain output.
  *   out           : device float32 [6*B*max_out]: scores [B,max_out] (pad -1), classes
  *                   [B,max_out] (pad -1), boxes [B,max_out,4] (pad 0), back to back
  *   order / keep  : NULL or device int32 [B,topn] (pad -1): image-major row index of the sorted
@@ -236,7 +244,8 @@ int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
 int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
                               const int32_t *classes, const void *const *reg, int reg_dtype,
                               int is_fcos, float min_score, int topn, int max_out, int nms_type,
-                              double nms_threshold, float *out, int32_t *order, int32_t *keep,
+                              double nms_threshold, const float *scales, const float *sizes,
+                              int to_xywh, float *out, int32_t *order, int32_t *keep,
                               int32_t *counts, void *workspace, size_t workspace_bytes,
                               void *stream);
 
@@ -254,6 +263,9 @@ typedef struct b200det_decode_params {
     int32_t is_fcos, reg_dtype, topn, max_out, nms_type;
     float min_score;
     double nms_threshold;
+    const float *scales;  /* device [B] or NULL, see b200det_select_decode_nms */
+    const float *sizes;   /* device [B,2] (h,w) or NULL */
+    int32_t to_xywh;
 } b200det_decode_params;
 
 /*
@@ -268,6 +280,20 @@ int b200det_loss_forward(const b200det_geometry *geo, const b200det_loss_params 
                          const void *const *reg, const void *const *ctr, int32_t *labels,
                          void *workspace, size_t workspace_bytes, double *sums, float *losses,
                          void *stream);
+
+/*
+ * Training-step forward of the losses in one call (single process group member; with a sharded
+ * normaliser use the per-kernel calls and all-reduce `sums` in between): assignment, sparse
+ * losses writing d(box)/d(reg) and d(ctr), reduce, label-aware focal sweep writing d(cls) already
+ * multiplied by w_cls / positives, reduce, finish.  reg_grad / ctr_grad must be zeroed by the
+ * caller (only the positives' rows are written).
+ */
+int b200det_loss_forward_grad(const b200det_geometry *geo, const b200det_loss_params *params,
+                              const float *annotations, int max_gt, const void *const *cls,
+                              const void *const *reg, const void *const *ctr, int32_t *labels,
+                              void *const *cls_grad, void *const *reg_grad,
+                              void *const *ctr_grad, void *workspace, size_t workspace_bytes,
+                              double *sums, float *losses, void *stream);
 
 /*
  * Whole RetinaDecoder.__call__ / FCOSDecoder.__call__ (decode.py:201-249, :293-348) up to the

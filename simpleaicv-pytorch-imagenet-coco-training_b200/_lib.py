@@ -71,6 +71,9 @@ class DecodeParams(ctypes.Structure):
         ('nms_type', ctypes.c_int32),
         ('min_score', ctypes.c_float),
         ('nms_threshold', ctypes.c_double),
+        ('scales', ctypes.c_void_p),
+        ('sizes', ctypes.c_void_p),
+        ('to_xywh', ctypes.c_int32),
     ]
 
 
@@ -90,6 +93,13 @@ SIGNATURES = {
     'b200det_loss_forward': (ctypes.c_int, [
         _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vp,
         ctypes.c_size_t, _vp, _vp, _vp
+    ]),
+    'b200det_loss_forward_grad': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vpp, _vpp,
+        _vpp, _vp, ctypes.c_size_t, _vp, _vp, _vp
+    ]),
+    'b200det_scale_levels': (ctypes.c_int, [
+        _vpp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp, _vp, ctypes.c_float, _vp
     ]),
     'b200det_decode': (ctypes.c_int, [
         _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp
@@ -117,7 +127,8 @@ SIGNATURES = {
     'b200det_score_argmax': (ctypes.c_int, [_geo, _vpp, _vpp, ctypes.c_float, _vp, _vp, _vp]),
     'b200det_select_decode_nms': (ctypes.c_int, [
         _geo, _vp, _vp, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
-        ctypes.c_int, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
+        ctypes.c_int, ctypes.c_int, ctypes.c_double, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp,
+        _vp, ctypes.c_size_t, _vp
     ]),
     'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
     'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),

@@ -44,6 +44,46 @@ extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_l
     return rc;
 }
 
+extern "C" int b200det_loss_forward_grad(const b200det_geometry *geo, const b200det_loss_params *p,
+                                         const float *annotations, int max_gt,
+                                         const void *const *cls, const void *const *reg,
+                                         const void *const *ctr, int32_t *labels,
+                                         void *const *cls_grad, void *const *reg_grad,
+                                         void *const *ctr_grad, void *workspace,
+                                         size_t workspace_bytes, double *sums, float *losses,
+                                         void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!p || !annotations || !cls || !labels || !workspace || !sums || !cls_grad || !losses)
+        return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    char *base = static_cast<char *>(workspace);
+    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
+                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
+                                    (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    g_skip_memset = true;
+    rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample, labels,
+                                          nullptr, nullptr, workspace, workspace_bytes, stream)
+                    : b200det_retina_assign(geo, annotations, max_gt, labels, nullptr, workspace,
+                                            workspace_bytes, stream);
+    if (!rc)
+        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
+                                   ctr, p->box_loss, p->beta, nullptr, p->alpha, p->gamma,
+                                   reg_grad, ctr_grad, workspace, workspace_bytes, stream);
+    // the positive count must exist before the sweep: it scales the gradient it writes
+    if (!rc) rc = b200det_loss_reduce(geo, 1, workspace, workspace_bytes, sums, stream);
+    if (!rc)
+        rc = b200det_focal_loss(geo, cls, labels, p->alpha, p->gamma, cls_grad, sums, p->w_cls,
+                                workspace, workspace_bytes, stream);
+    g_skip_memset = false;
+    if (!rc) rc = b200det_loss_reduce(geo, 2, workspace, workspace_bytes, sums, stream);
+    if (!rc) rc = b200det_loss_finish(sums, p->w_cls, p->w_box, p->w_ctr, losses, stream);
+    return rc;
+}
+
 extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *p,
                               const void *const *cls, const void *const *ctr,
                               const void *const *reg, uint32_t *keys, int32_t *classes,
@@ -55,7 +95,7 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
     if (!rc)
         rc = b200det_select_decode_nms(geo, keys, classes, reg, p->reg_dtype, p->is_fcos,
                                        p->min_score, p->topn, p->max_out, p->nms_type,
-                                       p->nms_threshold, out, order, keep, counts, nullptr, 0,
-                                       stream);
+                                       p->nms_threshold, p->scales, p->sizes, p->to_xywh, out,
+                                       order, keep, counts, nullptr, 0, stream);
     return rc;
 }

@@ -158,6 +158,9 @@ struct SelectArgs {
     BaseAnchors ba;
     PtrTab reg;
     int reg_dtype, is_fcos, topn, pad_n /* pow2 >= topn */, max_out, nms_type;
+    const float *scales;   // [B] or NULL: boxes /= scale  (tools/scripts.py:742)
+    const float *sizes;    // [B,2] (h, w) or NULL: clip to the original image (:749-754)
+    int to_xywh;           // with sizes: x2,y2 -> w,h (:757)
     uint32_t key_lo;   // flipped key of the score threshold: every candidate key is > key_lo
     int key_shift;     // pass-A bin = min((key - key_lo) >> key_shift, kBins - 1)
     float nms_thr_f;
@@ -583,6 +586,25 @@ __global__ void __launch_bounds__(kSelThreads)
             c = (float)scls[k];
             bx = sbox[k];
         }
+        // optional evaluation glue of the reference's test loop (tools/scripts.py:742-757); padded
+        // rows stay all-zero through it exactly as they do in NumPy
+        if (a.scales) {
+            const float sc = __ldg(a.scales + b);
+            bx.x = __fdiv_rn(bx.x, sc);
+            bx.y = __fdiv_rn(bx.y, sc);
+            bx.z = __fdiv_rn(bx.z, sc);
+            bx.w = __fdiv_rn(bx.w, sc);
+        }
+        if (a.sizes) {
+            bx.x = fmaxf(bx.x, 0.f);
+            bx.y = fmaxf(bx.y, 0.f);
+            bx.z = fminf(bx.z, __ldg(a.sizes + 2 * b + 1));
+            bx.w = fminf(bx.w, __ldg(a.sizes + 2 * b + 0));
+            if (a.to_xywh) {
+                bx.z = __fsub_rn(bx.z, bx.x);
+                bx.w = __fsub_rn(bx.w, bx.y);
+            }
+        }
         out_scores[i] = s;
         out_classes[i] = c;
         reinterpret_cast<float4 *>(out_boxes)[i] = bx;
@@ -682,6 +704,7 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
                                          const int32_t *classes, const void *const *reg,
                                          int reg_dtype, int is_fcos, float min_score, int topn,
                                          int max_out, int nms_type, double nms_threshold,
+                                         const float *scales, const float *sizes, int to_xywh,
                                          float *out,
                                          int32_t *order, int32_t *keep, int32_t *counts,
                                          void *workspace, size_t workspace_bytes, void *stream) {
@@ -721,6 +744,9 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
     a.nms_type = nms_type;
     a.nms_thr_f = (float)nms_threshold;
     a.nms_thr_d = nms_threshold;
+    a.scales = scales;
+    a.sizes = sizes;
+    a.to_xywh = to_xywh;
     {
         // host copies of flip_key(): bins span (min_score, max(1, 2*min_score)] in key space
         auto flip = [](float f) {

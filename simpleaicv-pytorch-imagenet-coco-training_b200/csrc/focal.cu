@@ -442,6 +442,26 @@ __global__ void loss_finish_kernel(const double *__restrict__ sums, float w_cls,
     }
 }
 
+struct ScaleArgs {
+    float *ptr[kMaxLevels];
+    long long count[kMaxLevels];
+};
+// x[l][i] *= (*g) * (sums ? weight / sums[0] : 1); whole call skipped when the factor is 1
+__global__ void scale_levels_kernel(ScaleArgs a, const float *__restrict__ g,
+                                    const double *__restrict__ sums, float weight) {
+    float k = *g;
+    if (sums) {
+        const double npos = sums[0];
+        k = npos > 0.0 ? (float)((double)k * (double)weight / npos) : 0.f;
+    }
+    if (k == 1.f) return;
+    float *x = a.ptr[blockIdx.y];
+    const long long n = a.count[blockIdx.y];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        x[i] *= k;
+}
+
 __global__ void scale_kernel(float *__restrict__ x, long long n, const float *__restrict__ s) {
     const float k = *s;
     if (k == 1.f) return;
@@ -651,6 +671,32 @@ extern "C" int b200det_loss_finish(const double *sums, float w_cls, float w_box,
     if (!sums || !losses) return B200DET_EINVAL;
     ProfScope prof(kKernFinish, stream);
     loss_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, w_cls, w_box, w_ctr, losses);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200det_scale_levels(void *const *ptrs, const long long *counts, int n_levels,
+                                    const float *g_dev, const double *sums, float weight,
+                                    void *stream) {
+    if (!ptrs || !counts || !g_dev || n_levels < 1 || n_levels > kMaxLevels) return B200DET_EINVAL;
+    ScaleArgs a;
+    long long mx = 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        a.ptr[l] = nullptr;
+        a.count[l] = 0;
+    }
+    for (int l = 0; l < n_levels; ++l) {
+        if (!ptrs[l] || counts[l] < 0) return B200DET_EINVAL;
+        a.ptr[l] = static_cast<float *>(ptrs[l]);
+        a.count[l] = counts[l];
+        if (counts[l] > mx) mx = counts[l];
+    }
+    if (mx == 0) return 0;
+    long long blocks = (mx + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    ProfScope prof(kKernOther, stream);
+    scale_levels_kernel<<<dim3((unsigned)blocks, (unsigned)n_levels), 256, 0, (cudaStream_t)stream>>>(
+        a, g_dev, sums, weight);
     count_launch();
     return (int)cudaGetLastError();
 }

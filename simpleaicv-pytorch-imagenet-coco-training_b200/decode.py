@@ -51,7 +51,7 @@ class _DecoderBase:
             self._pinned = torch.empty(numel, dtype=torch.float32, pin_memory=True)
         return self._pinned
 
-    def _run(self, preds, details=False):
+    def _run(self, preds, details=False, scales=None, sizes=None, to_xywh=False):
         lib = _lib.load()
         if self._is_fcos:
             cls_preds, reg_preds, center_preds = preds
@@ -85,6 +85,21 @@ class _DecoderBase:
             counts = torch.empty(batch * 3, dtype=torch.int32, device=device)
         params = self._params
         params.reg_dtype = reg_dtype
+        glue = []   # keeps the small device tensors alive until the call has been enqueued
+        params.scales = params.sizes = None
+        params.to_xywh = int(bool(to_xywh))
+        if scales is not None:
+            t = torch.as_tensor(np.asarray(scales, dtype=np.float32).reshape(-1)).to(device)
+            if t.numel() != batch:
+                raise ValueError('scales must have one entry per image')
+            glue.append(t)
+            params.scales = t.data_ptr()
+        if sizes is not None:
+            t = torch.as_tensor(np.asarray(sizes, dtype=np.float32).reshape(-1)).to(device)
+            if t.numel() != 2 * batch:
+                raise ValueError('sizes must be [B, 2] = (height, width) per image')
+            glue.append(t)
+            params.sizes = t.data_ptr()
         keys_ptr = scratch.data_ptr()
         _lib.check(
             lib.b200det_decode(geo_ref, ctypes.byref(params), _lib.ptr_array(cls),
@@ -115,8 +130,12 @@ class _DecoderBase:
         }
         return result, info
 
-    def __call__(self, preds):
-        return self._run(preds, details=False)
+    def __call__(self, preds, scales=None, sizes=None, to_xywh=False):
+        """decoder(preds) is the reference call.  The optional arguments fuse the evaluation glue
+        of the reference's test loop into the kernel epilogue (tools/scripts.py:742-757):
+        `scales` [B] -> boxes /= scale; `sizes` [B,2] = (h, w) -> clip to the original image and,
+        with to_xywh=True, convert x2,y2 to w,h (COCO json format)."""
+        return self._run(preds, details=False, scales=scales, sizes=sizes, to_xywh=to_xywh)
 
     def decode_with_details(self, preds):
         """Parity hook: also returns per image the sorted top-n row indices ('order', -1 padded),

@@ -211,49 +211,74 @@ class _DetLossFunction(torch.autograd.Function):
         w_box = float(owner.box_loss_weight)
         w_ctr = float(getattr(owner, 'center_ness_loss_weight', 0.))
 
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-        labels = torch.empty(plan.batch * plan.n_rows, dtype=torch.int32, device=device)
+        scratch = torch.empty(ws_bytes + 4 * plan.batch * plan.n_rows, dtype=torch.uint8,
+                              device=device)           # workspace | labels
+        ws_ptr = scratch.data_ptr()
+        labels_ptr = ws_ptr + ws_bytes
         out = torch.zeros(12, dtype=torch.float64, device=device)   # sums | focal sums | losses
         sums, focal = out[0:4], out[4:8]
         losses = out[8:12].view(torch.float32)
-        # the sparse kernel writes the rows of the positives only
-        reg_grad = [torch.zeros(r.shape, dtype=torch.float32, device=device) for r in reg]
-        ctr_grad = [torch.zeros_like(c) for c in ctr] if is_fcos else None
-        cls_grad = [torch.empty_like(c) for c in cls]
 
-        if is_fcos:
+        def flat_like(levels, dtype, zero):
+            """one allocation for all levels' gradients; returns (flat, per-level views)"""
+            sizes = [t.numel() for t in levels]
+            flat = (torch.zeros if zero else torch.empty)(sum(sizes), dtype=dtype, device=device)
+            views, o = [], 0
+            for t, n_el in zip(levels, sizes):
+                views.append(flat[o:o + n_el].view(t.shape))
+                o += n_el
+            return flat, views
+
+        # the sparse kernel writes the rows of the positives only -> zero-initialised
+        _, reg_grad = flat_like(reg, torch.float32, True)
+        ctr_grad = flat_like(ctr, torch.float32, True)[1] if is_fcos else None
+        _, cls_grad = flat_like(cls, torch.float32, False)
+
+        sync = owner.sync_normalizer and torch.distributed.is_available() \
+            and torch.distributed.is_initialized()
+        if not sync:
+            params = _loss_params(owner, reg_dtype)
             _lib.check(
-                lib.b200det_fcos_assign(geo, annotations.data_ptr(), max_gt,
-                                        int(owner.use_center_sample), labels.data_ptr(), None,
-                                        None, ws.data_ptr(), ws_bytes, st), 'b200det_fcos_assign')
+                lib.b200det_loss_forward_grad(geo, ctypes.byref(params), annotations.data_ptr(),
+                                              max_gt, _lib.ptr_array(cls), _lib.ptr_array(reg),
+                                              _lib.ptr_array(ctr), labels_ptr,
+                                              _lib.ptr_array(cls_grad), _lib.ptr_array(reg_grad),
+                                              _lib.ptr_array(ctr_grad), ws_ptr, ws_bytes,
+                                              sums.data_ptr(), losses.data_ptr(), st),
+                'b200det_loss_forward_grad')
         else:
+            group = owner.process_group
+            if is_fcos:
+                _lib.check(
+                    lib.b200det_fcos_assign(geo, annotations.data_ptr(), max_gt,
+                                            int(owner.use_center_sample), labels_ptr, None, None,
+                                            ws_ptr, ws_bytes, st), 'b200det_fcos_assign')
+            else:
+                _lib.check(
+                    lib.b200det_retina_assign(geo, annotations.data_ptr(), max_gt, labels_ptr,
+                                              None, ws_ptr, ws_bytes, st),
+                    'b200det_retina_assign')
             _lib.check(
-                lib.b200det_retina_assign(geo, annotations.data_ptr(), max_gt, labels.data_ptr(),
-                                          None, ws.data_ptr(), ws_bytes, st),
-                'b200det_retina_assign')
-        _lib.check(
-            lib.b200det_sparse_losses(geo, int(is_fcos), annotations.data_ptr(), max_gt,
-                                      labels.data_ptr(), _lib.ptr_array(reg), reg_dtype,
-                                      _lib.ptr_array(ctr), owner._box_code, float(owner.beta),
-                                      None, alpha, gamma, _lib.ptr_array(reg_grad),
-                                      _lib.ptr_array(ctr_grad), ws.data_ptr(), ws_bytes, st),
-            'b200det_sparse_losses')
-        # the focal gradient is written once, already divided by the (global) positive count, so
-        # the count has to exist before the sweep
-        _lib.check(lib.b200det_loss_reduce(geo, 1, ws.data_ptr(), ws_bytes, sums.data_ptr(), st),
-                   'b200det_loss_reduce')
-        sync, group = owner.sync_normalizer, owner.process_group
-        _maybe_all_reduce(sums, sync, group)
-        _lib.check(
-            lib.b200det_focal_loss(geo, _lib.ptr_array(cls), labels.data_ptr(), alpha, gamma,
-                                   _lib.ptr_array(cls_grad), sums.data_ptr(), w_cls,
-                                   ws.data_ptr(), ws_bytes, st), 'b200det_focal_loss')
-        _lib.check(lib.b200det_loss_reduce(geo, 2, ws.data_ptr(), ws_bytes, focal.data_ptr(), st),
-                   'b200det_loss_reduce')
-        _maybe_all_reduce(focal, sync, group)
-        sums.add_(focal)
-        _lib.check(lib.b200det_loss_finish(sums.data_ptr(), w_cls, w_box, w_ctr,
-                                           losses.data_ptr(), st), 'b200det_loss_finish')
+                lib.b200det_sparse_losses(geo, int(is_fcos), annotations.data_ptr(), max_gt,
+                                          labels_ptr, _lib.ptr_array(reg), reg_dtype,
+                                          _lib.ptr_array(ctr), owner._box_code,
+                                          float(owner.beta), None, alpha, gamma,
+                                          _lib.ptr_array(reg_grad), _lib.ptr_array(ctr_grad),
+                                          ws_ptr, ws_bytes, st), 'b200det_sparse_losses')
+            # the focal gradient is written once, already divided by the GLOBAL positive count
+            _lib.check(lib.b200det_loss_reduce(geo, 1, ws_ptr, ws_bytes, sums.data_ptr(), st),
+                       'b200det_loss_reduce')
+            _maybe_all_reduce(sums, True, group)
+            _lib.check(
+                lib.b200det_focal_loss(geo, _lib.ptr_array(cls), labels_ptr, alpha, gamma,
+                                       _lib.ptr_array(cls_grad), sums.data_ptr(), w_cls, ws_ptr,
+                                       ws_bytes, st), 'b200det_focal_loss')
+            _lib.check(lib.b200det_loss_reduce(geo, 2, ws_ptr, ws_bytes, focal.data_ptr(), st),
+                       'b200det_loss_reduce')
+            _maybe_all_reduce(focal, True, group)
+            sums.add_(focal)
+            _lib.check(lib.b200det_loss_finish(sums.data_ptr(), w_cls, w_box, w_ctr,
+                                               losses.data_ptr(), st), 'b200det_loss_finish')
 
         ctx.n_levels = n_levels
         ctx.is_fcos = is_fcos
@@ -277,25 +302,30 @@ class _DetLossFunction(torch.autograd.Function):
         ctr_grad = saved[1 + 2 * n:1 + 3 * n]
         want_cls, want_reg, want_ctr = ctx.want
         st = _stream()
-        npos = sums[0].float()
-        inv = torch.where(npos > 0, 1.0 / npos.clamp(min=1.), torch.zeros_like(npos))
         grads = [None] * (3 * n if ctx.is_fcos else 2 * n)
+
+        def scale(levels, g, with_norm, weight):
+            """levels[l] *= g * (weight / positives if with_norm else 1): one launch"""
+            counts = (ctypes.c_longlong * n)(*[t.numel() for t in levels])
+            g = g.detach().float().contiguous()
+            _lib.check(
+                lib.b200det_scale_levels(_lib.ptr_array(levels), counts, n, g.data_ptr(),
+                                         sums.data_ptr() if with_norm else None, weight, st),
+                'b200det_scale_levels')
+
         if want_cls:
-            g = grad_out[0].detach().float().contiguous()
+            # already scaled by cls_loss_weight / positives; only the upstream scalar is left
+            scale(cls_grad, grad_out[0], False, 1.0)
             for i in range(n):
-                # already scaled by cls_loss_weight / positives; only the upstream scalar is left
-                _lib.check(
-                    lib.b200det_scale_f32(cls_grad[i].data_ptr(), cls_grad[i].numel(),
-                                          g.data_ptr(), st), 'b200det_scale_f32')
                 grads[i] = cls_grad[i].view(ctx.in_shapes[i]).to(ctx.in_dtypes[i])
         if want_reg:
-            s = grad_out[1].detach().float() * ctx.weights[0] * inv
+            scale(reg_grad, grad_out[1], True, ctx.weights[0])
             for i in range(n):
-                grads[n + i] = (reg_grad[i] * s).view(ctx.in_shapes[n + i]).to(ctx.in_dtypes[n + i])
+                grads[n + i] = reg_grad[i].view(ctx.in_shapes[n + i]).to(ctx.in_dtypes[n + i])
         if want_ctr:
-            s = grad_out[2].detach().float() * ctx.weights[1] * inv
+            scale(ctr_grad, grad_out[2], True, ctx.weights[1])
             for i in range(n):
-                grads[2 * n + i] = (ctr_grad[i] * s).view(ctx.in_shapes[2 * n + i]).to(
+                grads[2 * n + i] = ctr_grad[i].view(ctx.in_shapes[2 * n + i]).to(
                     ctx.in_dtypes[2 * n + i])
         return (None, None, None, *grads)
 

@@ -436,6 +436,31 @@ def test_non_default_focal_parameters_and_weights():
                  [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, 'RetinaLoss')
 
 
+def test_fused_eval_glue_matches_numpy_post_processing():
+    """boxes /= scale, clip to the image, xyxy -> xywh
+    (tools/scripts.py:742-757) fused into the decoder epilogue; bit-exact vs NumPy on the oracle."""
+    preds = synth.make_tie_free(synth.make_retina_preds(3, 128, 8, seed=12))
+    scales = np.array([0.5, 1.25, 0.8], dtype=np.float32)
+    sizes = np.array([[200., 260.], [90., 100.], [150., 120.]], dtype=np.float32)   # (h, w)
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    s, c, b = dec(dev(preds), scales=scales, sizes=sizes, to_xywh=True)
+    (s0, c0, b0), _ = O.retina_decode(preds, **synth.RETINA_KW)
+    b0 = b0.copy()
+    b0 /= np.expand_dims(np.expand_dims(scales, axis=-1), axis=-1)
+    for i in range(3):
+        b0[i][:, 0] = np.maximum(b0[i][:, 0], 0)
+        b0[i][:, 1] = np.maximum(b0[i][:, 1], 0)
+        b0[i][:, 2] = np.minimum(b0[i][:, 2], sizes[i][1])
+        b0[i][:, 3] = np.minimum(b0[i][:, 3], sizes[i][0])
+        b0[i][:, 2:] -= b0[i][:, :2]
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0, 'rescaled / clipped / xywh boxes')
+    s1, c1, b1 = dec(dev(preds), scales=scales)       # rescale only
+    (_, _, b2), _ = O.retina_decode(preds, **synth.RETINA_KW)
+    G.assert_bit_equal(b1, b2 / scales[:, None, None], 'rescaled boxes')
+
+
 def test_cpu_tensors_are_rejected():
     preds = synth.make_retina_preds(1, 128, 8, seed=8)
     ann = synth.make_annotations(1, 4, 128, 8, seed=9)
