@@ -208,6 +208,9 @@ int b200det_scale_levels(void *const *ptrs, const long long *counts, int n_level
 int b200det_scale_f32(float *x, long long n, const float *scale_dev, void *stream);
 
 /* ---- decode ------------------------------------------------------------------------- */
+/* scratch for b200det_select_decode_nms / b200det_decode (per-image global histograms, counters
+ * and candidate lists of the multi-CTA selection front end).  Optional: with workspace == NULL
+ * the whole selection runs in one CTA per image (slower for small batches). */
 size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, int topn);
 
 /*
@@ -302,7 +305,7 @@ int b200det_loss_forward_grad(const b200det_geometry *geo, const b200det_loss_pa
 int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *params,
                    const void *const *cls, const void *const *ctr, const void *const *reg,
                    uint32_t *keys, int32_t *classes, float *out, int32_t *order, int32_t *keep,
-                   int32_t *counts, void *stream);
+                   int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- utilities (tests / parity outputs) ---------------------------------------------- */
 /* dst[b*N + off_l + i] = src[B*off_l + b*n_l + i] for `width` int32/float32 words per row */

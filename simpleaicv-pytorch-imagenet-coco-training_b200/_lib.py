@@ -102,7 +102,8 @@ SIGNATURES = {
         _vpp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp, _vp, ctypes.c_float, _vp
     ]),
     'b200det_decode': (ctypes.c_int, [
-        _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp
+        _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+        ctypes.c_size_t, _vp
     ]),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
     'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),

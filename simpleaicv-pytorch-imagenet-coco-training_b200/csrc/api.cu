@@ -88,7 +88,7 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
                               const void *const *cls, const void *const *ctr,
                               const void *const *reg, uint32_t *keys, int32_t *classes,
                               float *out, int32_t *order, int32_t *keep, int32_t *counts,
-                              void *stream) {
+                              void *workspace, size_t workspace_bytes, void *stream) {
     if (!p) return B200DET_EINVAL;
     int rc = b200det_score_argmax(geo, cls, p->is_fcos ? ctr : nullptr, p->min_score, keys,
                                   classes, stream);
@@ -96,6 +96,6 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
         rc = b200det_select_decode_nms(geo, keys, classes, reg, p->reg_dtype, p->is_fcos,
                                        p->min_score, p->topn, p->max_out, p->nms_type,
                                        p->nms_threshold, p->scales, p->sizes, p->to_xywh, out,
-                                       order, keep, counts, nullptr, 0, stream);
+                                       order, keep, counts, workspace, workspace_bytes, stream);
     return rc;
 }

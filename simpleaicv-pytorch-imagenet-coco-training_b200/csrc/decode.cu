@@ -146,6 +146,78 @@ __global__ void __launch_bounds__(kArgThreads)
     }
 }
 
+// Variant for class counts that are not a multiple of 4 (e.g. Objects365's 365): rows are not
+// 16-byte aligned, but a tile of R rows with R % 4 == 0 is, so the tile is still read as one flat
+// stream of 128-bit loads, parked RAW in shared memory, and each row is scanned from there by
+// t2 lanes (consecutive lanes read consecutive floats: conflict-free).
+__global__ void __launch_bounds__(kArgThreads)
+    score_argmax_raw_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
+    extern __shared__ __align__(16) unsigned char arg_smem[];
+    float *tile = reinterpret_cast<float *>(arg_smem);
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
+    const long long row0 = (long long)(blockIdx.x - a.block_off[l]) * a.rows_per_block;
+    const int n_rows = (int)min((long long)a.rows_per_block, a.rows[l] - row0);
+    const int n_floats = n_rows * a.C;
+    const int n_vec = n_floats >> 2;
+    const float *src = static_cast<const float *>(a.cls.p[l]) + row0 * a.C;   // 16-byte aligned
+
+    float4 v[kArgLoadsVec];
+#pragma unroll
+    for (int k = 0; k < kArgLoadsVec; ++k) {
+        const int u = k * kArgThreads + threadIdx.x;
+        if (u < n_vec) v[k] = __ldcs(reinterpret_cast<const float4 *>(src) + u);
+    }
+#pragma unroll
+    for (int k = 0; k < kArgLoadsVec; ++k) {
+        const int u = k * kArgThreads + threadIdx.x;
+        if (u < n_vec) reinterpret_cast<float4 *>(tile)[u] = v[k];
+    }
+    if (threadIdx.x < (n_floats & 3)) {   // tail of the last tile of a level
+        const int i = (n_vec << 2) + threadIdx.x;
+        tile[i] = __ldcs(src + i);
+    }
+    __syncthreads();
+
+    const int j = threadIdx.x & (a.t2 - 1);
+    for (int r = threadIdx.x >> a.t2_shift; r < a.rows_per_block; r += kArgThreads >> a.t2_shift) {
+        const bool live = r < n_rows;
+        float best = -__int_as_float(0x7f800000);
+        int best_c = 0x7fffffff;
+        if (live) {
+            const float *row = tile + r * a.C;
+            for (int c = j; c < a.C; c += a.t2) {
+                const float x = row[c];
+                if (x > best) {  // strict: first maximum in class order (np.argmax)
+                    best = x;
+                    best_c = c;
+                }
+            }
+        }
+        for (int o = a.t2 >> 1; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ov > best || (ov == best && oc < best_c)) {
+                best = ov;
+                best_c = oc;
+            }
+        }
+        if (live && j == 0) {
+            const long long row_g = row0 + r;
+            float score = best;
+            if (a.has_ctr) {
+                const float c = __ldg(static_cast<const float *>(a.ctr.p[l]) + row_g);
+                score = __fsqrt_rn(__fmul_rn(best, c));
+            }
+            const long long lm = a.row_base[l] + row_g;
+            keys[lm] = (score > a.min_score) ? flip_key(score) : 0u;
+            classes[lm] = best_c;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // per-image select + decode + NMS
 // ---------------------------------------------------------------------------------------
@@ -204,6 +276,140 @@ __device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t
     }
 }
 
+// Given a 2048-bin histogram in shared memory (bin index grows with the key), finds the bin where
+// the count from the top crosses `topn`: returns that bin, the number of keys in higher bins, the
+// bin's own count and the total.  Thread t owns bins 2t, 2t+1 (kSelThreads == kBins / 2).
+__device__ __forceinline__ void find_cut(const int *hist, int topn, int *scratch, int *s_digit,
+                                         int *s_above, int *s_count, int *s_total, int &cut_bin,
+                                         int &above, int &in_bin, int &total_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+    const int mine = h0 + h1;
+    int suf = mine;  // inclusive suffix sum within the warp (higher lanes = higher bins)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += t;
+    }
+    __syncthreads();
+    if (lane == 0) scratch[warp] = suf;
+    __syncthreads();
+    int above_warps = 0, total = 0;
+    for (int w = 0; w < kSelWarps; ++w) {
+        const int c = scratch[w];
+        total += c;
+        if (w > warp) above_warps += c;
+    }
+    const int need = min(topn, total);
+    const int above_excl = above_warps + suf - mine;
+    if (tid == 0) {
+        *s_digit = 0;      // fewer candidates than topn (or none): take everything
+        *s_above = 0;
+        *s_count = total;
+        *s_total = total;
+    }
+    __syncthreads();
+    if (total > topn && above_excl < need && need <= above_excl + mine) {
+        if (need <= above_excl + h1) {
+            *s_digit = 2 * tid + 1;
+            *s_above = above_excl;
+            *s_count = h1;
+        } else {
+            *s_digit = 2 * tid;
+            *s_above = above_excl + h1;
+            *s_count = h0;
+        }
+    }
+    __syncthreads();
+    cut_bin = *s_digit;
+    above = *s_above;
+    in_bin = *s_count;
+    total_out = *s_total;
+    __syncthreads();
+}
+
+// visit the keys of image b whose image-major row lies in [r0, r1)
+template <typename F>
+__device__ __forceinline__ void for_each_key_range(const Geo &g, int b,
+                                                   const uint32_t *__restrict__ keys, int r0, int r1,
+                                                   F f) {
+    for (int l = 0; l < g.n_levels; ++l) {
+        const int lo = max(r0, g.off[l]) - g.off[l];
+        const int hi = min(r1, g.off[l + 1]) - g.off[l];
+        if (lo >= hi) continue;
+        const uint32_t *p = keys + lm_index(g, b, l, 0);
+        const int off = g.off[l];
+#pragma unroll 4
+        for (int j = lo + (int)threadIdx.x; j < hi; j += kSelThreads) f(__ldg(p + j), off + j);
+    }
+}
+
+// ---- multi-CTA front end of the selection (used when an image has enough rows to split) ----
+// select_hist_kernel   : grid (slices, B): each CTA histograms its slice of the image's keys in
+//                        shared memory and adds the non-empty bins to the image's global histogram
+// select_collect_kernel: grid (slices, B): every CTA derives the cut bin from the global
+//                        histogram and appends its slice's keys at or above it to the image's list
+// select_nms_kernel then only loads the list (<= 2*pad_n entries), sorts, decodes and runs NMS.
+struct PreArgs {
+    Geo g;
+    uint32_t key_lo;
+    int key_shift, slices, rows_per_slice, topn, cap;
+};
+
+__global__ void __launch_bounds__(kSelThreads)
+    select_hist_kernel(PreArgs a, const uint32_t *__restrict__ keys, int *__restrict__ ghist) {
+    __shared__ int hist[kBins];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    const int r0 = blockIdx.x * a.rows_per_slice;
+    for_each_key_range(a.g, b, keys, r0, r0 + a.rows_per_slice, [&](uint32_t k, int) {
+        if (k) atomicAdd(&hist[min((k - a.key_lo) >> a.key_shift, (uint32_t)(kBins - 1))], 1);
+    });
+    __syncthreads();
+    for (int i = tid; i < kBins; i += kSelThreads)
+        if (hist[i]) atomicAdd(ghist + (size_t)b * kBins + i, hist[i]);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+    select_collect_kernel(PreArgs a, const uint32_t *__restrict__ keys,
+                          const int *__restrict__ ghist, unsigned long long *__restrict__ glist,
+                          int *__restrict__ gcount) {
+    extern __shared__ __align__(16) unsigned char pre_smem[];
+    int *hist = reinterpret_cast<int *>(pre_smem);
+    unsigned long long *slist = reinterpret_cast<unsigned long long *>(hist + kBins);  // cap
+    __shared__ int scratch[kSelWarps];
+    __shared__ int s_digit, s_above, s_count, s_total, s_base;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < kBins; i += kSelThreads) hist[i] = ghist[(size_t)b * kBins + i];
+    __syncthreads();
+    int cut_bin, above, in_bin, total;
+    find_cut(hist, a.topn, scratch, &s_digit, &s_above, &s_count, &s_total, cut_bin, above, in_bin,
+             total);
+    const int n_collect = total <= a.topn ? total : above + in_bin;
+    if (blockIdx.x == 0 && tid == 0) {
+        gcount[b * 4 + 0] = total;
+        gcount[b * 4 + 1] = n_collect;
+    }
+    if (n_collect > a.cap || n_collect == 0) return;   // crowded cut bin: the select kernel refines
+    uint32_t T = 1u;
+    if (total > a.topn && cut_bin > 0) T = a.key_lo + ((uint32_t)cut_bin << a.key_shift);
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const int r0 = blockIdx.x * a.rows_per_slice;
+    for_each_key_range(a.g, b, keys, r0, r0 + a.rows_per_slice, [&](uint32_t k, int row) {
+        if (k >= T && k != 0u)
+            slist[atomicAdd(&s_count, 1)] =
+                ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
+    });
+    __syncthreads();
+    const int n_local = s_count;
+    if (tid == 0) s_base = n_local ? atomicAdd(gcount + b * 4 + 2, n_local) : 0;
+    __syncthreads();
+    for (int i = tid; i < n_local; i += kSelThreads)
+        glist[(size_t)b * a.cap + s_base + i] = slist[i];
+}
+
 constexpr int kNmsWindow = 256;
 
 // does kept box kb suppress the later box ob?  (decode.py:45-100 / torchvision CPU nms)
@@ -243,7 +449,8 @@ __global__ void __launch_bounds__(kSelThreads)
     select_nms_kernel(SelectArgs a, const uint32_t *__restrict__ keys,
                       const int *__restrict__ classes, float *__restrict__ out,
                       int *__restrict__ order_out, int *__restrict__ keep_out,
-                      int *__restrict__ counts) {
+                      int *__restrict__ counts, const unsigned long long *__restrict__ glist,
+                      const int *__restrict__ gcount) {
     extern __shared__ __align__(16) unsigned char smem[];
     // carve: hist | key64 | box | cls | keep | removed
     int *hist = reinterpret_cast<int *>(smem);                                // kBins
@@ -265,6 +472,16 @@ __global__ void __launch_bounds__(kSelThreads)
     float *out_classes = out + (size_t)B * a.max_out + (size_t)b * a.max_out;
     float *out_boxes = out + (size_t)2 * B * a.max_out + (size_t)b * a.max_out * 4;
 
+    const int cap = 2 * a.pad_n;  // capacity of skey
+    int ncand, k_sel, n_got;
+    // ---- front end already done by select_hist/collect kernels? ----
+    const bool pre = glist != nullptr && gcount[b * 4 + 1] <= cap;
+    if (pre) {
+        ncand = gcount[b * 4 + 0];
+        k_sel = min(a.topn, ncand);
+        n_got = gcount[b * 4 + 1];
+        for (int i = tid; i < n_got; i += kSelThreads) skey[i] = glist[(size_t)b * cap + i];
+    } else {
     // ---- pass A: 2048-bin histogram of the keys over the expected score range ----
     // Candidate keys are > key_lo (the flipped threshold); keys above key_hi (scores > 1, not
     // produced by sigmoid heads) saturate into the top bin.  Bin D where the count from the top
@@ -277,52 +494,11 @@ __global__ void __launch_bounds__(kSelThreads)
         if (k) atomicAdd(&hist[min((k - lo) >> shift, (uint32_t)(kBins - 1))], 1);
     });
     __syncthreads();
-    int cut_bin, above, in_bin;
-    {
-        const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
-        const int mine = h0 + h1;
-        int suf = mine;  // inclusive suffix sum within the warp (higher lanes = higher bins)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(0xffffffffu, suf, o);
-            if (lane + o < 32) suf += t;
-        }
-        if (lane == 0) scratch[warp] = suf;
-        __syncthreads();
-        int above_warps = 0, total = 0;
-        for (int w = 0; w < kSelWarps; ++w) {
-            const int c = scratch[w];
-            total += c;
-            if (w > warp) above_warps += c;
-        }
-        const int need = min(a.topn, total);
-        const int above_excl = above_warps + suf - mine;
-        if (tid == 0) {
-            s_digit = 0;      // fewer candidates than topn (or none): take everything
-            s_above = 0;
-            s_count = total;
-            s_total = total;
-        }
-        __syncthreads();
-        if (total > a.topn && above_excl < need && need <= above_excl + mine) {
-            if (need <= above_excl + h1) {
-                s_digit = 2 * tid + 1;
-                s_above = above_excl;
-                s_count = h1;
-            } else {
-                s_digit = 2 * tid;
-                s_above = above_excl + h1;
-                s_count = h0;
-            }
-        }
-        __syncthreads();
-        cut_bin = s_digit;
-        above = s_above;
-        in_bin = s_count;
-    }
-    const int ncand = s_total;
-    const int k_sel = min(a.topn, ncand);
-    const int cap = 2 * a.pad_n;  // capacity of skey
+    int cut_bin, above, in_bin, ncand_all;
+    find_cut(hist, a.topn, scratch, &s_digit, &s_above, &s_count, &s_total, cut_bin, above, in_bin,
+             ncand_all);
+    ncand = ncand_all;
+    k_sel = min(a.topn, ncand);
     __syncthreads();
 
     uint32_t T = 1u;      // collect keys >= T ...
@@ -439,7 +615,9 @@ __global__ void __launch_bounds__(kSelThreads)
         }
     }
     __syncthreads();
-    const int n_got = s_count;  // == n_collect
+    n_got = s_count;  // == n_collect
+    }  // !pre
+    __syncthreads();
     const int n_sel = min(n_got, k_sel);  // after the sort only the first k_sel entries are used
     int sort_n = 1;
     while (sort_n < n_got) sort_n <<= 1;
@@ -511,39 +689,37 @@ __global__ void __launch_bounds__(kSelThreads)
     // the window test itself against it); when the window is exhausted the next kNmsWindow
     // candidates first test themselves against ALL boxes kept so far, then the loop resumes.
     // The keep list is identical to the full greedy scan.
+    // Only the kNmsWindow / 32 warps that own the window take part (named barrier 1); the other
+    // warps wait at the CTA barrier below.  One barrier per kept box: after it every participating
+    // warp re-derives the next alive index from the bitmask by itself.
     const int limit = keep_out ? n_sel : min(a.max_out, n_sel);
-    int n_keep = 0, cur = 0;
-    int win_end = min(n_sel, kNmsWindow);
-    while (n_keep < limit) {
-        if (warp == 0) {
-            // first alive index in [cur, win_end)
+    if (tid < kNmsWindow) {
+        int n_keep = 0, cur = 0;
+        int win_base = 0, win_end = min(n_sel, kNmsWindow);
+        while (n_keep < limit) {
+            // first alive index in [cur, win_end): the window spans <= 8 words, one per lane
             int found = -1;
-            const int win_words = (win_end + 31) >> 5;
-            for (int w0 = cur >> 5; w0 < win_words && found < 0; w0 += 32) {
-                const int w = w0 + lane;
+            {
+                const int w = (win_base >> 5) + lane;
                 uint32_t alive = 0u;
-                if (w < win_words) {
+                if (lane < (kNmsWindow >> 5) && (w << 5) < win_end) {
                     alive = ~srem[w];
                     if (w == (cur >> 5)) alive &= ~((1u << (cur & 31)) - 1u);
-                    if (w == win_words - 1 && (win_end & 31)) alive &= (1u << (win_end & 31)) - 1u;
+                    if (w < (cur >> 5)) alive = 0u;
+                    if (((w + 1) << 5) > win_end) alive &= (1u << (win_end & 31)) - 1u;
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, alive != 0u);
                 if (bal) {
                     const int src_lane = __ffs(bal) - 1;
                     const uint32_t word = __shfl_sync(0xffffffffu, alive, src_lane);
-                    found = ((w0 + src_lane) << 5) + (__ffs(word) - 1);
+                    found = (((win_base >> 5) + src_lane) << 5) + (__ffs(word) - 1);
                 }
             }
-            if (lane == 0) s_digit = found;
-        }
-        __syncthreads();
-        const int found = s_digit;
-        if (found < 0) {
-            if (win_end >= n_sel) break;
-            // slide the window: new candidates against everything kept so far
-            const int new_end = min(n_sel, win_end + kNmsWindow);
-            for (int j0 = win_end; j0 < new_end; j0 += kSelThreads) {
-                const int j = j0 + tid;
+            if (found < 0) {
+                if (win_end >= n_sel) break;
+                // slide the window: the new candidates against everything kept so far
+                const int new_end = min(n_sel, win_end + kNmsWindow);
+                const int j = win_end + tid;
                 bool suppress = false;
                 if (j < new_end) {
                     const float4 ob = sbox[j];
@@ -552,28 +728,28 @@ __global__ void __launch_bounds__(kSelThreads)
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, suppress);
                 if (lane == 0 && bal) srem[j >> 5] |= bal;  // each word is owned by one warp
+                cur = win_end;
+                win_base = win_end;
+                win_end = new_end;
+                asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
+                continue;
             }
-            cur = win_end;
-            win_end = new_end;
-            __syncthreads();
-            continue;
-        }
-        if (tid == 0) skeep[n_keep] = found;
-        ++n_keep;
-        if (n_keep >= limit) break;
-        const float4 kb = sbox[found];
-        for (int j0 = (found + 1) & ~31; j0 < win_end; j0 += kSelThreads) {
-            const int j = j0 + tid;
+            if (tid == 0) skeep[n_keep] = found;
+            ++n_keep;
+            if (n_keep >= limit) break;
+            const int j = win_base + tid;
             bool suppress = false;
             if (j > found && j < win_end)
-                suppress = nms_suppresses(kb, sbox[j], a.nms_type, a.nms_thr_f, a.nms_thr_d);
+                suppress = nms_suppresses(sbox[found], sbox[j], a.nms_type, a.nms_thr_f, a.nms_thr_d);
             const unsigned bal = __ballot_sync(0xffffffffu, suppress);
             if (lane == 0 && bal) srem[j >> 5] |= bal;
+            cur = found + 1;
+            asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
         }
-        cur = found + 1;
-        __syncthreads();
+        if (tid == 0) s_total = n_keep;
     }
     __syncthreads();
+    const int n_keep = s_total;
 
     // ---- outputs (decode.py:123-128, :158-167) ----
     const int n_out = min(n_keep, a.max_out);
@@ -634,10 +810,35 @@ static size_t select_smem_bytes(int pad_n) {
 
 using namespace b200det;
 
+// decode workspace: [global histograms B*kBins int | counters B*4 int | lists B*cap uint64]
+struct DecodeWs {
+    int slices, rows_per_slice, cap;
+    size_t off_hist, off_count, off_list, zero_bytes, total;
+};
+static DecodeWs decode_ws_layout(const Geo &g, int topn) {
+    DecodeWs w;
+    int pad_n = 32;
+    while (pad_n < topn) pad_n <<= 1;
+    w.cap = 2 * pad_n;
+    const int N = g.off[g.n_levels];
+    // one slice per ~16k rows: below two slices the single-CTA front end is just as fast
+    int slices = (N + 16383) / 16384;
+    if (slices > 16) slices = 16;
+    w.slices = slices;
+    w.rows_per_slice = (N + slices - 1) / slices;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    w.off_hist = 0;
+    w.off_count = up((size_t)g.batch * kBins * sizeof(int));
+    w.zero_bytes = w.off_count + up((size_t)g.batch * 4 * sizeof(int));
+    w.off_list = w.zero_bytes;
+    w.total = w.off_list + up((size_t)g.batch * w.cap * sizeof(unsigned long long));
+    return w;
+}
+
 extern "C" size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, int topn) {
-    (void)geo;
-    (void)topn;
-    return 256;  // the select kernel works entirely in shared memory; kept for ABI stability
+    Geo g;
+    if (make_geo(geo, &g) || topn < 1 || topn > B200DET_MAX_TOPN) return 0;
+    return decode_ws_layout(g, topn).total;
 }
 
 extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
@@ -649,21 +850,30 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
     if (!cls || !keys || !classes) return B200DET_EINVAL;
     ArgmaxArgs a;
     const int vec = (g.num_classes % 4 == 0) ? 4 : 1;
-    const uintptr_t amask = vec == 4 ? 15 : 3;
+    const uintptr_t amask = 15;   // both variants read the level tensors with 128-bit loads
     a.n_levels = g.n_levels;
     a.C = g.num_classes;
     a.min_score = min_score;
     a.has_ctr = ctr != nullptr;
     const int units = g.num_classes / vec;
     a.units_per_row = units;
-    // rows per CTA: 5 (vector) / <= 8 (scalar) loads per thread, all in flight at once
-    const int budget = kArgThreads * (vec == 4 ? kArgLoadsVec : kArgLoadsScalar);
-    int R = budget / units;
-    if (R < 1) R = 1;
-    if (R > kArgThreads) R = kArgThreads;
-    if (R * units > budget) return B200DET_ERANGE;  // more than 5120 (vector) / 2048 classes
+    const int budget = kArgThreads * kArgLoadsVec;   // 128-bit loads per CTA, all in flight
+    int R;
+    if (vec == 4) {
+        R = budget / units;
+        if (R < 1) R = 1;
+        if (R > kArgThreads) R = kArgThreads;
+        if (R * units > budget) return B200DET_ERANGE;   // more than 5120 classes
+        a.pitch = units | 1;
+    } else {
+        // raw tile: R rows, R % 4 == 0 so that every tile starts 16-byte aligned
+        R = (int)(((long long)budget * 4 / g.num_classes) & ~3ll);
+        if (R < 4) R = 4;
+        if (R > kArgThreads) R = kArgThreads;
+        if ((long long)R * g.num_classes > (long long)budget * 4) return B200DET_ERANGE;  // > 1280 classes
+        a.pitch = g.num_classes;
+    }
     a.rows_per_block = R;
-    a.pitch = units | 1;
     a.magic = (unsigned)(((1u << 24) + units - 1) / units);
     int t2 = 1, t2s = 0;
     while (t2 < 32 && (units + t2 - 1) / t2 > 32) {
@@ -689,13 +899,13 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
         blocks += (int)((a.rows[l] + R - 1) / R);
     }
     for (int l = g.n_levels; l <= kMaxLevels; ++l) a.block_off[l] = blocks;
-    const size_t smem = (size_t)R * a.pitch * 8;
+    const size_t smem = vec == 4 ? (size_t)R * a.pitch * 8 : (size_t)R * a.C * 4 + 16;
     if (smem > 48 * 1024) return B200DET_ERANGE;
     ProfScope prof(kKernArgmax, stream);
     if (vec == 4)
         score_argmax_kernel<4><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else
-        score_argmax_kernel<1><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
+        score_argmax_raw_kernel<<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -708,8 +918,6 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
                                          float *out,
                                          int32_t *order, int32_t *keep, int32_t *counts,
                                          void *workspace, size_t workspace_bytes, void *stream) {
-    (void)workspace;
-    (void)workspace_bytes;
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
@@ -770,9 +978,49 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
+    // multi-CTA front end (global histogram + collect) when the caller gave a workspace and an
+    // image is big enough to be worth splitting; otherwise the select kernel does it all
+    const unsigned long long *glist = nullptr;
+    const int *gcount = nullptr;
+    const DecodeWs dw = decode_ws_layout(g, topn);
     ProfScope prof(kKernSelect, stream);
-    select_nms_kernel<<<g.batch, kSelThreads, smem, (cudaStream_t)stream>>>(a, keys, classes, out,
-                                                                           order, keep, counts);
+    // (measured: at batch 256 every SM already holds two select CTAs and the extra launches cost
+    // more than they save; at batch 16 the front end is the critical path of 16 lonely CTAs)
+    if (workspace && workspace_bytes >= dw.total && dw.slices >= 2 && g.batch < 64) {
+        char *base = static_cast<char *>(workspace);
+        cudaError_t e = cudaMemsetAsync(base, 0, dw.zero_bytes, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+        PreArgs pa;
+        pa.g = g;
+        pa.key_lo = a.key_lo;
+        pa.key_shift = a.key_shift;
+        pa.slices = dw.slices;
+        pa.rows_per_slice = dw.rows_per_slice;
+        pa.topn = topn;
+        pa.cap = dw.cap;
+        int *ghist = reinterpret_cast<int *>(base + dw.off_hist);
+        int *gc = reinterpret_cast<int *>(base + dw.off_count);
+        unsigned long long *gl = reinterpret_cast<unsigned long long *>(base + dw.off_list);
+        const dim3 grid((unsigned)dw.slices, (unsigned)g.batch);
+        select_hist_kernel<<<grid, kSelThreads, 0, (cudaStream_t)stream>>>(pa, keys, ghist);
+        count_launch();
+        const size_t pre_smem = (size_t)kBins * 4 + (size_t)dw.cap * 8;
+        static bool pre_attr = false;
+        if (!pre_attr) {
+            e = cudaFuncSetAttribute(select_collect_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)kBins * 4 + (size_t)4 * B200DET_MAX_TOPN * 8));
+            if (e != cudaSuccess) return (int)e;
+            pre_attr = true;
+        }
+        select_collect_kernel<<<grid, kSelThreads, pre_smem, (cudaStream_t)stream>>>(pa, keys, ghist,
+                                                                                  gl, gc);
+        count_launch();
+        glist = gl;
+        gcount = gc;
+    }
+    select_nms_kernel<<<g.batch, kSelThreads, smem, (cudaStream_t)stream>>>(
+        a, keys, classes, out, order, keep, counts, glist, gcount);
     count_launch();
     return (int)cudaGetLastError();
 }

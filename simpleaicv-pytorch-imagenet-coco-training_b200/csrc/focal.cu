@@ -571,7 +571,18 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
 
     FocalArgs a;
-    const int vec = focal_vec(g);
+    int vec = focal_vec(g);
+    // the label-free sweep has no notion of rows: it can use 128-bit loads for ANY class count as
+    // long as every level holds a multiple of 4 floats and is 16-byte aligned (e.g. C = 365)
+    bool flat4 = false;
+    if (vec == 1 && labels == nullptr) {
+        flat4 = true;
+        for (int l = 0; l < g.n_levels; ++l) {
+            if (((long long)g.batch * g.rows[l] * g.num_classes) & 3) flat4 = false;
+            if (cls[l] && (reinterpret_cast<uintptr_t>(cls[l]) & 15)) flat4 = false;
+        }
+        if (flat4) vec = 4;
+    }
     const uintptr_t amask = vec == 4 ? 15 : 3;
     for (int l = 0; l < kMaxLevels; ++l) {
         a.cls.p[l] = nullptr;
@@ -589,7 +600,7 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
             a.grad.p[l] = cls_grad[l];
         }
     }
-    a.units_per_row = g.num_classes / vec;
+    a.units_per_row = flat4 ? 1 : g.num_classes / vec;
     // row = u / d for u < 2^31 by multiply-high: s = ceil(log2 d), m = floor(2^(31+s)/d) + 1,
     // row = umulhi(u, m) >> (s - 1)   (Granlund-Montgomery, 31-bit dividends)
     if (a.units_per_row == 1) {
@@ -608,14 +619,14 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     a.sums = sums;
     int chunks = 0;
     for (int l = 0; l < g.n_levels; ++l) {
-        a.units[l] = (long long)g.batch * g.rows[l] * a.units_per_row;
+        a.units[l] = flat4 ? (long long)g.batch * g.rows[l] * g.num_classes / 4
+                           : (long long)g.batch * g.rows[l] * a.units_per_row;
         if (a.units[l] >= (1ll << 31)) return B200DET_ERANGE;
         a.row_base[l] = (long long)g.batch * g.off[l];
         a.chunk_off[l] = chunks;
         chunks += (int)((a.units[l] + kChunkUnits - 1) / kChunkUnits);
     }
     for (int l = g.n_levels; l <= kMaxLevels; ++l) a.chunk_off[l] = chunks;
-    if ((size_t)chunks != ws.focal_chunks) return B200DET_EWORKSPACE;
 
     long long *partials =
         reinterpret_cast<long long *>(static_cast<char *>(workspace) + ws.off_focal);

@@ -69,14 +69,16 @@ class _DecoderBase:
         if plan is None:
             shapes = _geom.level_shapes(cls)
             geo = self._geometry(shapes, int(shape0[0]), int(shape0[-1]))
+            ws_bytes = int(lib.b200det_decode_workspace_bytes(ctypes.byref(geo), int(self.topn)))
             plan = (geo, ctypes.byref(geo), int(shape0[0]),
-                    _geom.rows_per_image(shapes, geo.per_loc))
+                    _geom.rows_per_image(shapes, geo.per_loc), ws_bytes)
             self._geo_cache = {key: plan}
-        _, geo_ref, batch, n_rows = plan
+        _, geo_ref, batch, n_rows, ws_bytes = plan
         m = int(self.max_object_num)
 
-        # scratch = keys | classes (int32 each) ; out = scores | classes | boxes
-        scratch = torch.empty(2 * batch * n_rows, dtype=torch.int32, device=device)
+        # scratch = keys | classes (int32 each) | selection workspace ; out = scores|classes|boxes
+        rows_bytes = (8 * batch * n_rows + 255) & ~255
+        scratch = torch.empty(rows_bytes + ws_bytes, dtype=torch.uint8, device=device)
         out = torch.empty(6 * batch * m, dtype=torch.float32, device=device)
         order = keep = counts = None
         if details:
@@ -108,6 +110,7 @@ class _DecoderBase:
                                order.data_ptr() if details else None,
                                keep.data_ptr() if details else None,
                                counts.data_ptr() if details else None,
+                               keys_ptr + rows_bytes, ws_bytes,
                                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
             'b200det_decode')
 
