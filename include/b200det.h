@@ -307,6 +307,20 @@ int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *par
                    uint32_t *keys, int32_t *classes, float *out, int32_t *order, int32_t *keep,
                    int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * OPTIONAL extension (not in the reference's call structure): loss forward + decode of one
+ * evaluation step with a SINGLE sweep over the classification tensors -- the score / arg-max
+ * sweep also accumulates the label-free focal sum.  Same results as b200det_loss_forward followed
+ * by b200det_decode; requires num_classes % 4 == 0.  Pass losses = NULL to all-reduce `sums`.
+ */
+int b200det_eval_step(const b200det_geometry *geo, const b200det_loss_params *loss_params,
+                      const b200det_decode_params *decode_params, const float *annotations,
+                      int max_gt, const void *const *cls, const void *const *reg,
+                      const void *const *ctr, int32_t *labels, void *loss_workspace,
+                      size_t loss_workspace_bytes, double *sums, float *losses, uint32_t *keys,
+                      int32_t *classes, float *out, void *decode_workspace,
+                      size_t decode_workspace_bytes, void *stream);
+
 /* ---- utilities (tests / parity outputs) ---------------------------------------------- */
 /* dst[b*N + off_l + i] = src[B*off_l + b*n_l + i] for `width` int32/float32 words per row */
 int b200det_rows_to_image_major(const b200det_geometry *geo, const void *src, void *dst,

@@ -49,9 +49,10 @@ def build(force=False, verbose=False):
     obj_dir = os.path.join(PKG_DIR, 'csrc', '_obj')
     os.makedirs(obj_dir, exist_ok=True)
     objs = []
+    tune = os.environ.get('B200DET_NVCC_EXTRA', '').split()
     for src, extra in SOURCES.items():
         obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
-        cmd = [nvcc] + ARCH + COMMON + extra + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + ARCH + COMMON + extra + tune + ['-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
             print(' '.join(cmd), file=sys.stderr)

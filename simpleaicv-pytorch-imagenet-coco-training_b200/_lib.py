@@ -101,6 +101,10 @@ SIGNATURES = {
     'b200det_scale_levels': (ctypes.c_int, [
         _vpp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp, _vp, ctypes.c_float, _vp
     ]),
+    'b200det_eval_step': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), ctypes.POINTER(DecodeParams), _vp, ctypes.c_int, _vpp,
+        _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
+    ]),
     'b200det_decode': (ctypes.c_int, [
         _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp

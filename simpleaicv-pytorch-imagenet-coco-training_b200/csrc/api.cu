@@ -99,3 +99,58 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
                                        order, keep, counts, workspace, workspace_bytes, stream);
     return rc;
 }
+
+// Loss forward + decode of one evaluation step with ONE sweep over the classification tensors:
+// the score/arg-max sweep also accumulates the label-free focal sum.  Not part of the reference's
+// call structure (criterion and decoder are separate calls there, tools/scripts.py:733-740); an
+// optional extension for eval loops that are willing to make one call instead of two.
+extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss_params *lp,
+                                 const b200det_decode_params *dp, const float *annotations,
+                                 int max_gt, const void *const *cls, const void *const *reg,
+                                 const void *const *ctr, int32_t *labels, void *loss_workspace,
+                                 size_t loss_workspace_bytes, double *sums, float *losses,
+                                 uint32_t *keys, int32_t *classes, float *out,
+                                 void *decode_workspace, size_t decode_workspace_bytes,
+                                 void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!lp || !dp || !annotations || !cls || !labels || !loss_workspace || !sums || !keys ||
+        !classes || !out)
+        return B200DET_EINVAL;
+    if (g.num_classes % 4) return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (loss_workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    char *base = static_cast<char *>(loss_workspace);
+    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
+                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
+                                    (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    g_skip_memset = true;
+    rc = score_argmax_impl(geo, cls, dp->is_fcos ? ctr : nullptr, dp->min_score, keys, classes,
+                           lp->alpha, lp->gamma, reinterpret_cast<long long *>(base + ws.off_focal),
+                           stream);
+    if (!rc) {
+        rc = lp->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, lp->use_center_sample,
+                                               labels, nullptr, nullptr, loss_workspace,
+                                               loss_workspace_bytes, stream)
+                         : b200det_retina_assign(geo, annotations, max_gt, labels, nullptr,
+                                                 loss_workspace, loss_workspace_bytes, stream);
+    }
+    if (!rc)
+        rc = b200det_sparse_losses(geo, lp->is_fcos, annotations, max_gt, labels, reg,
+                                   lp->reg_dtype, ctr, lp->box_loss, lp->beta, cls, lp->alpha,
+                                   lp->gamma, nullptr, nullptr, loss_workspace,
+                                   loss_workspace_bytes, stream);
+    g_skip_memset = false;
+    if (!rc) rc = b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
+    if (!rc && losses)
+        rc = b200det_loss_finish(sums, lp->w_cls, lp->w_box, lp->w_ctr, losses, stream);
+    if (!rc)
+        rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, dp->is_fcos,
+                                       dp->min_score, dp->topn, dp->max_out, dp->nms_type,
+                                       dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
+                                       nullptr, nullptr, nullptr, decode_workspace,
+                                       decode_workspace_bytes, stream);
+    return rc;
+}

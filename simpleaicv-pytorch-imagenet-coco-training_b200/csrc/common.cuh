@@ -76,6 +76,9 @@ struct LossWs {
         off_pos_queue /* int2 [B*N] */, off_ign_queue /* int [B*N] */, total;
 };
 LossWs loss_ws_layout(const Geo &g);
+int score_argmax_impl(const b200det_geometry *geo, const void *const *cls, const void *const *ctr,
+                      float min_score, uint32_t *keys, int32_t *classes, float alpha, float gamma,
+                      long long *focal_slots, void *stream);   // decode.cu
 // set by the fused entry points after they have cleared all accumulators with ONE memset
 extern thread_local bool g_skip_memset;
 int assign_blocks_per_image(const Geo &g);  // assign.cu

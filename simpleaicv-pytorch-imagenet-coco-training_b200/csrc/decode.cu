@@ -12,6 +12,7 @@
 // Compiled with -fmad=false: box / IoU arithmetic is one IEEE float32 op per reference op.
 #include <string.h>
 #include "common.cuh"
+#include "focal_terms.cuh"
 
 namespace b200det {
 
@@ -51,9 +52,13 @@ struct ArgmaxArgs {
     int t2, t2_shift;    // threads cooperating on one row in phase 2 (power of two <= 32)
     float min_score;
     int has_ctr;
+    // fused evaluation step (b200det_eval_step): the same sweep also accumulates the label-free
+    // focal sum, so cls is read ONCE for loss + decode
+    float alpha, gamma;
+    long long *focal_slots;
 };
 
-template <int VEC>
+template <int VEC, bool FOCAL>
 __global__ void __launch_bounds__(kArgThreads)
     score_argmax_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
     constexpr int kArgLoads = VEC == 4 ? kArgLoadsVec : kArgLoadsScalar;
@@ -104,6 +109,34 @@ __global__ void __launch_bounds__(kArgThreads)
             sval[row * a.pitch + col] = best;
             sidx[row * a.pitch + col] = col * VEC + bi;
         }
+    }
+    if (FOCAL) {
+        // label-free focal terms of the same registers (see focal.cu: focal_all_kernel)
+        const bool gamma2 = a.gamma == 2.f;
+        float acc = 0.f;
+        float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kArgLoads; ++k) {
+            const int u = k * kArgThreads + threadIdx.x;
+            if (u < n_units) {
+                float x[VEC];
+                float mx = 0.f;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    x[e] = fmaxf(v[k][e], kClampLo);
+                    mx = fmaxf(mx, x[e]);
+                }
+                if (gamma2 && mx <= kFastMax && VEC == 4) {
+                    float2 xr, xs;
+                    acc2 = neg_term_fast2_acc(make_float2(x[0], x[1 % VEC]), acc2, xr, xs);
+                    acc2 = neg_term_fast2_acc(make_float2(x[2 % VEC], x[3 % VEC]), acc2, xr, xs);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc += neg_term(v[k][e], a.gamma, gamma2);
+                }
+            }
+        }
+        sweep_accumulate<kArgThreads>((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
     }
     __syncthreads();
 
@@ -841,9 +874,22 @@ extern "C" size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, in
     return decode_ws_layout(g, topn).total;
 }
 
+namespace b200det {
+int score_argmax_impl(const b200det_geometry *geo, const void *const *cls, const void *const *ctr,
+                      float min_score, uint32_t *keys, int32_t *classes, float alpha, float gamma,
+                      long long *focal_slots, void *stream);
+}
+
 extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
                                     const void *const *ctr, float min_score, uint32_t *keys,
                                     int32_t *classes, void *stream) {
+    return score_argmax_impl(geo, cls, ctr, min_score, keys, classes, 0.f, 0.f, nullptr, stream);
+}
+
+int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *cls,
+                               const void *const *ctr, float min_score, uint32_t *keys,
+                               int32_t *classes, float alpha, float gamma,
+                               long long *focal_slots, void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
@@ -855,6 +901,10 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
     a.C = g.num_classes;
     a.min_score = min_score;
     a.has_ctr = ctr != nullptr;
+    a.alpha = alpha;
+    a.gamma = gamma;
+    a.focal_slots = focal_slots;
+    if (focal_slots && vec != 4) return B200DET_EINVAL;   // fused sweep: C % 4 == 0 only
     const int units = g.num_classes / vec;
     a.units_per_row = units;
     const int budget = kArgThreads * kArgLoadsVec;   // 128-bit loads per CTA, all in flight
@@ -902,8 +952,10 @@ extern "C" int b200det_score_argmax(const b200det_geometry *geo, const void *con
     const size_t smem = vec == 4 ? (size_t)R * a.pitch * 8 : (size_t)R * a.C * 4 + 16;
     if (smem > 48 * 1024) return B200DET_ERANGE;
     ProfScope prof(kKernArgmax, stream);
-    if (vec == 4)
-        score_argmax_kernel<4><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
+    if (vec == 4 && focal_slots)
+        score_argmax_kernel<4, true><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
+    else if (vec == 4)
+        score_argmax_kernel<4, false><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else
         score_argmax_raw_kernel<<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     count_launch();

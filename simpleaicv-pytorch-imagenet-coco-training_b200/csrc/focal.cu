@@ -86,12 +86,15 @@ int make_geo(const b200det_geometry *s, Geo *g) {
 }
 
 constexpr int kFocalThreads = 256;
-constexpr int kFocalUnroll = 4;                                    // loads in flight per thread
-constexpr int kFocalBatches = 2;                                   // batches per chunk
+#ifndef B200DET_FOCAL_UNROLL
+#define B200DET_FOCAL_UNROLL 4
+#endif
+#ifndef B200DET_FOCAL_BATCHES
+#define B200DET_FOCAL_BATCHES 2
+#endif
+constexpr int kFocalUnroll = B200DET_FOCAL_UNROLL;                 // loads in flight per thread
+constexpr int kFocalBatches = B200DET_FOCAL_BATCHES;               // batches per chunk
 constexpr int kChunkUnits = kFocalThreads * kFocalUnroll * kFocalBatches;  // 2048 units / CTA
-
-constexpr int kSweepSlots = 1024;
-constexpr double kFxSweep = 68719476736.0;   // 2^36 (see block_store_partial)
 
 static inline int focal_vec(const Geo &g) { return (g.num_classes % 4 == 0) ? 4 : 1; }
 
@@ -159,24 +162,8 @@ __device__ __forceinline__ void load_unit(const float *__restrict__ src, long lo
     }
 }
 
-// CTA sum -> one 64-bit fixed-point atomic into one of kSweepSlots accumulators.  Integer adds
-// commute, so the total does not depend on CTA scheduling order (deterministic), and the final
-// reduction reads kSweepSlots values instead of one partial per CTA (300k at batch 256).
-// Scale 2^36: resolution 1.5e-11 per CTA sum (typical CTA sums are ~1e-2), capacity 1.3e8 per slot.
 __device__ __forceinline__ void block_store_partial(float value, long long *slots) {
-    __shared__ float red[kFocalThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float w = warp_sum(value);
-    if (lane == 0) red[warp] = w;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < kFocalThreads / 32; ++i) s += red[i];
-        const long long fx = __double2ll_rn((double)s * kFxSweep);
-        atomicAdd(reinterpret_cast<unsigned long long *>(slots + (blockIdx.x & (kSweepSlots - 1))),
-                  (unsigned long long)fx);
-    }
+    sweep_accumulate<kFocalThreads>(value, slots);
 }
 
 // Label-free sweep (forward only): every element is treated as background; the rows that are

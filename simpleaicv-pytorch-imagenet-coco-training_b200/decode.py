@@ -51,6 +51,39 @@ class _DecoderBase:
             self._pinned = torch.empty(numel, dtype=torch.float32, pin_memory=True)
         return self._pinned
 
+    @staticmethod
+    def _set_glue(params, batch, device, scales, sizes, to_xywh):
+        """Fills the optional evaluation-glue fields of the decode params; returns the small
+        device tensors, which must stay alive until the call has been enqueued."""
+        glue = []
+        params.scales = params.sizes = None
+        params.to_xywh = int(bool(to_xywh))
+        if scales is not None:
+            t = torch.as_tensor(np.asarray(scales, dtype=np.float32).reshape(-1)).to(device)
+            if t.numel() != batch:
+                raise ValueError('scales must have one entry per image')
+            glue.append(t)
+            params.scales = t.data_ptr()
+        if sizes is not None:
+            t = torch.as_tensor(np.asarray(sizes, dtype=np.float32).reshape(-1)).to(device)
+            if t.numel() != 2 * batch:
+                raise ValueError('sizes must be [B, 2] = (height, width) per image')
+            glue.append(t)
+            params.sizes = t.data_ptr()
+        return glue
+
+    def _to_host(self, out, batch, m, device):
+        """The only D2H copy: 24*M bytes per image, through a cached pinned staging buffer; the
+        caller gets fresh, writable arrays (tools/scripts.py:742-758 mutates them in place)."""
+        staging = self._staging(out.numel())
+        staging.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        host = staging.numpy().copy()
+        scores = host[0:batch * m].reshape(batch, m)
+        out_classes = host[batch * m:2 * batch * m].reshape(batch, m)
+        boxes = host[2 * batch * m:].reshape(batch, m, 4)
+        return [scores, out_classes, boxes]
+
     def _run(self, preds, details=False, scales=None, sizes=None, to_xywh=False):
         lib = _lib.load()
         if self._is_fcos:
@@ -87,21 +120,7 @@ class _DecoderBase:
             counts = torch.empty(batch * 3, dtype=torch.int32, device=device)
         params = self._params
         params.reg_dtype = reg_dtype
-        glue = []   # keeps the small device tensors alive until the call has been enqueued
-        params.scales = params.sizes = None
-        params.to_xywh = int(bool(to_xywh))
-        if scales is not None:
-            t = torch.as_tensor(np.asarray(scales, dtype=np.float32).reshape(-1)).to(device)
-            if t.numel() != batch:
-                raise ValueError('scales must have one entry per image')
-            glue.append(t)
-            params.scales = t.data_ptr()
-        if sizes is not None:
-            t = torch.as_tensor(np.asarray(sizes, dtype=np.float32).reshape(-1)).to(device)
-            if t.numel() != 2 * batch:
-                raise ValueError('sizes must be [B, 2] = (height, width) per image')
-            glue.append(t)
-            params.sizes = t.data_ptr()
+        glue = self._set_glue(params, batch, device, scales, sizes, to_xywh)
         keys_ptr = scratch.data_ptr()
         _lib.check(
             lib.b200det_decode(geo_ref, ctypes.byref(params), _lib.ptr_array(cls),
@@ -114,16 +133,8 @@ class _DecoderBase:
                                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
             'b200det_decode')
 
-        # the only D2H copy: 24*M bytes per image, through a cached pinned staging buffer; the
-        # caller gets fresh, writable arrays (tools/scripts.py:742-758 mutates them in place)
-        staging = self._staging(out.numel())
-        staging.copy_(out, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
-        host = staging.numpy().copy()
-        scores = host[0:batch * m].reshape(batch, m)
-        out_classes = host[batch * m:2 * batch * m].reshape(batch, m)
-        boxes = host[2 * batch * m:].reshape(batch, m, 4)
-        result = [scores, out_classes, boxes]
+        del glue
+        result = self._to_host(out, batch, m, device)
         if not details:
             return result
         info = {

@@ -461,6 +461,55 @@ def test_fused_eval_glue_matches_numpy_post_processing():
     G.assert_bit_equal(b1, b2 / scales[:, None, None], 'rescaled boxes')
 
 
+def test_fused_eval_step_matches_separate_calls():
+    """Optional extension b200det.fused.EvalStep: one sweep over cls for loss + decode."""
+    from b200det import fused
+    preds = synth.make_tie_free(synth.make_retina_preds(3, 256, 8, seed=31))
+    ann = synth.make_annotations(3, 20, 256, 8, seed=32, empty_images=(1,))
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    with torch.no_grad():
+        ref_loss = O.retina_loss(preds, ann, **synth.RETINA_KW, box_loss_type='GIoU')
+    (s0, c0, b0), _ = O.retina_decode(preds, **synth.RETINA_KW)
+    loss, (s, c, b) = fused.EvalStep(crit, dec)(dev(preds), ann.cuda())
+    assert_close(loss_values(loss, ['cls_loss', 'reg_loss']),
+                 [ref_loss['cls_loss'].item(), ref_loss['reg_loss'].item()], LOSS_RTOL, 'fused loss')
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0)
+    fp = synth.make_tie_free(synth.make_fcos_preds(2, 256, 8, seed=33))
+    fa = synth.make_annotations(2, 20, 256, 8, seed=34)
+    fcrit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    fdec = decode.FCOSDecoder(strides=synth.STRIDES)
+    with torch.no_grad():
+        ref_loss = O.fcos_loss(fp, fa, synth.STRIDES, synth.MI)
+    (s0, c0, b0), _ = O.fcos_decode(fp, synth.STRIDES)
+    loss, (s, c, b) = fused.EvalStep(fcrit, fdec)(dev(fp), fa.cuda())
+    assert_close(loss_values(loss, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                 [ref_loss[k].item() for k in ('cls_loss', 'reg_loss', 'center_ness_loss')],
+                 LOSS_RTOL, 'fused FCOS loss')
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(b, b0)
+
+
+def test_heavy_ties_full_size_image_uses_refinement():
+    """120 087 rows with identical scores: the multi-CTA front end finds a crowded cut bin and
+    the select kernel falls back to the radix refinement + ordered tie pass."""
+    preds = synth.make_retina_preds(1, 800, 80, seed=41)
+    for c in preds[0]:
+        c.fill_(0.01)
+        c[..., 17] = 0.25
+    preds[0][0][0, 50, 50, 4, 3] = 0.6
+    preds[0][2][0, 3, 3, 1, 9] = 0.6          # two equal winners: lower row first
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **synth.RETINA_KW)
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0)
+    check_decode_details(info, extra['per_image'], 1000)
+
+
 def test_cpu_tensors_are_rejected():
     preds = synth.make_retina_preds(1, 128, 8, seed=8)
     ann = synth.make_annotations(1, 4, 128, 8, seed=9)
