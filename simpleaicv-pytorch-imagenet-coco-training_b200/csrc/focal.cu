@@ -267,8 +267,11 @@ __device__ __forceinline__ void slow_element(float p, bool is_target, float alph
 // Label-aware sweep: used when gradients are requested (one read of cls, one write of its
 // gradient already scaled by weight / positives), or when the caller did not let the
 // assignment kernel apply the corrections.
+#ifndef B200DET_FOCAL_GRAD_MINB
+#define B200DET_FOCAL_GRAD_MINB 6
+#endif
 template <int VEC, bool GRAD, bool GAMMA2>
-__global__ void __launch_bounds__(kFocalThreads)
+__global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
     focal_kernel(FocalArgs a, const int *__restrict__ labels, long long *__restrict__ partials) {
     const int l = chunk_level(a);
     const long long chunk_start = (long long)(blockIdx.x - a.chunk_off[l]) * kChunkUnits;
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(kFocalThreads)
     const float one_m_alpha = 1.f - a.alpha;
 
     float acc_neg = 0.f, acc_pos = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int bt = 0; bt < kFocalBatches; ++bt) {
         const long long u0 = chunk_start + (long long)bt * kFocalThreads * kFocalUnroll + threadIdx.x;
@@ -325,14 +329,31 @@ __global__ void __launch_bounds__(kFocalThreads)
                 }
                 const bool has_target = lab[k] > 0 && (unsigned)tgt[k] < (unsigned)VEC;
                 if (GAMMA2 && !has_target && mx <= kFastMax) {
+                    if (VEC == 4) {
+                        // packed FP32 (FFMA2): two elements per instruction
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
+                        for (int h = 0; h < 2; ++h) {
+                            float2 xr, xs;
+                            const float2 xx = make_float2(x[(2 * h) % VEC], x[(2 * h + 1) % VEC]);
+                            acc2 = neg_term_fast2_acc(xx, acc2, xr, xs);
+                            if (GRAD) {
+                                // (1-a) * x * (2*(-log q) + x/q), zero below the clamp
+                                const float2 rq = make_float2(__fdividef(1.f, 1.f - xr.x),
+                                                              __fdividef(1.f, 1.f - xr.y));
+                                const float2 t = __ffma2_rn(make_float2(2.f, 2.f), xs,
+                                                            __fmul2_rn(xr, rq));
+                                const float2 gg = __fmul2_rn(__fmul2_rn(xr, t),
+                                                             make_float2(one_m_alpha, one_m_alpha));
+                                g[(2 * h) % VEC] = v[k][(2 * h) % VEC] >= kClampLo ? gg.x : 0.f;
+                                g[(2 * h + 1) % VEC] = v[k][(2 * h + 1) % VEC] >= kClampLo ? gg.y : 0.f;
+                            }
+                        }
+                    } else {
                         float xr, xs;
-                        acc_neg += neg_term_fast(x[e], xr, xs);
+                        acc_neg += neg_term_fast(x[0], xr, xs);
                         if (GRAD) {
-                            // (1-a) * x * (2*(-log q) + x/q), zero below the clamp
                             const float t = fmaf(2.f, xs, __fdividef(xr, 1.f - xr));
-                            g[e] = v[k][e] >= kClampLo ? one_m_alpha * xr * t : 0.f;
+                            g[0] = v[k][0] >= kClampLo ? one_m_alpha * xr * t : 0.f;
                         }
                     }
                 } else {
@@ -352,7 +373,7 @@ __global__ void __launch_bounds__(kFocalThreads)
             }
         }
     }
-    block_store_partial(a.alpha * acc_pos + one_m_alpha * acc_neg, partials);
+    block_store_partial(a.alpha * acc_pos + one_m_alpha * (acc_neg + (acc2.x + acc2.y)), partials);
 }
 
 // ---------------------------------------------------------------------------------------

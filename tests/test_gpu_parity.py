@@ -510,6 +510,118 @@ def test_heavy_ties_full_size_image_uses_refinement():
     check_decode_details(info, extra['per_image'], 1000)
 
 
+def test_generic_anchor_layout_non_square_many_gt():
+    """Code paths the COCO configs never touch: 6 anchors per location (generic, not the 9-anchor
+    register kernel), non-square feature maps, odd strides / sizes, and 300 annotation rows per
+    image (several compaction rounds in the assignment kernel)."""
+    kw = dict(areas=[[24, 40], [48, 80], [96, 160]], ratios=[0.5, 1, 2], scales=[1, 1.5],
+              strides=[6, 12, 24])
+    gen = torch.Generator().manual_seed(5)
+    B, C = 2, 12
+    shapes = [(21, 37), (11, 19), (6, 10)]
+    cls = [torch.sigmoid(torch.randn((B, h, w, 6, C), generator=gen) - 3.0) for h, w in shapes]
+    reg = [torch.randn((B, h, w, 6, 4), generator=gen) * 0.2 for h, w in shapes]
+    preds = synth.make_tie_free([cls, reg])
+    ann = synth.make_annotations(B, 300, 220, C, seed=6, min_gt=280)
+    ann[..., 0:4] *= torch.tensor([1.0, 0.55, 1.0, 0.55])      # fit the 220 x 126 "image"
+    for box_type in ('SmoothL1', 'EIoU'):
+        crit = losses.RetinaLoss(**kw, box_loss_type=box_type)
+        with torch.no_grad():
+            d = crit(dev(preds), ann.cuda())
+            ref = O.retina_loss(preds, ann, **kw, box_loss_type=box_type)
+        got = crit.debug_assign(dev(preds), ann.cuda())
+        assert np.array_equal(got['labels'].cpu().numpy(), ref['labels'].numpy().astype(np.int32))
+        assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+        fast = crit.debug_assign(dev(preds), ann.cuda(), exact=False)
+        assert np.array_equal(fast['labels'].cpu().numpy(), ref['labels'].numpy().astype(np.int32))
+        assert ref['num_pos'] > 0
+        assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
+                     [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, box_type)
+    dec = decode.RetinaDecoder(**kw, topn=400, max_object_num=60)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **kw, topn=400, max_object_num=60)
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0)
+    check_decode_details(info, extra['per_image'], 400)
+    # FCOS on the same odd pyramid, 3 levels, custom ranges and radius
+    fkw = dict(strides=[6, 12, 24], mi=[[-1, 40], [40, 90], [90, 100000000]])
+    fcls = [torch.sigmoid(torch.randn((B, h, w, C), generator=gen) - 3.0) for h, w in shapes]
+    freg = [torch.randn((B, h, w, 4), generator=gen) * 0.5 + 2.5 for h, w in shapes]
+    fctr = [torch.sigmoid(torch.randn((B, h, w, 1), generator=gen)) for h, w in shapes]
+    fpreds = synth.make_tie_free([fcls, freg, fctr])
+    fcrit = losses.FCOSLoss(**fkw, center_sample_radius=2.0, box_loss_iou_type='DIoU')
+    with torch.no_grad():
+        d = fcrit(dev(fpreds), ann.cuda())
+        ref = O.fcos_loss(fpreds, ann, fkw['strides'], fkw['mi'], center_sample_radius=2.0,
+                          box_loss_iou_type='DIoU')
+    got = fcrit.debug_assign(dev(fpreds), ann.cuda())
+    assert_targets_equal(got['targets'].cpu().numpy(), ref['targets'].numpy(), 'targets')
+    assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                 [ref[k].item() for k in ('cls_loss', 'reg_loss', 'center_ness_loss')], LOSS_RTOL,
+                 'FCOS odd pyramid')
+    fdec = decode.FCOSDecoder(strides=fkw['strides'], topn=300, max_object_num=40)
+    (s, c, b), info = fdec.decode_with_details(dev(fpreds))
+    (s0, c0, b0), extra = O.fcos_decode(fpreds, fkw['strides'], topn=300, max_object_num=40)
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(b, b0)
+    check_decode_details(info, extra['per_image'], 300)
+
+
+def test_training_and_eval_loops_like_the_reference_scripts():
+    """Stub of the reference's loops with the drop-in classes: a tiny 'model' produces head
+    outputs, train steps follow tools/scripts.py:893-945 (criterion -> sum(values) -> backward ->
+    optimizer step; loss must go down), the eval step follows :733-758 (criterion, decoder,
+    in-place rescale / clip of the returned NumPy arrays)."""
+    torch.manual_seed(0)
+    B, C, S = 2, 8, 128
+    sizes = synth.pyramid_sizes(S)
+    feats = [torch.randn(B, 16, p, p, device='cuda') for p in sizes]
+
+    class Heads(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.cls = torch.nn.Conv2d(16, 9 * C, 3, padding=1)
+            self.reg = torch.nn.Conv2d(16, 9 * 4, 3, padding=1)
+            torch.nn.init.constant_(self.cls.bias, -4.595)
+
+        def forward(self, fs):
+            cls, reg = [], []
+            for f in fs:
+                c = self.cls(f).permute(0, 2, 3, 1).contiguous()
+                r = self.reg(f).permute(0, 2, 3, 1).contiguous()
+                cls.append(torch.sigmoid(c).view(B, f.shape[2], f.shape[3], 9, C).float())
+                reg.append(r.view(B, f.shape[2], f.shape[3], 9, 4))
+            return [cls, reg]
+
+    model = Heads().cuda()
+    criterion = losses.__dict__['RetinaLoss'](**synth.RETINA_KW).cuda()
+    decoder = decode.__dict__['RetinaDecoder'](**synth.RETINA_KW)
+    annots = synth.make_annotations(B, 6, S, C, seed=4, min_gt=4).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    history = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss_value = criterion(model(feats), annots)
+        loss = sum(loss_value.values())
+        assert not (torch.isnan(loss) or torch.isinf(loss)) and loss != 0.
+        loss.backward()
+        opt.step()
+        history.append(loss.item())
+    assert history[-1] < 0.8 * history[0], history
+    model.eval()
+    with torch.no_grad():
+        outs = model(feats)
+        loss_value = criterion(outs, annots)
+        scores, classes, boxes = decoder(outs)
+    assert set(loss_value) == {'cls_loss', 'reg_loss'}
+    scales = np.array([0.5, 0.8], dtype=np.float32)
+    boxes /= np.expand_dims(np.expand_dims(scales, axis=-1), axis=-1)      # scripts.py:742
+    boxes[0][:, 0] = np.maximum(boxes[0][:, 0], 0)                          # scripts.py:749
+    assert scores.shape == (B, 100) and boxes.shape == (B, 100, 4)
+
+
 def test_cpu_tensors_are_rejected():
     preds = synth.make_retina_preds(1, 128, 8, seed=8)
     ann = synth.make_annotations(1, 4, 128, 8, seed=9)

@@ -1,8 +1,9 @@
+#!/bin/bash
+# Tuning aid (run on the GPU box): rebuilds the library with different compile-time knobs of the
+# focal sweeps and prints the per-kernel times of a training step.  Leaves the default build.
 set -u
-for v in "4 2" "8 1" "4 4" "2 4" "8 2"; do
-  set -- $v
-  B200DET_NVCC_EXTRA="-DB200DET_FOCAL_UNROLL=$1 -DB200DET_FOCAL_BATCHES=$2" python -c "import b200det; b200det._build.build(force=True)" > /dev/null 2>&1
-  python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1 $2', round(d['value']), d['kernels_ms']['focal_loss'], d['kernels_ms']['score_argmax'])"
+for v in "1" "5" "6" "8"; do
+  B200DET_NVCC_EXTRA="-DB200DET_FOCAL_GRAD_MINB=$v" python -c "import b200det; b200det._build.build(force=True)" > /dev/null 2>&1
+  echo "minblocks=$v $(python tools/prof_train.py 2>&1 | tail -1)"
 done
 python -c "import b200det; b200det._build.build(force=True)" > /dev/null 2>&1
