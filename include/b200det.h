@@ -118,6 +118,9 @@ size_t b200det_loss_workspace_bytes(const b200det_geometry *geo);
  * Replaces RetinaLoss.get_batch_anchors_annotations (losses.py:322-388) and the assignment use of
  * IoUMethod (losses.py:33-70).
  *   annotations : device float32 [B, max_gt, 5] = x1,y1,x2,y2,class ; rows with class < 0 ignored
+ *   iou_neg/pos : best IoU < iou_neg -> background, >= iou_pos -> positive, between -> ignored:
+ *                 0.4 / 0.5 for RetinaLoss (losses.py:361-365), 0.35 / 0.35 for RetinaFaceLoss
+ *                 (simpleAICV/face_detection/losses.py:255-259), which shares this kernel
  *   labels      : device int32 [B*N] level-major, out: -1 ignore, 0 background, k = class k-1
  *   matched     : device int32 [B*N] level-major or NULL, out: arg-max GT index in the image's
  *                 filtered GT list (first maximum on ties), -1 if the image has no GT
@@ -128,8 +131,8 @@ size_t b200det_loss_workspace_bytes(const b200det_geometry *geo);
  * useful when the caller overlaps it with the HBM-bound sweep on another stream.
  */
 int b200det_retina_assign(const b200det_geometry *geo, const float *annotations, int max_gt,
-                          int32_t *labels, int32_t *matched, void *workspace,
-                          size_t workspace_bytes, void *stream);
+                          float iou_neg, float iou_pos, int32_t *labels, int32_t *matched,
+                          void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Point<->GT assignment with centre sampling of FCOSLoss.
@@ -260,6 +263,7 @@ typedef struct b200det_loss_params {
     int32_t use_center_sample;  /* FCOS */
     float alpha, gamma, beta;
     float w_cls, w_box, w_ctr;  /* cls_loss_weight, box_loss_weight, center_ness_loss_weight */
+    float iou_neg, iou_pos;     /* anchor assignment thresholds (Retina 0.4 / 0.5, RetinaFace 0.35 / 0.35) */
 } b200det_loss_params;
 
 typedef struct b200det_decode_params {

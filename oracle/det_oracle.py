@@ -211,8 +211,9 @@ def retina_decode_boxes(deltas, anchors):
     return torch.cat([ctr - 0.5 * wh, ctr + 0.5 * wh], dim=1)
 
 
-def retina_assign(anchors, annotations, box_loss_type='SmoothL1'):
-    """losses.py:322-388.  anchors [A,4] float32 tensor, annotations [B,G,5].
+def retina_assign(anchors, annotations, box_loss_type='SmoothL1', neg_thr=0.4, pos_thr=0.5):
+    """losses.py:322-388 (thresholds 0.4 / 0.5) and face_detection/losses.py:222-292
+    (thresholds 0.35 / 0.35).  anchors [A,4] float32 tensor, annotations [B,G,5].
 
     Returns (targets [B,A,5], labels [B,A] int64, matched [B,A] int64).  `matched` indexes the
     image's FILTERED GT list (rows with class >= 0); -1 for images without GT."""
@@ -229,8 +230,8 @@ def retina_assign(anchors, annotations, box_loss_type='SmoothL1'):
             ious = box_iou(anchors.unsqueeze(1), gt_boxes.unsqueeze(0), 'IoU')
             best_iou, matched = ious.max(axis=1)
             labels = torch.ones_like(best_iou) * -1
-            labels[best_iou < 0.4] = 0
-            labels[best_iou >= 0.5] = gt_cls[matched][best_iou >= 0.5] + 1
+            labels[best_iou < neg_thr] = 0
+            labels[best_iou >= pos_thr] = gt_cls[matched][best_iou >= pos_thr] + 1
             boxes = gt_boxes[matched]
             if box_loss_type == 'SmoothL1':
                 boxes = retina_encode(boxes, anchors)
@@ -243,15 +244,17 @@ def retina_assign(anchors, annotations, box_loss_type='SmoothL1'):
 
 def retina_loss(preds, annotations, areas, ratios, scales, strides, alpha=0.25, gamma=2,
                 beta=1.0 / 9.0, cls_loss_weight=1., box_loss_weight=1.,
-                box_loss_type='SmoothL1'):
+                box_loss_type='SmoothL1', level_anchors=None, neg_thr=0.4, pos_thr=0.5):
     """losses.py:161-320.  Returns dict with the reference's loss dict plus intermediates:
     'labels' [B,A], 'matched' [B,A], 'num_pos', 'cls_sum', 'reg_sum' (un-normalised)."""
     cls_levels, reg_levels = preds
     batch = annotations.shape[0]
-    level_anchors = retina_anchors(feature_sizes_of(cls_levels), areas, ratios, scales, strides)
+    if level_anchors is None:
+        level_anchors = retina_anchors(feature_sizes_of(cls_levels), areas, ratios, scales,
+                                       strides)
     device = annotations.device
     anchors = torch.cat([torch.tensor(a).view(-1, 4) for a in level_anchors], dim=0).to(device)
-    targets, labels, matched = retina_assign(anchors, annotations, box_loss_type)
+    targets, labels, matched = retina_assign(anchors, annotations, box_loss_type, neg_thr, pos_thr)
 
     cls = torch.cat([c.view(c.shape[0], -1, c.shape[-1]) for c in cls_levels], dim=1)
     reg = torch.cat([r.view(r.shape[0], -1, r.shape[-1]) for r in reg_levels], dim=1)
@@ -508,11 +511,13 @@ def _to_np_rows(level_tensors):
 
 def retina_decode(preds, areas, ratios, scales, strides, max_object_num=100,
                   min_score_threshold=0.05, topn=1000, nms_type='python_nms',
-                  nms_threshold=0.5, exp_fn=None):
+                  nms_threshold=0.5, exp_fn=None, level_anchors=None):
     """decode.py:201-271.  exp_fn defaults to the pinned NumPy-exp restatement."""
     exp_fn = exp_fn or np_exp_f32
     cls_levels, reg_levels = preds
-    level_anchors = retina_anchors(feature_sizes_of(cls_levels), areas, ratios, scales, strides)
+    if level_anchors is None:
+        level_anchors = retina_anchors(feature_sizes_of(cls_levels), areas, ratios, scales,
+                                       strides)
     cls = _to_np_rows(cls_levels)
     reg = _to_np_rows(reg_levels)
     anchors = np.concatenate([a.reshape(-1, 4) for a in level_anchors], axis=0)[None]
@@ -550,3 +555,47 @@ def fcos_decode(preds, strides, max_object_num=100, min_score_threshold=0.05, to
     result, extras = select_and_nms(scores, classes, boxes, max_object_num,
                                     min_score_threshold, topn, nms_type, nms_threshold)
     return result, {'per_image': extras, 'scores': scores, 'classes': classes, 'boxes': boxes}
+
+
+# ----------------------------------------------------------------------------------------
+# RetinaFace (simpleAICV/face_detection/{models/anchor,losses,decode}.py) -- SURVEY section 8f-2
+# ----------------------------------------------------------------------------------------
+def retinaface_anchors(feature_sizes, anchor_sizes, strides):
+    """face_detection/models/anchor.py:15-88: square anchors, one per size and location."""
+    out = []
+    for sizes, (fw, fh), stride in zip(anchor_sizes, feature_sizes, strides):
+        wh = np.array([[s, s] for s in sizes], dtype=np.float32)
+        base = np.zeros((len(sizes), 4), dtype=np.float32)
+        base[:, 2:] += wh
+        base[:, 0] -= base[:, 2] / 2
+        base[:, 1] -= base[:, 3] / 2
+        base[:, 2] /= 2
+        base[:, 3] /= 2
+        stride = np.float32(stride)
+        sx = ((np.arange(0, fw) + 0.5) * stride).astype(np.float32)
+        sy = ((np.arange(0, fh) + 0.5) * stride).astype(np.float32)
+        shifts = np.empty((fh, fw, 1, 4), dtype=np.float32)
+        shifts[:, :, 0, 0] = sx[None, :]
+        shifts[:, :, 0, 1] = sy[:, None]
+        shifts[:, :, 0, 2] = sx[None, :]
+        shifts[:, :, 0, 3] = sy[:, None]
+        out.append(np.ascontiguousarray(base[None, None, :, :] + shifts, dtype=np.float32))
+    return out
+
+
+def retinaface_loss(preds, annotations, anchor_sizes, strides, alpha=0.25, gamma=2,
+                    beta=1.0 / 9.0, cls_loss_weight=1., box_loss_weight=1., box_loss_type='CIoU'):
+    """face_detection/losses.py:54-292: RetinaLoss's arithmetic with square anchors and the
+    0.35 / 0.35 assignment thresholds (:255-259)."""
+    anchors = retinaface_anchors(feature_sizes_of(preds[0]), anchor_sizes, strides)
+    return retina_loss(preds, annotations, None, None, None, strides, alpha, gamma, beta,
+                       cls_loss_weight, box_loss_weight, box_loss_type, level_anchors=anchors,
+                       neg_thr=0.35, pos_thr=0.35)
+
+
+def retinaface_decode(preds, anchor_sizes, strides, max_object_num=100, min_score_threshold=0.3,
+                      topn=1000, nms_type='python_nms', nms_threshold=0.3, exp_fn=None):
+    """face_detection/decode.py:47-117."""
+    anchors = retinaface_anchors(feature_sizes_of(preds[0]), anchor_sizes, strides)
+    return retina_decode(preds, None, None, None, strides, max_object_num, min_score_threshold,
+                         topn, nms_type, nms_threshold, exp_fn, level_anchors=anchors)

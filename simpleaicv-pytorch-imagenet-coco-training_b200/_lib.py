@@ -58,6 +58,8 @@ class LossParams(ctypes.Structure):
         ('w_cls', ctypes.c_float),
         ('w_box', ctypes.c_float),
         ('w_ctr', ctypes.c_float),
+        ('iou_neg', ctypes.c_float),
+        ('iou_pos', ctypes.c_float),
     ]
 
 
@@ -111,8 +113,9 @@ SIGNATURES = {
     ]),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
     'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),
-    'b200det_retina_assign': (ctypes.c_int,
-                              [_geo, _vp, ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    'b200det_retina_assign': (ctypes.c_int, [
+        _geo, _vp, ctypes.c_int, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, ctypes.c_size_t, _vp
+    ]),
     'b200det_fcos_assign': (ctypes.c_int, [
         _geo, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
     ]),

@@ -31,8 +31,9 @@ extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_l
         rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample,
                                               labels, nullptr, nullptr, workspace,
                                               workspace_bytes, stream)
-                        : b200det_retina_assign(geo, annotations, max_gt, labels, nullptr,
-                                                workspace, workspace_bytes, stream);
+                        : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos,
+                                                labels, nullptr, workspace, workspace_bytes,
+                                                stream);
     }
     if (!rc)
         rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
@@ -67,8 +68,8 @@ extern "C" int b200det_loss_forward_grad(const b200det_geometry *geo, const b200
     g_skip_memset = true;
     rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample, labels,
                                           nullptr, nullptr, workspace, workspace_bytes, stream)
-                    : b200det_retina_assign(geo, annotations, max_gt, labels, nullptr, workspace,
-                                            workspace_bytes, stream);
+                    : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos, labels,
+                                            nullptr, workspace, workspace_bytes, stream);
     if (!rc)
         rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
                                    ctr, p->box_loss, p->beta, nullptr, p->alpha, p->gamma,
@@ -134,8 +135,9 @@ extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss
         rc = lp->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, lp->use_center_sample,
                                                labels, nullptr, nullptr, loss_workspace,
                                                loss_workspace_bytes, stream)
-                         : b200det_retina_assign(geo, annotations, max_gt, labels, nullptr,
-                                                 loss_workspace, loss_workspace_bytes, stream);
+                         : b200det_retina_assign(geo, annotations, max_gt, lp->iou_neg, lp->iou_pos,
+                                                 labels, nullptr, loss_workspace,
+                                                 loss_workspace_bytes, stream);
     }
     if (!rc)
         rc = b200det_sparse_losses(geo, lp->is_fcos, annotations, max_gt, labels, reg,

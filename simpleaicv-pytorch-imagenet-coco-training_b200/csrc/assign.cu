@@ -279,14 +279,19 @@ __device__ __forceinline__ void flush_queues(const Queues &q, const int2 *pos_q,
 // EXACT = false (production: the arg-max index of non-positive rows is not an output): a pair
 // whose IoU cannot reach the 0.4 "background" threshold can change neither a label nor a
 // positive's matched box, so it is dropped early with conservative float32 bounds
-// (IoU <= min(area)/max(area), and ov < 0.38*union) and the IEEE divide only runs for the few
-// pairs above 0.38.  EXACT = true reproduces the reference's max/arg-max for every row.
-constexpr float kIouFloor = 0.38f;
+// (IoU <= min(area)/max(area), and ov < floor*union, floor = 0.38 for RetinaLoss) and the IEEE
+// divide only runs for the few pairs above it.  EXACT = true reproduces the reference's
+// max/arg-max for every row.
+struct IouThresholds {
+    float neg;     // best IoU <  neg -> background   (RetinaLoss 0.4, RetinaFaceLoss 0.35)
+    float pos;     // best IoU >= pos -> positive     (RetinaLoss 0.5, RetinaFaceLoss 0.35)
+    float floor;   // 0.95 * min(neg, pos): pairs that cannot reach it are dropped (production scan)
+};
 
 template <int NA, bool EXACT>
 __device__ __forceinline__ void scan_candidates(const GtSmem &s, int n_cand, const float4 wreg,
                                                 const float4 (&A)[NA], float (&best)[NA],
-                                                int (&best_slot)[NA]) {
+                                                int (&best_slot)[NA], const float kIouFloor) {
     float area_a[NA], area_lo[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
@@ -335,9 +340,9 @@ __device__ __forceinline__ void scan_candidates(const GtSmem &s, int n_cand, con
 
 template <int PL>
 __global__ void __launch_bounds__(kAssignThreads)
-    retina_assign_kernel(Geo g, BaseAnchors ba, TileTab tt, const float *__restrict__ annots, int G,
-                         int *__restrict__ labels, int *__restrict__ matched, Queues q,
-                         int *__restrict__ npos_partials) {
+    retina_assign_kernel(Geo g, BaseAnchors ba, TileTab tt, IouThresholds thr,
+                         const float *__restrict__ annots, int G, int *__restrict__ labels,
+                         int *__restrict__ matched, Queues q, int *__restrict__ npos_partials) {
     constexpr int NA = PL > 0 ? PL : 1;
     constexpr int kQueue = kAssignThreads * (PL > 0 ? PL : kMaxPerLoc);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -390,17 +395,17 @@ __global__ void __launch_bounds__(kAssignThreads)
             A[a].w = __fadd_rn(ba.v[me.l][a0 + a][3], sy);
         }
         if (matched)
-            scan_candidates<NA, true>(s, n_cand, wreg, A, best, best_slot);
+            scan_candidates<NA, true>(s, n_cand, wreg, A, best, best_slot, thr.floor);
         else
-            scan_candidates<NA, false>(s, n_cand, wreg, A, best, best_slot);
+            scan_candidates<NA, false>(s, n_cand, wreg, A, best, best_slot, thr.floor);
         // labels (losses.py:358-365)
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
             int label = -1, match = -1, grow = -1;
             if (has_gt) {
                 match = best_slot[a] >= 0 ? s.fidx[best_slot[a]] : 0;
-                if (best[a] < 0.4f) label = 0;
-                if (best[a] >= 0.5f) {
+                if (best[a] < thr.neg) label = 0;
+                if (best[a] >= thr.pos) {
                     label = s.label[best_slot[a]];
                     grow = s.ridx[best_slot[a]];
                 }
@@ -874,13 +879,19 @@ static int raise_smem_limit(K kernel, bool *done) {
 }
 
 extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *annotations,
-                                     int max_gt, int32_t *labels, int32_t *matched,
-                                     void *workspace, size_t workspace_bytes, void *stream) {
+                                     int max_gt, float iou_neg, float iou_pos, int32_t *labels,
+                                     int32_t *matched, void *workspace, size_t workspace_bytes,
+                                     void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
     if (!annotations || !labels || !workspace) return B200DET_EINVAL;
     if (max_gt < 1 || max_gt > B200DET_MAX_GT) return B200DET_ERANGE;
+    if (!(iou_neg > 0.f) || !(iou_pos >= iou_neg)) return B200DET_EINVAL;
+    IouThresholds thr;
+    thr.neg = iou_neg;
+    thr.pos = iou_pos;
+    thr.floor = 0.95f * iou_neg;
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     BaseAnchors ba;
@@ -901,10 +912,10 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
     ProfScope prof(kKernAssign, stream);
     if (g.per_loc == 9)
         retina_assign_kernel<9><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
-            g, ba, tt, annotations, max_gt, labels, matched, q, npos);
+            g, ba, tt, thr, annotations, max_gt, labels, matched, q, npos);
     else
         retina_assign_kernel<0><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
-            g, ba, tt, annotations, max_gt, labels, matched, q, npos);
+            g, ba, tt, thr, annotations, max_gt, labels, matched, q, npos);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -919,7 +919,6 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
         // raw tile: R rows, R % 4 == 0 so that every tile starts 16-byte aligned
         R = (int)(((long long)budget * 4 / g.num_classes) & ~3ll);
         if (R < 4) R = 4;
-        if (R > kArgThreads) R = kArgThreads;
         if ((long long)R * g.num_classes > (long long)budget * 4) return B200DET_ERANGE;  // > 1280 classes
         a.pitch = g.num_classes;
     }

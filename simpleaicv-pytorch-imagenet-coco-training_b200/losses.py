@@ -145,6 +145,7 @@ def _loss_params(owner, reg_dtype):
     p.w_cls = float(owner.cls_loss_weight)
     p.w_box = float(owner.box_loss_weight)
     p.w_ctr = float(getattr(owner, 'center_ness_loss_weight', 0.))
+    p.iou_neg, p.iou_pos = owner._iou_thresholds
     return p
 
 
@@ -255,8 +256,9 @@ class _DetLossFunction(torch.autograd.Function):
                                             ws_ptr, ws_bytes, st), 'b200det_fcos_assign')
             else:
                 _lib.check(
-                    lib.b200det_retina_assign(geo, annotations.data_ptr(), max_gt, labels_ptr,
-                                              None, ws_ptr, ws_bytes, st),
+                    lib.b200det_retina_assign(geo, annotations.data_ptr(), max_gt,
+                                              owner._iou_thresholds[0], owner._iou_thresholds[1],
+                                              labels_ptr, None, ws_ptr, ws_bytes, st),
                     'b200det_retina_assign')
             _lib.check(
                 lib.b200det_sparse_losses(geo, int(is_fcos), annotations.data_ptr(), max_gt,
@@ -359,6 +361,7 @@ def _debug_assign(owner, preds, annotations, exact=True):
     else:
         _lib.check(
             lib.b200det_retina_assign(geo, annotations.data_ptr(), int(annotations.shape[1]),
+                                      owner._iou_thresholds[0], owner._iou_thresholds[1],
                                       labels.data_ptr(), matched_ptr, ws.data_ptr(), ws_bytes,
                                       st), 'b200det_retina_assign')
 
@@ -381,6 +384,7 @@ class RetinaLoss(nn.Module):
     """Drop-in for simpleAICV.detection.losses.RetinaLoss (losses.py:126-429)."""
 
     _is_fcos = False
+    _iou_thresholds = (0.4, 0.5)   # losses.py:361-365
 
     def __init__(self,
                  areas=[[32, 32], [64, 64], [128, 128], [256, 256], [512, 512]],
@@ -456,6 +460,7 @@ class FCOSLoss(nn.Module):
     """Drop-in for simpleAICV.detection.losses.FCOSLoss (losses.py:432-833)."""
 
     _is_fcos = True
+    _iou_thresholds = (0.4, 0.5)   # unused by the point assignment
 
     def __init__(self,
                  strides=[8, 16, 32, 64, 128],

@@ -177,10 +177,62 @@ def make_tables(path):
     np.savez_compressed(path, **out)
 
 
+FACE_SIZES = [[8, 16, 32], [32, 64, 128], [128, 256, 512]]
+FACE_STRIDES = [8, 16, 32]
+
+
+def make_face(path):
+    FL, FD = refload.load_face()
+    size, B, G = 256, 3, 10
+    gen = torch.Generator().manual_seed(11)
+    cls, reg = [], []
+    for p in (32, 16, 8):
+        cls.append(torch.sigmoid(torch.randn((B, p, p, 3, 1), generator=gen) - 1.5))
+        reg.append(torch.randn((B, p, p, 3, 4), generator=gen) * 0.2)
+    preds = synth.make_tie_free([cls, reg], min_score=0.3)
+    ann = edge_annotations(synth.make_annotations(B, G, size, 1, seed=12), size)
+    ann[..., 4] = torch.where(ann[..., 4] >= 0, torch.zeros_like(ann[..., 4]), ann[..., 4])
+    out = {'versions': versions(), 'size': size, 'annotations': ann.numpy()}
+    for i, (c, r) in enumerate(zip(*preds)):
+        out[f'cls{i}'] = c.numpy()
+        out[f'reg{i}'] = r.numpy()
+    for box_type in ['SmoothL1'] + IOU_TYPES:
+        crit = FL.RetinaFaceLoss(anchor_sizes=FACE_SIZES, strides=FACE_STRIDES,
+                                 box_loss_type=box_type)
+        with torch.no_grad():
+            d = crit(preds, ann)
+        out[f'loss_{box_type}'] = np.array([d['cls_loss'].item(), d['reg_loss'].item()],
+                                           dtype=np.float32)
+    crit = FL.RetinaFaceLoss(anchor_sizes=FACE_SIZES, strides=FACE_STRIDES)
+    anchors = crit.anchors([[c.shape[2], c.shape[1]] for c in preds[0]])
+    flat = torch.cat([torch.tensor(a).view(-1, 4) for a in anchors], dim=0)
+    out['assign'] = crit.get_batch_anchors_annotations(flat.unsqueeze(0).repeat(B, 1, 1),
+                                                       ann).numpy()
+    out['anchors'] = flat.numpy()
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+    d = crit(p, ann)
+    (d['cls_loss'] + 2.0 * d['reg_loss']).backward()
+    for i in range(3):
+        out[f'gcls_{i}'] = p[0][i].grad.numpy()
+        out[f'greg_{i}'] = p[1][i].grad.numpy()
+    for nms in ['python_nms', 'diou_python_nms']:
+        dec = FD.RetinaFaceDecoder(anchor_sizes=FACE_SIZES, strides=FACE_STRIDES, nms_type=nms)
+        s_, c_, b_ = dec(preds)
+        out[f'dec_{nms}_scores'] = s_
+        out[f'dec_{nms}_classes'] = c_
+        out[f'dec_{nms}_boxes'] = b_
+    np.savez_compressed(path, **out)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'face':
+        make_face(os.path.join(HERE, 'retinaface_small.npz'))
+        print('retinaface_small.npz', os.path.getsize(os.path.join(HERE, 'retinaface_small.npz')))
+        sys.exit(0)
     make_retina(os.path.join(HERE, 'retina_small.npz'))
     make_fcos(os.path.join(HERE, 'fcos_small.npz'))
     make_tables(os.path.join(HERE, 'tables.npz'))
+    make_face(os.path.join(HERE, 'retinaface_small.npz'))
     for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)))

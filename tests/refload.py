@@ -32,3 +32,11 @@ def load():
     from simpleAICV.detection import decode as ref_decode
     from simpleAICV.detection.models import anchor as ref_anchor
     return ref_losses, ref_decode, ref_anchor
+
+
+def load_face():
+    """Returns (losses_module, decode_module) of simpleAICV.face_detection in the reference."""
+    load()
+    from simpleAICV.face_detection import losses as face_losses
+    from simpleAICV.face_detection import decode as face_decode
+    return face_losses, face_decode

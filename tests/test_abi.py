@@ -52,7 +52,8 @@ def test_argument_errors_are_returned_not_raised():
     lib = _lib.load()
     geo = geometry.make_geometry([(4, 4)], 1, 1, 8, [8], mi=[[-1, 64]], center_sample_radius=1.5)
     # null pointers / bad sizes are rejected on the host before any CUDA call
-    assert lib.b200det_retina_assign(ctypes.byref(geo), None, 4, None, None, None, 0, None) == -1
+    assert lib.b200det_retina_assign(ctypes.byref(geo), None, 4, 0.4, 0.5, None, None, None, 0,
+                                     None) == -1
     assert lib.b200det_focal_loss(ctypes.byref(geo), None, None, 0.25, 2.0, None, None, 1.0,
                                   None, 0, None) == -1
     assert lib.b200det_loss_finish(None, 1.0, 1.0, 1.0, None, None) == -1
@@ -100,6 +101,14 @@ def test_drop_in_surface_matches_reference_signatures():
         losses.RetinaLoss(box_loss_type='L2')
     with pytest.raises(AssertionError):
         decode.RetinaDecoder(nms_type='soft_nms')
+    from b200det.face_detection import losses as fl, decode as fd
+    fsig = inspect.signature(fl.__dict__['RetinaFaceLoss'].__init__).parameters
+    assert [p for p in fsig if p not in ('self', 'sync_normalizer', 'process_group')] == [
+        'anchor_sizes', 'strides', 'alpha', 'gamma', 'beta', 'cls_loss_weight', 'box_loss_weight',
+        'box_loss_type']
+    assert fsig['box_loss_type'].default == 'CIoU'
+    dsig = inspect.signature(fd.__dict__['RetinaFaceDecoder'].__init__).parameters
+    assert dsig['min_score_threshold'].default == 0.3 and dsig['nms_threshold'].default == 0.3
     import torch
     assert isinstance(losses.RetinaLoss(), torch.nn.Module)      # train script calls .cuda() on it
 

@@ -622,6 +622,43 @@ def test_training_and_eval_loops_like_the_reference_scripts():
     assert scores.shape == (B, 100) and boxes.shape == (B, 100, 4)
 
 
+def test_retinaface_drop_in_golden():
+    """RetinaFaceLoss / RetinaFaceDecoder reuse the detection kernels
+    (square anchors, 0.35 / 0.35 thresholds, one class); checked against the reference's own
+    face_detection classes (golden vectors)."""
+    from b200det.face_detection import losses as face_losses, decode as face_decode
+    face = G.load('retinaface_small.npz')
+    preds, ann = G.retina_inputs(face)
+    sizes, strides = [[8, 16, 32], [32, 64, 128], [128, 256, 512]], [8, 16, 32]
+    for box_type in ['SmoothL1'] + G.IOU_TYPES:
+        crit = face_losses.__dict__['RetinaFaceLoss'](anchor_sizes=sizes, strides=strides,
+                                                      box_loss_type=box_type)
+        with torch.no_grad():
+            d = crit(dev(preds), ann.cuda())
+        assert_close(loss_values(d, ['cls_loss', 'reg_loss']), face[f'loss_{box_type}'],
+                     LOSS_RTOL, f'RetinaFaceLoss {box_type}')
+    crit = face_losses.RetinaFaceLoss(anchor_sizes=sizes, strides=strides)
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    assert np.array_equal(got['labels'].cpu().numpy(), face['assign'][..., 4].astype(np.int32))
+    fast = crit.debug_assign(dev(preds), ann.cuda(), exact=False)
+    assert np.array_equal(fast['labels'].cpu().numpy(), face['assign'][..., 4].astype(np.int32))
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(preds)]
+    d = crit(p, ann.cuda())
+    (d['cls_loss'] + 2.0 * d['reg_loss']).backward()
+    for i in range(3):
+        np.testing.assert_allclose(p[0][i].grad.cpu().numpy(), face[f'gcls_{i}'], rtol=GRAD_RTOL,
+                                   atol=GRAD_ATOL)
+        np.testing.assert_allclose(p[1][i].grad.cpu().numpy(), face[f'greg_{i}'], rtol=GRAD_RTOL,
+                                   atol=GRAD_ATOL)
+    for nms in ('python_nms', 'diou_python_nms'):
+        dec = face_decode.__dict__['RetinaFaceDecoder'](anchor_sizes=sizes, strides=strides,
+                                                        nms_type=nms)
+        s, c, b = dec(dev(preds))
+        G.assert_bit_equal(s, face[f'dec_{nms}_scores'], 'scores')
+        G.assert_bit_equal(c, face[f'dec_{nms}_classes'], 'classes')
+        G.assert_bit_equal(b, face[f'dec_{nms}_boxes'], 'boxes')
+
+
 def test_cpu_tensors_are_rejected():
     preds = synth.make_retina_preds(1, 128, 8, seed=8)
     ann = synth.make_annotations(1, 4, 128, 8, seed=9)
