@@ -659,6 +659,41 @@ def test_retinaface_drop_in_golden():
         G.assert_bit_equal(b, face[f'dec_{nms}_boxes'], 'boxes')
 
 
+def test_limits_topn_2048_many_outputs_2048_gt_single_level():
+    """Compiled limits: topn = 2048 (sort of 4096 entries), max_object_num = 300, 2048 annotation
+    rows per image (98 KB of staged GT, 16 compaction rounds), single-level pyramid, batch 1."""
+    kw = dict(areas=[[32, 32]], ratios=[0.5, 1, 2], scales=[2**0, 2**(1.0 / 3.0), 2**(2.0 / 3.0)],
+              strides=[8])
+    gen = torch.Generator().manual_seed(9)
+    cls = [torch.sigmoid(torch.randn((1, 40, 40, 9, 4), generator=gen) - 1.0)]
+    reg = [torch.randn((1, 40, 40, 9, 4), generator=gen) * 0.2]
+    preds = synth.make_tie_free([cls, reg])
+    ann = synth.make_annotations(1, 2048, 320, 4, seed=10, min_gt=2000)
+    ann[..., 0:4] = ann[..., 0:4].clamp(max=320.)
+    crit = losses.RetinaLoss(**kw, box_loss_type='IoU')
+    with torch.no_grad():
+        d = crit(dev(preds), ann.cuda())
+        ref = O.retina_loss(preds, ann, **kw, box_loss_type='IoU')
+    got = crit.debug_assign(dev(preds), ann.cuda())
+    assert np.array_equal(got['labels'].cpu().numpy(), ref['labels'].numpy().astype(np.int32))
+    assert np.array_equal(got['matched'].cpu().numpy(), ref['matched'].numpy().astype(np.int32))
+    assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
+                 [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, 'RetinaLoss G=2048')
+    dec = decode.RetinaDecoder(**kw, topn=2048, max_object_num=300, nms_threshold=0.7)
+    (s, c, b), info = dec.decode_with_details(dev(preds))
+    (s0, c0, b0), extra = O.retina_decode(preds, **kw, topn=2048, max_object_num=300,
+                                          nms_threshold=0.7)
+    G.assert_bit_equal(s, s0)
+    G.assert_bit_equal(c, c0)
+    G.assert_bit_equal(b, b0)
+    check_decode_details(info, extra['per_image'], 2048)
+    assert info['counts'][0, 1] == 2048
+    with pytest.raises(ValueError):
+        decode.RetinaDecoder(**kw, topn=4096)
+    with pytest.raises(ValueError):
+        crit(dev(preds), torch.full((1, 3000, 5), -1.).cuda())
+
+
 def test_cpu_tensors_are_rejected():
     preds = synth.make_retina_preds(1, 128, 8, seed=8)
     ann = synth.make_annotations(1, 4, 128, 8, seed=9)
