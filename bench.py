@@ -177,7 +177,9 @@ def run_reference(args, out):
         'vs_baseline': None,
         'dtype': 'f32',
         'data': 'synthetic',
-        'config': workload_config(per_step, 1),
+        # the arm's own config (what the sample is a sample OF); the sample size is below
+        'config': workload_config(args.batch, args.gpus),
+        'sample_images_per_step': per_step,
         'cpu_baseline': {
             'value': value,
             'unit': 'images/s',
