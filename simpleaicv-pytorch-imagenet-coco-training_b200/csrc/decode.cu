@@ -504,6 +504,7 @@ __global__ void __launch_bounds__(kSelThreads)
     float *out_scores = out + (size_t)b * a.max_out;
     float *out_classes = out + (size_t)B * a.max_out + (size_t)b * a.max_out;
     float *out_boxes = out + (size_t)2 * B * a.max_out + (size_t)b * a.max_out * 4;
+    const bool boxes_vec = (((size_t)2 * B * a.max_out) & 3) == 0;
 
     const int cap = 2 * a.pad_n;  // capacity of skey
     int ncand, k_sel, n_got;
@@ -816,7 +817,14 @@ __global__ void __launch_bounds__(kSelThreads)
         }
         out_scores[i] = s;
         out_classes[i] = c;
-        reinterpret_cast<float4 *>(out_boxes)[i] = bx;
+        if (boxes_vec) {
+            reinterpret_cast<float4 *>(out_boxes)[i] = bx;
+        } else {  // 2*B*max_out not a multiple of 4: the boxes block is only 4-byte aligned
+            out_boxes[4 * i + 0] = bx.x;
+            out_boxes[4 * i + 1] = bx.y;
+            out_boxes[4 * i + 2] = bx.z;
+            out_boxes[4 * i + 3] = bx.w;
+        }
     }
     if (keep_out) {
         for (int i = tid; i < a.topn; i += kSelThreads)
@@ -978,8 +986,6 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
     if (reg_dtype != B200DET_F32 && reg_dtype != B200DET_F16 && reg_dtype != B200DET_BF16)
         return B200DET_EINVAL;
     if (reinterpret_cast<uintptr_t>(out) & 15) return B200DET_EALIGN;
-    // the boxes block starts at out + 2*B*max_out floats and is written as float4
-    if (((size_t)2 * g.batch * max_out) & 3) return B200DET_EALIGN;
     SelectArgs a;
     a.g = g;
     for (int l = 0; l < kMaxLevels; ++l) {
