@@ -602,7 +602,14 @@ struct SparseArgs {
 // 64-bit fixed point: integer adds commute, so the sums are independent of the visiting order
 constexpr double kFxBox = 4294967296.0;          // 2^32
 constexpr double kFxFocal = 1099511627776.0;     // 2^40
-__device__ __forceinline__ long long to_fx(float v, double scale) {
+// NaN / inf terms cannot be represented: they set `bad` and the CTA's partial becomes NaN, which the
+// fp64 reduction propagates (the reference's float sum would be NaN or inf; the caller's training
+// loop skips the step either way, tools/scripts.py:922-930).
+__device__ __forceinline__ long long to_fx(float v, double scale, unsigned &bad, unsigned bit) {
+    if (!(fabsf(v) <= 3.402823466e38f)) {
+        bad |= bit;
+        return 0;
+    }
     return __double2ll_rn((double)v * scale);
 }
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -634,6 +641,7 @@ __global__ void __launch_bounds__(kSparseThreads)
     const int gtid = blockIdx.x * kSparseThreads + threadIdx.x;
     const int gsize = gridDim.x * kSparseThreads;
     long long box_fx = 0, ctr_fx = 0, foc_fx = 0;
+    unsigned bad = 0;  // bit 0 box, bit 1 centre-ness, bit 2 focal corrections
 
     // ---- positives: one thread each ----
     for (int k = gtid; k < n_pos; k += gsize) {
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(kSparseThreads)
             float4 grad = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!a.is_fcos) {
                 const float4 an = anchor_of(g, a.ba, l, local);
-                box_fx += to_fx(retina_box_term(an, gt, t, a.box_loss, a.beta, grad), kFxBox);
+                box_fx += to_fx(retina_box_term(an, gt, t, a.box_loss, a.beta, grad), kFxBox, bad, 1u);
             } else {
                 // IoU loss, losses.py:550-586: boxes rebuilt around the point from l,t,r,b
                 const float2 pt = point_of(g, l, local);
@@ -663,15 +671,15 @@ __global__ void __launch_bounds__(kSparseThreads)
                 const float gg[4] = {__fsub_rn(pt.x, bl), __fsub_rn(pt.y, bt), __fadd_rn(pt.x, br),
                                      __fadd_rn(pt.y, bb)};
                 const Dual iou = iou_family(p, gg, a.box_loss);
-                box_fx += to_fx(__fmul_rn(__fsub_rn(1.f, iou.v), ctr_t), kFxBox);
+                box_fx += to_fx(__fmul_rn(__fsub_rn(1.f, iou.v), ctr_t), kFxBox, bad, 1u);
                 grad = make_float4(-iou.d[0] * ctr_t, -iou.d[1] * ctr_t, -iou.d[2] * ctr_t,
                                    -iou.d[3] * ctr_t);
                 // centre-ness BCE, losses.py:588-610 (prob clamped at losses.py:494)
                 const float craw = __ldg(static_cast<const float *>(a.ctr.p[l]) + rrow);
-                const float cp = fminf(fmaxf(craw, kClampLo), kClampHi);
+                const float cp = clamp_prob(craw);
                 const float one_m = __fsub_rn(1.f, cp), one_t = __fsub_rn(1.f, ctr_t);
                 ctr_fx += to_fx(-__fadd_rn(__fmul_rn(ctr_t, logf(cp)), __fmul_rn(one_t, logf(one_m))),
-                                kFxBox);
+                                kFxBox, bad, 2u);
                 if (a.ctr_grad.p[0] != nullptr) {
                     const float cgrad =
                         (craw >= kClampLo && craw <= kClampHi) ? -(ctr_t / cp - one_t / one_m) : 0.f;
@@ -685,7 +693,7 @@ __global__ void __launch_bounds__(kSparseThreads)
             const float p = __ldg(static_cast<const float *>(a.cls.p[l]) + rrow * a.C + (label - 1));
             foc_fx += to_fx(a.alpha * pos_term(p, a.gamma, gamma2) -
                                 (1.f - a.alpha) * neg_term(p, a.gamma, gamma2),
-                            kFxFocal);
+                            kFxFocal, bad, 4u);
         }
     }
 
@@ -720,7 +728,7 @@ __global__ void __launch_bounds__(kSparseThreads)
 #pragma unroll
             for (int t = 0; t < kRowsInFlight; ++t) {
                 const float s = warp_sum(sum[t]);
-                if (lane == 0 && live[t]) foc_fx -= to_fx((1.f - a.alpha) * s, kFxFocal);
+                if (lane == 0 && live[t]) foc_fx -= to_fx((1.f - a.alpha) * s, kFxFocal, bad, 4u);
             }
         }
     }
@@ -735,7 +743,10 @@ __global__ void __launch_bounds__(kSparseThreads)
         red[1][warp] = ctr_fx;
         red[2][warp] = foc_fx;
     }
-    __syncthreads();
+    // __syncthreads_or returns a truth value, not the bitwise OR: one vote per loss
+    const bool bad_box = __syncthreads_or((int)(bad & 1u)) != 0;
+    const bool bad_ctr = __syncthreads_or((int)(bad & 2u)) != 0;
+    const bool bad_foc = __syncthreads_or((int)(bad & 4u)) != 0;
     if (threadIdx.x == 0) {
         long long sb = 0, sc = 0, sf = 0;
         for (int w = 0; w < kSparseThreads / 32; ++w) {
@@ -747,6 +758,10 @@ __global__ void __launch_bounds__(kSparseThreads)
         p.box = (double)sb / kFxBox;
         p.ctr = (double)sc / kFxBox;
         p.focal = (double)sf / kFxFocal;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        if (bad_box) p.box = nan;
+        if (bad_ctr) p.ctr = nan;
+        if (bad_foc) p.focal = nan;
         partials[blockIdx.x] = p;
     }
 }

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kArgThreads)
                 float mx = 0.f;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    x[e] = fmaxf(v[k][e], kClampLo);
+                    x[e] = fmax_nan(v[k][e], kClampLo);
                     mx = fmaxf(mx, x[e]);
                 }
                 if (gamma2 && mx <= kFastMax && VEC == 4) {

@@ -5,8 +5,12 @@
 //   * clamp(min=c) passes the gradient where x >= c (inclusive),
 //   * CIoU's alpha is a constant (torch.no_grad, losses.py:104-105).
 // Only positives (a few thousand rows per batch) evaluate this, so clarity beats speed.
+//   * max / min / clamp propagate NaN like torch does (fmax_nan / fmin_nan), so a NaN regression
+//     output yields a NaN loss instead of silently disappearing.
 #pragma once
 #include <cuda_runtime.h>
+
+#include "focal_terms.cuh"
 
 namespace b200det {
 
@@ -111,7 +115,7 @@ __device__ __forceinline__ Dual datan(const Dual &a) {
 // max / min against a constant
 __device__ __forceinline__ Dual dmax(const Dual &a, float b) {
     Dual r;
-    r.v = fmaxf(a.v, b);
+    r.v = fmax_nan(a.v, b);
     const float w = a.v > b ? 1.f : (a.v == b ? 0.5f : 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.d[i] = w * a.d[i];
@@ -119,7 +123,7 @@ __device__ __forceinline__ Dual dmax(const Dual &a, float b) {
 }
 __device__ __forceinline__ Dual dmin(const Dual &a, float b) {
     Dual r;
-    r.v = fminf(a.v, b);
+    r.v = fmin_nan(a.v, b);
     const float w = a.v < b ? 1.f : (a.v == b ? 0.5f : 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.d[i] = w * a.d[i];
@@ -128,7 +132,7 @@ __device__ __forceinline__ Dual dmin(const Dual &a, float b) {
 // torch.clamp(x, min=c): gradient passes where x >= c
 __device__ __forceinline__ Dual dclamp_min(const Dual &a, float c) {
     Dual r;
-    r.v = fmaxf(a.v, c);
+    r.v = fmax_nan(a.v, c);
     const float w = a.v >= c ? 1.f : 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.d[i] = w * a.d[i];

@@ -116,7 +116,7 @@ LossWs loss_ws_layout(const Geo &g) {
     w.off_assign = 0;
     w.off_sparse = up(w.assign_blocks * sizeof(int));
     w.off_focal = w.off_sparse + up(w.sparse_blocks * sizeof(SparsePartial));
-    w.off_counters = w.off_focal + up(kSweepSlots * sizeof(long long));
+    w.off_counters = w.off_focal + up(kSweepWords * sizeof(long long));
     w.off_pos_queue = w.off_counters + 256;
     w.off_ign_queue = w.off_pos_queue + up((size_t)g.batch * (size_t)N * sizeof(int2));
     w.total = w.off_ign_queue + up((size_t)g.batch * (size_t)N * sizeof(int));
@@ -194,7 +194,7 @@ __device__ __forceinline__ float focal_all_chunk(const float *__restrict__ src, 
             float mx = 0.f;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                x[e] = fmaxf(v[k][e], kClampLo);
+                x[e] = fmax_nan(v[k][e], kClampLo);
                 mx = fmaxf(mx, x[e]);
             }
             if (!FULL && v[k][0] < 0.f) continue;
@@ -238,7 +238,7 @@ template <bool GRAD>
 __device__ __forceinline__ void slow_element(float p, bool is_target, float alpha, float gamma,
                                              bool gamma2, float &acc_pos, float &acc_neg,
                                              float &g) {
-    const float pc = fminf(fmaxf(p, kClampLo), kClampHi);
+    const float pc = clamp_prob(p);
     const bool in_range = (p >= kClampLo) && (p <= kClampHi);
     if (is_target) {
         const float om = 1.f - pc;  // 1 - pt
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
                 float mx = 0.f;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    x[e] = fmaxf(v[k][e], kClampLo);
+                    x[e] = fmax_nan(v[k][e], kClampLo);
                     mx = fmaxf(mx, x[e]);
                 }
                 const bool has_target = lab[k] > 0 && (unsigned)tgt[k] < (unsigned)VEC;
@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(1024)
     if (which & 2) {
         for (long long i = threadIdx.x; i < n_focal; i += blockDim.x)
             s_cls += (double)fp[i] / kFxSweep;
+        if (threadIdx.x == 0 && fp[n_focal] != 0) s_cls = __longlong_as_double(0x7ff8000000000000ll);
     }
     // fixed-order tree: xor-shuffle inside the warp, then warp 0 over the 32 warp sums
 #pragma unroll
@@ -639,7 +640,7 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     long long *partials =
         reinterpret_cast<long long *>(static_cast<char *>(workspace) + ws.off_focal);
     if (!g_skip_memset) {
-        cudaError_t me = cudaMemsetAsync(partials, 0, kSweepSlots * sizeof(long long),
+        cudaError_t me = cudaMemsetAsync(partials, 0, kSweepWords * sizeof(long long),
                                          (cudaStream_t)stream);
         if (me != cudaSuccess) return (int)me;
     }

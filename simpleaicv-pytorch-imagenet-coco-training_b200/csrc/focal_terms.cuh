@@ -14,6 +14,23 @@ constexpr float kClampLo = 1e-4f;    // float32(1e-4)      (losses.py:196, :493)
 constexpr float kClampHi = 0.9999f;  // float32(1. - 1e-4)
 constexpr float kFastMax = 0.25f;
 
+// torch.clamp propagates NaN (fmaxf / fminf do not): a NaN probability must reach the loss value,
+// because the caller's training loop skips steps whose loss is NaN (tools/scripts.py:922-930).
+// max.NaN / min.NaN are single FMNMX.NAN instructions.
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float clamp_prob(float p) {
+    return fmin_nan(fmax_nan(p, kClampLo), kClampHi);
+}
+
 // S(x) = -log(1 - x) / x on [0, 0.25]; Chebyshev-node fit, max rel err 1.3e-7 in float32 Horner
 __device__ __forceinline__ float neg_log1m_over_x(float x) {
     float s = 0.3386436402797699f;
@@ -59,7 +76,7 @@ __device__ __forceinline__ float2 neg_term_fast2_acc(float2 x_clamped_lo, float2
 
 // exact-form background term (any p, any gamma): accurate logf / powf
 static __device__ __noinline__ float neg_term_slow(float p, float gamma, bool gamma2) {
-    const float pc = fminf(fmaxf(p, kClampLo), kClampHi);
+    const float pc = clamp_prob(p);
     const float q = 1.f - pc;  // pt
     const float x = 1.f - q;   // 1 - pt
     const float w = gamma2 ? x * x : powf(x, gamma);
@@ -67,7 +84,7 @@ static __device__ __noinline__ float neg_term_slow(float p, float gamma, bool ga
 }
 
 __device__ __forceinline__ float neg_term(float p, float gamma, bool gamma2) {
-    const float x = fmaxf(p, kClampLo);
+    const float x = fmax_nan(p, kClampLo);
     if (gamma2 && x <= kFastMax) {
         float a, b;
         return neg_term_fast(x, a, b);
@@ -77,7 +94,7 @@ __device__ __forceinline__ float neg_term(float p, float gamma, bool gamma2) {
 
 // target-class term
 __device__ __forceinline__ float pos_term(float p, float gamma, bool gamma2) {
-    const float pc = fminf(fmaxf(p, kClampLo), kClampHi);
+    const float pc = clamp_prob(p);
     const float om = 1.f - pc;  // 1 - pt
     const float w = gamma2 ? om * om : powf(om, gamma);
     return w * (-logf(pc));
@@ -87,7 +104,10 @@ __device__ __forceinline__ float pos_term(float p, float gamma, bool gamma2) {
 // commute, so the total does not depend on CTA scheduling order (deterministic), and the final
 // reduction reads kSweepSlots values instead of one partial per CTA (300k at batch 256).
 // Scale 2^36: resolution 1.5e-11 per CTA sum (typical CTA sums are ~1e-2), capacity 1.3e8 per slot.
+// slots[kSweepSlots] is a poison flag: set when a CTA sum is NaN / inf (the reduction then reports
+// NaN like the reference's float sum would).
 constexpr int kSweepSlots = 1024;
+constexpr int kSweepWords = kSweepSlots + 1;
 constexpr double kFxSweep = 68719476736.0;   // 2^36
 template <int THREADS>
 __device__ __forceinline__ void sweep_accumulate(float value, long long *slots) {
@@ -102,9 +122,13 @@ __device__ __forceinline__ void sweep_accumulate(float value, long long *slots) 
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < THREADS / 32; ++i) s += sweep_red[i];
-        const long long fx = __double2ll_rn((double)s * kFxSweep);
-        atomicAdd(reinterpret_cast<unsigned long long *>(slots + (blockIdx.x & (kSweepSlots - 1))),
-                  (unsigned long long)fx);
+        if (!(fabsf(s) <= 3.402823466e38f)) {
+            slots[kSweepSlots] = 1;
+        } else {
+            const long long fx = __double2ll_rn((double)s * kFxSweep);
+            atomicAdd(reinterpret_cast<unsigned long long *>(slots + (blockIdx.x & (kSweepSlots - 1))),
+                      (unsigned long long)fx);
+        }
     }
 }
 

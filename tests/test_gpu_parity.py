@@ -694,6 +694,62 @@ def test_limits_topn_2048_many_outputs_2048_gt_single_level():
         crit(dev(preds), torch.full((1, 3000, 5), -1.).cuda())
 
 
+def test_nan_and_inf_inputs_reach_the_loss_like_the_reference():
+    """The reference's training loop skips steps whose loss is NaN / inf (tools/scripts.py:922-930);
+    torch.clamp propagates NaN (losses.py:196), so a NaN probability or a NaN / overflowing box
+    regression at a positive row must make the matching loss non-finite here too, while values at
+    rows the loss never reads (regression of negatives) must not."""
+    from b200det import fused
+    clean = synth.make_retina_preds(2, 128, 8, seed=41)
+    ann = synth.make_annotations(2, 6, 128, 8, seed=42, min_gt=3)
+    kw = dict(**synth.RETINA_KW, box_loss_type='GIoU')
+    crit = losses.RetinaLoss(**kw)
+    with torch.no_grad():
+        ref = O.retina_loss(clean, ann, **kw)
+    labels = ref['labels'].numpy()
+    n0 = clean[0][0][0].numel() // 8                      # rows of level 0 per image
+    pos = int(np.nonzero(labels[1, :n0] > 0)[0][0])
+    neg = int(np.nonzero(labels[1, :n0] == 0)[0][0])
+
+    def variant(kind, row, value):
+        p = [[t.clone() for t in grp] for grp in clean]
+        grp = 0 if kind == 'cls' else 1
+        width = 8 if kind == 'cls' else 4
+        p[grp][0].view(2, -1, width)[1, row, 1] = value
+        return p
+
+    cases = [('cls', neg, float('nan')), ('cls', pos, float('nan')), ('reg', pos, float('nan')),
+             ('reg', neg, float('nan')), ('reg', pos, 200.0), ('reg', neg, float('inf'))]
+    for kind, row, value in cases:
+        p = variant(kind, row, value)
+        with torch.no_grad():
+            want = O.retina_loss(p, ann, **kw)
+            got = crit(dev(p), ann.cuda())
+            both, _ = fused.EvalStep(crit, decode.RetinaDecoder(**synth.RETINA_KW))(dev(p), ann.cuda())
+        pt = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(p)]
+        train = crit(pt, ann.cuda())
+        for name, d in (('eval', got), ('fused', both), ('train', train)):
+            for k in ('cls_loss', 'reg_loss'):
+                w, g = want[k].item(), d[k].item()
+                assert np.isfinite(w) == np.isfinite(g), f'{name} {kind} row {row} = {value}: {k} {g} vs {w}'
+                if np.isfinite(w):
+                    assert_close([g], [w], LOSS_RTOL, f'{name} {k}')
+    # FCOS: centre-ness NaN at a positive point
+    fclean = synth.make_fcos_preds(2, 128, 8, seed=43)
+    fcrit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    with torch.no_grad():
+        fref = O.fcos_loss(fclean, ann, synth.STRIDES, synth.MI)
+    fpos = int(np.nonzero(fref['labels'].numpy()[0, :256] > 0)[0][0])
+    fp = [[t.clone() for t in grp] for grp in fclean]
+    fp[2][0].view(2, -1)[0, fpos] = float('nan')
+    with torch.no_grad():
+        want = O.fcos_loss(fp, ann, synth.STRIDES, synth.MI)
+        got = fcrit(dev(fp), ann.cuda())
+    assert np.isnan(want['center_ness_loss'].item()) and np.isnan(got['center_ness_loss'].item())
+    assert_close(loss_values(got, ['cls_loss', 'reg_loss']),
+                 [want['cls_loss'].item(), want['reg_loss'].item()], LOSS_RTOL, 'FCOS other losses')
+
+
 def test_cpu_tensors_are_rejected():
     preds = synth.make_retina_preds(1, 128, 8, seed=8)
     ann = synth.make_annotations(1, 4, 128, 8, seed=9)
