@@ -334,6 +334,22 @@ int b200det_generate_rows(const b200det_geometry *geo, int is_fcos, float *out, 
 /* y[i] = exp(x[i]) with the NumPy float32 algorithm used by the decoders (test hook) */
 int b200det_npexp_f32(const float *x, float *y, long long n, void *stream);
 
+/* ---- head tail: sigmoid + NCHW -> NHWC in one pass --------------------------------
+ * Replaces `x = x.float(); x = self.sigmoid(x)` (models/head.py:46-50 RetinaClsHead.forward,
+ * :176-179 FCOSClsRegCntHead.forward) followed by `permute(0, 2, 3, 1).contiguous()`
+ * (models/retinanet.py:73-77, models/fcos.py:70-79).
+ *   src  [batch, channels, hw]  convolution output, B200DET_F32 / F16 / BF16, contiguous
+ *   dst  [batch, hw, channels]  float32 probabilities = 1 / (1 + expf(-float(src))); 16-byte
+ *        aligned when channels % 4 == 0
+ * batch <= 65535, channels * hw < 2^31. */
+int b200det_head_sigmoid_permute(const void *src, int src_dtype, int batch, int channels,
+                                 long long hw, float *dst, void *stream);
+/* Backward of the above (torch sigmoid_backward + permute + `.float()` backward):
+ *   grad_in[b, c, i] = grad_dtype( (grad_out[b, i, c] * (1 - probs[b, i, c])) * probs[b, i, c] ) */
+int b200det_head_sigmoid_permute_backward(const float *grad_out, const float *probs, int batch,
+                                          int channels, long long hw, void *grad_in,
+                                          int grad_dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -599,3 +599,16 @@ def retinaface_decode(preds, anchor_sizes, strides, max_object_num=100, min_scor
     anchors = retinaface_anchors(feature_sizes_of(preds[0]), anchor_sizes, strides)
     return retina_decode(preds, None, None, None, strides, max_object_num, min_score_threshold,
                          topn, nms_type, nms_threshold, exp_fn, level_anchors=anchors)
+
+
+# ----------------------------------------------------------------------------------------
+# Head tail (models/head.py:46-50, :176-179; models/retinanet.py:73-76; models/fcos.py:70-79)
+# ----------------------------------------------------------------------------------------
+def head_tail(x, num_classes=None):
+    """`x.float()` -> sigmoid -> permute(0, 2, 3, 1).contiguous() (-> view [B,H,W,A,C] for
+    RetinaNet).  Runs on x's device; differentiable through torch autograd."""
+    y = torch.sigmoid(x.float())
+    y = y.permute(0, 2, 3, 1).contiguous()
+    if num_classes is not None:
+        y = y.view(y.shape[0], y.shape[1], y.shape[2], -1, num_classes)
+    return y

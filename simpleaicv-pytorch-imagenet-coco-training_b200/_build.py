@@ -22,6 +22,7 @@ SOURCES = {
     'decode.cu': ['-fmad=false'],
     'focal.cu': [],
     'api.cu': [],
+    'heads.cu': [],
 }
 
 

@@ -141,6 +141,10 @@ SIGNATURES = {
     'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
     'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),
     'b200det_npexp_f32': (ctypes.c_int, [_vp, _vp, ctypes.c_longlong, _vp]),
+    'b200det_head_sigmoid_permute': (ctypes.c_int, [
+        _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, _vp, _vp]),
+    'b200det_head_sigmoid_permute_backward': (ctypes.c_int, [
+        _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, _vp, ctypes.c_int, _vp]),
 }
 
 _LIB = None
@@ -201,7 +205,7 @@ def profile_stop():
     lib = load()
     lib.b200det_profile(0)
     out = {}
-    for kid in range(8):
+    for kid in range(9):
         ms = ctypes.c_double(0.0)
         n = ctypes.c_int(0)
         check(lib.b200det_profile_read(kid, ctypes.byref(ms), ctypes.byref(n)), 'profile_read')

@@ -55,6 +55,7 @@ enum KernelId {
     kKernArgmax,
     kKernSelect,
     kKernOther,
+    kKernHeadTail,
     kKernCount
 };
 struct ProfScope {   // records start on construction, stop on destruction (no-op when disabled)

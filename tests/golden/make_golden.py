@@ -224,8 +224,40 @@ def make_face(path):
     np.savez_compressed(path, **out)
 
 
+def make_heads(path):
+    """Head tail: the reference's RetinaClsHead (models/head.py:15-52) on a seeded
+    feature map; the convolution output is captured with a hook, the head's own `.float()` +
+    sigmoid produce the probabilities, and the three lines of RetinaNet.forward
+    (models/retinanet.py:73-76) permute / view them.  Also the gradient w.r.t. the conv output."""
+    refload.load()
+    from simpleAICV.detection.models import head as H
+    torch.manual_seed(5)
+    A, C = 3, 5
+    m = H.RetinaClsHead(16, A, C, num_layers=1)
+    torch.nn.init.normal_(m.cls_out.weight, std=1.5)      # spread the logits (bias is -4.6)
+    captured = {}
+
+    def hook(_mod, _inp, out):
+        out.retain_grad()
+        captured['x'] = out
+
+    m.cls_out.register_forward_hook(hook)
+    feat = torch.randn(2, 16, 7, 9) * 2
+    y = m(feat)
+    y = y.permute(0, 2, 3, 1).contiguous()
+    y = y.view(y.shape[0], y.shape[1], y.shape[2], -1, C)
+    wgt = torch.randn(y.shape)
+    (y * wgt).sum().backward()
+    np.savez_compressed(path, versions=versions(), x=captured['x'].detach().numpy(),
+                        y=y.detach().numpy(), wgt=wgt.numpy(), gx=captured['x'].grad.numpy())
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'heads':
+        make_heads(os.path.join(HERE, 'head_tail.npz'))
+        print('head_tail.npz', os.path.getsize(os.path.join(HERE, 'head_tail.npz')))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'face':
         make_face(os.path.join(HERE, 'retinaface_small.npz'))
         print('retinaface_small.npz', os.path.getsize(os.path.join(HERE, 'retinaface_small.npz')))
@@ -234,5 +266,6 @@ if __name__ == '__main__':
     make_fcos(os.path.join(HERE, 'fcos_small.npz'))
     make_tables(os.path.join(HERE, 'tables.npz'))
     make_face(os.path.join(HERE, 'retinaface_small.npz'))
+    make_heads(os.path.join(HERE, 'head_tail.npz'))
     for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)))
