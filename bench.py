@@ -391,8 +391,23 @@ def run_e2e(args, preds, ann, crit, dec, dev, distributed, world):
             B = max(8, B // 8)
     except Exception:
         pass
-    host = [[t[:B].cpu().pin_memory() for t in grp] for grp in preds]
-    host_ann = ann[:B].cpu().pin_memory()
+    # allocate the pinned staging buffers from the NUMA node next to this GPU (first touch), then
+    # give the thread its old CPU mask back (the CPU baseline must keep all host cores)
+    old_mask = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0))
+        print(f'[bench] rank {os.environ.get("RANK", "0")}: pinned buffers allocated from CPUs '
+              f'{sorted(os.sched_getaffinity(0))[:4]}.. ({len(os.sched_getaffinity(0))} cpus)',
+              file=sys.stderr)
+    except Exception as e:  # restricted cpuset, no NVML: keep the default placement
+        print(f'[bench] NUMA binding skipped: {e}', file=sys.stderr)
+    try:
+        host = [[t[:B].cpu().pin_memory() for t in grp] for grp in preds]
+        host_ann = ann[:B].cpu().pin_memory()
+    finally:
+        os.sched_setaffinity(0, old_mask)
     h2d = sum(t.numel() * t.element_size() for grp in host for t in grp)
     h2d += host_ann.numel() * host_ann.element_size()
     d2h = 6 * B * 100 * 4 + 2 * 4
