@@ -504,7 +504,6 @@ __global__ void __launch_bounds__(kSelThreads)
     float *out_scores = out + (size_t)b * a.max_out;
     float *out_classes = out + (size_t)B * a.max_out + (size_t)b * a.max_out;
     float *out_boxes = out + (size_t)2 * B * a.max_out + (size_t)b * a.max_out * 4;
-    const bool boxes_vec = (((size_t)2 * B * a.max_out) & 3) == 0;
 
     const int cap = 2 * a.pad_n;  // capacity of skey
     int ncand, k_sel, n_got;
@@ -817,14 +816,11 @@ __global__ void __launch_bounds__(kSelThreads)
         }
         out_scores[i] = s;
         out_classes[i] = c;
-        if (boxes_vec) {
-            reinterpret_cast<float4 *>(out_boxes)[i] = bx;
-        } else {  // 2*B*max_out not a multiple of 4: the boxes block is only 4-byte aligned
-            out_boxes[4 * i + 0] = bx.x;
-            out_boxes[4 * i + 1] = bx.y;
-            out_boxes[4 * i + 2] = bx.z;
-            out_boxes[4 * i + 3] = bx.w;
-        }
+        // scalar stores: the boxes block is only 4-byte aligned when 2*B*max_out % 4 != 0
+        out_boxes[4 * i + 0] = bx.x;
+        out_boxes[4 * i + 1] = bx.y;
+        out_boxes[4 * i + 2] = bx.z;
+        out_boxes[4 * i + 3] = bx.w;
     }
     if (keep_out) {
         for (int i = tid; i < a.topn; i += kSelThreads)
