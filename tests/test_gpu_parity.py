@@ -805,3 +805,48 @@ def test_decoder_output_invariants_full_size():
     s2, c2, b2 = dec(preds)
     G.assert_bit_equal(s, s2)
     G.assert_bit_equal(b, b2)
+
+
+def test_batch_with_more_than_2_31_elements_per_level():
+    """Maximum sizes: batch 384 at 800x800 / 80 classes puts 2.76e9 floats (> 2^31) into the first
+    pyramid level alone, so element offsets need 64 bits everywhere.  Size-independent checks:
+    the unsharded sums equal the sum of two half-batch calls, decoder outputs of images from both
+    ends of the batch equal decoding those images alone, and the training path's gradient of the
+    last image equals the half-batch gradient rescaled by the positive counts."""
+    B, H = 384, 192
+    preds = synth.make_retina_preds(B, 800, 80, seed=5, device='cuda')
+    ann = synth.make_annotations(B, 100, 800, 80, seed=6).cuda()
+    assert preds[0][0].numel() > 2**31
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+    halves = [[[t[lo:lo + H] for t in grp] for grp in preds] for lo in (0, H)]   # contiguous views
+    with torch.no_grad():
+        crit(preds, ann)
+        full = crit.last_stats['sums'].cpu().numpy().copy()
+        parts = []
+        for i, lo in enumerate((0, H)):
+            crit(halves[i], ann[lo:lo + H])
+            parts.append(crit.last_stats['sums'].cpu().numpy().copy())
+    assert parts[0][0] + parts[1][0] == full[0] > 0
+    np.testing.assert_allclose(parts[0][1:] + parts[1][1:], full[1:], rtol=1e-6)
+
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    s, c, b = dec(preds)
+    for img in (0, H - 1, H, B - 1):
+        one = [[t[img:img + 1] for t in grp] for grp in preds]
+        s1, c1, b1 = dec(one)
+        G.assert_bit_equal(s[img], s1[0], f'scores of image {img}')
+        G.assert_bit_equal(c[img], c1[0], f'classes of image {img}')
+        G.assert_bit_equal(b[img], b1[0], f'boxes of image {img}')
+
+    # training path on the big batch (writes a second 2.76e9-element tensor)
+    cls0 = preds[0][0].requires_grad_(True)
+    d = crit(preds, ann)
+    d['cls_loss'].backward()
+    g_last = cls0.grad[B - 1].clone()
+    cls0.grad = None
+    preds[0][0].requires_grad_(False)
+    half_cls0 = halves[1][0][0].detach().requires_grad_(True)
+    shard = [[half_cls0] + [t.detach() for t in halves[1][0][1:]], halves[1][1]]
+    crit(shard, ann[H:])['cls_loss'].backward()
+    scale = parts[1][0] / full[0]
+    torch.testing.assert_close(g_last, half_cls0.grad[H - 1] * scale, rtol=1e-5, atol=1e-12)
