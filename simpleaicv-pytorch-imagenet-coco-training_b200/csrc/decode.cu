@@ -10,6 +10,7 @@
 //                        row asc), box decode with NumPy's exp + x86 int32 truncation, greedy
 //                        NMS driven by warp ballots into a removed-bitmask, max_object_num cap.
 // Compiled with -fmad=false: box / IoU arithmetic is one IEEE float32 op per reference op.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "focal_terms.cuh"
@@ -177,6 +178,105 @@ __global__ void __launch_bounds__(kArgThreads)
             classes[lm] = best_c;
         }
     }
+}
+
+// Row-group variant (C % 4 == 0, C <= 640): T = 2^ts lanes share one row, lane j reads the 128-bit
+// units j, j+T, j+2T, ... of that row.  A warp instruction therefore covers 32/T consecutive rows
+// with one 16*T-byte segment each (64 B for C = 80: full sectors), and the K loads of a warp cover a
+// contiguous 32/T-row span completely.  Everything stays in registers: a strict '>' scan in class
+// order inside the lane (3 instructions per element), log2(T) shuffle steps between the lanes of a
+// row (larger value wins, equal values -> lower class), no shared memory and no index division.
+#ifndef B200DET_ROWS_ITERS
+#define B200DET_ROWS_ITERS 4
+#endif
+constexpr int kRowIters = B200DET_ROWS_ITERS;   // row groups per thread: amortises the set-up
+template <int K, bool FOCAL>
+__global__ void __launch_bounds__(kArgThreads)
+    score_argmax_rows_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
+    const int ts = a.t2_shift, T = a.t2;
+    const int j = threadIdx.x & (T - 1);
+    const int rows_per_iter = kArgThreads >> ts;
+    const int U = a.units_per_row;
+    const long long n_rows = a.rows[l];
+    long long row = (long long)(blockIdx.x - a.block_off[l]) * (rows_per_iter * kRowIters) +
+                    (threadIdx.x >> ts);
+    const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.cls.p[l]) + row * U + j;
+    const float *__restrict__ ctr = static_cast<const float *>(a.ctr.p[l]);
+    uint32_t *__restrict__ kout = keys + a.row_base[l];
+    int *__restrict__ cout = classes + a.row_base[l];
+    const float ninf = -__int_as_float(0x7f800000);
+    float acc = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+    for (int it = 0; it < kRowIters; ++it, row += rows_per_iter, src += (size_t)rows_per_iter * U) {
+        const bool live = row < n_rows;
+        float4 v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (live && (k << ts) + j < U) v[k] = __ldcs(src + (k << ts));
+
+        float best = ninf;
+        int code = 0;   // (k << 2) | e of the lane's first maximum
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (live && (k << ts) + j < U) {
+                const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e4[e] > best) {  // strict: first maximum in class order (np.argmax)
+                        best = e4[e];
+                        code = (k << 2) | e;
+                    }
+                }
+            }
+        }
+        int best_c = best > ninf ? ((((code >> 2) << ts) + j) << 2) + (code & 3) : 0x7fffffff;
+        if (FOCAL) {
+            // label-free focal terms of the same registers (see focal.cu: focal_all_kernel)
+            const bool gamma2 = a.gamma == 2.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (live && (k << ts) + j < U) {
+                    const float x0 = fmax_nan(v[k].x, kClampLo), x1 = fmax_nan(v[k].y, kClampLo);
+                    const float x2 = fmax_nan(v[k].z, kClampLo), x3 = fmax_nan(v[k].w, kClampLo);
+                    const float mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+                    if (gamma2 && mx <= kFastMax) {
+                        float2 xr, xs;
+                        acc2 = neg_term_fast2_acc(make_float2(x0, x1), acc2, xr, xs);
+                        acc2 = neg_term_fast2_acc(make_float2(x2, x3), acc2, xr, xs);
+                    } else {
+                        acc += neg_term(v[k].x, a.gamma, gamma2) + neg_term(v[k].y, a.gamma, gamma2) +
+                               neg_term(v[k].z, a.gamma, gamma2) + neg_term(v[k].w, a.gamma, gamma2);
+                    }
+                }
+            }
+        }
+        // combine the row's lanes: larger value wins, equal values -> lower class index
+        for (int o = T >> 1; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ov > best || (ov == best && oc < best_c)) {
+                best = ov;
+                best_c = oc;
+            }
+        }
+        if (live && j == 0) {
+            float score = best;
+            if (a.has_ctr) {
+                // np.sqrt(cls_scores * center_preds)  (decode.py:338): one mul, one IEEE sqrt
+                score = __fsqrt_rn(__fmul_rn(best, __ldg(ctr + row)));
+            }
+            kout[row] = (score > a.min_score) ? flip_key(score) : 0u;  // strict '>' (decode.py:133-138)
+            cout[row] = best_c;
+        }
+    }
+    if (FOCAL)
+        sweep_accumulate<kArgThreads>((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
 }
 
 // Variant for class counts that are not a multiple of 4 (e.g. Objects365's 365): rows are not
@@ -912,8 +1012,24 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     const int units = g.num_classes / vec;
     a.units_per_row = units;
     const int budget = kArgThreads * kArgLoadsVec;   // 128-bit loads per CTA, all in flight
+    constexpr int kRowsK = 5;                        // 128-bit loads per lane in the row-group kernel
+    // Measured at batch 256 (B200): alone, the shared-memory tile kernel is 1.5 % faster (1.418 vs
+    // 1.439 ms, both at the HBM ceiling); with the focal terms fused in, the tile kernel is issue-bound
+    // (24 instructions / element, 3.12 ms per eval step) and the row-group kernel is not (2.70 ms).
+    static const bool force_rows = getenv("B200DET_ARGMAX_ROWS") != nullptr;
+    const bool row_groups = vec == 4 && units <= kRowsK * 32 && (focal_slots != nullptr || force_rows);
     int R;
-    if (vec == 4) {
+    if (row_groups) {
+        int t = 1, tsft = 0;
+        while (t * kRowsK < units) {
+            t <<= 1;
+            ++tsft;
+        }
+        a.t2 = t;
+        a.t2_shift = tsft;
+        R = (kArgThreads >> tsft) * kRowIters;
+        a.pitch = 0;
+    } else if (vec == 4) {
         R = budget / units;
         if (R < 1) R = 1;
         if (R > kArgThreads) R = kArgThreads;
@@ -928,13 +1044,15 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     }
     a.rows_per_block = R;
     a.magic = (unsigned)(((1u << 24) + units - 1) / units);
-    int t2 = 1, t2s = 0;
-    while (t2 < 32 && (units + t2 - 1) / t2 > 32) {
-        t2 <<= 1;
-        ++t2s;
+    if (!row_groups) {
+        int t2 = 1, t2s = 0;
+        while (t2 < 32 && (units + t2 - 1) / t2 > 32) {
+            t2 <<= 1;
+            ++t2s;
+        }
+        a.t2 = t2;
+        a.t2_shift = t2s;
     }
-    a.t2 = t2;
-    a.t2_shift = t2s;
     int blocks = 0;
     for (int l = 0; l < kMaxLevels; ++l) {
         a.cls.p[l] = a.ctr.p[l] = nullptr;
@@ -955,7 +1073,11 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     const size_t smem = vec == 4 ? (size_t)R * a.pitch * 8 : (size_t)R * a.C * 4 + 16;
     if (smem > 48 * 1024) return B200DET_ERANGE;
     ProfScope prof(kKernArgmax, stream);
-    if (vec == 4 && focal_slots)
+    if (row_groups && focal_slots)
+        score_argmax_rows_kernel<kRowsK, true><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+    else if (row_groups)
+        score_argmax_rows_kernel<kRowsK, false><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+    else if (vec == 4 && focal_slots)
         score_argmax_kernel<4, true><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else if (vec == 4)
         score_argmax_kernel<4, false><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);

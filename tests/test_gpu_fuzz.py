@@ -18,7 +18,7 @@ from test_gpu_parity import (LOSS_RTOL, assert_close, assert_targets_equal, chec
 
 pytestmark = pytest.mark.gpu
 
-CLASS_COUNTS = [1, 2, 3, 4, 7, 20, 33, 80, 91]
+CLASS_COUNTS = [1, 2, 3, 4, 7, 20, 33, 80, 91, 92, 364, 640]
 NMS_TYPES = ['python_nms', 'diou_python_nms', 'torch_nms']
 
 
@@ -119,6 +119,14 @@ def test_fuzz_retina(seed):
     G.assert_bit_equal(c, c0, f'classes {dkw}')
     G.assert_bit_equal(b, b0, f'boxes {dkw}')
     check_decode_details(info, extra['per_image'], dkw['topn'])
+    if C % 4 == 0:   # fused eval step: the row-group sweep (lane split depends on C)
+        from b200det import fused
+        loss, (s1, c1, b1) = fused.EvalStep(crit, dec)(dev(preds), ann.cuda())
+        G.assert_bit_equal(s1, s0, 'fused scores')
+        G.assert_bit_equal(c1, c0, 'fused classes')
+        G.assert_bit_equal(b1, b0, 'fused boxes')
+        if ref['num_pos'] > 0:
+            assert_close(loss_values(loss, ['cls_loss', 'reg_loss']), want, LOSS_RTOL, 'fused loss')
 
 
 @pytest.mark.parametrize('seed', range(32))
@@ -183,3 +191,11 @@ def test_fuzz_fcos(seed):
     G.assert_bit_equal(c, c0, f'classes {dkw}')
     G.assert_bit_equal(b, b0, f'boxes {dkw}')
     check_decode_details(info, extra['per_image'], dkw['topn'])
+    if C % 4 == 0:
+        from b200det import fused
+        loss, (s1, c1, b1) = fused.EvalStep(crit, dec)(dev(preds), ann.cuda())
+        G.assert_bit_equal(s1, s0, 'fused scores')
+        G.assert_bit_equal(c1, c0, 'fused classes')
+        G.assert_bit_equal(b1, b0, 'fused boxes')
+        if ref['num_pos'] > 0:
+            assert_close(loss_values(loss, keys), want, LOSS_RTOL, 'fused loss')
