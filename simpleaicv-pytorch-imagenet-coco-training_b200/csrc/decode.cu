@@ -190,8 +190,11 @@ __global__ void __launch_bounds__(kArgThreads)
 #define B200DET_ROWS_ITERS 4
 #endif
 constexpr int kRowIters = B200DET_ROWS_ITERS;   // row groups per thread: amortises the set-up
+#ifndef B200DET_ROWS_MINB
+#define B200DET_ROWS_MINB 6
+#endif
 template <int K, bool FOCAL>
-__global__ void __launch_bounds__(kArgThreads)
+__global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
     score_argmax_rows_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
     int l = 0;
 #pragma unroll
@@ -597,7 +600,6 @@ __global__ void __launch_bounds__(kSelThreads)
 
     const Geo &g = a.g;
     const int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = g.off[g.n_levels];
     const int B = g.batch;
 
@@ -811,7 +813,6 @@ __global__ void __launch_bounds__(kSelThreads)
     }
     if (order_out)
         for (int i = n_sel + tid; i < a.topn; i += kSelThreads) order_out[(size_t)b * a.topn + i] = -1;
-    const int n_words = (n_sel + 31) >> 5;
     for (int i = tid; i < (a.pad_n >> 5); i += kSelThreads) srem[i] = 0u;
     __syncthreads();
 
