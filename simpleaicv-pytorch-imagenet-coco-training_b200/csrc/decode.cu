@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kSelThreads)
 
     const Geo &g = a.g;
     const int b = blockIdx.x;
-    const int N = g.off[g.n_levels];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int B = g.batch;
 
     float *out_scores = out + (size_t)b * a.max_out;
