@@ -301,14 +301,37 @@ __device__ __forceinline__ void scan_candidates(const GtSmem &s, int n_cand, con
         best[a] = 0.f;
         best_slot[a] = -1;
     }
+    // Bounds over the location's anchors (identical in every lane: a warp's patch lies on one level)
+    float amin = area_a[0], amax = area_a[0], amin_lo = area_lo[0];
+    float awmax = __fsub_rn(A[0].z, A[0].x), ahmax = __fsub_rn(A[0].w, A[0].y);
+#pragma unroll
+    for (int a = 1; a < NA; ++a) {
+        amin = fminf(amin, area_a[a]);
+        amax = fmaxf(amax, area_a[a]);
+        amin_lo = fminf(amin_lo, area_lo[a]);
+        awmax = fmaxf(awmax, __fsub_rn(A[a].z, A[a].x));
+        ahmax = fmaxf(ahmax, __fsub_rn(A[a].w, A[a].y));
+    }
     const int lane = threadIdx.x & 31;
     for (int c0 = 0; c0 < n_cand; c0 += 32) {
         // warp-level cull: one candidate per lane against the warp's anchor bounding box
         bool hit = false;
         if (c0 + lane < n_cand) {
             const float4 gt = s.box[c0 + lane];
-            hit = (fminf(wreg.z, gt.z) > fmaxf(wreg.x, gt.x)) &&
-                  (fminf(wreg.w, gt.w) > fmaxf(wreg.y, gt.y));
+            const float ox = __fsub_rn(fminf(wreg.z, gt.z), fmaxf(wreg.x, gt.x));
+            const float oy = __fsub_rn(fminf(wreg.w, gt.w), fmaxf(wreg.y, gt.y));
+            hit = ox > 0.f && oy > 0.f;
+            if (!EXACT && hit) {
+                // production scan: drop the candidate for the whole patch when no anchor of this
+                // level can reach the IoU floor with it.  (a) area ratio, the per-anchor test below
+                // taken over all anchors; (b) IoU <= min(ox, aw_max) * min(oy, ah_max) /
+                // max(gt area, smallest anchor area), with the overlap measured against the patch's
+                // bounding box.  The floor sits 5 % under the threshold, far above rounding error.
+                const float garea = s.area[c0 + lane];
+                if (garea < amin_lo || kIouFloor * garea > amax) hit = false;
+                else if (fminf(ox, awmax) * fminf(oy, ahmax) < kIouFloor * fmaxf(garea, amin))
+                    hit = false;
+            }
         }
         unsigned m = __ballot_sync(0xffffffffu, hit);
         while (m) {
