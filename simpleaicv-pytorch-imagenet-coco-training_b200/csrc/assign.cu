@@ -221,6 +221,10 @@ __device__ __forceinline__ float4 reduce_region(bool active, float x1, float y1,
 struct TileTab {
     int tile_off[kMaxLevels + 1];   // patches of one image before level l
     int tiles_x[kMaxLevels];
+    // Retina: extent of a level's base anchors {min x1, min y1, max x2, max y2}.  Rounding is
+    // monotonic, so min_a fl(base_a + shift) == fl(min_a base_a + shift): four adds give the exact
+    // bounding box of a location's anchors.
+    float ext[kMaxLevels][4];
 };
 struct Loc {
     bool active;
@@ -391,13 +395,8 @@ __global__ void __launch_bounds__(kAssignThreads)
     const int per_loc = PL > 0 ? PL : g.per_loc;
     const float sx = shift_of(me.x, g.stride[me.l]), sy = shift_of(me.y, g.stride[me.l]);
     // bounding box of this location's anchors (models/anchor.py:59-86: base + shift in float32)
-    float tx1 = 3.0e38f, ty1 = 3.0e38f, tx2 = -3.0e38f, ty2 = -3.0e38f;
-    for (int a = 0; a < per_loc; ++a) {
-        tx1 = fminf(tx1, __fadd_rn(ba.v[me.l][a][0], sx));
-        ty1 = fminf(ty1, __fadd_rn(ba.v[me.l][a][1], sy));
-        tx2 = fmaxf(tx2, __fadd_rn(ba.v[me.l][a][2], sx));
-        ty2 = fmaxf(ty2, __fadd_rn(ba.v[me.l][a][3], sy));
-    }
+    const float tx1 = __fadd_rn(tt.ext[me.l][0], sx), ty1 = __fadd_rn(tt.ext[me.l][1], sy);
+    const float tx2 = __fadd_rn(tt.ext[me.l][2], sx), ty2 = __fadd_rn(tt.ext[me.l][3], sy);
     const float4 wreg = reduce_region(me.active, tx1, ty1, tx2, ty2, red, region);
     stage_rows_wait(&mbar, bulk);  // contains a __syncthreads(): region[] is visible too
     const int2 cnt = compact_gt(s, G, kCullOverlap, region[0], region[1], region[2], region[3],
@@ -421,6 +420,17 @@ __global__ void __launch_bounds__(kAssignThreads)
             scan_candidates<NA, true>(s, n_cand, wreg, A, best, best_slot, thr.floor);
         else
             scan_candidates<NA, false>(s, n_cand, wreg, A, best, best_slot, thr.floor);
+        // Most patches see no GT above the IoU floor: every anchor is background (label 0)
+        bool any_hit = false;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) any_hit |= best_slot[a] >= 0;
+        if (!matched && has_gt && !__any_sync(0xffffffffu, any_hit)) {
+            if (me.active) {
+#pragma unroll
+                for (int a = 0; a < NA; ++a) labels[lm0 + a0 + a] = 0;
+            }
+            continue;
+        }
         // labels (losses.py:358-365)
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
@@ -832,7 +842,20 @@ static TileTab make_tiles(const Geo &g) {
         }
     }
     for (int l = g.n_levels; l <= kMaxLevels; ++l) t.tile_off[l] = off;
+    for (int l = 0; l < kMaxLevels; ++l)
+        for (int k = 0; k < 4; ++k) t.ext[l][k] = 0.f;
     return t;
+}
+static void set_anchor_extents(TileTab *t, const Geo &g, const BaseAnchors &ba) {
+    for (int l = 0; l < g.n_levels; ++l) {
+        for (int k = 0; k < 4; ++k) t->ext[l][k] = ba.v[l][0][k];
+        for (int a = 1; a < g.per_loc; ++a) {
+            t->ext[l][0] = fminf(t->ext[l][0], ba.v[l][a][0]);
+            t->ext[l][1] = fminf(t->ext[l][1], ba.v[l][a][1]);
+            t->ext[l][2] = fmaxf(t->ext[l][2], ba.v[l][a][2]);
+            t->ext[l][3] = fmaxf(t->ext[l][3], ba.v[l][a][3]);
+        }
+    }
 }
 
 static Queues queues_of(char *base, const LossWs &ws) {
@@ -934,7 +957,8 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     BaseAnchors ba;
     copy_base(geo, &ba);
-    const TileTab tt = make_tiles(g);
+    TileTab tt = make_tiles(g);
+    set_anchor_extents(&tt, g, ba);
     static bool a9 = false, a0 = false;
     if ((rc = raise_smem_limit(retina_assign_kernel<9>, &a9))) return rc;
     if ((rc = raise_smem_limit(retina_assign_kernel<0>, &a0))) return rc;
