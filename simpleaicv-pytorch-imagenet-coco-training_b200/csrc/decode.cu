@@ -404,11 +404,27 @@ __device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t *scratch)
 template <typename F>
 __device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t *__restrict__ keys,
                                              F f) {
+    // 128-bit loads over the 16-byte-aligned middle of every level segment (the visiting order is
+    // irrelevant to the callers): 4x the bytes in flight of a scalar loop, which is what bounds these
+    // passes (one CTA per image, keys coming from L2 / HBM).
     for (int l = 0; l < g.n_levels; ++l) {
         const uint32_t *p = keys + lm_index(g, b, l, 0);
         const int n = g.rows[l], off = g.off[l];
-#pragma unroll 4
-        for (int j = threadIdx.x; j < n; j += kSelThreads) f(__ldg(p + j), off + j);
+        const int head = min(n, (int)((4u - ((unsigned)(reinterpret_cast<uintptr_t>(p) >> 2) & 3u)) & 3u));
+        if ((int)threadIdx.x < head) f(__ldg(p + threadIdx.x), off + (int)threadIdx.x);
+        const uint4 *q = reinterpret_cast<const uint4 *>(p + head);
+        const int nv = (n - head) >> 2;
+#pragma unroll 2
+        for (int j = threadIdx.x; j < nv; j += kSelThreads) {
+            const uint4 v = __ldg(q + j);
+            const int r = off + head + 4 * j;
+            f(v.x, r);
+            f(v.y, r + 1);
+            f(v.z, r + 2);
+            f(v.w, r + 3);
+        }
+        const int t0 = head + 4 * nv + (int)threadIdx.x;
+        if (t0 < n) f(__ldg(p + t0), off + t0);
     }
 }
 
