@@ -661,7 +661,10 @@ __device__ __forceinline__ int split_row(const Geo &g, int i, long long &rrow) {
     return l;
 }
 
-__global__ void __launch_bounds__(kSparseThreads)
+#ifndef B200DET_SPARSE_MINB
+#define B200DET_SPARSE_MINB 4
+#endif
+__global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
     sparse_loss_kernel(SparseArgs a, const float *__restrict__ annots,
                        const int *__restrict__ labels, Queues q,
                        SparsePartial *__restrict__ partials) {
@@ -731,37 +734,43 @@ __global__ void __launch_bounds__(kSparseThreads)
     }
 
     // ---- ignored rows (Retina: 0.4 <= IoU < 0.5, or image without GT) take no part in the focal
-    // loss (losses.py:228-230): remove what the label-free sweep added.  One warp per row, four rows
-    // in flight; a row's sum has a fixed order (lane-strided partials + xor tree) and is converted
-    // to fixed point once, so the result is independent of the queue order.
+    // loss (losses.py:228-230): remove what the label-free sweep added.  Flat grid-stride loop over
+    // (ignored row, 16-byte unit) pairs, four independent pairs in flight per thread; every unit's
+    // four terms are summed in a fixed order and converted to fixed point on their own, so the
+    // total does not depend on the queue order or on which thread visits which unit.
     if (want_fix) {
-        constexpr int kRowsInFlight = 4;
-        const int gwarp = gtid >> 5, n_warps = gsize >> 5;
-        for (int r0 = gwarp; r0 < n_ign; r0 += kRowsInFlight * n_warps) {
-            const float *p[kRowsInFlight];
-            bool live[kRowsInFlight];
+        const bool vec = (a.C & 3) == 0;
+        const int U = vec ? (a.C >> 2) : a.C;              // units per row
+        const long long n_pairs = (long long)n_ign * U;
+        const float one_m_alpha = 1.f - a.alpha;
+        constexpr int kInFlight = 4;
+        for (long long p0 = gtid; p0 < n_pairs; p0 += (long long)kInFlight * gsize) {
+            float4 v[kInFlight];
+            bool live[kInFlight];
 #pragma unroll
-            for (int t = 0; t < kRowsInFlight; ++t) {
-                const int r = r0 + t * n_warps;
-                live[t] = r < n_ign;
-                long long rr;
-                const int l = split_row(g, q.ign[live[t] ? r : r0], rr);
-                p[t] = static_cast<const float *>(a.cls.p[l]) + rr * a.C;
+            for (int t = 0; t < kInFlight; ++t) {
+                const long long p = p0 + (long long)t * gsize;
+                live[t] = p < n_pairs;
+                v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[t]) {
+                    const int r = (int)(p / U), u = (int)(p - (long long)r * U);
+                    long long rr;
+                    const int l = split_row(g, __ldg(q.ign + r), rr);
+                    const float *row = static_cast<const float *>(a.cls.p[l]) + rr * a.C;
+                    if (vec) v[t] = __ldg(reinterpret_cast<const float4 *>(row) + u);
+                    else v[t].x = __ldg(row + u);
+                }
             }
-            float sum[kRowsInFlight];
 #pragma unroll
-            for (int t = 0; t < kRowsInFlight; ++t) sum[t] = 0.f;
-            for (int c = lane; c < a.C; c += 32) {
-                float v[kRowsInFlight];
-#pragma unroll
-                for (int t = 0; t < kRowsInFlight; ++t) v[t] = __ldg(p[t] + c);
-#pragma unroll
-                for (int t = 0; t < kRowsInFlight; ++t) sum[t] += neg_term(v[t], a.gamma, gamma2);
-            }
-#pragma unroll
-            for (int t = 0; t < kRowsInFlight; ++t) {
-                const float s = warp_sum(sum[t]);
-                if (lane == 0 && live[t]) foc_fx -= to_fx((1.f - a.alpha) * s, kFxFocal, bad, 4u);
+            for (int t = 0; t < kInFlight; ++t) {
+                if (!live[t]) continue;
+                float sum = neg_term(v[t].x, a.gamma, gamma2);
+                if (vec) {
+                    sum += neg_term(v[t].y, a.gamma, gamma2);
+                    sum += neg_term(v[t].z, a.gamma, gamma2);
+                    sum += neg_term(v[t].w, a.gamma, gamma2);
+                }
+                foc_fx -= to_fx(one_m_alpha * sum, kFxFocal, bad, 4u);
             }
         }
     }
