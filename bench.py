@@ -261,7 +261,11 @@ def run_b200(args, out):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        # per-kernel CUDA events on every `profile_every`-th step of the timed region (bracketing
+        # every launch costs ~14 event records per step)
+        if args.profile_every > 1:
+            (_lib.profile_resume if i % args.profile_every == 0 else _lib.profile_pause)()
         d, r = step()
     stop.record()
     barrier()
@@ -483,6 +487,7 @@ def main():
     ap.add_argument('--ref-size', type=int, default=SIZE,
                     help='image size of the --impl reference sample (tests use a small one)')
     ap.add_argument('--no-fused', action='store_true')
+    ap.add_argument('--profile-every', type=int, default=1)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -97,7 +97,8 @@ const char *b200det_error_string(int code);
 unsigned long long b200det_launch_count(void);
 /*
  * Optional per-kernel timing: while enabled, every kernel launched by the library is bracketed
- * by CUDA events on its stream.  b200det_profile(1) clears and starts, b200det_profile(0) stops;
+ * by CUDA events on its stream.  b200det_profile(1) clears and starts, b200det_profile(0) pauses (records are kept),
+ * b200det_profile(2) resumes without clearing;
  * b200det_profile_read() waits for the recorded events and returns the summed device time and the
  * number of launches of one kernel id (0 focal_loss, 1 assign, 2 sparse_losses, 3 loss_reduce,
  * 4 loss_finish, 5 score_argmax, 6 select_decode_nms; see b200det_kernel_name).

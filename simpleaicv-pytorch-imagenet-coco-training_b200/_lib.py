@@ -200,6 +200,14 @@ def profile_start():
     load().b200det_profile(1)
 
 
+def profile_pause():
+    load().b200det_profile(0)
+
+
+def profile_resume():
+    load().b200det_profile(2)
+
+
 def profile_stop():
     """Stops the timing and returns {kernel name: (launches, mean ms)}; synchronises the events."""
     lib = load()

@@ -500,14 +500,14 @@ extern "C" unsigned long long b200det_launch_count(void) { return launches(); }
 
 extern "C" int b200det_profile(int enable) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (enable) {
+    if (enable == 1) {
         for (auto &r : g_prof) {
             cudaEventDestroy(r.a);
             cudaEventDestroy(r.b);
         }
         g_prof.clear();
     }
-    g_prof_on = enable != 0;
+    g_prof_on = enable != 0;   // 1: clear + record, 2: resume (keep the records), 0: pause
     return 0;
 }
 

@@ -10,6 +10,7 @@ here the head outputs stay in HBM, one C call (b200det_decode) enqueues two kern
 and only the [B, M, 6] result (2.4 KB per image) crosses PCIe.  There is no CPU path.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -17,6 +18,8 @@ import torch
 from . import _lib
 from . import geometry as _geom
 from .losses import _prep_f32, _prep_reg
+
+_ZERO_COPY = os.environ.get('B200DET_ZERO_COPY', '1') != '0'
 
 __all__ = ['RetinaDecoder', 'FCOSDecoder']
 
@@ -72,11 +75,22 @@ class _DecoderBase:
             params.sizes = t.data_ptr()
         return glue
 
+    def _out_buffer(self, numel, device):
+        """Where the select kernel writes scores | classes | boxes.  Default: straight into the
+        cached pinned host buffer (mapped into the device's address space under UVA), so the 24*M
+        bytes per image cross PCIe as posted writes while other images are still being processed
+        and no separate copy is enqueued.  B200DET_ZERO_COPY=0 uses a device buffer + one D2H."""
+        if _ZERO_COPY:
+            return self._staging(numel)
+        return torch.empty(numel, dtype=torch.float32, device=device)
+
     def _to_host(self, out, batch, m, device):
-        """The only D2H copy: 24*M bytes per image, through a cached pinned staging buffer; the
+        """The only device->host traffic: 24*M bytes per image into a cached pinned buffer; the
         caller gets fresh, writable arrays (tools/scripts.py:742-758 mutates them in place)."""
-        staging = self._staging(out.numel())
-        staging.copy_(out, non_blocking=True)
+        staging = out
+        if out.is_cuda:
+            staging = self._staging(out.numel())
+            staging.copy_(out, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
         host = staging.numpy().copy()
         scores = host[0:batch * m].reshape(batch, m)
@@ -112,7 +126,7 @@ class _DecoderBase:
         # scratch = keys | classes (int32 each) | selection workspace ; out = scores|classes|boxes
         rows_bytes = (8 * batch * n_rows + 255) & ~255
         scratch = torch.empty(rows_bytes + ws_bytes, dtype=torch.uint8, device=device)
-        out = torch.empty(6 * batch * m, dtype=torch.float32, device=device)
+        out = self._out_buffer(6 * batch * m, device)
         order = keep = counts = None
         if details:
             order = torch.empty(batch * self.topn, dtype=torch.int32, device=device)

@@ -60,7 +60,7 @@ class EvalStep:
         classes_ptr = keys_ptr + rows_bytes
         dws_ptr = classes_ptr + rows_bytes
         small = torch.empty(8, dtype=torch.float64, device=device)   # sums | losses
-        out = torch.empty(6 * batch * m, dtype=torch.float32, device=device)
+        out = dec._out_buffer(6 * batch * m, device)
         lp = _loss_params(crit, reg_dtype)
         dp = dec._params
         dp.reg_dtype = reg_dtype
