@@ -101,7 +101,8 @@ unsigned long long b200det_launch_count(void);
  * b200det_profile(2) resumes without clearing;
  * b200det_profile_read() waits for the recorded events and returns the summed device time and the
  * number of launches of one kernel id (0 focal_loss, 1 assign, 2 sparse_losses, 3 loss_reduce,
- * 4 loss_finish, 5 score_argmax, 6 select_decode_nms; see b200det_kernel_name).
+ * 4 loss_finish, 5 score_argmax, 6 select_decode_nms, 7 other, 8 head_tail, 9 logits_sweep; see
+ * b200det_kernel_name).
  */
 int b200det_profile(int enable);
 int b200det_profile_read(int kernel_id, double *total_ms, int *launches);
@@ -350,6 +351,34 @@ int b200det_head_sigmoid_permute(const void *src, int src_dtype, int batch, int 
 int b200det_head_sigmoid_permute_backward(const float *grad_out, const float *probs, int batch,
                                           int channels, long long hw, void *grad_in,
                                           int grad_dtype, void *stream);
+
+/* ---- classification branch straight from NCHW logits (second half) ------------------
+ * One pass over the head's logits [batch, per_loc * num_classes, H, W] (B200DET_F32 / F16 / BF16,
+ * contiguous) instead of sigmoid + permute (models/head.py:46-50, models/retinanet.py:73-76) followed
+ * by the focal loss (losses.py:220-261) and / or the decoder's arg-max / score / threshold
+ * (decode.py:208-238).  No probability tensor is written.
+ *   ctr_logits     FCOS centre-ness logits [batch, H*W] float32 per level (score = sqrt(cls * ctr)),
+ *                  or NULL
+ *   labels         level-major labels from b200det_*_assign; NULL: every row counts as background
+ *   loss_workspace NULL: no focal sum; else the label-aware focal sum is accumulated into the
+ *                  workspace's sweep accumulators (read it with b200det_loss_reduce, which = 2 or 3)
+ *   keys, classes  NULL: no arg-max; else the decoder keys / classes of b200det_score_argmax,
+ *                  bit-identical to running it on torch's CUDA sigmoid of the logits
+ * kernel id 9 (logits_sweep). */
+int b200det_logits_sweep(const b200det_geometry *geo, const void *const *cls_logits, int cls_dtype,
+                         const void *const *ctr_logits, const int32_t *labels, float alpha,
+                         float gamma, void *loss_workspace, size_t loss_workspace_bytes,
+                         float min_score, uint32_t *keys, int32_t *classes, void *stream);
+/* b200det_eval_step for RetinaNet-style heads whose classification tensors are NCHW logits:
+ * assignment, box loss, ONE sweep over the logits (focal sum + decoder keys), reduce / finish,
+ * select + decode + NMS.  reg stays [B, H, W, A, 4] as in the reference. */
+int b200det_logits_eval_step(const b200det_geometry *geo, const b200det_loss_params *lp,
+                             const b200det_decode_params *dp, const float *annotations, int max_gt,
+                             const void *const *cls_logits, int cls_dtype, const void *const *reg,
+                             int32_t *labels, void *loss_workspace, size_t loss_workspace_bytes,
+                             double *sums, float *losses, uint32_t *keys, int32_t *classes,
+                             float *out, void *decode_workspace, size_t decode_workspace_bytes,
+                             void *stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ SOURCES = {
     'focal.cu': [],
     'api.cu': [],
     'heads.cu': [],
+    'logits.cu': [],
 }
 
 

@@ -141,6 +141,15 @@ SIGNATURES = {
     'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
     'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),
     'b200det_npexp_f32': (ctypes.c_int, [_vp, _vp, ctypes.c_longlong, _vp]),
+    'b200det_logits_sweep': (ctypes.c_int, [
+        _geo, _vpp, ctypes.c_int, _vpp, _vp, ctypes.c_float, ctypes.c_float, _vp, ctypes.c_size_t,
+        ctypes.c_float, _vp, _vp, _vp
+    ]),
+    'b200det_logits_eval_step': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), ctypes.POINTER(DecodeParams), _vp, ctypes.c_int, _vpp,
+        ctypes.c_int, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp,
+        ctypes.c_size_t, _vp
+    ]),
     'b200det_head_sigmoid_permute': (ctypes.c_int, [
         _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, _vp, _vp]),
     'b200det_head_sigmoid_permute_backward': (ctypes.c_int, [
@@ -213,7 +222,7 @@ def profile_stop():
     lib = load()
     lib.b200det_profile(0)
     out = {}
-    for kid in range(9):
+    for kid in range(10):
         ms = ctypes.c_double(0.0)
         n = ctypes.c_int(0)
         check(lib.b200det_profile_read(kid, ctypes.byref(ms), ctypes.byref(n)), 'profile_read')

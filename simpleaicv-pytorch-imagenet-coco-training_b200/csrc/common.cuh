@@ -56,6 +56,7 @@ enum KernelId {
     kKernSelect,
     kKernOther,
     kKernHeadTail,
+    kKernLogits,
     kKernCount
 };
 struct ProfScope {   // records start on construction, stop on destruction (no-op when disabled)

@@ -533,7 +533,7 @@ extern "C" int b200det_profile_read(int kernel_id, double *total_ms, int *n_laun
 extern "C" const char *b200det_kernel_name(int kernel_id) {
     static const char *names[kKernCount] = {"focal_loss",  "assign",       "sparse_losses",
                                             "loss_reduce", "loss_finish",  "score_argmax",
-                                            "select_decode_nms", "other", "head_tail"};
+                                            "select_decode_nms", "other", "head_tail", "logits_sweep"};
     return (kernel_id >= 0 && kernel_id < kKernCount) ? names[kernel_id] : "?";
 }
 

@@ -20,10 +20,11 @@ import ctypes
 import torch
 
 from . import _lib
-from .losses import (_loss_params, _maybe_all_reduce, _plan_for, _prep_annotations, _prep_f32,
-                     _prep_reg)
+from . import geometry as _geom
+from .losses import (_DTYPES, _Plan, _loss_params, _maybe_all_reduce, _plan_for, _prep_annotations,
+                     _prep_f32, _prep_reg)
 
-__all__ = ['EvalStep']
+__all__ = ['EvalStep', 'LogitsEvalStep']
 
 
 class EvalStep:
@@ -87,3 +88,94 @@ class EvalStep:
         if is_fcos:
             loss_dict['center_ness_loss'] = losses[2]
         return loss_dict, dec._to_host(out, batch, m, device)
+
+
+class LogitsEvalStep:
+    """EvalStep for detectors that hand over the classification head's raw convolution output:
+
+        step = fused.LogitsEvalStep(criterion, decoder)
+        loss_value, (scores, classes, boxes) = step([cls_logits, reg_heads], annots)
+
+    cls_logits[l] is [B, A * num_classes, H, W] (NCHW, float32 / float16 / bfloat16), i.e. what
+    RetinaClsHead computes BEFORE `x.float(); sigmoid(x)` (models/head.py:46-50) and before the
+    permute of models/retinanet.py:73-76; reg_heads[l] stays [B, H, W, A, 4].  One sweep over the
+    logits produces the focal sum and the decoder's keys; no probability tensor is written.
+    Detections are bit-identical to decoder(sigmoid + permute of the logits); the loss agrees
+    within the 1e-5 tolerance.  RetinaNet-style heads only; evaluation only (no gradients)."""
+
+    def __init__(self, criterion, decoder):
+        if criterion._is_fcos or decoder._is_fcos:
+            raise ValueError('LogitsEvalStep supports RetinaLoss / RetinaDecoder heads')
+        self.criterion = criterion
+        self.decoder = decoder
+        self._plans = {}
+
+    def _plan(self, cls):
+        crit = self.criterion
+        shape0 = cls[0].shape
+        key = (tuple(t.shape[2:4] for t in cls), shape0[0], shape0[1])
+        plan = self._plans.get(key)
+        if plan is None:
+            per_loc = crit._per_loc
+            if shape0[1] % per_loc:
+                raise ValueError('logit channels are not a multiple of the anchors per location')
+            shapes = [(int(t.shape[2]), int(t.shape[3])) for t in cls]
+            batch, num_classes = int(shape0[0]), int(shape0[1]) // per_loc
+            geo = crit._geometry(shapes, batch, num_classes)
+            plan = _Plan(geo, batch, _geom.rows_per_image(shapes, geo.per_loc))
+            self._plans = {key: plan}
+        return plan
+
+    def __call__(self, preds, annotations, scales=None, sizes=None, to_xywh=False):
+        lib = _lib.load()
+        crit, dec = self.criterion, self.decoder
+        cls = [t.detach() for t in preds[0]]
+        if not cls or any((not t.is_cuda) or t.dim() != 4 for t in cls):
+            raise RuntimeError('cls logits must be CUDA tensors [B, A*C, H, W]')
+        dtype = cls[0].dtype
+        if dtype not in _DTYPES or any(t.dtype != dtype for t in cls):
+            raise RuntimeError('cls logits must share one dtype: float32, float16 or bfloat16')
+        cls = [t if t.is_contiguous() else t.contiguous() for t in cls]
+        reg, reg_dtype = _prep_reg([t.detach() for t in preds[1]])
+        annotations = _prep_annotations(annotations)
+        plan = self._plan(cls)
+        if annotations.shape[0] != plan.batch:
+            raise ValueError('annotations and predictions disagree on the batch size')
+        device = cls[0].device
+        batch, n_rows = plan.batch, plan.n_rows
+        m = int(dec.max_object_num)
+        dws_bytes = int(lib.b200det_decode_workspace_bytes(plan.geo_ref, int(dec.topn)))
+        rows_bytes = (4 * batch * n_rows + 255) & ~255
+        scratch = torch.empty(plan.ws_bytes + 3 * rows_bytes + dws_bytes, dtype=torch.uint8,
+                              device=device)
+        base = scratch.data_ptr()
+        labels_ptr = base + plan.ws_bytes
+        keys_ptr = labels_ptr + rows_bytes
+        classes_ptr = keys_ptr + rows_bytes
+        dws_ptr = classes_ptr + rows_bytes
+        small = torch.empty(8, dtype=torch.float64, device=device)   # sums | losses
+        out = dec._out_buffer(6 * batch * m, device)
+        lp = _loss_params(crit, reg_dtype)
+        dp = dec._params
+        dp.reg_dtype = reg_dtype
+        glue = dec._set_glue(dp, batch, device, scales, sizes, to_xywh)
+        sync = crit.sync_normalizer and torch.distributed.is_available() \
+            and torch.distributed.is_initialized()
+        st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        sums_ptr = small.data_ptr()
+        _lib.check(
+            lib.b200det_logits_eval_step(plan.geo_ref, ctypes.byref(lp), ctypes.byref(dp),
+                                         annotations.data_ptr(), int(annotations.shape[1]),
+                                         _lib.ptr_array(cls), _DTYPES[dtype], _lib.ptr_array(reg),
+                                         labels_ptr, base, plan.ws_bytes, sums_ptr,
+                                         None if sync else sums_ptr + 32, keys_ptr, classes_ptr,
+                                         out.data_ptr(), dws_ptr, dws_bytes, st),
+            'b200det_logits_eval_step')
+        if sync:
+            _maybe_all_reduce(small[0:4], True, crit.process_group)
+            _lib.check(lib.b200det_loss_finish(sums_ptr, lp.w_cls, lp.w_box, lp.w_ctr,
+                                               sums_ptr + 32, st), 'b200det_loss_finish')
+        del glue
+        crit.last_stats = {'sums': small[0:4]}
+        losses = small[4:8].view(torch.float32)
+        return {'cls_loss': losses[0], 'reg_loss': losses[1]}, dec._to_host(out, batch, m, device)
