@@ -39,6 +39,7 @@
 namespace b200det {
 
 constexpr int kLgThreads = 128;
+constexpr int kLgMinCtas = 10;          // 48 registers: 1280 threads x 8 loads in flight per SM
 constexpr int kLgUnroll = 8;             // loads in flight per thread
 constexpr float kTLo = 1.00010001e-4f;   // 1e-4 / (1 - 1e-4): the probability clamp in t = e^x
 constexpr float kTMax = 0.33333334f;     // p <= 0.25
@@ -61,12 +62,12 @@ struct LogitsArgs {
 template <typename T>
 __device__ __forceinline__ float lg_load(const T *p);
 template <>
-__device__ __forceinline__ float lg_load<float>(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ float lg_load<float>(const float *p) { return __ldg(p); }
 template <>
-__device__ __forceinline__ float lg_load<__half>(const __half *p) { return __half2float(__ldcs(p)); }
+__device__ __forceinline__ float lg_load<__half>(const __half *p) { return __half2float(__ldg(p)); }
 template <>
 __device__ __forceinline__ float lg_load<__nv_bfloat16>(const __nv_bfloat16 *p) {
-    return __bfloat162float(__ushort_as_bfloat16(__ldcs(reinterpret_cast<const unsigned short *>(p))));
+    return __bfloat162float(__ushort_as_bfloat16(__ldg(reinterpret_cast<const unsigned short *>(p))));
 }
 
 // torch's CUDA sigmoid for float32 (accurate expf, IEEE division)
@@ -88,12 +89,13 @@ __device__ __forceinline__ float2 bg_term2_acc(float2 t, float2 acc) {
     return __ffma2_rn(t3, s, acc);
 }
 
-// e^x with one MUFU.EX2 (flush-to-zero: results below 2^-126 are clamped to kTLo anyway)
-__device__ __forceinline__ float exp_fast(float x) {
+// 2^y with one MUFU.EX2 (flush-to-zero: results below 2^-126 are clamped to kTLo anyway)
+__device__ __forceinline__ float ex2_fast(float y) {
     float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
     return r;
 }
+__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * 1.4426950408889634f); }
 
 // background term of one class outside the packed fast path (p > 0.25, gamma != 2, NaN): exact form
 __device__ __noinline__ float lg_slow_bg(float x, float gamma, bool gamma2) {
@@ -110,135 +112,207 @@ __device__ __forceinline__ float lg_bg_term(float x, float gamma, bool gamma2) {
     return lg_slow_bg(x, gamma, gamma2);
 }
 
+// One CTA owns kLgThreads consecutive locations of one image and level, and ALL their anchors: the
+// A * kLgThreads rows it produces are contiguous in the level-major row order, so labels are read
+// and keys / classes written as full coalesced runs through shared memory.  (With one anchor per
+// CTA every 32-byte sector of keys / classes was written by 9 different CTAs at different times:
+// ncu showed 8x the key bytes in DRAM writes and as many fill reads.)
 template <typename T, bool FOCAL, bool ARGMAX>
-__global__ void __launch_bounds__(kLgThreads)
+__global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
     logits_sweep_kernel(LogitsArgs a) {
+    // parked winning groups | [kLgThreads * A] labels, then keys | [kLgThreads * A] classes
+    extern __shared__ __align__(16) int lg_smem[];
     int l = 0;
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i)
         if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
     const int rel = blockIdx.x - a.block_off[l];
     const int b = rel / a.tiles[l];
-    const int hw = (rel - b * a.tiles[l]) * kLgThreads + threadIdx.x;
-    const int anchor = blockIdx.y;
-    const int HW = a.hw[l], C = a.C;
+    const int hw0 = (rel - b * a.tiles[l]) * kLgThreads;
+    const int hw = hw0 + threadIdx.x;
+    const int HW = a.hw[l], C = a.C, A = a.A;
     const bool live = hw < HW;
-    const T *__restrict__ src = static_cast<const T *>(a.cls.p[l]) +
-                                ((size_t)b * a.A + anchor) * C * HW + (live ? hw : 0);
-    const long long row = a.row_base[l] + ((long long)b * HW + hw) * a.A + anchor;
-
-    int target = -1;        // class index of the row's target, -1: none
-    bool counted = live;    // ignored rows take no part in the focal loss (losses.py:228-230)
-    if (FOCAL && live && a.labels) {
-        const int label = __ldg(a.labels + row);
-        counted = label >= 0;
-        target = label - 1;
+    float4 *s_win = reinterpret_cast<float4 *>(lg_smem);   // [kLgUnroll / 4][kLgThreads]
+    int *s_key = lg_smem + kLgUnroll * kLgThreads;
+    int *s_cls = s_key + kLgThreads * A;
+    const long long row0 = a.row_base[l] + ((long long)b * HW + hw0) * A;   // first row of the tile
+    const int tile_rows = min(kLgThreads, HW - hw0) * A;
+    if (FOCAL && a.labels) {
+        for (int i = threadIdx.x; i < tile_rows; i += kLgThreads) s_key[i] = __ldg(a.labels + row0 + i);
+        __syncthreads();
     }
+
     const bool gamma2 = a.gamma == 2.f;
     const float one_m_alpha = 1.f - a.alpha;
     const float ninf = -__int_as_float(0x7f800000);
-    float m1 = ninf, m2 = ninf;
-    int i1 = 0;
-    float2 acc2 = make_float2(0.f, 0.f);
-    float acc_slow = 0.f;   // exact-form background terms, without (1 - alpha)
+    const int off0 = live ? (int)threadIdx.x : 0;
+    const size_t plane_bytes = (size_t)HW * sizeof(T);
+    float cta_total = 0.f;
+    float cp = 0.f;   // FCOS centre-ness probability of this location
+    if (ARGMAX && live && a.ctr.p[l])
+        cp = sigmoid_exact(__ldg(static_cast<const float *>(a.ctr.p[l]) + (size_t)b * HW + hw));
 
-    // one group of kLgUnroll classes; FULL: no class-count predicate
-    auto group = [&](int c0, auto full_tag) {
-        constexpr bool FULL = decltype(full_tag)::value;
-        float x[kLgUnroll];
-#pragma unroll
-        for (int k = 0; k < kLgUnroll; ++k) {
-            x[k] = ninf;
-            if (live && (FULL || c0 + k < C)) x[k] = lg_load<T>(src + (size_t)(c0 + k) * HW);
+    for (int anchor = 0; anchor < A; ++anchor) {
+        // CTA-uniform base of this (image, anchor, tile) block of C class planes + a 32-bit element
+        // offset (C * HW < 2^31 is checked on the host): one integer add and one address per load
+        const T *__restrict__ src =
+            static_cast<const T *>(a.cls.p[l]) + ((size_t)b * A + anchor) * C * HW + hw0 + off0;
+        const T *ptr = src;   // walks the class planes: one 64-bit add per load
+        const int slot = threadIdx.x * A + anchor;   // odd A: conflict-free; even A: 2-way at worst
+
+        int target = -1;        // class index of the row's target, -1: none
+        bool counted = live;    // ignored rows take no part in the focal loss (losses.py:228-230)
+        if (FOCAL && live && a.labels) {
+            const int label = s_key[slot];
+            counted = label >= 0;
+            target = label - 1;
         }
-        if (ARGMAX) {
+        // arg-max bookkeeping per GROUP of kLgUnroll classes (one max tree + 5 instructions per
+        // group instead of 5 per class): m1 / m2 are the two largest group maxima, ig the first
+        // group that holds the maximum; the winning group is rescanned after the loop
+        float m1 = ninf, m2 = ninf;
+        int ig = 0;
+        float2 acc2 = make_float2(0.f, 0.f);
+        float acc_slow = 0.f;   // exact-form background terms, without (1 - alpha)
+
+        // one group of kLgUnroll classes; FULL: no class-count predicate.  Dead threads of a ragged
+        // tile read location 0 of the tile (off0) and discard the result: no load is predicated
+        auto group = [&](int c0, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            float x[kLgUnroll];
 #pragma unroll
             for (int k = 0; k < kLgUnroll; ++k) {
-                m2 = fmaxf(m2, fminf(m1, x[k]));
-                if (x[k] > m1) i1 = c0 + k;   // strict: first maximum in class order
-                m1 = fmaxf(m1, x[k]);
+                x[k] = ninf;
+                if (FULL || c0 + k < C) x[k] = lg_load<T>(ptr);
+                ptr = reinterpret_cast<const T *>(reinterpret_cast<const char *>(ptr) + plane_bytes);
             }
-        }
-        if (FOCAL && counted) {
-            // every class as background here; the target class is corrected after the loop
-            float t[kLgUnroll];
+            if (ARGMAX) {
+                float g = x[0];
 #pragma unroll
-            for (int k = 0; k < kLgUnroll; ++k) {
-                // t = e^x; NaN logits stay NaN through the clamp and take the exact-form path
-                const float tk = fmax_nan(exp_fast(x[k]), kTLo);
-                t[k] = tk <= kTMax ? tk : 0.f;   // t = 0 contributes exactly 0 to the polynomial sum;
-                                                 // padding (x = -inf) gives t = kTLo
+                for (int k = 1; k < kLgUnroll; ++k) g = fmaxf(g, x[k]);
+                m2 = fmaxf(m2, fminf(m1, g));
+                if (g > m1) {   // strict: the first group that reaches the maximum; park its logits
+                    ig = c0;
+#pragma unroll
+                    for (int k = 0; k < kLgUnroll; k += 4)
+                        s_win[(k / 4) * kLgThreads + threadIdx.x] =
+                            make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+                }
+                m1 = fmaxf(m1, g);
             }
+            if (FOCAL && counted) {
+                // every class as background here; the target class is corrected after the loop
+                float t[kLgUnroll];
 #pragma unroll
-            for (int k = 0; k < kLgUnroll; k += 2) acc2 = bg_term2_acc(make_float2(t[k], t[k + 1]), acc2);
-            float tmin = t[0];
+                for (int k = 0; k < kLgUnroll; k += 2) {
+                    // t = e^x; NaN logits stay NaN through the clamp and take the exact-form path
+                    const float2 y = __fmul2_rn(make_float2(x[k], x[k + 1]),
+                                                make_float2(1.4426950408889634f, 1.4426950408889634f));
+                    const float t0 = fmax_nan(ex2_fast(y.x), kTLo), t1 = fmax_nan(ex2_fast(y.y), kTLo);
+                    t[k] = t0 <= kTMax ? t0 : 0.f;   // t = 0 contributes exactly 0 to the polynomial
+                    t[k + 1] = t1 <= kTMax ? t1 : 0.f;   // sum; padding (x = -inf) gives t = kTLo
+                }
 #pragma unroll
-            for (int k = 1; k < kLgUnroll; ++k) tmin = fminf(tmin, t[k]);
-            if (!FULL) {
-                // remove the padding classes' kTLo terms again
+                for (int k = 0; k < kLgUnroll; k += 2)
+                    acc2 = bg_term2_acc(make_float2(t[k], t[k + 1]), acc2);
+                float tmin = t[0];
 #pragma unroll
-                for (int k = 0; k < kLgUnroll; ++k)
-                    if (c0 + k >= C) acc2.x -= bg_term2_acc(make_float2(kTLo, 0.f), make_float2(0.f, 0.f)).x;
-            }
-            if (tmin == 0.f || !gamma2) {   // rare: some class is outside the polynomial's range
+                for (int k = 1; k < kLgUnroll; ++k) tmin = fminf(tmin, t[k]);
+                if (!FULL) {
+                    // remove the padding classes' kTLo terms again
 #pragma unroll
-                for (int k = 0; k < kLgUnroll; ++k) {
-                    if ((FULL || c0 + k < C) && (t[k] == 0.f || !gamma2)) {
-                        if (!gamma2 && t[k] != 0.f)   // undo the gamma == 2 polynomial
-                            acc2.x -= bg_term2_acc(make_float2(t[k], 0.f), make_float2(0.f, 0.f)).x;
-                        acc_slow += lg_slow_bg(x[k], a.gamma, gamma2);
+                    for (int k = 0; k < kLgUnroll; ++k)
+                        if (c0 + k >= C)
+                            acc2.x -= bg_term2_acc(make_float2(kTLo, 0.f), make_float2(0.f, 0.f)).x;
+                }
+                if (tmin == 0.f || !gamma2) {   // rare: some class is outside the polynomial's range
+#pragma unroll
+                    for (int k = 0; k < kLgUnroll; ++k) {
+                        if ((FULL || c0 + k < C) && (t[k] == 0.f || !gamma2)) {
+                            if (!gamma2 && t[k] != 0.f)   // undo the gamma == 2 polynomial
+                                acc2.x -= bg_term2_acc(make_float2(t[k], 0.f), make_float2(0.f, 0.f)).x;
+                            acc_slow += lg_slow_bg(x[k], a.gamma, gamma2);
+                        }
                     }
                 }
             }
-        }
-    };
-    int c0 = 0;
-    for (; c0 + kLgUnroll <= C; c0 += kLgUnroll) group(c0, std::true_type());
-    if (c0 < C) group(c0, std::false_type());
+        };
+        int c0 = 0;
+        for (; c0 + kLgUnroll <= C; c0 += kLgUnroll) group(c0, std::true_type());
+        if (c0 < C) group(c0, std::false_type());
 
-    if (FOCAL) {
-        float total = one_m_alpha * ((acc2.x + acc2.y) + acc_slow);
-        if (counted && target >= 0 && target < C) {
-            // the target class was counted as background: swap in the positive term
-            const float xt = lg_load<T>(src + (size_t)target * HW);
-            total += a.alpha * pos_term(sigmoid_exact(xt), a.gamma, gamma2) -
-                     one_m_alpha * lg_bg_term(xt, a.gamma, gamma2);
-        }
-        sweep_accumulate<kLgThreads>(total, a.focal_slots);
-    }
-
-    if (ARGMAX && live) {
-        float p1 = sigmoid_exact(m1);
-        if (p1 > a.thr_lo) {
-            const float p2 = sigmoid_exact(m2);
-            if ((int)(__float_as_uint(p1) - __float_as_uint(p2)) <= 4) {
-                // the two best classes are (almost) tied in probability space: exact rescan
-                float best = ninf;
-                int bi = 0;
-                for (int c = 0; c < C; ++c) {
-                    const float pe = sigmoid_exact(lg_load<T>(src + (size_t)c * HW));
-                    if (pe > best) {
-                        best = pe;
-                        bi = c;
-                    }
-                }
-                p1 = best;
-                i1 = bi;
+        if (FOCAL) {
+            float total = one_m_alpha * ((acc2.x + acc2.y) + acc_slow);
+            if (counted && target >= 0 && target < C) {
+                // the target class was counted as background: swap in the positive term
+                const float xt = lg_load<T>(src + (size_t)target * HW);
+                total += a.alpha * pos_term(sigmoid_exact(xt), a.gamma, gamma2) -
+                         one_m_alpha * lg_bg_term(xt, a.gamma, gamma2);
             }
+            cta_total += total;
         }
-        float score = p1;
-        if (a.ctr.p[l]) {
+
+        if (ARGMAX && live) {
+            float p1 = sigmoid_exact(m1);
+            int i1 = ig;
+            if (p1 > a.thr_lo) {
+                // the parked winning group: first class equal to the maximum, and the largest of
+                // the group's other classes -> second-largest logit of the whole row
+                float w[kLgUnroll];
+#pragma unroll
+                for (int k = 0; k < kLgUnroll; k += 4) {
+                    const float4 v = s_win[(k / 4) * kLgThreads + threadIdx.x];
+                    w[k] = v.x, w[k + 1] = v.y, w[k + 2] = v.z, w[k + 3] = v.w;
+                }
+                if (m1 != ninf) {   // a row of -inf never parks a group: class 0, p1 == p2 == 0
+                    bool found = false;
+#pragma unroll
+                    for (int k = 0; k < kLgUnroll; ++k) {
+                        if (!found && w[k] == m1) {
+                            found = true;
+                            i1 = ig + k;
+                        } else {
+                            m2 = fmaxf(m2, w[k]);
+                        }
+                    }
+                } else {
+                    m2 = m1;
+                }
+                const float p2 = sigmoid_exact(m2);
+                if ((int)(__float_as_uint(p1) - __float_as_uint(p2)) <= 4) {
+                    // the two best classes are (almost) tied in probability space: exact rescan
+                    float best = ninf;
+                    int bi = 0;
+                    for (int c = 0; c < C; ++c) {
+                        const float pe = sigmoid_exact(lg_load<T>(src + (size_t)c * HW));
+                        if (pe > best) {
+                            best = pe;
+                            bi = c;
+                        }
+                    }
+                    p1 = best;
+                    i1 = bi;
+                }
+            }
+            float score = p1;
             // np.sqrt(cls_scores * center_preds)  (decode.py:338) on the exact probabilities
-            const float cp = sigmoid_exact(__ldg(static_cast<const float *>(a.ctr.p[l]) +
-                                                 (size_t)b * HW + hw));
-            score = __fsqrt_rn(__fmul_rn(p1, cp));
+            if (a.ctr.p[l]) score = __fsqrt_rn(__fmul_rn(p1, cp));
+            s_key[slot] = (int)((score > a.min_score) ? ((__float_as_uint(score) & 0x80000000u)
+                                                             ? ~__float_as_uint(score)
+                                                             : (__float_as_uint(score) | 0x80000000u))
+                                                      : 0u);   // strict '>' (decode.py:133-138)
+            s_cls[slot] = i1;
         }
-        a.keys[row] = (score > a.min_score) ? ((__float_as_uint(score) & 0x80000000u)
-                                                   ? ~__float_as_uint(score)
-                                                   : (__float_as_uint(score) | 0x80000000u))
-                                            : 0u;   // strict '>' (decode.py:133-138)
-        a.classes[row] = i1;
     }
+
+    if (ARGMAX) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < tile_rows; i += kLgThreads) {
+            a.keys[row0 + i] = (uint32_t)s_key[i];
+            a.classes[row0 + i] = s_cls[i];
+        }
+    }
+    if (FOCAL) sweep_accumulate<kLgThreads>(cta_total, a.focal_slots);
 }
 
 }  // namespace b200det
@@ -304,20 +378,22 @@ extern "C" int b200det_logits_sweep(const b200det_geometry *geo, const void *con
         a.row_base[l] = (long long)g.batch * g.off[l];
         a.hw[l] = g.H[l] * g.W[l];
         a.tiles[l] = (a.hw[l] + kLgThreads - 1) / kLgThreads;
+        if ((long long)g.num_classes * a.hw[l] + a.hw[l] >= (1ll << 31)) return B200DET_ERANGE;
         a.block_off[l] = blocks;
         const long long nb = (long long)g.batch * a.tiles[l];
         if (blocks + nb > 0x7fffffffLL) return B200DET_ERANGE;
         blocks += (int)nb;
     }
     for (int l = g.n_levels; l <= kMaxLevels; ++l) a.block_off[l] = blocks;
-    const dim3 grid((unsigned)blocks, (unsigned)g.per_loc);
+    const unsigned grid = (unsigned)blocks;
+    const size_t smem = sizeof(int) * kLgThreads * (2 * (size_t)g.per_loc + kLgUnroll);
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(kKernLogits, stream);
 #define B200DET_LG(T)                                                                         \
     do {                                                                                      \
-        if (focal && argmax) logits_sweep_kernel<T, true, true><<<grid, kLgThreads, 0, st>>>(a);   \
-        else if (focal) logits_sweep_kernel<T, true, false><<<grid, kLgThreads, 0, st>>>(a);       \
-        else logits_sweep_kernel<T, false, true><<<grid, kLgThreads, 0, st>>>(a);                  \
+        if (focal && argmax) logits_sweep_kernel<T, true, true><<<grid, kLgThreads, smem, st>>>(a);   \
+        else if (focal) logits_sweep_kernel<T, true, false><<<grid, kLgThreads, smem, st>>>(a);       \
+        else logits_sweep_kernel<T, false, true><<<grid, kLgThreads, smem, st>>>(a);                  \
     } while (0)
     if (cls_dtype == B200DET_F32) B200DET_LG(float);
     else if (cls_dtype == B200DET_F16) B200DET_LG(__half);
