@@ -39,10 +39,14 @@
 namespace b200det {
 
 constexpr int kLgThreads = 128;
-constexpr int kLgMinCtas = 10;          // 48 registers: 1280 threads x 8 loads in flight per SM
-constexpr int kLgUnroll = 8;             // loads in flight per thread
-constexpr float kTLo = 1.00010001e-4f;   // 1e-4 / (1 - 1e-4): the probability clamp in t = e^x
-constexpr float kTMax = 0.33333334f;     // p <= 0.25
+constexpr int kLgMinCtas = 8;           // 64 registers: 1024 threads x 16 loads in flight per SM
+constexpr int kLgUnroll = 16;            // loads in flight per thread
+// The probability clamp [1e-4, .] and the polynomial's range p <= 0.25 as clamps of y = x * log2(e):
+// t = 2^y in [1e-4 / (1 - 1e-4), 1/3]
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kYLo = -13.287568f;      // log2(1.00010001e-4)
+constexpr float kYHi = -1.5849625f;      // log2(1/3)
+constexpr float kXHi = -1.0986123f;      // ln(1/3): logits above take the exact-form path
 
 struct LogitsArgs {
     PtrTab cls;                      // [B, A*C, HW] logits per level
@@ -89,27 +93,36 @@ __device__ __forceinline__ float2 bg_term2_acc(float2 t, float2 acc) {
     return __ffma2_rn(t3, s, acc);
 }
 
-// 2^y with one MUFU.EX2 (flush-to-zero: results below 2^-126 are clamped to kTLo anyway)
+// 2^y with one MUFU.EX2
 __device__ __forceinline__ float ex2_fast(float y) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
     return r;
 }
-__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * 1.4426950408889634f); }
+// t = e^x clamped to the polynomial's range; NaN stays NaN (and poisons the sum like the reference's)
+__device__ __forceinline__ float lg_t_of_y(float y) {
+    return ex2_fast(fmin_nan(fmax_nan(y, kYLo), kYHi));
+}
 
-// background term of one class outside the packed fast path (p > 0.25, gamma != 2, NaN): exact form
+// background term of one class outside the packed fast path (p > 0.25, gamma != 2): exact form
 __device__ __noinline__ float lg_slow_bg(float x, float gamma, bool gamma2) {
     return neg_term_slow(sigmoid_exact(x), gamma, gamma2);
 }
 
 // the background term the sweep adds for logit x, WITHOUT (1 - alpha): fast polynomial or exact form
 __device__ __forceinline__ float lg_bg_term(float x, float gamma, bool gamma2) {
-    const float t = fmax_nan(exp_fast(x), kTLo);
-    if (gamma2 && t <= kTMax) {
-        const float2 r = bg_term2_acc(make_float2(t, 0.f), make_float2(0.f, 0.f));
-        return r.x;
-    }
+    if (gamma2 && !(x > kXHi))
+        return bg_term2_acc(make_float2(lg_t_of_y(x * kLog2e), 0.f), make_float2(0.f, 0.f)).x;
     return lg_slow_bg(x, gamma, gamma2);
+}
+
+// p + k * stride (bytes) as ONE 64-bit multiply-add (IMAD.WIDE.U32), independent of the other loads
+template <typename T>
+__device__ __forceinline__ const T *lg_plane(const T *p, unsigned stride_bytes, unsigned k) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(stride_bytes), "r"(k),
+        "l"(reinterpret_cast<unsigned long long>(p)));
+    return reinterpret_cast<const T *>(r);
 }
 
 // One CTA owns kLgThreads consecutive locations of one image and level, and ALL their anchors: the
@@ -146,7 +159,7 @@ __global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
     const float one_m_alpha = 1.f - a.alpha;
     const float ninf = -__int_as_float(0x7f800000);
     const int off0 = live ? (int)threadIdx.x : 0;
-    const size_t plane_bytes = (size_t)HW * sizeof(T);
+    const unsigned plane_bytes = (unsigned)HW * (unsigned)sizeof(T);
     float cta_total = 0.f;
     float cp = 0.f;   // FCOS centre-ness probability of this location
     if (ARGMAX && live && a.ctr.p[l])
@@ -183,13 +196,13 @@ __global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
 #pragma unroll
             for (int k = 0; k < kLgUnroll; ++k) {
                 x[k] = ninf;
-                if (FULL || c0 + k < C) x[k] = lg_load<T>(ptr);
-                ptr = reinterpret_cast<const T *>(reinterpret_cast<const char *>(ptr) + plane_bytes);
+                if (FULL || c0 + k < C) x[k] = lg_load<T>(lg_plane(ptr, plane_bytes, k));
             }
-            if (ARGMAX) {
-                float g = x[0];
+            ptr = lg_plane(ptr, plane_bytes, kLgUnroll);
+            float g = x[0];   // largest logit of the group
 #pragma unroll
-                for (int k = 1; k < kLgUnroll; ++k) g = fmaxf(g, x[k]);
+            for (int k = 1; k < kLgUnroll; ++k) g = fmaxf(g, x[k]);
+            if (ARGMAX) {
                 m2 = fmaxf(m2, fminf(m1, g));
                 if (g > m1) {   // strict: the first group that reaches the maximum; park its logits
                     ig = c0;
@@ -205,32 +218,25 @@ __global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
                 float t[kLgUnroll];
 #pragma unroll
                 for (int k = 0; k < kLgUnroll; k += 2) {
-                    // t = e^x; NaN logits stay NaN through the clamp and take the exact-form path
-                    const float2 y = __fmul2_rn(make_float2(x[k], x[k + 1]),
-                                                make_float2(1.4426950408889634f, 1.4426950408889634f));
-                    const float t0 = fmax_nan(ex2_fast(y.x), kTLo), t1 = fmax_nan(ex2_fast(y.y), kTLo);
-                    t[k] = t0 <= kTMax ? t0 : 0.f;   // t = 0 contributes exactly 0 to the polynomial
-                    t[k + 1] = t1 <= kTMax ? t1 : 0.f;   // sum; padding (x = -inf) gives t = kTLo
+                    const float2 y = __fmul2_rn(make_float2(x[k], x[k + 1]), make_float2(kLog2e, kLog2e));
+                    t[k] = lg_t_of_y(y.x);       // padding (x = -inf) gives 2^kYLo
+                    t[k + 1] = lg_t_of_y(y.y);
                 }
 #pragma unroll
                 for (int k = 0; k < kLgUnroll; k += 2)
                     acc2 = bg_term2_acc(make_float2(t[k], t[k + 1]), acc2);
-                float tmin = t[0];
-#pragma unroll
-                for (int k = 1; k < kLgUnroll; ++k) tmin = fminf(tmin, t[k]);
                 if (!FULL) {
-                    // remove the padding classes' kTLo terms again
+                    // remove the padding classes' terms again
 #pragma unroll
                     for (int k = 0; k < kLgUnroll; ++k)
                         if (c0 + k >= C)
-                            acc2.x -= bg_term2_acc(make_float2(kTLo, 0.f), make_float2(0.f, 0.f)).x;
+                            acc2.x -= bg_term2_acc(make_float2(t[k], 0.f), make_float2(0.f, 0.f)).x;
                 }
-                if (tmin == 0.f || !gamma2) {   // rare: some class is outside the polynomial's range
+                if (g > kXHi || !gamma2) {   // rare: some class is outside the polynomial's range
 #pragma unroll
                     for (int k = 0; k < kLgUnroll; ++k) {
-                        if ((FULL || c0 + k < C) && (t[k] == 0.f || !gamma2)) {
-                            if (!gamma2 && t[k] != 0.f)   // undo the gamma == 2 polynomial
-                                acc2.x -= bg_term2_acc(make_float2(t[k], 0.f), make_float2(0.f, 0.f)).x;
+                        if ((FULL || c0 + k < C) && (x[k] > kXHi || !gamma2)) {
+                            acc2.x -= bg_term2_acc(make_float2(t[k], 0.f), make_float2(0.f, 0.f)).x;
                             acc_slow += lg_slow_bg(x[k], a.gamma, gamma2);
                         }
                     }
