@@ -67,6 +67,17 @@ extern "C" {
 #define B200DET_NMS_PYTHON 0
 #define B200DET_NMS_DIOU_PYTHON 1
 #define B200DET_NMS_TORCH 2
+#define B200DET_NMS_NONE 3 /* DETRDecoder(nms_type=None): top-n only (decode.py:373-385, :453) */
+
+/* box source of b200det_select_decode_nms (`is_fcos` argument) */
+#define B200DET_DECODE_ANCHORS 0 /* (tx,ty,tw,th) against generated anchors, int32 truncation */
+#define B200DET_DECODE_POINTS 1  /* (l,t,r,b) against generated points, int32 truncation */
+#define B200DET_DECODE_BOXES 2   /* reg[l] holds float32 x1,y1,x2,y2 rows, used as they are */
+
+/* class-score source of b200det_query_scores */
+#define B200DET_SCORES_PROBS 0   /* probabilities as given */
+#define B200DET_SCORES_SIGMOID 1 /* sigmoid(float(logits))            (DINODETRDecoder, decode.py:515-516) */
+#define B200DET_SCORES_SOFTMAX 2 /* softmax(logits) over the channels (DETRDecoder, decode.py:391) */
 
 /*
  * Pyramid geometry shared by every call.  Replaces what the reference re-derives on the host
@@ -236,7 +247,9 @@ int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
  * Replaces DecodeMethod.__call__ (decode.py:121-172), DetNMSMethod.__call__ (:34-104),
  * RetinaDecoder.snap_txtytwth_to_x1y1x2y2 (:251-271) / FCOSDecoder.snap_ltrb_to_x1y1x2y2
  * (:350-364) incl. NumPy's float32 exp and the int32 truncation.
- *   is_fcos       : 0 = anchor (tx,ty,tw,th) decoding, 1 = point (l,t,r,b) decoding
+ *   is_fcos       : B200DET_DECODE_*: 0 = anchor (tx,ty,tw,th) decoding, 1 = point (l,t,r,b)
+ *                   decoding, 2 = reg[l] already holds float32 boxes (DecodeMethod on its own,
+ *                   DETR-style decoders; the geometry is then one level of 1 x N rows)
  *   min_score     : the threshold given to b200det_score_argmax (sizes the selection histogram)
  *   scales/sizes/to_xywh : optional evaluation glue of the reference's test loop, fused into the
  *                   epilogue (tools/scripts.py:742-757): scales = device float32 [B] -> boxes /=
@@ -256,6 +269,29 @@ int b200det_select_decode_nms(const b200det_geometry *geo, const uint32_t *keys,
                               int to_xywh, float *out, int32_t *order, int32_t *keep,
                               int32_t *counts, void *workspace, size_t workspace_bytes,
                               void *stream);
+
+/*
+ * Front end of the query-based decoders and of a stand-alone DecodeMethod: per (image, query) row
+ * the class scores, their first-maximum class, the class / score filters and the box transform.
+ * Replaces DETRDecoder.__call__ (decode.py:388-431: softmax, argmax, score gather, cxcywh ->
+ * xyxy, * [w,h,w,h], `class < num_classes`, `score > min_score_threshold`) and
+ * DINODETRDecoder.__call__ (:512-556: the same with sigmoid and no class filter); the sort /
+ * top-n / NMS / cap that follow (:433-470, :558-592) are b200det_select_decode_nms with
+ * B200DET_DECODE_BOXES on a one-level geometry of 1 x queries rows.
+ *   cls          : device [batch, queries, channels]; float32 (F16 / BF16 also for SIGMOID)
+ *   mode         : B200DET_SCORES_*.  SOFTMAX reproduces torch's CUDA softmax kernel for rows of
+ *                  <= 1024 channels bit for bit (per-lane strided sums, xor-butterfly reduction)
+ *   boxes_cxcywh : device float32 [batch, queries, 4] normalised cx,cy,w,h, or NULL (no boxes)
+ *   sizes_hw     : device float32 [batch, 2] = scaled (h, w) of every image (with boxes_cxcywh)
+ *   num_classes  : rows whose arg-max class is >= num_classes are dropped (DETR's no-object
+ *                  channel); pass `channels` to keep every row
+ *   keys/classes : device uint32 / int32 [batch*queries], as b200det_score_argmax
+ *   boxes_xyxy   : device float32 [batch, queries, 4] out (with boxes_cxcywh), 16-byte aligned
+ */
+int b200det_query_scores(const void *cls, int cls_dtype, int mode, const float *boxes_cxcywh,
+                         const float *sizes_hw, int batch, int queries, int channels,
+                         int num_classes, float min_score, uint32_t *keys, int32_t *classes,
+                         float *boxes_xyxy, void *stream);
 
 /* ---- fused host entries (one C call per loss forward / per decode) -------------------- */
 typedef struct b200det_loss_params {

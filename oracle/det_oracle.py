@@ -11,6 +11,8 @@ primitives the reference itself runs on) of the reference's dense-detection hot 
     simpleAICV/detection/decode.py:107-172        DecodeMethod
     simpleAICV/detection/decode.py:175-271        RetinaDecoder
     simpleAICV/detection/decode.py:274-364        FCOSDecoder
+    simpleAICV/detection/decode.py:367-482        DETRDecoder
+    simpleAICV/detection/decode.py:485-594        DINODETRDecoder
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import this module; the product (``b200det``) never does and has no
@@ -434,7 +436,10 @@ def fcos_loss(preds, annotations, strides, mi, alpha=0.25, gamma=2., cls_loss_we
 # NMS + selection (decode.py:26-172)
 # ----------------------------------------------------------------------------------------
 def nms_keep(boxes, scores, nms_type='python_nms', nms_threshold=0.5):
-    """decode.py:34-104.  boxes [n,4] float32 sorted by score; returns kept positions."""
+    """decode.py:34-104.  boxes [n,4] float32 sorted by score; returns kept positions.
+    nms_type None: the query decoders' "no NMS" setting (decode.py:453, :577) keeps everything."""
+    if nms_type is None:
+        return np.arange(scores.shape[0])
     assert nms_type in ('torch_nms', 'python_nms', 'diou_python_nms')
     if nms_type == 'torch_nms':
         from torchvision.ops import nms
@@ -500,6 +505,42 @@ def select_and_nms(scores, classes, boxes, max_object_num=100, min_score_thresho
             out_boxes[i, 0:n, :] = b[keep][0:n, :]
         extras.append(info)
     return [out_scores, out_classes, out_boxes], extras
+
+
+def query_decode(cls_logits, reg_preds, scaled_sizes, activation, num_classes=None,
+                 max_object_num=100, min_score_threshold=0.05, topn=100, nms_type=None,
+                 nms_threshold=0.5, prob_fn=None):
+    """DETRDecoder.__call__ (decode.py:388-470, activation='softmax', rows whose arg-max is the
+    no-object channel >= num_classes dropped) / DINODETRDecoder.__call__ (:512-592,
+    activation='sigmoid', num_classes None).  cls_logits [B,Q,C] and reg_preds [B,Q,4]
+    (normalised cx,cy,w,h) are torch tensors; the activation runs in torch on their device like
+    the reference's, everything after it in NumPy.  prob_fn overrides the activation (the GPU
+    parity tests pass torch's CUDA softmax / sigmoid, which is what a CUDA run of the reference
+    computes)."""
+    if prob_fn is not None:
+        probs = prob_fn(cls_logits)
+    elif activation == 'softmax':
+        probs = torch.nn.functional.softmax(cls_logits, dim=2)
+    else:
+        probs = torch.sigmoid(cls_logits.float())
+    probs = probs.cpu().detach().numpy()
+    reg = reg_preds.cpu().detach().numpy()
+    classes = np.argmax(probs, axis=2)
+    scores = np.take_along_axis(probs, classes[:, :, None], axis=2)[:, :, 0]
+    boxes = []
+    for idx in range(reg.shape[0]):
+        cx, cy, w, h = reg[idx][:, 0], reg[idx][:, 1], reg[idx][:, 2], reg[idx][:, 3]
+        b = np.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], axis=1)
+        ih, iw = scaled_sizes[idx][0], scaled_sizes[idx][1]
+        boxes.append((b * np.array([[iw, ih, iw, ih]], dtype=np.float32))[None])
+    boxes = np.concatenate(boxes, axis=0)
+    if num_classes is not None:
+        # decode.py:423-431: dropped rows never reach the threshold / sort; a score of -inf keeps
+        # them out of select_and_nms in the same way
+        scores = np.where(classes < num_classes, scores, -np.inf).astype(np.float32)
+    result, extras = select_and_nms(scores, classes, boxes, max_object_num, min_score_threshold,
+                                    topn, nms_type, nms_threshold)
+    return result, {'per_image': extras, 'scores': scores, 'classes': classes, 'boxes': boxes}
 
 
 def _to_np_rows(level_tensors):

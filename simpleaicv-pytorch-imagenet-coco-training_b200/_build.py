@@ -24,6 +24,7 @@ SOURCES = {
     'api.cu': [],
     'heads.cu': [],
     'logits.cu': [],
+    'queries.cu': [],
 }
 
 

@@ -15,7 +15,9 @@ MAX_TOPN = 2048
 
 F32, F16, BF16 = 0, 1, 2
 BOX_NONE, BOX_SMOOTHL1, BOX_IOU, BOX_GIOU, BOX_DIOU, BOX_CIOU, BOX_EIOU = range(7)
-NMS_PYTHON, NMS_DIOU_PYTHON, NMS_TORCH = range(3)
+NMS_PYTHON, NMS_DIOU_PYTHON, NMS_TORCH, NMS_NONE = range(4)
+DECODE_ANCHORS, DECODE_POINTS, DECODE_BOXES = range(3)
+SCORES_PROBS, SCORES_SIGMOID, SCORES_SOFTMAX = range(3)
 
 BOX_LOSS_CODES = {
     'SmoothL1': BOX_SMOOTHL1,
@@ -25,7 +27,8 @@ BOX_LOSS_CODES = {
     'CIoU': BOX_CIOU,
     'EIoU': BOX_EIOU,
 }
-NMS_CODES = {'python_nms': NMS_PYTHON, 'diou_python_nms': NMS_DIOU_PYTHON, 'torch_nms': NMS_TORCH}
+NMS_CODES = {'python_nms': NMS_PYTHON, 'diou_python_nms': NMS_DIOU_PYTHON, 'torch_nms': NMS_TORCH,
+             None: NMS_NONE}
 
 
 class Geometry(ctypes.Structure):
@@ -137,6 +140,10 @@ SIGNATURES = {
         _geo, _vp, _vp, _vpp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
         ctypes.c_int, ctypes.c_int, ctypes.c_double, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp,
         _vp, ctypes.c_size_t, _vp
+    ]),
+    'b200det_query_scores': (ctypes.c_int, [
+        _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp
     ]),
     'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
     'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),

@@ -567,6 +567,7 @@ constexpr int kNmsWindow = 256;
 // does kept box kb suppress the later box ob?  (decode.py:45-100 / torchvision CPU nms)
 __device__ __forceinline__ bool nms_suppresses(const float4 kb, const float4 ob, int nms_type,
                                                float thr_f, double thr_d) {
+    if (nms_type == B200DET_NMS_NONE) return false;   // DETRDecoder(nms_type=None), decode.py:453
     const float karea_raw = __fmul_rn(__fsub_rn(kb.z, kb.x), __fsub_rn(kb.w, kb.y));
     const float oarea_raw = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
     const float iw = fmaxf(__fsub_rn(fminf(kb.z, ob.z), fmaxf(kb.x, ob.x)), 0.f);
@@ -801,6 +802,13 @@ __global__ void __launch_bounds__(kSelThreads)
         scls[i] = __ldg(classes + lm_index(g, b, l, local));
         const float4 t = load_reg4(a.reg.p[l], a.reg_dtype, (long long)b * g.rows[l] + local);
         float x1, y1, x2, y2;
+        if (a.is_fcos == B200DET_DECODE_BOXES) {
+            // pre-decoded x1,y1,x2,y2 (DecodeMethod's pred_bboxes, decode.py:121-172; DETR-style
+            // decoders): used as they are, no integer truncation
+            sbox[i] = t;
+            if (order_out) order_out[(size_t)b * a.topn + i] = row;
+            continue;
+        }
         if (a.is_fcos) {
             // decode.py:356-361
             const float2 p = point_of(g, l, local);
@@ -1117,9 +1125,11 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
     if (rc) return rc;
     if (!keys || !classes || !reg || !out) return B200DET_EINVAL;
     if (topn < 1 || topn > B200DET_MAX_TOPN || max_out < 1) return B200DET_ERANGE;
-    if (nms_type < B200DET_NMS_PYTHON || nms_type > B200DET_NMS_TORCH) return B200DET_EINVAL;
+    if (nms_type < B200DET_NMS_PYTHON || nms_type > B200DET_NMS_NONE) return B200DET_EINVAL;
     if (reg_dtype != B200DET_F32 && reg_dtype != B200DET_F16 && reg_dtype != B200DET_BF16)
         return B200DET_EINVAL;
+    if (is_fcos < 0 || is_fcos > B200DET_DECODE_BOXES) return B200DET_EINVAL;
+    if (is_fcos == B200DET_DECODE_BOXES && reg_dtype != B200DET_F32) return B200DET_EINVAL;
     if (reinterpret_cast<uintptr_t>(out) & 15) return B200DET_EALIGN;
     SelectArgs a;
     a.g = g;

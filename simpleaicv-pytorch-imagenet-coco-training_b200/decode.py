@@ -1,4 +1,6 @@
-"""b200det.decode -- drop-in RetinaDecoder / FCOSDecoder backed by libb200det.so (sm_100a CUDA).
+"""b200det.decode -- drop-in RetinaDecoder / FCOSDecoder (and the query-based DETRDecoder /
+DINODETRDecoder plus the stand-alone DecodeMethod / DetNMSMethod) backed by libb200det.so
+(sm_100a CUDA).
 
 Same class names, constructor kwargs, __call__(preds) signature and return value (a list of
 three writable float32 NumPy arrays: scores [B,M] padded with -1, classes [B,M] padded with -1,
@@ -21,7 +23,8 @@ from .losses import _prep_f32, _prep_reg
 
 _ZERO_COPY = os.environ.get('B200DET_ZERO_COPY', '1') != '0'
 
-__all__ = ['RetinaDecoder', 'FCOSDecoder']
+__all__ = ['RetinaDecoder', 'FCOSDecoder', 'DETRDecoder', 'DINODETRDecoder', 'DecodeMethod',
+           'DetNMSMethod']
 
 
 class _DecoderBase:
@@ -218,3 +221,199 @@ class FCOSDecoder(_DecoderBase):
 
     def _geometry(self, shapes, batch, num_classes):
         return _geom.make_geometry(shapes, batch, 1, num_classes, self.strides)
+
+
+class _FlatDecoder(_DecoderBase):
+    """Shared tail of the decoders whose candidates are a flat list of (score, class, box) rows per
+    image: b200det_select_decode_nms with B200DET_DECODE_BOXES on a one-level 1 x N geometry."""
+
+    def _init_flat(self, max_object_num, min_score_threshold, topn, nms_type, nms_threshold):
+        if nms_type is not None:
+            assert nms_type in ['torch_nms', 'python_nms', 'diou_python_nms'], 'wrong nms type!'
+        if topn > _lib.MAX_TOPN:
+            raise ValueError(f'topn <= {_lib.MAX_TOPN} is supported')
+        self.max_object_num = max_object_num
+        self.min_score_threshold = min_score_threshold
+        self.topn = topn
+        self.nms_type = nms_type
+        self.nms_threshold = nms_threshold
+        self._pinned = None
+
+    @staticmethod
+    def _flat_geometry(batch, rows):
+        geo = _lib.Geometry()
+        geo.n_levels, geo.batch, geo.per_loc, geo.num_classes = 1, int(batch), 1, 1
+        geo.height[0], geo.width[0], geo.stride[0] = 1, int(rows), 1.0
+        return geo
+
+    def _select(self, keys, classes, boxes, batch, rows, topn, max_out, min_score, details=False):
+        """keys uint32 / classes int32 [batch*rows], boxes float32 [batch, rows, 4] on the device."""
+        lib = _lib.load()
+        device = boxes.device
+        geo = self._flat_geometry(batch, rows)
+        ws_bytes = int(lib.b200det_decode_workspace_bytes(ctypes.byref(geo), int(topn)))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=device)
+        out = self._out_buffer(6 * batch * max_out, device)
+        order = keep = None
+        if details:
+            order = torch.empty(batch * topn, dtype=torch.int32, device=device)
+            keep = torch.empty(batch * topn, dtype=torch.int32, device=device)
+        _lib.check(
+            lib.b200det_select_decode_nms(
+                ctypes.byref(geo), keys.data_ptr(), classes.data_ptr(), _lib.ptr_array([boxes]),
+                _lib.F32, _lib.DECODE_BOXES, float(np.float32(min_score)), int(topn), int(max_out),
+                _lib.NMS_CODES[self.nms_type],
+                float(self.nms_threshold if self.nms_threshold is not None else 0.5), None, None, 0,
+                out.data_ptr(), order.data_ptr() if details else None,
+                keep.data_ptr() if details else None, None, ws.data_ptr(), ws_bytes,
+                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+            'b200det_select_decode_nms')
+        result = self._to_host(out, batch, max_out, device)
+        if not details:
+            return result
+        return result, {'order': order.view(batch, topn).cpu().numpy(),
+                        'keep': keep.view(batch, topn).cpu().numpy()}
+
+    def _query_scores(self, cls, mode, boxes, sizes, num_classes, min_score):
+        """One warp per (image, query) row: keys, classes and xyxy boxes (b200det_query_scores)."""
+        lib = _lib.load()
+        batch, queries, channels = (int(v) for v in cls.shape)
+        device = cls.device
+        keys = torch.empty(batch * queries, dtype=torch.int32, device=device)
+        classes = torch.empty(batch * queries, dtype=torch.int32, device=device)
+        xyxy = torch.empty((batch, queries, 4), dtype=torch.float32, device=device) \
+            if boxes is not None else None
+        dtype = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}[cls.dtype]
+        _lib.check(
+            lib.b200det_query_scores(
+                cls.data_ptr(), dtype, mode, boxes.data_ptr() if boxes is not None else None,
+                sizes.data_ptr() if sizes is not None else None, batch, queries, channels,
+                int(num_classes), float(np.float32(min_score)), keys.data_ptr(), classes.data_ptr(),
+                xyxy.data_ptr() if xyxy is not None else None,
+                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+            'b200det_query_scores')
+        return keys, classes, xyxy
+
+
+def _device_f32(x, what, device=None):
+    """CUDA float32 contiguous tensor from a CUDA tensor or a host array (the reference's DecodeMethod
+    / DetNMSMethod take NumPy arrays: those are uploaded).  There is no CPU compute path."""
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError(f'{what} must be a CUDA tensor (or a NumPy array to upload)')
+        return x.detach().to(torch.float32).contiguous()
+    if not torch.cuda.is_available():
+        raise RuntimeError('b200det needs a CUDA device (B200); there is no CPU fallback')
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(device or 'cuda')
+
+
+class DetNMSMethod(_FlatDecoder):
+    """Drop-in for simpleAICV.detection.decode.DetNMSMethod (decode.py:24-104): keep indices of
+    greedy NMS over boxes that are already sorted by score."""
+
+    def __init__(self, nms_type='python_nms', nms_threshold=0.5):
+        assert nms_type in ['torch_nms', 'python_nms', 'diou_python_nms'], 'wrong nms type!'
+        self._init_flat(1, -np.inf, 1, nms_type, nms_threshold)
+
+    def __call__(self, sorted_bboxes, sorted_scores):
+        n = int(sorted_scores.shape[0])
+        if n == 0:
+            return np.array([], dtype=np.int64 if self.nms_type == 'torch_nms' else np.float64)
+        if n > _lib.MAX_TOPN:
+            raise ValueError(f'at most {_lib.MAX_TOPN} boxes are supported')
+        boxes = _device_f32(sorted_bboxes, 'sorted_bboxes').view(1, n, 4)
+        device = boxes.device
+        if self.nms_type == 'torch_nms':
+            # torchvision orders by the scores it is given
+            scores = _device_f32(sorted_scores, 'sorted_scores', device).view(1, n, 1)
+        else:
+            # python_nms never looks at the scores: it walks the boxes in the order given
+            scores = torch.arange(n, 0, -1, dtype=torch.float32, device=device).view(1, n, 1)
+        keys, classes, _ = self._query_scores(scores, _lib.SCORES_PROBS, None, None, 1, -np.inf)
+        _, info = self._select(keys, classes, boxes, 1, n, n, 1, -np.inf, details=True)
+        keep = info['keep'][0]
+        keep = info['order'][0][keep[keep >= 0]]
+        return keep.astype(np.int64 if self.nms_type == 'torch_nms' else np.int32)
+
+
+class DecodeMethod(_FlatDecoder):
+    """Drop-in for simpleAICV.detection.decode.DecodeMethod (decode.py:107-172): score threshold,
+    descending sort, top-n, NMS and the max_object_num cap over pre-decoded boxes."""
+
+    def __init__(self, max_object_num=100, min_score_threshold=0.05, topn=1000,
+                 nms_type='python_nms', nms_threshold=0.5):
+        assert nms_type in ['torch_nms', 'python_nms', 'diou_python_nms'], 'wrong nms type!'
+        self._init_flat(max_object_num, min_score_threshold, topn, nms_type, nms_threshold)
+
+    def __call__(self, cls_scores, cls_classes, pred_bboxes):
+        scores = _device_f32(cls_scores, 'cls_scores')
+        device = scores.device
+        batch, rows = (int(v) for v in scores.shape)
+        boxes = _device_f32(pred_bboxes, 'pred_bboxes', device).view(batch, rows, 4)
+        if isinstance(cls_classes, torch.Tensor):
+            classes = cls_classes.detach().to(device=device, dtype=torch.int32).contiguous()
+        else:
+            classes = torch.as_tensor(np.ascontiguousarray(cls_classes).astype(np.int32)).to(device)
+        keys, _, _ = self._query_scores(scores.view(batch, rows, 1), _lib.SCORES_PROBS, None, None,
+                                        1, self.min_score_threshold)
+        return self._select(keys, classes.view(-1), boxes, batch, rows, self.topn,
+                            int(self.max_object_num), self.min_score_threshold)
+
+
+class _QueryDecoder(_FlatDecoder):
+    _mode = _lib.SCORES_SIGMOID
+
+    def _decode(self, cls_preds, reg_preds, scaled_sizes, num_classes, details=False):
+        if not (cls_preds.is_cuda and reg_preds.is_cuda):
+            raise RuntimeError('b200det decoders need CUDA tensors; there is no CPU fallback')
+        cls = cls_preds.detach().contiguous()
+        if self._mode == _lib.SCORES_SOFTMAX and cls.dtype != torch.float32:
+            raise RuntimeError('DETRDecoder: float32 class logits are supported')
+        reg = reg_preds.detach().to(torch.float32).contiguous()
+        batch, queries, channels = (int(v) for v in cls.shape)
+        sizes = torch.as_tensor(np.asarray(scaled_sizes, dtype=np.float32).reshape(-1)).to(cls.device)
+        if sizes.numel() != 2 * batch:
+            raise ValueError('scaled_sizes must hold (height, width) per image')
+        keys, classes, boxes = self._query_scores(
+            cls, self._mode, reg, sizes, channels if num_classes is None else num_classes,
+            self.min_score_threshold)
+        return self._select(keys, classes, boxes, batch, queries, self.topn,
+                            int(self.max_object_num), self.min_score_threshold, details=details)
+
+
+class DETRDecoder(_QueryDecoder):
+    """Drop-in for simpleAICV.detection.decode.DETRDecoder (decode.py:367-482): softmax over the
+    num_classes + 1 channels of the last decoder layer, no-object rows dropped, optional NMS."""
+
+    _mode = _lib.SCORES_SOFTMAX
+
+    def __init__(self, num_classes=80, max_object_num=100, min_score_threshold=0.05, topn=100,
+                 nms_type=None, nms_threshold=0.5):
+        self.num_classes = num_classes
+        self._init_flat(max_object_num, min_score_threshold, topn, nms_type, nms_threshold)
+
+    def __call__(self, preds, scaled_sizes):
+        return self._decode(preds[0][-1, :, :, :], preds[1][-1, :, :, :], scaled_sizes,
+                            self.num_classes)
+
+    def decode_with_details(self, preds, scaled_sizes):
+        return self._decode(preds[0][-1, :, :, :], preds[1][-1, :, :, :], scaled_sizes,
+                            self.num_classes, details=True)
+
+
+class DINODETRDecoder(_QueryDecoder):
+    """Drop-in for simpleAICV.detection.decode.DINODETRDecoder (decode.py:485-594): sigmoid class
+    scores of preds['pred_logits'], boxes from preds['pred_boxes']."""
+
+    _mode = _lib.SCORES_SIGMOID
+
+    def __init__(self, max_object_num=100, min_score_threshold=0.05, topn=300,
+                 nms_type='python_nms', nms_threshold=0.5):
+        self._init_flat(max_object_num, min_score_threshold, topn, nms_type, nms_threshold)
+
+    def __call__(self, preds, scaled_sizes):
+        return self._decode(preds['pred_logits'], preds['pred_boxes'], scaled_sizes, None)
+
+    def decode_with_details(self, preds, scaled_sizes):
+        return self._decode(preds['pred_logits'], preds['pred_boxes'], scaled_sizes, None,
+                            details=True)

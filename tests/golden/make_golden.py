@@ -10,7 +10,8 @@ reference's own classes returned for them:
     get_batch_position_annotations) and FCOS regression/centre-ness targets;
   * RetinaDecoder / FCOSDecoder: the three returned arrays for python_nms, diou_python_nms and
     torch_nms, default and small (topn, max_object_num) settings;
-  * RetinaAnchors / FCOSPositions tables; np.exp samples.
+  * RetinaAnchors / FCOSPositions tables; np.exp samples;
+  * DETRDecoder / DINODETRDecoder / DecodeMethod / DetNMSMethod outputs (queries.npz).
 numpy / torch / torchvision versions used are recorded in the fixture.
 """
 import os
@@ -224,6 +225,59 @@ def make_face(path):
     np.savez_compressed(path, **out)
 
 
+def make_queries(path):
+    """Query-based decoders + the stand-alone DecodeMethod / DetNMSMethod: the
+    reference's DETRDecoder (softmax, no-object channel, with and without NMS), DINODETRDecoder
+    (sigmoid) and DecodeMethod / DetNMSMethod on float boxes."""
+    _, D, _ = refload.load()
+    gen = torch.Generator().manual_seed(21)
+    B, Q, C = 3, 300, 12
+    detr_cls = torch.randn((2, B, Q, C + 1), generator=gen) * 2.5      # [layers, B, Q, C+1]
+    detr_cls[..., C] += 1.0                                              # no-object wins often
+    ctr = torch.rand((2, B, Q, 2), generator=gen)
+    wh = torch.rand((2, B, Q, 2), generator=gen) * 0.4 + 0.02
+    detr_reg = torch.cat([ctr, wh], dim=-1)
+    sizes = [[480, 640], [600, 800], [333, 500]]
+    out = {'versions': versions(), 'detr_cls': detr_cls.numpy(), 'detr_reg': detr_reg.numpy(),
+           'sizes': np.array(sizes, dtype=np.int64), 'num_classes': C}
+    for tag, kw in (('none', dict(nms_type=None)), ('nms', dict(nms_type='python_nms', topn=80,
+                                                              max_object_num=20)),
+                    ('low', dict(nms_type='diou_python_nms', min_score_threshold=0.3))):
+        dec = D.DETRDecoder(num_classes=C, **kw)
+        s_, c_, b_ = dec([detr_cls, detr_reg], sizes)
+        out[f'detr_{tag}_scores'], out[f'detr_{tag}_classes'], out[f'detr_{tag}_boxes'] = s_, c_, b_
+    dino_cls = torch.randn((B, 900, C), generator=gen) * 1.5 - 2.0
+    dctr = torch.rand((B, 900, 2), generator=gen)
+    dwh = torch.rand((B, 900, 2), generator=gen) * 0.5 + 0.02
+    dino_reg = torch.cat([dctr, dwh], dim=-1)
+    out['dino_cls'], out['dino_reg'] = dino_cls.numpy(), dino_reg.numpy()
+    for nms in ('python_nms', 'diou_python_nms', 'torch_nms'):
+        dec = D.DINODETRDecoder(nms_type=nms)
+        s_, c_, b_ = dec({'pred_logits': dino_cls, 'pred_boxes': dino_reg}, sizes)
+        out[f'dino_{nms}_scores'], out[f'dino_{nms}_classes'], out[f'dino_{nms}_boxes'] = s_, c_, b_
+    dec = D.DINODETRDecoder(nms_type='python_nms', min_score_threshold=0.5, nms_threshold=0.3,
+                            topn=50, max_object_num=40)
+    s_, c_, b_ = dec({'pred_logits': dino_cls, 'pred_boxes': dino_reg}, sizes)
+    out['dino_hi_scores'], out['dino_hi_classes'], out['dino_hi_boxes'] = s_, c_, b_
+    # DecodeMethod / DetNMSMethod on float boxes
+    N = 5000
+    scores = torch.rand((2, N), generator=gen).numpy().astype(np.float32)
+    classes = torch.randint(0, 7, (2, N), generator=gen).numpy()
+    xy = torch.rand((2, N, 2), generator=gen) * 400
+    bwh = torch.rand((2, N, 2), generator=gen) * 120 + 4
+    boxes = torch.cat([xy, xy + bwh], dim=-1).numpy().astype(np.float32)
+    out['dm_scores'], out['dm_classes'], out['dm_boxes'] = scores, classes, boxes
+    for nms in ('python_nms', 'diou_python_nms', 'torch_nms'):
+        dm = D.DecodeMethod(max_object_num=100, min_score_threshold=0.6, topn=1000, nms_type=nms,
+                            nms_threshold=0.5)
+        s_, c_, b_ = dm(scores, classes, boxes)
+        out[f'dm_{nms}_scores'], out[f'dm_{nms}_classes'], out[f'dm_{nms}_boxes'] = s_, c_, b_
+        order = np.argsort(-scores[0], kind='stable')[:700]
+        keep = D.DetNMSMethod(nms_type=nms, nms_threshold=0.4)(boxes[0][order], scores[0][order])
+        out[f'nms_{nms}_keep'] = np.asarray(keep)
+    np.savez_compressed(path, **out)
+
+
 def make_heads(path):
     """Head tail: the reference's RetinaClsHead (models/head.py:15-52) on a seeded
     feature map; the convolution output is captured with a hook, the head's own `.float()` +
@@ -258,6 +312,10 @@ if __name__ == '__main__':
         make_heads(os.path.join(HERE, 'head_tail.npz'))
         print('head_tail.npz', os.path.getsize(os.path.join(HERE, 'head_tail.npz')))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'queries':
+        make_queries(os.path.join(HERE, 'queries.npz'))
+        print('queries.npz', os.path.getsize(os.path.join(HERE, 'queries.npz')))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'face':
         make_face(os.path.join(HERE, 'retinaface_small.npz'))
         print('retinaface_small.npz', os.path.getsize(os.path.join(HERE, 'retinaface_small.npz')))
@@ -267,5 +325,6 @@ if __name__ == '__main__':
     make_tables(os.path.join(HERE, 'tables.npz'))
     make_face(os.path.join(HERE, 'retinaface_small.npz'))
     make_heads(os.path.join(HERE, 'head_tail.npz'))
+    make_queries(os.path.join(HERE, 'queries.npz'))
     for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)))
