@@ -63,6 +63,10 @@ extern "C" {
 #define B200DET_BOX_CIOU 5
 #define B200DET_BOX_EIOU 6
 
+/* b200det_sparse_losses: OR into `is_fcos` when `ctr` holds the centre-ness head's float32 LOGITS
+ * (the logits path) instead of probabilities; forward only */
+#define B200DET_FCOS_CTR_LOGITS 2
+
 /* DetNMSMethod nms_type (decode.py:28-32) */
 #define B200DET_NMS_PYTHON 0
 #define B200DET_NMS_DIOU_PYTHON 1
@@ -405,13 +409,16 @@ int b200det_logits_sweep(const b200det_geometry *geo, const void *const *cls_log
                          const void *const *ctr_logits, const int32_t *labels, float alpha,
                          float gamma, void *loss_workspace, size_t loss_workspace_bytes,
                          float min_score, uint32_t *keys, int32_t *classes, void *stream);
-/* b200det_eval_step for RetinaNet-style heads whose classification tensors are NCHW logits:
- * assignment, box loss, ONE sweep over the logits (focal sum + decoder keys), reduce / finish,
- * select + decode + NMS.  reg stays [B, H, W, A, 4] as in the reference. */
+/* b200det_eval_step for heads whose classification tensors are NCHW logits: assignment, box (and
+ * centre-ness) loss, ONE sweep over the logits (focal sum + decoder keys), reduce / finish,
+ * select + decode + NMS.  reg stays [B, H, W, A, 4] / [B, H, W, 4] as in the reference; FCOS heads
+ * (lp->is_fcos, dp->is_fcos) pass their float32 centre-ness logits [B, 1, H, W] as ctr_logits,
+ * RetinaNet-style heads pass NULL. */
 int b200det_logits_eval_step(const b200det_geometry *geo, const b200det_loss_params *lp,
                              const b200det_decode_params *dp, const float *annotations, int max_gt,
                              const void *const *cls_logits, int cls_dtype, const void *const *reg,
-                             int32_t *labels, void *loss_workspace, size_t loss_workspace_bytes,
+                             const void *const *ctr_logits, int32_t *labels, void *loss_workspace,
+                             size_t loss_workspace_bytes,
                              double *sums, float *losses, uint32_t *keys, int32_t *classes,
                              float *out, void *decode_workspace, size_t decode_workspace_bytes,
                              void *stream);

@@ -154,7 +154,7 @@ SIGNATURES = {
     ]),
     'b200det_logits_eval_step': (ctypes.c_int, [
         _geo, ctypes.POINTER(LossParams), ctypes.POINTER(DecodeParams), _vp, ctypes.c_int, _vpp,
-        ctypes.c_int, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp,
+        ctypes.c_int, _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp
     ]),
     'b200det_head_sigmoid_permute': (ctypes.c_int, [

@@ -629,6 +629,7 @@ struct SparseArgs {
     PtrTab reg, ctr, cls;        // cls.p[0] == nullptr: no focal corrections
     MutPtrTab reg_grad, ctr_grad;
     int reg_dtype, box_loss, is_fcos, G, C;
+    int ctr_logits;              // FCOS: ctr holds the head's logits (the logits path), not probabilities
     float beta, alpha, gamma;
 };
 
@@ -711,7 +712,9 @@ __global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
                 grad = make_float4(-iou.d[0] * ctr_t, -iou.d[1] * ctr_t, -iou.d[2] * ctr_t,
                                    -iou.d[3] * ctr_t);
                 // centre-ness BCE, losses.py:588-610 (prob clamped at losses.py:494)
-                const float craw = __ldg(static_cast<const float *>(a.ctr.p[l]) + rrow);
+                float craw = __ldg(static_cast<const float *>(a.ctr.p[l]) + rrow);
+                // logits path: torch's CUDA sigmoid of the head's centre-ness logit (models/head.py:176-179)
+                if (a.ctr_logits) craw = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-craw)));
                 const float cp = clamp_prob(craw);
                 const float one_m = __fsub_rn(1.f, cp), one_t = __fsub_rn(1.f, ctr_t);
                 ctr_fx += to_fx(-__fadd_rn(__fmul_rn(ctr_t, logf(cp)), __fmul_rn(one_t, logf(one_m))),
@@ -1040,6 +1043,9 @@ extern "C" int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos,
     if (!annotations || !labels || !workspace) return B200DET_EINVAL;
     if (max_gt < 1 || max_gt > B200DET_MAX_GT) return B200DET_ERANGE;
     if (box_loss < B200DET_BOX_NONE || box_loss > B200DET_BOX_EIOU) return B200DET_EINVAL;
+    const bool ctr_logits = (is_fcos & B200DET_FCOS_CTR_LOGITS) != 0;
+    is_fcos &= 1;
+    if (ctr_logits && (!is_fcos || ctr_grad)) return B200DET_EINVAL;
     if (is_fcos && (box_loss == B200DET_BOX_SMOOTHL1 || g.per_loc != 1)) return B200DET_EINVAL;
     const bool with_loss = box_loss != B200DET_BOX_NONE;
     if (with_loss && (!reg || (is_fcos && !ctr))) return B200DET_EINVAL;
@@ -1059,6 +1065,7 @@ extern "C" int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos,
     a.reg_dtype = reg_dtype;
     a.box_loss = box_loss;
     a.is_fcos = is_fcos;
+    a.ctr_logits = ctr_logits ? 1 : 0;
     a.G = max_gt;
     a.C = g.num_classes;
     a.beta = beta;

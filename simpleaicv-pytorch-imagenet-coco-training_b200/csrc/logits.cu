@@ -409,24 +409,27 @@ extern "C" int b200det_logits_sweep(const b200det_geometry *geo, const void *con
     return (int)cudaGetLastError();
 }
 
-// Evaluation step from logits: assignment -> box loss of the positives -> ONE sweep over the
-// classification logits (label-aware focal sum + decoder keys) -> reduce / finish -> select + NMS.
-// Argument meaning as b200det_eval_step; cls are NCHW logits [B, A*C, H, W] of dtype cls_dtype.
+// Evaluation step from logits: assignment -> box (and centre-ness) loss of the positives -> ONE
+// sweep over the classification logits (label-aware focal sum + decoder keys) -> reduce / finish ->
+// select + NMS.  Argument meaning as b200det_eval_step; cls are NCHW logits [B, A*C, H, W] of dtype
+// cls_dtype; FCOS heads also pass their float32 centre-ness logits [B, 1, H, W].
 extern "C" int b200det_logits_eval_step(const b200det_geometry *geo, const b200det_loss_params *lp,
                                         const b200det_decode_params *dp, const float *annotations,
                                         int max_gt, const void *const *cls_logits, int cls_dtype,
-                                        const void *const *reg, int32_t *labels,
-                                        void *loss_workspace, size_t loss_workspace_bytes,
-                                        double *sums, float *losses, uint32_t *keys,
-                                        int32_t *classes, float *out, void *decode_workspace,
-                                        size_t decode_workspace_bytes, void *stream) {
+                                        const void *const *reg, const void *const *ctr_logits,
+                                        int32_t *labels, void *loss_workspace,
+                                        size_t loss_workspace_bytes, double *sums, float *losses,
+                                        uint32_t *keys, int32_t *classes, float *out,
+                                        void *decode_workspace, size_t decode_workspace_bytes,
+                                        void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
     if (!lp || !dp || !annotations || !cls_logits || !reg || !labels || !loss_workspace || !sums ||
         !keys || !classes || !out)
         return B200DET_EINVAL;
-    if (lp->is_fcos || dp->is_fcos) return B200DET_EINVAL;   // RetinaNet-style heads only (so far)
+    const bool fcos = lp->is_fcos != 0;
+    if ((dp->is_fcos != 0) != fcos || (fcos && !ctr_logits)) return B200DET_EINVAL;
     const LossWs ws = loss_ws_layout(g);
     if (loss_workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     char *base = static_cast<char *>(loss_workspace);
@@ -435,24 +438,28 @@ extern "C" int b200det_logits_eval_step(const b200det_geometry *geo, const b200d
                                     (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
     g_skip_memset = true;
-    rc = b200det_retina_assign(geo, annotations, max_gt, lp->iou_neg, lp->iou_pos, labels, nullptr,
-                               loss_workspace, loss_workspace_bytes, stream);
-    if (!rc)   // box loss of the positives only: the sweep below is label-aware, nothing to correct
-        rc = b200det_sparse_losses(geo, 0, annotations, max_gt, labels, reg, lp->reg_dtype, nullptr,
+    rc = fcos ? b200det_fcos_assign(geo, annotations, max_gt, lp->use_center_sample, labels, nullptr,
+                                    nullptr, loss_workspace, loss_workspace_bytes, stream)
+              : b200det_retina_assign(geo, annotations, max_gt, lp->iou_neg, lp->iou_pos, labels,
+                                      nullptr, loss_workspace, loss_workspace_bytes, stream);
+    if (!rc)   // losses of the positives only: the sweep below is label-aware, nothing to correct
+        rc = b200det_sparse_losses(geo, fcos ? (1 | B200DET_FCOS_CTR_LOGITS) : 0, annotations,
+                                   max_gt, labels, reg, lp->reg_dtype, fcos ? ctr_logits : nullptr,
                                    lp->box_loss, lp->beta, nullptr, lp->alpha, lp->gamma, nullptr,
                                    nullptr, loss_workspace, loss_workspace_bytes, stream);
     if (!rc)
-        rc = b200det_logits_sweep(geo, cls_logits, cls_dtype, nullptr, labels, lp->alpha, lp->gamma,
-                                  loss_workspace, loss_workspace_bytes, dp->min_score, keys, classes,
-                                  stream);
+        rc = b200det_logits_sweep(geo, cls_logits, cls_dtype, fcos ? ctr_logits : nullptr, labels,
+                                  lp->alpha, lp->gamma, loss_workspace, loss_workspace_bytes,
+                                  dp->min_score, keys, classes, stream);
     g_skip_memset = false;
     if (!rc) rc = b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
     if (!rc && losses)
         rc = b200det_loss_finish(sums, lp->w_cls, lp->w_box, lp->w_ctr, losses, stream);
     if (!rc)
-        rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, 0, dp->min_score,
-                                       dp->topn, dp->max_out, dp->nms_type, dp->nms_threshold,
-                                       dp->scales, dp->sizes, dp->to_xywh, out, nullptr, nullptr,
-                                       nullptr, decode_workspace, decode_workspace_bytes, stream);
+        rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, fcos ? 1 : 0,
+                                       dp->min_score, dp->topn, dp->max_out, dp->nms_type,
+                                       dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
+                                       nullptr, nullptr, nullptr, decode_workspace,
+                                       decode_workspace_bytes, stream);
     return rc;
 }

@@ -101,11 +101,17 @@ class LogitsEvalStep:
     permute of models/retinanet.py:73-76; reg_heads[l] stays [B, H, W, A, 4].  One sweep over the
     logits produces the focal sum and the decoder's keys; no probability tensor is written.
     Detections are bit-identical to decoder(sigmoid + permute of the logits); the loss agrees
-    within the 1e-5 tolerance.  RetinaNet-style heads only; evaluation only (no gradients)."""
+    within the 1e-5 tolerance.  Evaluation only (no gradients).
+
+    FCOS heads (FCOSLoss + FCOSDecoder): preds = [cls_logits, reg_heads, center_logits] with
+    cls_logits[l] [B, num_classes, H, W], reg_heads[l] [B, H, W, 4] as in the reference and
+    center_logits[l] [B, 1, H, W] (what FCOSClsRegCntHead computes before its sigmoid,
+    models/head.py:176-179); the centre-ness BCE and the decoder's sqrt(cls * centre-ness) use
+    torch's CUDA sigmoid of those logits."""
 
     def __init__(self, criterion, decoder):
-        if criterion._is_fcos or decoder._is_fcos:
-            raise ValueError('LogitsEvalStep supports RetinaLoss / RetinaDecoder heads')
+        if criterion._is_fcos != decoder._is_fcos:
+            raise ValueError('criterion and decoder belong to different detectors')
         self.criterion = criterion
         self.decoder = decoder
         self._plans = {}
@@ -116,7 +122,7 @@ class LogitsEvalStep:
         key = (tuple(t.shape[2:4] for t in cls), shape0[0], shape0[1])
         plan = self._plans.get(key)
         if plan is None:
-            per_loc = crit._per_loc
+            per_loc = 1 if crit._is_fcos else crit._per_loc
             if shape0[1] % per_loc:
                 raise ValueError('logit channels are not a multiple of the anchors per location')
             shapes = [(int(t.shape[2]), int(t.shape[3])) for t in cls]
@@ -137,6 +143,14 @@ class LogitsEvalStep:
             raise RuntimeError('cls logits must share one dtype: float32, float16 or bfloat16')
         cls = [t if t.is_contiguous() else t.contiguous() for t in cls]
         reg, reg_dtype = _prep_reg([t.detach() for t in preds[1]])
+        ctr = None
+        if crit._is_fcos:
+            if len(preds) != 3:
+                raise RuntimeError('FCOS heads: preds = [cls_logits, reg_heads, center_logits]')
+            ctr = [t.detach().float().contiguous() for t in preds[2]]
+            if any((not t.is_cuda) or t.numel() != c.shape[0] * c.shape[2] * c.shape[3]
+                   for t, c in zip(ctr, cls)) or len(ctr) != len(cls):
+                raise RuntimeError('center logits must be CUDA tensors [B, 1, H, W]')
         annotations = _prep_annotations(annotations)
         plan = self._plan(cls)
         if annotations.shape[0] != plan.batch:
@@ -167,7 +181,8 @@ class LogitsEvalStep:
             lib.b200det_logits_eval_step(plan.geo_ref, ctypes.byref(lp), ctypes.byref(dp),
                                          annotations.data_ptr(), int(annotations.shape[1]),
                                          _lib.ptr_array(cls), _DTYPES[dtype], _lib.ptr_array(reg),
-                                         labels_ptr, base, plan.ws_bytes, sums_ptr,
+                                         _lib.ptr_array(ctr), labels_ptr, base, plan.ws_bytes,
+                                         sums_ptr,
                                          None if sync else sums_ptr + 32, keys_ptr, classes_ptr,
                                          out.data_ptr(), dws_ptr, dws_bytes, st),
             'b200det_logits_eval_step')
@@ -178,4 +193,7 @@ class LogitsEvalStep:
         del glue
         crit.last_stats = {'sums': small[0:4]}
         losses = small[4:8].view(torch.float32)
-        return {'cls_loss': losses[0], 'reg_loss': losses[1]}, dec._to_host(out, batch, m, device)
+        loss_dict = {'cls_loss': losses[0], 'reg_loss': losses[1]}
+        if crit._is_fcos:
+            loss_dict['center_ness_loss'] = losses[2]
+        return loss_dict, dec._to_host(out, batch, m, device)

@@ -144,10 +144,100 @@ def test_logits_full_size_and_nan():
     assert np.isnan(loss['cls_loss'].item()) and np.isfinite(loss['reg_loss'].item())
 
 
+def fcos_logits(batch, sizes, num_classes, seed, dtype=torch.float32, mean=-4.595):
+    gen = torch.Generator().manual_seed(seed)
+    cls, reg, ctr = [], [], []
+    for l, (h, w) in enumerate(sizes):
+        cls.append((torch.randn((batch, num_classes, h, w), generator=gen) + mean).to(dtype).cuda())
+        reg.append((torch.randn((batch, h, w, 4), generator=gen) * 0.5
+                    + float(np.log(8.0 * 2**l))).cuda())
+        ctr.append(torch.randn((batch, 1, h, w), generator=gen).cuda())
+    return cls, reg, ctr
+
+
+def fcos_both_paths(cls, reg, ctr, ann, strides, mi, loss_kw=None, dec_kw=None):
+    crit = losses.FCOSLoss(strides=strides, mi=mi, **(loss_kw or {}))
+    dec = decode.FCOSDecoder(strides=strides, **(dec_kw or {}))
+    # the reference's ops on CUDA: sigmoid(x.float()) then permute(0, 2, 3, 1)  (models/fcos.py:70-79)
+    probs = [O.head_tail(x) for x in cls]
+    cprobs = [O.head_tail(x) for x in ctr]
+    with torch.no_grad():
+        want_loss = crit([probs, reg, cprobs], ann)
+        want_det = dec([probs, reg, cprobs])
+        got_loss, got_det = fused.LogitsEvalStep(crit, dec)([cls, reg, ctr], ann)
+    return want_loss, want_det, got_loss, got_det
+
+
+def check_fcos(want_loss, want_det, got_loss, got_det, what=''):
+    for name, a, b in zip(('scores', 'classes', 'boxes'), got_det, want_det):
+        G.assert_bit_equal(a, b, f'{what} {name}')
+    keys = ['cls_loss', 'reg_loss', 'center_ness_loss']
+    w, g = loss_values(want_loss, keys), loss_values(got_loss, keys)
+    if (w == 0).all():
+        assert (g == 0).all()
+    else:
+        assert_close(g, w, LOSS_RTOL, f'{what} loss')
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('iou_type', ['GIoU', 'CIoU'])
+def test_fcos_logits_eval_step_matches_probability_path(iou_type, dtype):
+    C = 20
+    sizes = [(p, p) for p in synth.pyramid_sizes(256)]
+    cls, reg, ctr = fcos_logits(3, sizes, C, seed=21, dtype=dtype)
+    ann = synth.make_annotations(3, 20, 256, C, seed=22, empty_images=(1,)).cuda()
+    check_fcos(*fcos_both_paths(cls, reg, ctr, ann, synth.STRIDES, synth.MI,
+                                dict(box_loss_iou_type=iou_type)), what=f'FCOS {iou_type} {dtype}')
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_fcos_logits_fuzz(seed):
+    rng = np.random.RandomState(4000 + seed)
+    n_levels = int(rng.randint(1, 6))
+    h, w = int(rng.randint(3, 40)), int(rng.randint(3, 40))
+    sizes, strides, mi = [], [], []
+    s0, lo = 8.0, -1.0
+    for l in range(n_levels):
+        sizes.append((h, w))
+        strides.append(s0 * 2**l)
+        hi = 64.0 * 2**l if l < n_levels - 1 else 100000000.0
+        mi.append([lo, hi])
+        lo = hi
+        h, w = (h + 1) // 2, (w + 1) // 2
+    C = int(rng.choice([1, 3, 7, 16, 80, 365]))
+    B = int(rng.randint(1, 4))
+    dtype = [torch.float32, torch.float16, torch.bfloat16][seed % 3]
+    cls, reg, ctr = fcos_logits(B, sizes, C, seed=seed, dtype=dtype,
+                                mean=float(rng.choice([-4.595, -2.0])))
+    ann = synth.make_annotations(B, int(rng.choice([1, 5, 40])),
+                                 max(int(sizes[0][1] * strides[0]), 17), C, seed=seed + 3).cuda()
+    loss_kw = dict(box_loss_iou_type=str(rng.choice(['IoU', 'GIoU', 'DIoU', 'EIoU'])),
+                   use_center_sample=bool(rng.randint(0, 2)),
+                   alpha=float(rng.choice([0.25, 0.4])), gamma=float(rng.choice([2.0, 1.5])))
+    dec_kw = dict(min_score_threshold=float(rng.choice([0.01, 0.05, 0.3])),
+                  topn=int(rng.choice([50, 1000])), max_object_num=int(rng.choice([10, 100])),
+                  nms_type=str(rng.choice(['python_nms', 'diou_python_nms', 'torch_nms'])))
+    check_fcos(*fcos_both_paths(cls, reg, ctr, ann, strides, mi, loss_kw, dec_kw),
+               what=f'FCOS seed {seed} C={C} {dtype}')
+
+
+def test_fcos_logits_full_size():
+    """BASELINE configs[2] shape (FCOS 800x800, 80 classes) at a reduced batch."""
+    C, B = 80, 4
+    sizes = [(p, p) for p in synth.pyramid_sizes(800)]
+    cls, reg, ctr = fcos_logits(B, sizes, C, seed=31)
+    ann = synth.make_annotations(B, 100, 800, C, seed=32).cuda()
+    check_fcos(*fcos_both_paths(cls, reg, ctr, ann, synth.STRIDES, synth.MI), what='FCOS 800x800')
+
+
 def test_logits_step_rejects_unsupported_inputs():
     crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
     with pytest.raises(ValueError):
-        fused.LogitsEvalStep(crit, decode.FCOSDecoder(strides=synth.STRIDES))
+        fused.LogitsEvalStep(crit, decode.RetinaDecoder(**synth.RETINA_KW))
+    fstep = fused.LogitsEvalStep(crit, decode.FCOSDecoder(strides=synth.STRIDES))
+    with pytest.raises(RuntimeError):   # FCOS heads need their centre-ness logits
+        fstep([[torch.zeros(1, 80, 4, 4).cuda()], [torch.zeros(1, 4, 4, 4).cuda()]],
+              torch.zeros(1, 1, 5).cuda())
     rc = losses.RetinaLoss(**synth.RETINA_KW)
     step = fused.LogitsEvalStep(rc, decode.RetinaDecoder(**synth.RETINA_KW))
     with pytest.raises(RuntimeError):
