@@ -264,6 +264,26 @@ __device__ __forceinline__ void slow_element(float p, bool is_target, float alph
     }
 }
 
+// One 4-class unit through the exact-form path, out of line: it runs for < 1 % of the units (a
+// target class inside the unit, a probability above the polynomial's range, gamma != 2), and
+// inlining it at all 32 call sites made the kernel 77 KB of code (instruction-fetch stalls were the
+// top stall reason in ncu).
+struct SlowUnit {
+    float4 g;
+    float pos, neg;
+};
+template <bool GRAD>
+__device__ __noinline__ SlowUnit slow_unit4(float4 v, int tgt, float alpha, float gamma, bool gamma2) {
+    SlowUnit r;
+    r.pos = r.neg = 0.f;
+    r.g = make_float4(0.f, 0.f, 0.f, 0.f);
+    slow_element<GRAD>(v.x, tgt == 0, alpha, gamma, gamma2, r.pos, r.neg, r.g.x);
+    slow_element<GRAD>(v.y, tgt == 1, alpha, gamma, gamma2, r.pos, r.neg, r.g.y);
+    slow_element<GRAD>(v.z, tgt == 2, alpha, gamma, gamma2, r.pos, r.neg, r.g.z);
+    slow_element<GRAD>(v.w, tgt == 3, alpha, gamma, gamma2, r.pos, r.neg, r.g.w);
+    return r;
+}
+
 // Label-aware sweep: used when gradients are requested (one read of cls, one write of its
 // gradient already scaled by weight / positives), or when the caller did not let the
 // assignment kernel apply the corrections.
@@ -356,6 +376,13 @@ __global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
                             g[0] = v[k][0] >= kClampLo ? one_m_alpha * xr * t : 0.f;
                         }
                     }
+                } else if (VEC == 4) {
+                    const SlowUnit r = slow_unit4<GRAD>(
+                        make_float4(v[k][0], v[k][1 % VEC], v[k][2 % VEC], v[k][3 % VEC]),
+                        has_target ? tgt[k] : -1, a.alpha, a.gamma, GAMMA2);
+                    acc_pos += r.pos;
+                    acc_neg += r.neg;
+                    g[0] = r.g.x, g[1 % VEC] = r.g.y, g[2 % VEC] = r.g.z, g[3 % VEC] = r.g.w;
                 } else {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
@@ -373,7 +400,8 @@ __global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
             }
         }
     }
-    block_store_partial(a.alpha * acc_pos + one_m_alpha * (acc_neg + (acc2.x + acc2.y)), partials);
+    // one fixed-point atomic per WARP: no CTA barrier at the end of these short CTAs
+    sweep_accumulate_warp(a.alpha * acc_pos + one_m_alpha * (acc_neg + (acc2.x + acc2.y)), partials);
 }
 
 // ---------------------------------------------------------------------------------------

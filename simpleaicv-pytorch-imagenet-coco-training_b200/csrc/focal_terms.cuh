@@ -132,4 +132,21 @@ __device__ __forceinline__ void sweep_accumulate(float value, long long *slots) 
     }
 }
 
+// Warp-level variant: no shared memory, no barrier; 8x the atomics of the CTA version (still a few
+// hundred thousand per launch spread over kSweepSlots addresses).
+__device__ __forceinline__ void sweep_accumulate_warp(float value, long long *slots) {
+    float w = value;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (!(fabsf(w) <= 3.402823466e38f)) {
+            slots[kSweepSlots] = 1;
+        } else {
+            const long long fx = __double2ll_rn((double)w * kFxSweep);
+            const unsigned slot = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (kSweepSlots - 1);
+            atomicAdd(reinterpret_cast<unsigned long long *>(slots + slot), (unsigned long long)fx);
+        }
+    }
+}
+
 }  // namespace b200det

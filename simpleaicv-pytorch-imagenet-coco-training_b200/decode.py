@@ -22,6 +22,9 @@ from . import geometry as _geom
 from .losses import _prep_f32, _prep_reg
 
 _ZERO_COPY = os.environ.get('B200DET_ZERO_COPY', '1') != '0'
+# the returned arrays are views of the call's own pinned buffer (no host memcpy); '1' hands out
+# pageable copies instead (for callers that keep thousands of results alive)
+_RESULT_COPY = os.environ.get('B200DET_RESULT_COPY', '0') != '0'
 
 __all__ = ['RetinaDecoder', 'FCOSDecoder', 'DETRDecoder', 'DINODETRDecoder', 'DecodeMethod',
            'DetNMSMethod']
@@ -84,7 +87,11 @@ class _DecoderBase:
         bytes per image cross PCIe as posted writes while other images are still being processed
         and no separate copy is enqueued.  B200DET_ZERO_COPY=0 uses a device buffer + one D2H."""
         if _ZERO_COPY:
-            return self._staging(numel)
+            if _RESULT_COPY:
+                return self._staging(numel)
+            # a fresh block from torch's caching pinned allocator per call (reused once the
+            # previous result has been dropped): the caller owns it through the returned arrays
+            return torch.empty(numel, dtype=torch.float32, pin_memory=True)
         return torch.empty(numel, dtype=torch.float32, device=device)
 
     def _to_host(self, out, batch, m, device):
@@ -95,7 +102,9 @@ class _DecoderBase:
             staging = self._staging(out.numel())
             staging.copy_(out, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
-        host = staging.numpy().copy()
+        host = staging.numpy()
+        if _RESULT_COPY or staging is self._pinned:
+            host = host.copy()
         scores = host[0:batch * m].reshape(batch, m)
         out_classes = host[batch * m:2 * batch * m].reshape(batch, m)
         boxes = host[2 * batch * m:].reshape(batch, m, 4)
