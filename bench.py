@@ -195,8 +195,10 @@ def run_reference(args, out):
     out.emit(json.dumps(line))
 
 
-def workload_config(batch_per_gpu, n_gpus):
+def workload_config(batch_per_gpu, n_gpus, exchange='nccl'):
     loss_b, dec_b = algorithmic_bytes_per_image()
+    how = ('4 doubles per step exchanged over NVLink peer memory inside the reduction kernel'
+           if exchange == 'p2p' else 'NCCL all-reduce of 4 doubles per step')
     return {
         'workload': 'BASELINE configs[4]: RetinaNet-R50 head outputs, RetinaLoss(GIoU) forward + '
                     'RetinaDecoder(python_nms), COCO 80 cls, 800x800, 9 anchors/loc, <=100 GT/img',
@@ -204,7 +206,7 @@ def workload_config(batch_per_gpu, n_gpus):
         'global_batch': batch_per_gpu * n_gpus,
         'rows_per_image': rows_per_image(),
         'algorithmic_bytes_per_image': loss_b + dec_b,
-        'parallelism': f'image-sharded x{n_gpus}, NCCL all-reduce of 4 doubles per step',
+        'parallelism': f'image-sharded x{n_gpus}, {how}',
         'l2_policy': 'inputs (>= 10 GB per GPU at the default batch) far exceed the 126 MB L2',
     }
 
@@ -235,8 +237,26 @@ def run_b200(args, out):
     B = args.batch
     preds = synth.make_retina_preds(B, SIZE, NUM_CLASSES, seed=100 + rank, device=dev)
     ann = synth.make_annotations(B, MAX_GT, SIZE, NUM_CLASSES, seed=200 + rank).to(dev)
+    # the normaliser's exchange: fused into the reduction kernel over NVLink peer memory when every
+    # rank can map every peer (decided collectively), else torch.distributed / NCCL
+    exchange = 'nccl'
     crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU',
                              sync_normalizer=distributed)
+    if distributed and args.sync in ('auto', 'p2p'):
+        ok = torch.ones(1, device=dev)
+        try:
+            from b200det.peer import PeerExchange
+            crit._peer = PeerExchange(None, dev)
+        except Exception as exc:   # noqa: BLE001 -- any failure means "use NCCL"
+            print(f'[bench] rank {rank}: peer exchange unavailable ({exc}); using NCCL',
+                  file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0:
+            crit.sync_normalizer = 'p2p'
+            exchange = 'p2p'
+        elif args.sync == 'p2p':
+            raise RuntimeError('--sync p2p requested but the peer exchange could not be set up')
     dec = decode.RetinaDecoder(**synth.RETINA_KW)
 
     def step():
@@ -342,7 +362,7 @@ def run_b200(args, out):
         'vs_baseline': None,
         'dtype': 'f32',
         'data': 'synthetic',
-        'config': workload_config(B, world),
+        'config': workload_config(B, world, exchange),
         'roofline': {
             'bound': 'hbm',
             'kernel': dom,
@@ -486,6 +506,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=20)
     ap.add_argument('--ref-size', type=int, default=SIZE,
                     help='image size of the --impl reference sample (tests use a small one)')
+    ap.add_argument('--sync', default='auto', choices=['auto', 'p2p', 'nccl'],
+                    help='N > 1: how the loss normaliser crosses GPUs')
     ap.add_argument('--no-fused', action='store_true')
     ap.add_argument('--profile-every', type=int, default=1)
     ap.add_argument('--no-e2e', action='store_true')

@@ -42,6 +42,7 @@ extern "C" {
 #define B200DET_MAX_PER_LOC 16
 #define B200DET_MAX_GT 2048   /* annotation rows per image staged in shared memory */
 #define B200DET_MAX_TOPN 2048
+#define B200DET_MAX_PEERS 16  /* ranks of one NVLink domain in a peer exchange */
 
 /* error codes (negative) */
 #define B200DET_EINVAL (-1)    /* null pointer / bad enum / bad size */
@@ -422,6 +423,50 @@ int b200det_logits_eval_step(const b200det_geometry *geo, const b200det_loss_par
                              double *sums, float *losses, uint32_t *keys, int32_t *classes,
                              float *out, void *decode_workspace, size_t decode_workspace_bytes,
                              void *stream);
+
+/* ---- multi-GPU: the loss normaliser exchanged over NVLink peer memory ---------------------- */
+/*
+ * The path shards by image; the only cross-rank coupling is the whole-batch positive count and the
+ * loss sums (losses.py:231-259 on the unsharded batch): 4 doubles.  Instead of reduce -> host call
+ * -> NCCL all-reduce -> finish, b200det_loss_reduce_exchange is ONE kernel per rank: it reduces the
+ * rank's block partials, stores its 4 doubles into every peer's exchange buffer (peer memory mapped
+ * with CUDA IPC, st.release.sys), waits (ld.acquire.sys, bounded) for the peers' stores in its own
+ * buffer, adds the contributions in rank order (bit-identical totals on every rank) and writes the
+ * normalised losses.  One process per GPU, all ranks on one NVLink / NVSwitch domain.
+ *
+ * Exchange buffers are the one thing this library allocates (4 KB of device memory each, owned by
+ * the caller through these handles):
+ *   b200det_peer_buffer_create   cudaMalloc + zero + cudaIpcGetMemHandle (64-byte handle to send to
+ *                                the peers, e.g. with torch.distributed.all_gather_object)
+ *   b200det_peer_buffer_open     maps a peer's buffer into this process (enables peer access)
+ *   b200det_peer_buffer_close / _destroy
+ */
+int b200det_peer_buffer_create(void **buffer, unsigned char *handle64);
+int b200det_peer_buffer_open(const unsigned char *handle64, void **mapped);
+int b200det_peer_buffer_close(void *mapped);
+int b200det_peer_buffer_destroy(void *buffer);
+
+typedef struct b200det_peer_exchange {
+    int32_t rank, world;            /* world <= B200DET_MAX_PEERS */
+    uint64_t epoch;                 /* 1, 2, 3, ...: the same value on every rank for one exchange */
+    uint64_t timeout_cycles;        /* spin budget in SM cycles (0: ~30 s); on expiry the sums become
+                                       NaN and *status = 1 -- the kernel never hangs */
+    void *peer[B200DET_MAX_PEERS];  /* peer[r]: rank r's buffer as mapped here; peer[rank]: own */
+} b200det_peer_exchange;
+
+/* reduce (which = 3) + exchange + finish; sums = device double[4] GLOBAL totals out; losses = device
+ * float[3] or NULL; status = device int32 (set to 1 on a timeout) or NULL */
+int b200det_loss_reduce_exchange(const b200det_geometry *geo, const void *workspace,
+                                 size_t workspace_bytes, const b200det_peer_exchange *px,
+                                 float w_cls, float w_box, float w_ctr, double *sums, float *losses,
+                                 int32_t *status, void *stream);
+/* b200det_loss_forward ending in b200det_loss_reduce_exchange */
+int b200det_loss_forward_exchange(const b200det_geometry *geo, const b200det_loss_params *params,
+                                  const float *annotations, int max_gt, const void *const *cls,
+                                  const void *const *reg, const void *const *ctr, int32_t *labels,
+                                  void *workspace, size_t workspace_bytes,
+                                  const b200det_peer_exchange *px, double *sums, float *losses,
+                                  int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

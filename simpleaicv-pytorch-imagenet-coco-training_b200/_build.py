@@ -25,6 +25,7 @@ SOURCES = {
     'heads.cu': [],
     'logits.cu': [],
     'queries.cu': [],
+    'exchange.cu': [],
 }
 
 

@@ -66,6 +66,20 @@ class LossParams(ctypes.Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class PeerExchange(ctypes.Structure):
+    """Mirror of `b200det_peer_exchange`."""
+    _fields_ = [
+        ('rank', ctypes.c_int32),
+        ('world', ctypes.c_int32),
+        ('epoch', ctypes.c_uint64),
+        ('timeout_cycles', ctypes.c_uint64),
+        ('peer', ctypes.c_void_p * MAX_PEERS),
+    ]
+
+
 class DecodeParams(ctypes.Structure):
     """Mirror of `b200det_decode_params`."""
     _fields_ = [
@@ -156,6 +170,18 @@ SIGNATURES = {
         _geo, ctypes.POINTER(LossParams), ctypes.POINTER(DecodeParams), _vp, ctypes.c_int, _vpp,
         ctypes.c_int, _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp
+    ]),
+    'b200det_peer_buffer_create': (ctypes.c_int, [_vpp, ctypes.c_char_p]),
+    'b200det_peer_buffer_open': (ctypes.c_int, [ctypes.c_char_p, _vpp]),
+    'b200det_peer_buffer_close': (ctypes.c_int, [_vp]),
+    'b200det_peer_buffer_destroy': (ctypes.c_int, [_vp]),
+    'b200det_loss_reduce_exchange': (ctypes.c_int, [
+        _geo, _vp, ctypes.c_size_t, ctypes.POINTER(PeerExchange), ctypes.c_float, ctypes.c_float,
+        ctypes.c_float, _vp, _vp, _vp, _vp
+    ]),
+    'b200det_loss_forward_exchange': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vp,
+        ctypes.c_size_t, ctypes.POINTER(PeerExchange), _vp, _vp, _vp, _vp
     ]),
     'b200det_head_sigmoid_permute': (ctypes.c_int, [
         _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, _vp, _vp]),

@@ -97,6 +97,16 @@ def _maybe_all_reduce(t, sync, group):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
 
 
+def _peer_exchange(owner, device):
+    """The owner's PeerExchange (created on first use: one all_gather_object + one barrier)."""
+    px = getattr(owner, '_peer', None)
+    if px is None:
+        from .peer import PeerExchange
+        px = PeerExchange(owner.process_group, device)
+        owner._peer = px
+    return px
+
+
 def _wants_grad(tensors):
     if not torch.is_grad_enabled():
         return False
@@ -170,6 +180,20 @@ def _forward_eval(owner, annotations, cls_in, reg_in, ctr_in):
         and torch.distributed.is_initialized()
     st = _stream()
     params = _loss_params(owner, reg_dtype)
+    if sync and owner.sync_normalizer == 'p2p':
+        # reduce + exchange over NVLink peer memory + normalisation in ONE kernel (csrc/exchange.cu)
+        px = _peer_exchange(owner, device)
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        _lib.check(
+            lib.b200det_loss_forward_exchange(plan.geo_ref, ctypes.byref(params),
+                                              annotations.data_ptr(), int(annotations.shape[1]),
+                                              _lib.ptr_array(cls), _lib.ptr_array(reg),
+                                              _lib.ptr_array(ctr), ws_ptr + plan.ws_bytes, ws_ptr,
+                                              plan.ws_bytes, px.next(), sums_ptr, sums_ptr + 32,
+                                              status.data_ptr(), st),
+            'b200det_loss_forward_exchange')
+        owner.last_stats = {'sums': out[0:4], 'exchange_status': status}
+        return out[4:8].view(torch.float32)
     _lib.check(
         lib.b200det_loss_forward(plan.geo_ref, ctypes.byref(params), annotations.data_ptr(),
                                  int(annotations.shape[1]), _lib.ptr_array(cls),

@@ -1,0 +1,101 @@
+"""Multi-GPU check of the peer-memory exchange (csrc/exchange.cu), run under torchrun on >= 2 GPUs:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
+        --master-port 29511 tests/p2p_check.py
+
+Every rank holds a shard of one batch.  RetinaLoss / FCOSLoss with sync_normalizer='p2p' (ONE kernel
+per rank: reduce + NVLink exchange + normalise) must give, on every rank, (a) bit-identical values
+across ranks, (b) the same losses as sync_normalizer=True (NCCL all-reduce of the same sums: equal up
+to the summation order of W doubles) and (c) the oracle's loss of the UNSHARDED batch within the
+1e-5 tolerance of north_star.  Also times both exchanges.  Lives under tests/ because it calls the
+oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from b200det import synth, losses  # noqa: E402
+from oracle import det_oracle as O  # noqa: E402
+
+
+def timed(fn, iters=200):
+    for _ in range(10):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    per = 2
+    B = per * world
+    ok = True
+    report = {}
+    for name in ('retina', 'fcos'):
+        if name == 'retina':
+            preds = synth.make_retina_preds(B, 256, 20, seed=5)
+            kw = dict(**synth.RETINA_KW, box_loss_type='GIoU')
+            make = lambda **k: losses.RetinaLoss(**kw, **k)   # noqa: E731
+            with torch.no_grad():
+                ref = O.retina_loss(preds, synth.make_annotations(B, 30, 256, 20, seed=6), **kw)
+            keys = ['cls_loss', 'reg_loss']
+        else:
+            preds = synth.make_fcos_preds(B, 256, 20, seed=7)
+            make = lambda **k: losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, **k)   # noqa: E731
+            with torch.no_grad():
+                ref = O.fcos_loss(preds, synth.make_annotations(B, 30, 256, 20, seed=6),
+                                  synth.STRIDES, synth.MI)
+            keys = ['cls_loss', 'reg_loss', 'center_ness_loss']
+        ann = synth.make_annotations(B, 30, 256, 20, seed=6)
+        lo, hi = rank * per, (rank + 1) * per
+        shard = [[t[lo:hi].contiguous().to(dev) for t in grp] for grp in preds]
+        ann_s = ann[lo:hi].contiguous().to(dev)
+        c_p2p, c_nccl = make(sync_normalizer='p2p'), make(sync_normalizer=True)
+        with torch.no_grad():
+            for it in range(5):   # several epochs: both buffer sets, repeated use
+                a = c_p2p(shard, ann_s)
+                b = c_nccl(shard, ann_s)
+            va = np.array([a[k].item() for k in keys], dtype=np.float32)
+            vb = np.array([b[k].item() for k in keys], dtype=np.float32)
+            want = np.array([ref[k].item() for k in keys], dtype=np.float32)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, va.tobytes())
+            same_everywhere = all(g == gathered[0] for g in gathered)
+            status = int(c_p2p.last_stats['exchange_status'].item())
+            rel_nccl = float(np.max(np.abs(va - vb) / np.maximum(np.abs(vb), 1e-12)))
+            rel_ref = float(np.max(np.abs(va - want) / np.maximum(np.abs(want), 1e-12)))
+            good = same_everywhere and status == 0 and rel_nccl <= 1e-6 and rel_ref <= 1e-5
+            ok = ok and good
+            t_p2p = timed(lambda: c_p2p(shard, ann_s))
+            t_nccl = timed(lambda: c_nccl(shard, ann_s))
+        report[name] = dict(p2p=va.tolist(), nccl=vb.tolist(), oracle_unsharded=want.tolist(),
+                            identical_on_all_ranks=same_everywhere, status=status,
+                            rel_vs_nccl=rel_nccl, rel_vs_oracle=rel_ref,
+                            ms_per_call_p2p=round(t_p2p, 4), ms_per_call_nccl=round(t_nccl, 4))
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        import json
+        print(json.dumps({'world': world, 'ok': bool(flag.item() > 0), **report}))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() > 0 else 1)
+
+
+if __name__ == '__main__':
+    main()

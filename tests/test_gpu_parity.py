@@ -850,3 +850,20 @@ def test_batch_with_more_than_2_31_elements_per_level():
     crit(shard, ann[H:])['cls_loss'].backward()
     scale = parts[1][0] / full[0]
     torch.testing.assert_close(g_last, half_cls0.grad[H - 1] * scale, rtol=1e-5, atol=1e-12)
+
+
+def test_peer_exchange_two_gpus():
+    """The loss normaliser exchanged over NVLink peer memory inside the reduction kernel
+    (sync_normalizer='p2p', csrc/exchange.cu) against NCCL and against the oracle's unsharded
+    loss: tests/p2p_check.py under torchrun.  Needs >= 2 GPUs (skipped on the 1-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                          '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port',
+                          '29517', os.path.join(root, 'tests', 'p2p_check.py')],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
