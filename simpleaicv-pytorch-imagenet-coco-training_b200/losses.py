@@ -19,6 +19,9 @@ Extra, keyword-only constructor arguments (defaults keep reference behaviour):
     sync_normalizer / process_group : all-reduce {positives, loss sums} over the process
         group so that an image-sharded batch reproduces the single-process full-batch loss
         (SURVEY.md section 8e).  Default False = the reference's per-rank normalisation.
+        True = torch.distributed.all_reduce (NCCL); 'p2p' = the no-grad forward exchanges the 4
+        doubles over NVLink peer memory inside its reduction kernel (b200det.peer, csrc/exchange.cu;
+        one node, every GPU a peer of every other); the training path uses NCCL either way.
 """
 import ctypes
 
