@@ -199,6 +199,9 @@ def workload_config(batch_per_gpu, n_gpus, exchange='nccl'):
     loss_b, dec_b = algorithmic_bytes_per_image()
     how = ('4 doubles per step exchanged over NVLink peer memory inside the reduction kernel'
            if exchange == 'p2p' else 'NCCL all-reduce of 4 doubles per step')
+    if n_gpus == 1:
+        how = 'no exchange'
+
     return {
         'workload': 'BASELINE configs[4]: RetinaNet-R50 head outputs, RetinaLoss(GIoU) forward + '
                     'RetinaDecoder(python_nms), COCO 80 cls, 800x800, 9 anchors/loc, <=100 GT/img',

@@ -455,7 +455,7 @@ typedef struct b200det_peer_exchange {
 } b200det_peer_exchange;
 
 /* reduce (which = 3) + exchange + finish; sums = device double[4] GLOBAL totals out; losses = device
- * float[3] or NULL; status = device int32 (set to 1 on a timeout) or NULL */
+ * float[3] or NULL; status = device int32 (0 = ok, 1 = a peer timed out; written every call) or NULL */
 int b200det_loss_reduce_exchange(const b200det_geometry *geo, const void *workspace,
                                  size_t workspace_bytes, const b200det_peer_exchange *px,
                                  float w_cls, float w_box, float w_ctr, double *sums, float *losses,

@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(1024)
         if (failed) {
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
             tot[0] = tot[1] = tot[2] = tot[3] = nan;
-            if (status) *status = 1;
         }
+        if (status) *status = failed;   // written on every call: the caller need not clear it
         for (int k = 0; k < 4; ++k) sums[k] = tot[k];
         if (losses) {
             // as loss_finish_kernel: float32 sum / count, then * weight (losses.py:259, :293, :318,

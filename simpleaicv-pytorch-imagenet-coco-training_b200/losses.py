@@ -186,7 +186,7 @@ def _forward_eval(owner, annotations, cls_in, reg_in, ctr_in):
     if sync and owner.sync_normalizer == 'p2p':
         # reduce + exchange over NVLink peer memory + normalisation in ONE kernel (csrc/exchange.cu)
         px = _peer_exchange(owner, device)
-        status = torch.zeros(1, dtype=torch.int32, device=device)
+        status = out[6:7].view(torch.int32)[0:1]   # written by the kernel on every call
         _lib.check(
             lib.b200det_loss_forward_exchange(plan.geo_ref, ctypes.byref(params),
                                               annotations.data_ptr(), int(annotations.shape[1]),

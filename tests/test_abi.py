@@ -142,3 +142,13 @@ def test_synthetic_generators_are_deterministic_and_tie_free():
     assert (ann[1] == -1).all() and (ann[0][:, 4] >= 0).any()
     assert synth.pyramid_sizes(800) == [100, 50, 25, 13, 7]
     assert synth.pyramid_sizes(1024) == [128, 64, 32, 16, 8]
+
+
+def test_peer_exchange_needs_a_process_group():
+    """b200det.peer (NVLink peer-memory exchange of the loss normaliser) refuses to start without
+    torch.distributed; the struct mirror has the header's layout."""
+    import ctypes
+    from b200det import _lib, peer
+    with pytest.raises(RuntimeError):
+        peer.PeerExchange()
+    assert ctypes.sizeof(_lib.PeerExchange) == 4 + 4 + 8 + 8 + 8 * _lib.MAX_PEERS
