@@ -207,3 +207,38 @@ def test_gpu_query_decoder_edges():
     G.assert_bit_equal(b[0, 0], want, 'single query box')
     with pytest.raises(RuntimeError):
         decode.DETRDecoder()([cls, reg], [[10, 10], [20, 20]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nms', ['python_nms', 'torch_nms'])
+def test_gpu_nms_threshold_band(nms):
+    """The select kernel decides most NMS pairs without the IEEE division (a pair is only sent to the
+    exact function when inter / union is within 5e-7 of the threshold).  Thresholds placed exactly
+    on, one ulp below and one ulp above the float32 IoU of real pairs -- where `iou < thr` flips --
+    must give the reference's keep list."""
+    from b200det import decode
+    rng = np.random.RandomState(7)
+    n = 300
+    xy = rng.randint(0, 60, size=(n, 2)).astype(np.float32)
+    wh = rng.randint(4, 40, size=(n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], axis=1)
+    boxes[1] = [0, 0, 2, 2]
+    boxes[2] = [0, 0, 2, 1]                       # IoU with box 1 is exactly 0.5
+    scores = np.linspace(1.0, 0.1, n).astype(np.float32)
+    # float32 IoUs of some overlapping pairs, computed like decode.py:45-76
+    thrs = [0.5]
+    for i, j in [(0, 5), (3, 9), (10, 11), (20, 40), (7, 8), (1, 2)]:
+        a, b = boxes[i], boxes[j]
+        iw = max(np.float32(min(a[2], b[2]) - max(a[0], b[0])), np.float32(0))
+        ih = max(np.float32(min(a[3], b[3]) - max(a[1], b[1])), np.float32(0))
+        inter = np.float32(iw * ih)
+        area = lambda t: np.float32((t[2] - t[0]) * (t[3] - t[1]))   # noqa: E731
+        union = np.float32(max(np.float32(np.float32(area(a) + area(b)) - inter), np.float32(1e-4)))
+        iou = np.float32(inter / union)
+        if 0 < iou < 1:
+            thrs += [float(iou), float(np.nextafter(iou, np.float32(0))),
+                     float(np.nextafter(iou, np.float32(1)))]
+    for thr in thrs:
+        want = O.nms_keep(boxes, scores, nms, thr)
+        got = decode.DetNMSMethod(nms_type=nms, nms_threshold=thr)(boxes, scores)
+        assert np.array_equal(got, want), f'{nms} thr={thr!r}'
