@@ -460,6 +460,10 @@ int b200det_loss_reduce_exchange(const b200det_geometry *geo, const void *worksp
                                  size_t workspace_bytes, const b200det_peer_exchange *px,
                                  float w_cls, float w_box, float w_ctr, double *sums, float *losses,
                                  int32_t *status, void *stream);
+/* the exchange alone: sums = device double[4] of this rank in, totals over the ranks out (in place);
+ * losses as above or NULL.  world <= 32 threads: one warp. */
+int b200det_sums_exchange(const b200det_peer_exchange *px, float w_cls, float w_box, float w_ctr,
+                          double *sums, float *losses, int32_t *status, void *stream);
 /* b200det_loss_forward ending in b200det_loss_reduce_exchange */
 int b200det_loss_forward_exchange(const b200det_geometry *geo, const b200det_loss_params *params,
                                   const float *annotations, int max_gt, const void *const *cls,

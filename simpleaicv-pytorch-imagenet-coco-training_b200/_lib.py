@@ -175,6 +175,10 @@ SIGNATURES = {
     'b200det_peer_buffer_open': (ctypes.c_int, [ctypes.c_char_p, _vpp]),
     'b200det_peer_buffer_close': (ctypes.c_int, [_vp]),
     'b200det_peer_buffer_destroy': (ctypes.c_int, [_vp]),
+    'b200det_sums_exchange': (ctypes.c_int, [
+        ctypes.POINTER(PeerExchange), ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp,
+        _vp
+    ]),
     'b200det_loss_reduce_exchange': (ctypes.c_int, [
         _geo, _vp, ctypes.c_size_t, ctypes.POINTER(PeerExchange), ctypes.c_float, ctypes.c_float,
         ctypes.c_float, _vp, _vp, _vp, _vp

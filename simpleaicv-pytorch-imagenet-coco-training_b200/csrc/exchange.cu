@@ -95,21 +95,14 @@ __device__ __forceinline__ void reduce_partials(const int *__restrict__ npos, lo
     }
 }
 
-__global__ void __launch_bounds__(1024)
-    loss_reduce_exchange_kernel(const int *__restrict__ npos, long long n_assign,
-                                const SparsePartial *__restrict__ sp, long long n_sparse,
-                                const long long *__restrict__ fp, long long n_focal, ExchangeArgs x,
-                                float w_cls, float w_box, float w_ctr, double *__restrict__ sums,
-                                float *__restrict__ losses, int *__restrict__ status) {
-    __shared__ double local[4];
+// After `local` (shared) holds this rank's 4 doubles: store them into every peer's buffer, wait for
+// the peers', add in rank order, write totals / losses / status.  All threads of the CTA call it.
+__device__ __forceinline__ void exchange_tail(const double *local, const ExchangeArgs &x, float w_cls,
+                                              float w_box, float w_ctr, double *__restrict__ sums,
+                                              float *__restrict__ losses, int *__restrict__ status) {
     __shared__ double gathered[kMaxPeers][4];
     __shared__ int failed;
-    double mine[4] = {0.0, 0.0, 0.0, 0.0};
-    reduce_partials(npos, n_assign, sp, n_sparse, fp, n_focal, mine);
-    if (threadIdx.x == 0) {
-        local[0] = mine[0], local[1] = mine[1], local[2] = mine[2], local[3] = mine[3];
-        failed = 0;
-    }
+    if (threadIdx.x == 0) failed = 0;
     __syncthreads();
     const int set = (int)(x.epoch & 1ull);
     const int t = threadIdx.x;
@@ -162,6 +155,31 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+__global__ void __launch_bounds__(1024)
+    loss_reduce_exchange_kernel(const int *__restrict__ npos, long long n_assign,
+                                const SparsePartial *__restrict__ sp, long long n_sparse,
+                                const long long *__restrict__ fp, long long n_focal, ExchangeArgs x,
+                                float w_cls, float w_box, float w_ctr, double *__restrict__ sums,
+                                float *__restrict__ losses, int *__restrict__ status) {
+    __shared__ double local[4];
+    double mine[4] = {0.0, 0.0, 0.0, 0.0};
+    reduce_partials(npos, n_assign, sp, n_sparse, fp, n_focal, mine);
+    if (threadIdx.x == 0) local[0] = mine[0], local[1] = mine[1], local[2] = mine[2], local[3] = mine[3];
+    __syncthreads();
+    exchange_tail(local, x, w_cls, w_box, w_ctr, sums, losses, status);
+}
+
+// The exchange alone: sums[0..3] (this rank's) -> totals over the ranks, in place (+ losses).
+__global__ void __launch_bounds__(32)
+    sums_exchange_kernel(ExchangeArgs x, float w_cls, float w_box, float w_ctr,
+                         double *__restrict__ sums, float *__restrict__ losses,
+                         int *__restrict__ status) {
+    __shared__ double local[4];
+    if (threadIdx.x < 4) local[threadIdx.x] = sums[threadIdx.x];
+    __syncthreads();
+    exchange_tail(local, x, w_cls, w_box, w_ctr, sums, losses, status);
+}
+
 }  // namespace b200det
 
 using namespace b200det;
@@ -205,21 +223,12 @@ extern "C" int b200det_peer_buffer_destroy(void *buffer) {
     return buffer ? (int)cudaFree(buffer) : B200DET_EINVAL;
 }
 
-extern "C" int b200det_loss_reduce_exchange(const b200det_geometry *geo, const void *workspace,
-                                            size_t workspace_bytes,
-                                            const b200det_peer_exchange *px, float w_cls,
-                                            float w_box, float w_ctr, double *sums, float *losses,
-                                            int32_t *status, void *stream) {
-    Geo g;
-    int rc = make_geo(geo, &g);
-    if (rc) return rc;
-    if (!workspace || !px || !sums) return B200DET_EINVAL;
+static int fill_exchange(const b200det_peer_exchange *px, ExchangeArgs *out) {
+    if (!px) return B200DET_EINVAL;
     if (px->world < 1 || px->world > kMaxPeers || px->rank < 0 || px->rank >= px->world)
         return B200DET_ERANGE;
     if (px->epoch == 0) return B200DET_EINVAL;
-    const LossWs ws = loss_ws_layout(g);
-    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
-    ExchangeArgs x;
+    ExchangeArgs &x = *out;
     for (int r = 0; r < kMaxPeers; ++r) x.peer[r] = nullptr;
     for (int r = 0; r < px->world; ++r) {
         if (!px->peer[r]) return B200DET_EINVAL;
@@ -230,6 +239,36 @@ extern "C" int b200det_loss_reduce_exchange(const b200det_geometry *geo, const v
     x.world = px->world;
     x.epoch = px->epoch;
     x.timeout_cycles = px->timeout_cycles ? px->timeout_cycles : 60000000000ull;   // ~30 s
+    return 0;
+}
+
+extern "C" int b200det_sums_exchange(const b200det_peer_exchange *px, float w_cls, float w_box,
+                                     float w_ctr, double *sums, float *losses, int32_t *status,
+                                     void *stream) {
+    if (!sums) return B200DET_EINVAL;
+    ExchangeArgs x;
+    int rc = fill_exchange(px, &x);
+    if (rc) return rc;
+    ProfScope prof(kKernReduce, stream);
+    sums_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(x, w_cls, w_box, w_ctr, sums, losses,
+                                                             status);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200det_loss_reduce_exchange(const b200det_geometry *geo, const void *workspace,
+                                            size_t workspace_bytes,
+                                            const b200det_peer_exchange *px, float w_cls,
+                                            float w_box, float w_ctr, double *sums, float *losses,
+                                            int32_t *status, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!workspace || !px || !sums) return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    ExchangeArgs x;
+    if ((rc = fill_exchange(px, &x))) return rc;
     const char *base = static_cast<const char *>(workspace);
     ProfScope prof(kKernReduce, stream);
     loss_reduce_exchange_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(

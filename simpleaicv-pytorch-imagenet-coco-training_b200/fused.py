@@ -21,8 +21,8 @@ import torch
 
 from . import _lib
 from . import geometry as _geom
-from .losses import (_DTYPES, _Plan, _loss_params, _maybe_all_reduce, _plan_for, _prep_annotations,
-                     _prep_f32, _prep_reg)
+from .losses import (_DTYPES, _Plan, _loss_params, _plan_for, _prep_annotations, _prep_f32,
+                     _prep_reg, _sync_sums)
 
 __all__ = ['EvalStep', 'LogitsEvalStep']
 
@@ -78,9 +78,8 @@ class EvalStep:
                                   None if sync else sums_ptr + 32, keys_ptr, classes_ptr,
                                   out.data_ptr(), dws_ptr, dws_bytes, st), 'b200det_eval_step')
         if sync:
-            _maybe_all_reduce(small[0:4], True, crit.process_group)
-            _lib.check(lib.b200det_loss_finish(sums_ptr, lp.w_cls, lp.w_box, lp.w_ctr,
-                                               sums_ptr + 32, st), 'b200det_loss_finish')
+            _sync_sums(crit, small[0:4], crit.process_group, st,
+                       finish=(lp.w_cls, lp.w_box, lp.w_ctr, sums_ptr + 32))
         del glue
         crit.last_stats = {'sums': small[0:4]}
         losses = small[4:8].view(torch.float32)
@@ -187,9 +186,8 @@ class LogitsEvalStep:
                                          out.data_ptr(), dws_ptr, dws_bytes, st),
             'b200det_logits_eval_step')
         if sync:
-            _maybe_all_reduce(small[0:4], True, crit.process_group)
-            _lib.check(lib.b200det_loss_finish(sums_ptr, lp.w_cls, lp.w_box, lp.w_ctr,
-                                               sums_ptr + 32, st), 'b200det_loss_finish')
+            _sync_sums(crit, small[0:4], crit.process_group, st,
+                       finish=(lp.w_cls, lp.w_box, lp.w_ctr, sums_ptr + 32))
         del glue
         crit.last_stats = {'sums': small[0:4]}
         losses = small[4:8].view(torch.float32)

@@ -21,7 +21,8 @@ Extra, keyword-only constructor arguments (defaults keep reference behaviour):
         (SURVEY.md section 8e).  Default False = the reference's per-rank normalisation.
         True = torch.distributed.all_reduce (NCCL); 'p2p' = the no-grad forward exchanges the 4
         doubles over NVLink peer memory inside its reduction kernel (b200det.peer, csrc/exchange.cu;
-        one node, every GPU a peer of every other); the training path uses NCCL either way.
+        one node, every GPU a peer of every other); the training path and the fused steps
+        exchange their sums with the stand-alone b200det_sums_exchange kernel.
 """
 import ctypes
 
@@ -98,6 +99,23 @@ def _prep_annotations(annotations):
 def _maybe_all_reduce(t, sync, group):
     if sync and torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
+
+
+def _sync_sums(owner, t, group, st, finish=None):
+    """Sums `t` (device float64[4]) over the ranks in place: torch.distributed.all_reduce (NCCL), or,
+    with sync_normalizer='p2p', ONE small kernel that exchanges the 4 doubles over NVLink peer
+    memory (b200det_sums_exchange).  finish = (w_cls, w_box, w_ctr, losses_ptr) also normalises."""
+    lib = _lib.load()
+    if owner.sync_normalizer == 'p2p':
+        px = _peer_exchange(owner, t.device)
+        w = finish if finish is not None else (0., 0., 0., None)
+        _lib.check(lib.b200det_sums_exchange(px.next(), w[0], w[1], w[2], t.data_ptr(), w[3], None,
+                                             st), 'b200det_sums_exchange')
+        return
+    _maybe_all_reduce(t, True, group)
+    if finish is not None:
+        _lib.check(lib.b200det_loss_finish(t.data_ptr(), finish[0], finish[1], finish[2], finish[3],
+                                           st), 'b200det_loss_finish')
 
 
 def _peer_exchange(owner, device):
@@ -297,14 +315,14 @@ class _DetLossFunction(torch.autograd.Function):
             # the focal gradient is written once, already divided by the GLOBAL positive count
             _lib.check(lib.b200det_loss_reduce(geo, 1, ws_ptr, ws_bytes, sums.data_ptr(), st),
                        'b200det_loss_reduce')
-            _maybe_all_reduce(sums, True, group)
+            _sync_sums(owner, sums, group, st)
             _lib.check(
                 lib.b200det_focal_loss(geo, _lib.ptr_array(cls), labels_ptr, alpha, gamma,
                                        _lib.ptr_array(cls_grad), sums.data_ptr(), w_cls, ws_ptr,
                                        ws_bytes, st), 'b200det_focal_loss')
             _lib.check(lib.b200det_loss_reduce(geo, 2, ws_ptr, ws_bytes, focal.data_ptr(), st),
                        'b200det_loss_reduce')
-            _maybe_all_reduce(focal, True, group)
+            _sync_sums(owner, focal, group, st)
             sums.add_(focal)
             _lib.check(lib.b200det_loss_finish(sums.data_ptr(), w_cls, w_box, w_ctr,
                                                losses.data_ptr(), st), 'b200det_loss_finish')

@@ -83,10 +83,34 @@ def main():
             ok = ok and good
             t_p2p = timed(lambda: c_p2p(shard, ann_s))
             t_nccl = timed(lambda: c_nccl(shard, ann_s))
+        # training path (two exchanges per call: positives first, focal sum after the sweep) and the
+        # fused evaluation step: same values and gradients as with NCCL
+        grads = {}
+        for tag, crit in (('p2p', c_p2p), ('nccl', c_nccl)):
+            req = [[t.clone().requires_grad_(True) for t in grp] for grp in shard]
+            d = crit(req, ann_s)
+            sum(d.values()).backward()
+            grads[tag] = ([d[k].item() for k in keys], [t.grad for grp in req for t in grp])
+        train_same = grads['p2p'][0] == grads['nccl'][0] and all(
+            torch.equal(a_, b_) for a_, b_ in zip(grads['p2p'][1], grads['nccl'][1]))
+        rel_train = float(np.max(np.abs(np.array(grads['p2p'][0], dtype=np.float32) - want)
+                                 / np.maximum(np.abs(want), 1e-12)))
+        from b200det import decode, fused
+        dec = (decode.RetinaDecoder(**synth.RETINA_KW) if name == 'retina'
+               else decode.FCOSDecoder(strides=synth.STRIDES))
+        with torch.no_grad():
+            fa, da = fused.EvalStep(c_p2p, dec)(shard, ann_s)
+            fb, db = fused.EvalStep(c_nccl, dec)(shard, ann_s)
+        fused_same = all(fa[k].item() == fb[k].item() for k in keys) and all(
+            np.array_equal(x_, y_) for x_, y_ in zip(da, db))
+        good = good and train_same and fused_same and rel_train <= 1e-5
+        ok = ok and good
         report[name] = dict(p2p=va.tolist(), nccl=vb.tolist(), oracle_unsharded=want.tolist(),
                             identical_on_all_ranks=same_everywhere, status=status,
                             rel_vs_nccl=rel_nccl, rel_vs_oracle=rel_ref,
-                            ms_per_call_p2p=round(t_p2p, 4), ms_per_call_nccl=round(t_nccl, 4))
+                            ms_per_call_p2p=round(t_p2p, 4), ms_per_call_nccl=round(t_nccl, 4),
+                            training_identical_to_nccl=train_same, training_rel_vs_oracle=rel_train,
+                            fused_step_identical_to_nccl=fused_same)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
