@@ -221,6 +221,11 @@ int b200det_loss_reduce(const b200det_geometry *geo, int which, const void *work
 int b200det_loss_finish(const double *sums, float w_cls, float w_box, float w_ctr,
                         float *losses, void *stream);
 
+/* b200det_loss_reduce(which = 3) + b200det_loss_finish in one launch */
+int b200det_loss_reduce_finish(const b200det_geometry *geo, const void *workspace,
+                               size_t workspace_bytes, float w_cls, float w_box, float w_ctr,
+                               double *sums, float *losses, void *stream);
+
 /* x[l][i] *= *g * (sums ? weight / sums[0] : 1) for n_levels float32 buffers in one launch
  * (autograd backward: upstream scalar, loss weight, positive count); no-op when the factor is 1 */
 int b200det_scale_levels(void *const *ptrs, const long long *counts, int n_levels,

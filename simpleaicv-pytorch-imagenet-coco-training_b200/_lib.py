@@ -145,6 +145,9 @@ SIGNATURES = {
         ctypes.c_size_t, _vp
     ]),
     'b200det_loss_reduce': (ctypes.c_int, [_geo, ctypes.c_int, _vp, ctypes.c_size_t, _vp, _vp]),
+    'b200det_loss_reduce_finish': (ctypes.c_int, [
+        _geo, _vp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp
+    ]),
     'b200det_loss_finish': (ctypes.c_int,
                             [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp]),
     'b200det_scale_f32': (ctypes.c_int, [_vp, ctypes.c_longlong, _vp, _vp]),

@@ -40,8 +40,10 @@ extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_l
                                    ctr, p->box_loss, p->beta, cls, p->alpha, p->gamma, nullptr,
                                    nullptr, workspace, workspace_bytes, stream);
     g_skip_memset = false;
-    if (!rc) rc = b200det_loss_reduce(geo, 3, workspace, workspace_bytes, sums, stream);
-    if (!rc && losses) rc = b200det_loss_finish(sums, p->w_cls, p->w_box, p->w_ctr, losses, stream);
+    if (!rc)   // reduction and normalisation in one launch unless the caller all-reduces in between
+        rc = losses ? b200det_loss_reduce_finish(geo, workspace, workspace_bytes, p->w_cls, p->w_box,
+                                                 p->w_ctr, sums, losses, stream)
+                    : b200det_loss_reduce(geo, 3, workspace, workspace_bytes, sums, stream);
     return rc;
 }
 
@@ -145,9 +147,10 @@ extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss
                                    lp->gamma, nullptr, nullptr, loss_workspace,
                                    loss_workspace_bytes, stream);
     g_skip_memset = false;
-    if (!rc) rc = b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
-    if (!rc && losses)
-        rc = b200det_loss_finish(sums, lp->w_cls, lp->w_box, lp->w_ctr, losses, stream);
+    if (!rc)   // reduction and normalisation in one launch unless the caller all-reduces in between
+        rc = losses ? b200det_loss_reduce_finish(geo, loss_workspace, loss_workspace_bytes, lp->w_cls,
+                                                 lp->w_box, lp->w_ctr, sums, losses, stream)
+                    : b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
     if (!rc)
         rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, dp->is_fcos,
                                        dp->min_score, dp->topn, dp->max_out, dp->nms_type,

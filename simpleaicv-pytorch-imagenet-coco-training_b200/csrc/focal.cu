@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(1024)
     loss_reduce_kernel(const int *__restrict__ npos, long long n_assign,
                        const SparsePartial *__restrict__ sp, long long n_sparse,
                        const long long *__restrict__ fp, long long n_focal, int which,
-                       double *__restrict__ sums) {
+                       double *__restrict__ sums, float w_cls, float w_box, float w_ctr,
+                       float *__restrict__ losses) {
     __shared__ double red[4][32];
     double s_pos = 0.0, s_cls = 0.0, s_box = 0.0, s_ctr = 0.0;
     if (which & 1) {
@@ -460,6 +461,17 @@ __global__ void __launch_bounds__(1024)
                 sums[3] = d;
             }
             sums[1] = b;  // focal partials (bit 1) + the sparse kernel's corrections (bit 0)
+            if (losses) {
+                // loss_finish_kernel fused (which == 3): float32 sum / count, then * weight
+                const float w[3] = {w_cls, w_box, w_ctr};
+                const double t[3] = {b, c, d};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float v = 0.f;
+                    if (a > 0.0) v = w[i] * ((float)t[i] / (float)a);
+                    losses[i] = v;
+                }
+            }
         }
     }
 }
@@ -709,7 +721,28 @@ extern "C" int b200det_loss_reduce(const b200det_geometry *geo, int which, const
         reinterpret_cast<const int *>(base + ws.off_assign), (long long)ws.assign_blocks,
         reinterpret_cast<const SparsePartial *>(base + ws.off_sparse), (long long)ws.sparse_blocks,
         reinterpret_cast<const long long *>(base + ws.off_focal), (long long)kSweepSlots, which,
-        sums);
+        sums, 0.f, 0.f, 0.f, nullptr);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// b200det_loss_reduce(which = 3) + b200det_loss_finish in one launch (the single-process forward)
+extern "C" int b200det_loss_reduce_finish(const b200det_geometry *geo, const void *workspace,
+                                          size_t workspace_bytes, float w_cls, float w_box,
+                                          float w_ctr, double *sums, float *losses, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!workspace || !sums || !losses) return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    const char *base = static_cast<const char *>(workspace);
+    ProfScope prof(kKernReduce, stream);
+    loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const int *>(base + ws.off_assign), (long long)ws.assign_blocks,
+        reinterpret_cast<const SparsePartial *>(base + ws.off_sparse), (long long)ws.sparse_blocks,
+        reinterpret_cast<const long long *>(base + ws.off_focal), (long long)kSweepSlots, 3, sums,
+        w_cls, w_box, w_ctr, losses);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -452,9 +452,10 @@ extern "C" int b200det_logits_eval_step(const b200det_geometry *geo, const b200d
                                   lp->alpha, lp->gamma, loss_workspace, loss_workspace_bytes,
                                   dp->min_score, keys, classes, stream);
     g_skip_memset = false;
-    if (!rc) rc = b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
-    if (!rc && losses)
-        rc = b200det_loss_finish(sums, lp->w_cls, lp->w_box, lp->w_ctr, losses, stream);
+    if (!rc)   // reduction and normalisation in one launch unless the caller all-reduces in between
+        rc = losses ? b200det_loss_reduce_finish(geo, loss_workspace, loss_workspace_bytes, lp->w_cls,
+                                                 lp->w_box, lp->w_ctr, sums, losses, stream)
+                    : b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
     if (!rc)
         rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, fcos ? 1 : 0,
                                        dp->min_score, dp->topn, dp->max_out, dp->nms_type,
