@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 constexpr int kNmsWindow = 256;
+constexpr int kNmsGroup = 8;     // candidates resolved per NMS step (28 pairwise tests = one ballot)
 
 // does kept box kb suppress the later box ob?  (decode.py:45-100 / torchvision CPU nms)
 __device__ __forceinline__ bool nms_suppresses(const float4 kb, const float4 ob, int nms_type,
@@ -656,9 +657,10 @@ __global__ void __launch_bounds__(kSelThreads, 2)
     float4 *sbox = reinterpret_cast<float4 *>(skey + 2 * a.pad_n);            // pad_n
     int *scls = reinterpret_cast<int *>(sbox + a.pad_n);                      // pad_n
     int *skeep = scls + a.pad_n;                                              // pad_n
-    uint32_t *srem = reinterpret_cast<uint32_t *>(skeep + a.pad_n);           // pad_n/32
+    uint32_t *srem = reinterpret_cast<uint32_t *>(skeep + a.pad_n);           // max(pad_n, 256)/32
     __shared__ int scratch[kSelWarps];
     __shared__ int s_digit, s_above, s_count, s_total;
+    __shared__ int sgroup[kNmsGroup];
 
     const Geo &g = a.g;
     const int b = blockIdx.x;
@@ -882,44 +884,50 @@ __global__ void __launch_bounds__(kSelThreads, 2)
     }
     if (order_out)
         for (int i = n_sel + tid; i < a.topn; i += kSelThreads) order_out[(size_t)b * a.topn + i] = -1;
-    for (int i = tid; i < (a.pad_n >> 5); i += kSelThreads) srem[i] = 0u;
+    // bit = "not a candidate": everything at or beyond n_sel from the start
+    for (int i = tid; i < (max(a.pad_n, kNmsWindow) >> 5); i += kSelThreads) {
+        const int i0 = i << 5;
+        srem[i] = i0 >= n_sel ? 0xffffffffu : (i0 + 32 <= n_sel ? 0u : ~((1u << (n_sel - i0)) - 1u));
+    }
     __syncthreads();
 
-    // ---- greedy NMS (decode.py:45-100): ballots build the removed-bitmask ----
-    // Only the first max_object_num survivors are returned, and they almost always come from the
-    // head of the sorted list, so the scan works on a window of kNmsWindow candidates: inside
-    // the window it is the plain greedy loop (pick the first alive box, let every later box of
-    // the window test itself against it); when the window is exhausted the next kNmsWindow
-    // candidates first test themselves against ALL boxes kept so far, then the loop resumes.
-    // The keep list is identical to the full greedy scan.
-    // Only the kNmsWindow / 32 warps that own the window take part (named barrier 1); the other
-    // warps wait at the CTA barrier below.  One barrier per kept box: after it every participating
-    // warp re-derives the next alive index from the bitmask by itself.
+    // ---- greedy NMS (decode.py:45-100), up to kNmsGroup kept boxes per step ----
+    // Greedy NMS is a chain of dependent steps, so the kernel waits for step LATENCY, not throughput
+    // (one kept box per step with a barrier measured ~750-1100 cycles per box).  Each step therefore
+    // takes the first G <= 8 candidates that are still alive, resolves the greedy order INSIDE that
+    // group from its 28 pairwise tests (every warp does that redundantly: one ballot, no exchange
+    // between warps), and lets every later candidate test itself against the group's kept members
+    // at once.  That is the reference's scan: the group members are the next candidates in order
+    // (everything between them is already dead), a member is kept iff no kept earlier member
+    // suppresses it, and later candidates are only ever tested against kept boxes.  The scan works
+    // on a window of kNmsWindow candidates (srem bit = "no longer a candidate": removed, kept, or
+    // beyond n_sel); when the window is exhausted the next kNmsWindow candidates first test themselves
+    // against ALL boxes kept so far.  Only the kNmsWindow / 32 warps of the window take part (named
+    // barrier 1); two barriers per step.
     const int limit = keep_out ? n_sel : min(a.max_out, n_sel);
     if (tid < kNmsWindow) {
         const NmsFast nf = nms_fast_of(a.nms_type, a.nms_thr_f);
-        int n_keep = 0, cur = 0;
+        // pair p = b (b - 1) / 2 + a  (a < b < 8) is tested by lane p
+        const int pb = lane >= 21 ? 7 : lane >= 15 ? 6 : lane >= 10 ? 5 : lane >= 6 ? 4
+                       : lane >= 3 ? 3 : lane >= 1 ? 2 : 1;
+        const int pa = lane - pb * (pb - 1) / 2;
+        int n_keep = 0;
         int win_base = 0, win_end = min(n_sel, kNmsWindow);
         while (n_keep < limit) {
-            // first alive index in [cur, win_end): the window spans <= 8 words, one per lane
-            int found = -1;
-            {
-                const int w = (win_base >> 5) + lane;
-                uint32_t alive = 0u;
-                if (lane < (kNmsWindow >> 5) && (w << 5) < win_end) {
-                    alive = ~srem[w];
-                    if (w == (cur >> 5)) alive &= ~((1u << (cur & 31)) - 1u);
-                    if (w < (cur >> 5)) alive = 0u;
-                    if (((w + 1) << 5) > win_end) alive &= (1u << (win_end & 31)) - 1u;
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, alive != 0u);
-                if (bal) {
-                    const int src_lane = __ffs(bal) - 1;
-                    const uint32_t word = __shfl_sync(0xffffffffu, alive, src_lane);
-                    found = (((win_base >> 5) + src_lane) << 5) + (__ffs(word) - 1);
-                }
+            // ---- A: rank of every alive candidate of the window (the 8 words are read by all)
+            const uint4 *wp = reinterpret_cast<const uint4 *>(srem + (win_base >> 5));
+            const uint4 w0 = wp[0], w1 = wp[1];
+            const uint32_t aw[8] = {~w0.x, ~w0.y, ~w0.z, ~w0.w, ~w1.x, ~w1.y, ~w1.z, ~w1.w};
+            int total = 0, before = 0;
+            uint32_t mine_word = 0u;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int c = __popc(aw[w]);
+                total += c;
+                if (w < warp) before += c;
+                if (w == warp) mine_word = aw[w];
             }
-            if (found < 0) {
+            if (total == 0) {
                 if (win_end >= n_sel) break;
                 // slide the window: the new candidates against everything kept so far
                 const int new_end = min(n_sel, win_end + kNmsWindow);
@@ -933,23 +941,52 @@ __global__ void __launch_bounds__(kSelThreads, 2)
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, suppress);
                 if (lane == 0 && bal) srem[j >> 5] |= bal;  // each word is owned by one warp
-                cur = win_end;
                 win_base = win_end;
                 win_end = new_end;
                 asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
                 continue;
             }
-            if (tid == 0) skeep[n_keep] = found;
-            ++n_keep;
-            if (n_keep >= limit) break;
             const int j = win_base + tid;
-            bool suppress = false;
-            if (j > found && j < win_end)
-                suppress = nms_suppresses_fast(sbox[found], sbox[j], a.nms_type, a.nms_thr_f,
-                                               a.nms_thr_d, nf);
-            const unsigned bal = __ballot_sync(0xffffffffu, suppress);
-            if (lane == 0 && bal) srem[j >> 5] |= bal;
-            cur = found + 1;
+            const bool mine = (mine_word >> lane) & 1u;
+            const int rank = before + __popc(mine_word & ((1u << lane) - 1u));
+            const int G = min(kNmsGroup, total);
+            if (mine && rank < kNmsGroup) sgroup[rank] = j;
+            asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
+            // ---- B: the group's pairwise tests (lane p: does member pa suppress member pb?)
+            bool psup = false;
+            if (lane < 28 && pb < G)
+                psup = nms_suppresses_fast(sbox[sgroup[pa]], sbox[sgroup[pb]], a.nms_type,
+                                           a.nms_thr_f, a.nms_thr_d, nf);
+            const unsigned pm = __ballot_sync(0xffffffffu, psup);
+            unsigned kept = 1u;   // member 0 is always kept
+#pragma unroll
+            for (int m = 1; m < kNmsGroup; ++m) {
+                const unsigned by = (pm >> (m * (m - 1) / 2)) & ((1u << m) - 1u);   // who would suppress m
+                if (m < G && (by & kept) == 0u) kept |= 1u << m;
+            }
+            // never more than `limit` boxes: drop the group's last kept members (the scan ends here)
+            while (n_keep + __popc(kept) > limit) kept &= ~(0x80000000u >> __clz(kept));
+            if (tid < kNmsGroup && ((kept >> tid) & 1u))
+                skeep[n_keep + __popc(kept & ((1u << tid) - 1u))] = sgroup[tid];
+            // ---- C: group members leave the candidate set; later candidates against the kept ones
+            bool gone = false;
+            if (mine) {
+                if (rank < G) {
+                    gone = true;
+                } else {
+                    const float4 ob = sbox[j];
+                    unsigned k = kept;
+                    while (k && !gone) {
+                        const int m = __ffs(k) - 1;
+                        k &= k - 1u;
+                        gone = nms_suppresses_fast(sbox[sgroup[m]], ob, a.nms_type, a.nms_thr_f,
+                                                   a.nms_thr_d, nf);
+                    }
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, gone);
+            if (lane == 0 && bal) srem[(win_base >> 5) + warp] |= bal;
+            n_keep += __popc(kept);
             asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
         }
         if (tid == 0) s_total = n_keep;
@@ -1013,7 +1050,8 @@ __global__ void npexp_kernel(const float *__restrict__ x, float *__restrict__ y,
 }
 
 static size_t select_smem_bytes(int pad_n) {
-    return (size_t)kBins * 4 + (size_t)pad_n * (16 + 16 + 4 + 4) + (size_t)(pad_n / 32) * 4 + 16;
+    const int rem_bits = pad_n > kNmsWindow ? pad_n : kNmsWindow;   // whole windows of the bitmask
+    return (size_t)kBins * 4 + (size_t)pad_n * (16 + 16 + 4 + 4) + (size_t)(rem_bits / 32) * 4 + 16;
 }
 
 }  // namespace b200det
