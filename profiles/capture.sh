@@ -12,7 +12,7 @@ $CMD > $OUT/${TAG}_plain.json 2> $OUT/${TAG}_plain.err || { echo "plain run fail
 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 $CMD > /dev/null 2>&1 || exit 1
-# skip the 3 warm-up + first timed step (7 b200det kernels per step), then take one step
+# skip the 3 warm-up + first timed step (6 matching kernels per step), then take one step
 ncu --set full --clock-control none --import-source on \
     -k regex:"focal_all_kernel|retina_assign_kernel|sparse_loss_kernel|score_argmax_kernel|select_nms_kernel|loss_reduce_kernel" \
     -s 24 -c 6 -o $OUT/${TAG}_full $CMD > $OUT/${TAG}_ncu_full.log 2>&1
