@@ -126,6 +126,10 @@ const char *b200det_kernel_name(int kernel_id);
 /* rows per image (N) for a geometry; negative on error */
 long long b200det_rows_per_image(const b200det_geometry *geo);
 
+/* blocks the calling host thread until `stream` has drained (cudaStreamSynchronize): the decoders'
+ * only host wait, right before they hand out the result arrays */
+int b200det_stream_synchronize(void *stream);
+
 /* ---- loss --------------------------------------------------------------------------- */
 /* bytes of scratch the loss calls of one step share (per-CTA partials + the matched annotation
  * row of every row, 2 bytes each); the same buffer must be passed to every call of the step */

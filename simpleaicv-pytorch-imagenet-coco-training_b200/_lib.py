@@ -128,6 +128,7 @@ SIGNATURES = {
         _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp
     ]),
+    'b200det_stream_synchronize': (ctypes.c_int, [_vp]),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
     'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),
     'b200det_retina_assign': (ctypes.c_int, [
@@ -238,6 +239,28 @@ def ptr_array(tensors):
     for i, t in enumerate(tensors):
         arr[i] = t.data_ptr()
     return arr
+
+
+try:   # raw cudaStream_t of torch's current stream without building a torch.cuda.Stream object
+    import torch as _torch
+    _RAW_STREAM = _torch._C._cuda_getCurrentRawStream
+except (ImportError, AttributeError):   # pragma: no cover
+    _RAW_STREAM = None
+
+
+def raw_stream(device=None):
+    """ctypes void* of torch's current stream on `device` (torch.device, index or None = current).
+    torch.cuda.current_stream() costs ~7-15 us per call; this is ~0.5 us."""
+    import torch
+    if device is None:
+        index = torch.cuda.current_device()
+    elif isinstance(device, int):
+        index = device
+    else:
+        index = device.index if device.index is not None else torch.cuda.current_device()
+    if _RAW_STREAM is not None:
+        return ctypes.c_void_p(_RAW_STREAM(index))
+    return ctypes.c_void_p(torch.cuda.current_stream(index).cuda_stream)
 
 
 def launch_count():

@@ -159,3 +159,9 @@ extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss
                                        decode_workspace_bytes, stream);
     return rc;
 }
+
+// cudaStreamSynchronize for the host layer (the decoder's only host wait): avoids building a
+// torch.cuda.Stream object per call; ctypes releases the GIL while it blocks.
+extern "C" int b200det_stream_synchronize(void *stream) {
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}

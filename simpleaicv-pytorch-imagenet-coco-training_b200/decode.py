@@ -101,7 +101,8 @@ class _DecoderBase:
         if out.is_cuda:
             staging = self._staging(out.numel())
             staging.copy_(out, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
+        _lib.check(_lib.load().b200det_stream_synchronize(_lib.raw_stream(device)),
+                   'b200det_stream_synchronize')
         host = staging.numpy()
         if _RESULT_COPY or staging is self._pinned:
             host = host.copy()
@@ -156,7 +157,7 @@ class _DecoderBase:
                                keep.data_ptr() if details else None,
                                counts.data_ptr() if details else None,
                                keys_ptr + rows_bytes, ws_bytes,
-                               ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+                               _lib.raw_stream(device)),
             'b200det_decode')
 
         del glue
@@ -275,7 +276,7 @@ class _FlatDecoder(_DecoderBase):
                 float(self.nms_threshold if self.nms_threshold is not None else 0.5), None, None, 0,
                 out.data_ptr(), order.data_ptr() if details else None,
                 keep.data_ptr() if details else None, None, ws.data_ptr(), ws_bytes,
-                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+                _lib.raw_stream(device)),
             'b200det_select_decode_nms')
         result = self._to_host(out, batch, max_out, device)
         if not details:
@@ -299,7 +300,7 @@ class _FlatDecoder(_DecoderBase):
                 sizes.data_ptr() if sizes is not None else None, batch, queries, channels,
                 int(num_classes), float(np.float32(min_score)), keys.data_ptr(), classes.data_ptr(),
                 xyxy.data_ptr() if xyxy is not None else None,
-                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+                _lib.raw_stream(device)),
             'b200det_query_scores')
         return keys, classes, xyxy
 

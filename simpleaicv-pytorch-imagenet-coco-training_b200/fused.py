@@ -68,7 +68,7 @@ class EvalStep:
         glue = dec._set_glue(dp, batch, device, scales, sizes, to_xywh)
         sync = crit.sync_normalizer and torch.distributed.is_available() \
             and torch.distributed.is_initialized()
-        st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        st = _lib.raw_stream(device)
         sums_ptr = small.data_ptr()
         _lib.check(
             lib.b200det_eval_step(plan.geo_ref, ctypes.byref(lp), ctypes.byref(dp),
@@ -174,7 +174,7 @@ class LogitsEvalStep:
         glue = dec._set_glue(dp, batch, device, scales, sizes, to_xywh)
         sync = crit.sync_normalizer and torch.distributed.is_available() \
             and torch.distributed.is_initialized()
-        st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        st = _lib.raw_stream(device)
         sums_ptr = small.data_ptr()
         _lib.check(
             lib.b200det_logits_eval_step(plan.geo_ref, ctypes.byref(lp), ctypes.byref(dp),

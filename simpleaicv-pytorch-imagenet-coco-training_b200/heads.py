@@ -21,7 +21,7 @@ _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _li
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _lib.raw_stream()
 
 
 class _SigmoidPermute(torch.autograd.Function):
