@@ -242,3 +242,39 @@ def test_gpu_nms_threshold_band(nms):
         want = O.nms_keep(boxes, scores, nms, thr)
         got = decode.DetNMSMethod(nms_type=nms, nms_threshold=thr)(boxes, scores)
         assert np.array_equal(got, want), f'{nms} thr={thr!r}'
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nms', NMS_TYPES)
+@pytest.mark.parametrize('seed', range(4))
+def test_gpu_nms_clustered_boxes(nms, seed):
+    """Heavily overlapping candidates (clusters of jittered boxes, integer and fractional
+    coordinates): most candidates are suppressed, groups of the select kernel's 8-per-step greedy
+    scan contain suppressed members, windows slide, and the max_object_num cut falls inside a
+    group.  Full keep lists and capped outputs must equal the reference's scan."""
+    from b200det import decode
+    rng = np.random.RandomState(900 + seed)
+    n = int(rng.choice([37, 300, 1000, 2048]))
+    centers = rng.uniform(50, 400, size=(int(rng.choice([1, 3, 12])), 2))
+    c = centers[rng.randint(0, len(centers), size=n)]
+    wh = rng.uniform(20, 90, size=(n, 2))
+    xy = c + rng.normal(0, float(rng.choice([2.0, 10.0, 30.0])), size=(n, 2)) - wh / 2
+    boxes = np.concatenate([xy, xy + wh], axis=1).astype(np.float32)
+    if seed % 2:
+        boxes = np.trunc(boxes)                   # the dense decoders' integer-valued boxes
+    scores = np.sort(rng.uniform(0.06, 1.0, size=n).astype(np.float32))[::-1].copy()
+    scores = np.unique(scores)[::-1].copy()
+    boxes = boxes[:len(scores)]
+    n = len(scores)
+    thr = float(rng.choice([0.3, 0.5, 0.7]))
+    want = O.nms_keep(boxes, scores, nms, thr)
+    got = decode.DetNMSMethod(nms_type=nms, nms_threshold=thr)(boxes, scores)
+    assert np.array_equal(got, want), f'{nms} n={n} thr={thr}: keep list'
+    classes = rng.randint(0, 5, size=n)
+    for m in (1, 7, 8, 9, 100):
+        dm = decode.DecodeMethod(max_object_num=m, min_score_threshold=0.05, topn=min(n, 2048),
+                                 nms_type=nms, nms_threshold=thr)
+        got3 = dm(scores[None], classes[None], boxes[None])
+        want3, _ = O.select_and_nms(scores[None], classes[None], boxes[None], m, 0.05,
+                                    min(n, 2048), nms, thr)
+        assert_triplet(got3, want3, f'{nms} n={n} thr={thr} max_object_num={m}')
