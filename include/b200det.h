@@ -433,6 +433,23 @@ int b200det_logits_eval_step(const b200det_geometry *geo, const b200det_loss_par
                              float *out, void *decode_workspace, size_t decode_workspace_bytes,
                              void *stream);
 
+/* ---- evaluation: the per-batch part of the VOC evaluator --------------------------------------- */
+/* compute_ious (tools/scripts.py:487-508): out[i*m + j] = IoU(a[i], b[j]) in float32 with the
+ * reference's op order and no clamps (degenerate pairs give NaN / inf like NumPy).  a, b: device
+ * float32 [n,4] / [m,4] x1,y1,x2,y2, 16-byte aligned. */
+int b200det_pair_ious(const float *a, int n, const float *b, int m, float *out, void *stream);
+/* The matching loop of evaluate_voc_detection (tools/scripts.py:626-651) for a batch: detection d of
+ * image b (decoder order; class <= -1 = padding) is a true positive at threshold t iff the ground-
+ * truth box of its class with the largest IoU (np.argmax: first maximum, NaN counts as maximum) has
+ * IoU >= thresholds[t] and was not taken by an earlier detection of that image.
+ *   pred_boxes [batch,max_det,4], pred_classes [batch,max_det], gt_boxes [batch,max_gt,4],
+ *   gt_classes [batch,max_gt] (<= -1 = padding), thresholds [n_thresholds]: device float32
+ *   tp : device uint8 [n_thresholds, batch, max_det] out */
+int b200det_voc_match(const float *pred_boxes, const float *pred_classes, int max_det,
+                      const float *gt_boxes, const float *gt_classes, int max_gt,
+                      const float *thresholds, int n_thresholds, int batch, unsigned char *tp,
+                      void *stream);
+
 /* ---- multi-GPU: the loss normaliser exchanged over NVLink peer memory ---------------------- */
 /*
  * The path shards by image; the only cross-rank coupling is the whole-batch positive count and the

@@ -13,6 +13,8 @@ primitives the reference itself runs on) of the reference's dense-detection hot 
     simpleAICV/detection/decode.py:274-364        FCOSDecoder
     simpleAICV/detection/decode.py:367-482        DETRDecoder
     simpleAICV/detection/decode.py:485-594        DINODETRDecoder
+    tools/scripts.py:455-508, 592-684             compute_voc_ap / compute_ious / the matching and
+                                                  AP loop of evaluate_voc_detection
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import this module; the product (``b200det``) never does and has no
@@ -653,3 +655,86 @@ def head_tail(x, num_classes=None):
     if num_classes is not None:
         y = y.view(y.shape[0], y.shape[1], y.shape[2], -1, num_classes)
     return y
+
+
+# ----------------------------------------------------------------------------------------
+# VOC evaluator (tools/scripts.py:455-508, 592-684)
+# ----------------------------------------------------------------------------------------
+def compute_ious(a, b):
+    """tools/scripts.py:487-508: [N,4] x [M,4] -> [N,M]; no clamps: degenerate pairs give NaN / inf."""
+    a = np.expand_dims(a, axis=1)
+    b = np.expand_dims(b, axis=0)
+    overlap = np.maximum(0.0, np.minimum(a[..., 2:], b[..., 2:]) - np.maximum(a[..., :2], b[..., :2]))
+    overlap = np.prod(overlap, axis=-1)
+    area_a = np.prod(a[..., 2:] - a[..., :2], axis=-1)
+    area_b = np.prod(b[..., 2:] - b[..., :2], axis=-1)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return overlap / (area_a + area_b - overlap)
+
+
+def compute_voc_ap(recall, precision, use_07_metric=False):
+    """tools/scripts.py:455-484."""
+    if use_07_metric:
+        ap = 0.
+        for t in np.arange(0., 1.1, 0.1):
+            p = 0 if np.sum(recall >= t) == 0 else np.max(precision[recall >= t])
+            ap = ap + p / 11.
+        return ap
+    mrecall = np.concatenate(([0.], recall, [1.]))
+    mprecision = np.concatenate(([0.], precision, [0.]))
+    for i in range(mprecision.size - 1, 0, -1):
+        mprecision[i - 1] = np.maximum(mprecision[i - 1], mprecision[i])
+    i = np.where(mrecall[1:] != mrecall[:-1])[0]
+    return np.sum((mrecall[i + 1] - mrecall[i]) * mprecision[i + 1])
+
+
+def voc_match(pred_classes, pred_boxes, gt_boxes, gt_classes, iou_threshold):
+    """The per-image matching of tools/scripts.py:626-651 for ONE image and threshold, over all
+    classes at once: detection d (in the decoder's order) is a true positive iff the ground-truth
+    box of ITS class with the largest IoU (np.argmax: first maximum, NaN counts as maximum) has
+    IoU >= threshold and was not taken by an earlier detection.  Returns bool [n_det]."""
+    tp = np.zeros((len(pred_classes),), dtype=bool)
+    assigned = {}
+    for d in range(len(pred_classes)):
+        c = pred_classes[d]
+        idx = np.nonzero(gt_classes == c)[0]
+        if idx.shape[0] == 0:
+            continue
+        iou = compute_ious(gt_boxes[idx], np.expand_dims(pred_boxes[d], axis=0))
+        g = np.argmax(iou, axis=0)
+        if iou[g, 0] >= iou_threshold and int(g[0]) not in assigned.setdefault(c, []):
+            tp[d] = True
+            assigned[c].append(int(g[0]))
+    return tp
+
+
+def voc_map(preds, gts, iou_thresholds, num_classes, tp_flags=None):
+    """tools/scripts.py:614-684.  preds[i] = [boxes, classes, scores], gts[i] = [boxes, classes] per
+    image.  tp_flags[t][i] (bool per detection) may come from elsewhere (the CUDA matcher); default:
+    voc_match.  Returns ({key: mAP}, {key: [AP per class]}) with the reference's keys."""
+    maps, per_class = {}, {}
+    for t, thr in enumerate(iou_thresholds):
+        aps = []
+        for c in range(num_classes):
+            tps, scores, total_gts = [], [], 0
+            for i, (p, g) in enumerate(zip(preds, gts)):
+                total_gts += int(np.sum(g[1] == c))
+                flags = tp_flags[t][i] if tp_flags is not None else voc_match(p[1], p[0], g[0], g[1], thr)
+                sel = p[1] == c
+                tps.append(np.asarray(flags)[sel])
+                scores.append(p[2][sel])
+            tp = np.concatenate(tps).astype(np.float64) if tps else np.zeros((0,))
+            sc = np.concatenate(scores).astype(np.float64) if scores else np.zeros((0,))
+            fp = 1.0 - tp
+            order = np.argsort(-sc)
+            fp, tp = np.cumsum(fp[order]), np.cumsum(tp[order])
+            with np.errstate(invalid='ignore', divide='ignore'):
+                recall = tp / total_gts
+            precision = tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
+            aps.append(compute_voc_ap(recall, precision, use_07_metric=False) * 100)
+        m = 0.
+        for ap in aps:
+            m += float(ap)
+        maps[f'IoU={thr:.2f},area=all,maxDets=100,mAP'] = m / num_classes
+        per_class[f'IoU={thr:.2f},area=all,maxDets=100,per_class_ap'] = aps
+    return maps, per_class

@@ -26,6 +26,7 @@ SOURCES = {
     'logits.cu': [],
     'queries.cu': [],
     'exchange.cu': [],
+    'evaluate.cu': ['-fmad=false'],
 }
 
 

@@ -175,6 +175,10 @@ SIGNATURES = {
         ctypes.c_int, _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp
     ]),
+    'b200det_pair_ious': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
+    'b200det_voc_match': (ctypes.c_int, [
+        _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp
+    ]),
     'b200det_peer_buffer_create': (ctypes.c_int, [_vpp, ctypes.c_char_p]),
     'b200det_peer_buffer_open': (ctypes.c_int, [ctypes.c_char_p, _vpp]),
     'b200det_peer_buffer_close': (ctypes.c_int, [_vp]),

@@ -278,6 +278,100 @@ def make_queries(path):
     np.savez_compressed(path, **out)
 
 
+def _reference_voc_pieces():
+    """compute_voc_ap / compute_ious and the matching + AP loop of evaluate_voc_detection, taken
+    verbatim from the reference's tools/scripts.py (the module itself cannot be imported here:
+    it needs pycocotools and thop).  Returns (namespace with the two functions, source of the
+    loop dedented to top level)."""
+    import ast
+    import textwrap
+    path = os.path.join(refload.REFERENCE_ROOT, 'tools', 'scripts.py')
+    src = open(path).read()
+    tree = ast.parse(src)
+    lines = src.splitlines()
+    ns = {'np': np}
+    loop_src = None
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ('compute_voc_ap', 'compute_ious'):
+            exec(compile('\n'.join(lines[node.lineno - 1:node.end_lineno]), path, 'exec'), ns)
+        if isinstance(node, ast.FunctionDef) and node.name == 'evaluate_voc_detection':
+            body = lines[node.lineno - 1:node.end_lineno]
+            start = next(i for i, l in enumerate(body)
+                         if 'all_iou_threshold_map = collections.OrderedDict()' in l)
+            end = next(i for i, l in enumerate(body)
+                       if 'for key, value in all_iou_threshold_map.items()' in l)
+            loop_src = textwrap.dedent('\n'.join(body[start:end]))
+    assert loop_src is not None and 'compute_ious' in ns and 'compute_voc_ap' in ns
+    return ns, loop_src
+
+
+def make_voc(path):
+    """VOC evaluator matching (tools/scripts.py:455-508, 592-684): the reference's own
+    source lines run on synthetic detections / ground truth."""
+    import collections
+    import types
+    ns, loop_src = _reference_voc_pieces()
+    rng = np.random.RandomState(31)
+    n_img, n_cls, M, G = 12, 4, 30, 9
+    preds, gts = [], []
+    raw = {'pred_scores': [], 'pred_classes': [], 'pred_boxes': [], 'gt_boxes': [], 'gt_classes': []}
+    for i in range(n_img):
+        ng = int(rng.randint(0, G + 1))
+        gxy = rng.uniform(0, 200, size=(ng, 2))
+        gwh = rng.uniform(10, 120, size=(ng, 2))
+        gt_boxes = np.concatenate([gxy, gxy + gwh], axis=1).astype(np.float32)
+        gt_classes = rng.randint(0, n_cls, size=ng).astype(np.float32)
+        if i == 3 and ng >= 2:
+            gt_boxes[1] = gt_boxes[0]            # duplicated GT: first maximum wins
+            gt_classes[1] = gt_classes[0]
+        nd = int(rng.randint(0, M + 1))
+        # detections: jittered copies of GT boxes (hits), plus random boxes (misses)
+        boxes = np.zeros((nd, 4), dtype=np.float32)
+        classes = rng.randint(0, n_cls, size=nd).astype(np.float32)
+        for d in range(nd):
+            if ng and rng.rand() < 0.7:
+                g = int(rng.randint(0, ng))
+                boxes[d] = gt_boxes[g] + rng.normal(0, 6, size=4).astype(np.float32)
+                classes[d] = gt_classes[g]
+            else:
+                xy = rng.uniform(0, 200, size=2)
+                boxes[d] = np.concatenate([xy, xy + rng.uniform(10, 120, size=2)])
+        if nd >= 2:
+            boxes[1] = boxes[0]                   # two detections on the same GT: the second is a FP
+            classes[1] = classes[0]
+        scores = np.sort(rng.uniform(0.05, 1, size=nd).astype(np.float32))[::-1].copy()
+        preds.append([boxes, classes, scores])
+        gts.append([gt_boxes, gt_classes])
+        for k, v in zip(raw, (scores, classes, boxes, gt_boxes, gt_classes)):
+            raw[k].append(v)
+    thresholds = [0.5, 0.75, 0.3]
+    config = types.SimpleNamespace(eval_voc_iou_threshold_list=thresholds, num_classes=n_cls)
+    env = dict(ns)
+    env.update(collections=collections, tqdm=lambda x: x, config=config, preds=preds, gts=gts)
+    exec(loop_src, env)
+    out = {'versions': versions(), 'thresholds': np.array(thresholds), 'num_classes': n_cls,
+           'n_images': n_img}
+    for i in range(n_img):
+        for k in raw:
+            out[f'{k}_{i}'] = raw[k][i]
+    for key, value in env['all_iou_threshold_map'].items():
+        out['map::' + key] = np.float64(value)
+    for key, per_class in env['all_iou_threshold_per_class_ap'].items():
+        out['ap::' + key] = np.array([per_class[c] for c in range(n_cls)], dtype=np.float64)
+    # compute_ious on its own (incl. a degenerate pair -> NaN) and compute_voc_ap both ways
+    a = np.concatenate([raw['gt_boxes'][0], np.array([[5, 5, 5, 5]], dtype=np.float32)])
+    b = np.concatenate([raw['pred_boxes'][0][:7], np.array([[5, 5, 5, 5]], dtype=np.float32)])
+    out['ious_a'], out['ious_b'] = a, b
+    with np.errstate(invalid='ignore', divide='ignore'):
+        out['ious'] = ns['compute_ious'](a, b)
+    rec = np.array([0.1, 0.1, 0.2, 0.4, 0.4, 0.7])
+    prec = np.array([1.0, 0.5, 0.66, 0.75, 0.6, 0.58])
+    out['ap_rec'], out['ap_prec'] = rec, prec
+    out['ap_07'] = np.float64(ns['compute_voc_ap'](rec, prec, use_07_metric=True))
+    out['ap_10'] = np.float64(ns['compute_voc_ap'](rec, prec, use_07_metric=False))
+    np.savez_compressed(path, **out)
+
+
 def make_heads(path):
     """Head tail: the reference's RetinaClsHead (models/head.py:15-52) on a seeded
     feature map; the convolution output is captured with a hook, the head's own `.float()` +
@@ -312,6 +406,10 @@ if __name__ == '__main__':
         make_heads(os.path.join(HERE, 'head_tail.npz'))
         print('head_tail.npz', os.path.getsize(os.path.join(HERE, 'head_tail.npz')))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'voc':
+        make_voc(os.path.join(HERE, 'voc_eval.npz'))
+        print('voc_eval.npz', os.path.getsize(os.path.join(HERE, 'voc_eval.npz')))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'queries':
         make_queries(os.path.join(HERE, 'queries.npz'))
         print('queries.npz', os.path.getsize(os.path.join(HERE, 'queries.npz')))
@@ -326,5 +424,6 @@ if __name__ == '__main__':
     make_face(os.path.join(HERE, 'retinaface_small.npz'))
     make_heads(os.path.join(HERE, 'head_tail.npz'))
     make_queries(os.path.join(HERE, 'queries.npz'))
+    make_voc(os.path.join(HERE, 'voc_eval.npz'))
     for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)))
