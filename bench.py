@@ -506,7 +506,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
     ap.add_argument('--e2e-batch', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=3)
-    ap.add_argument('--cpu-steps', type=int, default=20)
+    ap.add_argument('--cpu-steps', type=int, default=40)
     ap.add_argument('--ref-size', type=int, default=SIZE,
                     help='image size of the --impl reference sample (tests use a small one)')
     ap.add_argument('--sync', default='auto', choices=['auto', 'p2p', 'nccl'],

@@ -433,6 +433,19 @@ int b200det_logits_eval_step(const b200det_geometry *geo, const b200det_loss_par
                              float *out, void *decode_workspace, size_t decode_workspace_bytes,
                              void *stream);
 
+/* ---- IoUMethod as a stand-alone operator ------------------------------------------------------ */
+/* IoUMethod.__call__ (simpleAICV/detection/losses.py:28-123): out[i*m + j] = iou_type(boxes1 row
+ * i*s1n + j*s1m, boxes2 row i*s2n + j*s2m), float32, the reference's op order.  Element-wise use:
+ * m = 1, strides (1, 0); the assignment's [N,1,4] x [1,M,4] broadcast (losses.py:350-353):
+ * strides (1, 0) and (0, 1).  Strides count boxes (4 floats).  iou_type: B200DET_BOX_IOU ..
+ * B200DET_BOX_EIOU; xywh != 0: boxes are [x_ctr, y_ctr, w, h] (losses.py:44-52).
+ * jac1 / jac2 (optional, 16-byte aligned, float32 [n*m, 4]): d out / d (the four inputs of the
+ * boxes1 / boxes2 row) with autograd's conventions (0.5 / 0.5 on max / min ties, inclusive clamp
+ * masks, CIoU's alpha constant). */
+int b200det_iou_method(const float *boxes1, long long s1n, long long s1m, const float *boxes2,
+                       long long s2n, long long s2m, long long n, long long m, int iou_type,
+                       int xywh, float *out, float *jac1, float *jac2, void *stream);
+
 /* ---- evaluation: the per-batch part of the VOC evaluator --------------------------------------- */
 /* compute_ious (tools/scripts.py:487-508): out[i*m + j] = IoU(a[i], b[j]) in float32 with the
  * reference's op order and no clamps (degenerate pairs give NaN / inf like NumPy).  a, b: device

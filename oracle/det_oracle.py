@@ -176,6 +176,17 @@ def box_iou(b1, b2, iou_type='IoU'):
     return iou - (p2 / c2 + pw2 / cw2 + ph2 / ch2)
 
 
+def iou_method(boxes1, boxes2, iou_type='IoU', box_type='xyxy'):
+    """IoUMethod.__call__ (losses.py:33-123) incl. the 'xywh' input option (:44-52, 2-D boxes)."""
+    assert box_type in ['xyxy', 'xywh']
+    if box_type == 'xywh':
+        boxes1 = torch.cat([boxes1[..., 0:2] - boxes1[..., 2:4] / 2,
+                            boxes1[..., 0:2] + boxes1[..., 2:4] / 2], dim=1)
+        boxes2 = torch.cat([boxes2[..., 0:2] - boxes2[..., 2:4] / 2,
+                            boxes2[..., 0:2] + boxes2[..., 2:4] / 2], dim=1)
+    return box_iou(boxes1, boxes2, iou_type)
+
+
 # ----------------------------------------------------------------------------------------
 # shared focal loss (losses.py:220-261 and :513-548)
 # ----------------------------------------------------------------------------------------

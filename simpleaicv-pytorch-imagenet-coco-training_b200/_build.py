@@ -27,6 +27,7 @@ SOURCES = {
     'queries.cu': [],
     'exchange.cu': [],
     'evaluate.cu': ['-fmad=false'],
+    'iou.cu': ['-fmad=false'],
 }
 
 

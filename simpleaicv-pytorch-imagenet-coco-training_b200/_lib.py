@@ -175,6 +175,10 @@ SIGNATURES = {
         ctypes.c_int, _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp
     ]),
+    'b200det_iou_method': (ctypes.c_int, [
+        _vp, ctypes.c_longlong, ctypes.c_longlong, _vp, ctypes.c_longlong, ctypes.c_longlong,
+        ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp
+    ]),
     'b200det_pair_ious': (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
     'b200det_voc_match': (ctypes.c_int, [
         _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp

@@ -32,7 +32,7 @@ import torch.nn as nn
 from . import _lib
 from . import geometry as _geom
 
-__all__ = ['RetinaLoss', 'FCOSLoss']
+__all__ = ['IoUMethod', 'RetinaLoss', 'FCOSLoss']
 
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
@@ -430,6 +430,93 @@ def _debug_assign(owner, preds, annotations, exact=True):
     if targets is not None:
         res['targets'] = to_image_major(targets, 6).view(batch, n_rows, 6)
     return res
+
+
+class _IoUFunction(torch.autograd.Function):
+    """out[n, m] = iou_type(boxes1 row n*s1[0] + m*s1[1], boxes2 row n*s2[0] + m*s2[1]); the kernel
+    also writes the Jacobians w.r.t. the inputs that require grad."""
+
+    @staticmethod
+    def forward(ctx, boxes1, boxes2, n, m, s1, s2, code, xywh):
+        device = boxes1.device
+        out = torch.empty((n, m), dtype=torch.float32, device=device)
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        jac1 = torch.empty((n, m, 4), dtype=torch.float32, device=device) if need1 else None
+        jac2 = torch.empty((n, m, 4), dtype=torch.float32, device=device) if need2 else None
+        with torch.cuda.device(device):
+            _lib.check(
+                _lib.load().b200det_iou_method(
+                    boxes1.data_ptr(), s1[0], s1[1], boxes2.data_ptr(), s2[0], s2[1], n, m, code,
+                    int(xywh), out.data_ptr(), jac1.data_ptr() if need1 else None,
+                    jac2.data_ptr() if need2 else None, _stream(device)), 'b200det_iou_method')
+        ctx.save_for_backward(*[j for j in (jac1, jac2) if j is not None])
+        ctx.need = (need1, need2)
+        ctx.shapes = (boxes1.shape, boxes2.shape)
+        ctx.bcast = (s1, s2)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = list(ctx.saved_tensors)
+        grads = [None, None]
+        g = grad_out.float().unsqueeze(-1)
+        for k in range(2):
+            if not ctx.need[k]:
+                continue
+            full = saved.pop(0) * g                      # [n, m, 4]
+            sn, sm = ctx.bcast[k]
+            if sn == 0:
+                full = full.sum(0, keepdim=True)
+            if sm == 0 and full.shape[1] != 1:
+                full = full.sum(1, keepdim=True)
+            grads[k] = full.reshape(ctx.shapes[k])
+        return (grads[0], grads[1], None, None, None, None, None, None)
+
+
+class IoUMethod:
+    """simpleAICV/detection/losses.py:28-123 on the GPU: IoU / GIoU / DIoU /
+    CIoU / EIoU between `boxes1` and `boxes2` ([..., 4], 'xyxy' or 'xywh'), float32 with the
+    reference's op order, differentiable w.r.t. both.  Same constructor, call signature and asserts.
+    Element-wise inputs and the assignment's [N,1,4] x [1,M,4] broadcast (losses.py:350-353) are
+    computed in place; other broadcasts are expanded first.  Like the reference's indexing
+    (`[:, 0]`, `torch.cat(dim=1)`), GIoU / CIoU and box_type 'xywh' need 2-D [N, 4] inputs.
+    CUDA tensors only; there is no fallback."""
+
+    _CODES = {'IoU': _lib.BOX_IOU, 'GIoU': _lib.BOX_GIOU, 'DIoU': _lib.BOX_DIOU,
+              'CIoU': _lib.BOX_CIOU, 'EIoU': _lib.BOX_EIOU}
+
+    def __init__(self):
+        pass
+
+    def __call__(self, boxes1, boxes2, iou_type='IoU', box_type='xyxy'):
+        assert iou_type in ['IoU', 'GIoU', 'DIoU', 'CIoU', 'EIoU'], 'wrong IoU type!'
+        assert box_type in ['xyxy', 'xywh'], 'wrong box_type type!'
+        _require_cuda(boxes1, 'boxes1')
+        _require_cuda(boxes2, 'boxes2')
+        if boxes1.shape[-1] != 4 or boxes2.shape[-1] != 4:
+            raise RuntimeError('boxes must be [..., 4]')
+        if (iou_type in ('GIoU', 'CIoU') or box_type == 'xywh') and \
+                (boxes1.dim() != 2 or boxes2.dim() != 2):
+            raise RuntimeError(f'{iou_type} / {box_type} need 2-D [N, 4] boxes, as in the reference '
+                               '(losses.py:46-52, 99-100, 118-120)')
+        boxes1, boxes2 = boxes1.float(), boxes2.float()
+        lead1, lead2 = tuple(boxes1.shape[:-1]), tuple(boxes2.shape[:-1])
+        out_shape = torch.broadcast_shapes(lead1, lead2)
+        if len(lead1) == 2 and len(lead2) == 2 and lead1[1] == 1 and lead2[0] == 1:
+            n, m, s1, s2 = lead1[0], lead2[1], (1, 0), (0, 1)        # [N,1,4] x [1,M,4]
+        elif len(lead1) == 2 and len(lead2) == 2 and lead1[0] == 1 and lead2[1] == 1:
+            n, m, s1, s2 = lead2[0], lead1[1], (0, 1), (1, 0)        # [1,M,4] x [N,1,4]
+        else:
+            if lead1 != out_shape:
+                boxes1 = boxes1.expand(out_shape + (4,))
+            if lead2 != out_shape:
+                boxes2 = boxes2.expand(out_shape + (4,))
+            n, m, s1, s2 = 1, 1, (1, 0), (1, 0)
+            for d in out_shape:
+                n *= d
+        out = _IoUFunction.apply(boxes1.contiguous(), boxes2.contiguous(), n, m, s1, s2,
+                                 self._CODES[iou_type], box_type == 'xywh')
+        return out.view(out_shape)
 
 
 class RetinaLoss(nn.Module):

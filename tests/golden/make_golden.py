@@ -372,6 +372,61 @@ def make_voc(path):
     np.savez_compressed(path, **out)
 
 
+def iou_method_boxes(seed=5, n=96):
+    """Box pairs for the IoUMethod fixtures: overlapping, disjoint, nested, identical (max / min
+    ties), shared edges, zero-area and inverted boxes."""
+    rng = np.random.RandomState(seed)
+    xy = rng.uniform(0, 200, size=(n, 2))
+    b1 = np.concatenate([xy, xy + rng.uniform(4, 120, size=(n, 2))], axis=1).astype(np.float32)
+    b2 = (b1 + rng.normal(0, 12, size=(n, 4))).astype(np.float32)
+    far = rng.uniform(300, 500, size=(n, 2))
+    b2[0:8] = np.concatenate([far, far + rng.uniform(4, 60, size=(n, 2))], axis=1)[0:8]   # disjoint
+    b2[8:12] = b1[8:12]                                                   # identical
+    b2[12:16, 0:2] = b1[12:16, 0:2]                                       # shared corner
+    b2[16:20] = b1[16:20] + np.array([10, 10, -10, -10], dtype=np.float32)  # nested
+    b2[20, 2] = b2[20, 0]                                                 # zero width
+    b1[21, 3] = b1[21, 1]                                                 # zero height
+    b2[22] = b2[22][[2, 3, 0, 1]]                                         # inverted
+    b1[23] = np.trunc(b1[23]); b2[23] = b1[23] + np.array([0, 0, 5, 0], dtype=np.float32)
+    return b1, b2
+
+
+def make_iou_method(path):
+    """IoUMethod (losses.py:28-123): values and autograd gradients w.r.t. both
+    inputs from the unmodified reference class, all IoU types x both box formats (2-D), and the
+    assignment's [N,1,4] x [1,M,4] broadcast for the types whose indexing allows it."""
+    L, _, _ = refload.load()
+    fn = L.IoUMethod()
+    b1, b2 = iou_method_boxes()
+    out = {'versions': versions(), 'b1': b1, 'b2': b2}
+    rng = np.random.RandomState(9)
+    up = rng.uniform(0.5, 1.5, size=b1.shape[0]).astype(np.float32)
+    out['upstream'] = up
+    # xywh inputs: the same boxes re-expressed (inverted / degenerate ones give w, h <= 0)
+    def to_xywh(b):
+        return np.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0],
+                         b[:, 3] - b[:, 1]], axis=1).astype(np.float32)
+    out['b1_xywh'], out['b2_xywh'] = to_xywh(b1), to_xywh(b2)
+    for box_type, (x1, x2) in (('xyxy', (b1, b2)), ('xywh', (out['b1_xywh'], out['b2_xywh']))):
+        for iou_type in IOU_TYPES:
+            t1 = torch.from_numpy(x1.copy()).requires_grad_(True)
+            t2 = torch.from_numpy(x2.copy()).requires_grad_(True)
+            v = fn(t1, t2, iou_type=iou_type, box_type=box_type)
+            (v * torch.from_numpy(up)).sum().backward()
+            out[f'{box_type}_{iou_type}'] = v.detach().numpy()
+            out[f'{box_type}_{iou_type}_g1'] = t1.grad.numpy()
+            out[f'{box_type}_{iou_type}_g2'] = t2.grad.numpy()
+    a, g = torch.from_numpy(b1[:40].copy()), torch.from_numpy(b2[:17].copy())
+    for iou_type in ('IoU', 'DIoU', 'EIoU'):
+        out[f'bcast_{iou_type}'] = fn(a.unsqueeze(1), g.unsqueeze(0), iou_type=iou_type).numpy()
+    a.requires_grad_(True)
+    g.requires_grad_(True)
+    w = torch.from_numpy(rng.uniform(0.5, 1.5, size=(40, 17)).astype(np.float32))
+    (fn(a.unsqueeze(1), g.unsqueeze(0), iou_type='DIoU') * w).sum().backward()
+    out['bcast_w'], out['bcast_DIoU_g1'], out['bcast_DIoU_g2'] = w.numpy(), a.grad.numpy(), g.grad.numpy()
+    np.savez_compressed(path, **out)
+
+
 def make_heads(path):
     """Head tail: the reference's RetinaClsHead (models/head.py:15-52) on a seeded
     feature map; the convolution output is captured with a hook, the head's own `.float()` +
@@ -406,6 +461,10 @@ if __name__ == '__main__':
         make_heads(os.path.join(HERE, 'head_tail.npz'))
         print('head_tail.npz', os.path.getsize(os.path.join(HERE, 'head_tail.npz')))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'iou':
+        make_iou_method(os.path.join(HERE, 'iou_method.npz'))
+        print('iou_method.npz', os.path.getsize(os.path.join(HERE, 'iou_method.npz')))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'voc':
         make_voc(os.path.join(HERE, 'voc_eval.npz'))
         print('voc_eval.npz', os.path.getsize(os.path.join(HERE, 'voc_eval.npz')))
@@ -425,5 +484,6 @@ if __name__ == '__main__':
     make_heads(os.path.join(HERE, 'head_tail.npz'))
     make_queries(os.path.join(HERE, 'queries.npz'))
     make_voc(os.path.join(HERE, 'voc_eval.npz'))
+    make_iou_method(os.path.join(HERE, 'iou_method.npz'))
     for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)))

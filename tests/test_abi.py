@@ -109,6 +109,9 @@ def test_drop_in_surface_matches_reference_signatures():
     assert fsig['box_loss_type'].default == 'CIoU'
     dsig = inspect.signature(fd.__dict__['RetinaFaceDecoder'].__init__).parameters
     assert dsig['min_score_threshold'].default == 0.3 and dsig['nms_threshold'].default == 0.3
+    isig = inspect.signature(losses.__dict__['IoUMethod'].__call__).parameters    # losses.py:33
+    assert list(isig) == ['self', 'boxes1', 'boxes2', 'iou_type', 'box_type']
+    assert isig['iou_type'].default == 'IoU' and isig['box_type'].default == 'xyxy'
     import torch
     assert isinstance(losses.RetinaLoss(), torch.nn.Module)      # train script calls .cuda() on it
 
