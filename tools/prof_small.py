@@ -39,5 +39,49 @@ for name, B, fcos in (('retina_b1', 1, False), ('retina_b16', 16, False), ('fcos
             prof = _lib.profile_stop()
         res[what] = {'wall_ms': round(wall, 4),
                      'kernels_ms': {k: round(ms * n / 50, 4) for k, (n, ms) in prof.items()}}
+    # the same calls replayed from CUDA graphs (no Python, no launch gaps): no-grad loss forward and
+    # the training forward + backward (tests/test_gpu_graphs.py checks the replays bit for bit)
+    req = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+
+    def fwd():
+        with torch.no_grad():
+            return crit(preds, ann)
+
+    def train():
+        sum(crit(req, ann).values()).backward()
+
+    def cleared():
+        for grp in req:
+            for t in grp:
+                t.grad = None
+        train()
+
+    for what, fn in (('loss', fwd), ('loss_fwd_bwd', train)):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for grp in req:
+            for t in grp:
+                t.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        row = res.setdefault(what, {})
+        for key, call in (('eager_ms', fwd if what == 'loss' else cleared), ('graph_replay_ms', graph.replay)):
+            for _ in range(10):
+                call()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(100):
+                call()
+            b.record()
+            torch.cuda.synchronize()
+            row[key] = round(a.elapsed_time(b) / 100, 4)
+        del graph
     out[name] = res
 print(json.dumps(out, indent=1))
