@@ -35,54 +35,6 @@ constexpr int kAssignWarps = kAssignThreads / 32;
 constexpr int kTileW = 8, kTileH = 4;   // locations per warp: 8 wide x 4 high
 constexpr int kSparseThreads = 256;
 
-// ---------------------------------------------------------------------------------------
-// GT staging: global [G,5] float rows -> shared memory, via TMA bulk copy when aligned.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void stage_rows_begin(float *dst, const float *src, int n_floats,
-                                                 uint64_t *mbar, bool bulk) {
-    if (bulk) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t bytes = (uint32_t)n_floats * 4u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                             smem_u32(mbar)),
-                         "r"(bytes)
-                         : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                    "r"(smem_u32(dst)),
-                "l"(src), "r"(bytes), "r"(smem_u32(mbar))
-                : "memory");
-        }
-    } else {
-        for (int i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-}
-
-__device__ __forceinline__ void stage_rows_wait(uint64_t *mbar, bool bulk) {
-    __syncthreads();  // mbarrier init visible to all waiters / plain stores visible
-    if (bulk) {
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
-                "selp.u32 %0, 1, 0, p;\n"
-                "}\n"
-                : "=r"(done)
-                : "r"(smem_u32(mbar))
-                : "memory");
-        }
-    }
-}
-
 // Shared-memory carve-up (dynamic): raw rows, then the compacted candidate arrays.
 struct GtSmem {
     float *raw;    // [G*5]

@@ -192,4 +192,55 @@ __device__ __forceinline__ int x86_f2i(float v) {
     return __float2int_rz(v);
 }
 
+// ---------------------------------------------------------------------------------------
+// Staging of a contiguous float range, global -> shared memory, via one TMA bulk copy
+// (cp.async.bulk + mbarrier; needs 16-byte aligned ends) or plain loads.  Users: the annotation rows
+// of the assignment kernels, the raw class tiles of score_argmax_raw_kernel.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void stage_rows_begin(float *dst, const float *src, int n_floats,
+                                                 uint64_t *mbar, bool bulk) {
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bytes = (uint32_t)n_floats * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                             smem_u32(mbar)),
+                         "r"(bytes)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(smem_u32(dst)),
+                "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                : "memory");
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+
+__device__ __forceinline__ void stage_rows_wait(uint64_t *mbar, bool bulk) {
+    __syncthreads();  // mbarrier init visible to all waiters / plain stores visible
+    if (bulk) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(smem_u32(mbar))
+                : "memory");
+        }
+    }
+}
+
+
 }  // namespace b200det

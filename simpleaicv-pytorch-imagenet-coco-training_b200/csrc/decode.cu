@@ -53,6 +53,7 @@ struct ArgmaxArgs {
     int t2, t2_shift;    // threads cooperating on one row in phase 2 (power of two <= 32)
     float min_score;
     int has_ctr;
+    int raw_bulk;        // raw-tile kernel: stage the tile with one TMA bulk copy
     // fused evaluation step (b200det_eval_step): the same sweep also accumulates the label-free
     // focal sum, so cls is read ONCE for loss + decode
     float alpha, gamma;
@@ -70,6 +71,12 @@ __global__ void __launch_bounds__(kArgThreads)
         if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
     const long long row0 = (long long)(blockIdx.x - a.block_off[l]) * a.rows_per_block;
     const int n_rows = (int)min((long long)a.rows_per_block, a.rows[l] - row0);
+    // FCOS centre-ness of the row this thread finishes first: requested with the tile instead of as
+    // a dependent load on the CTA's tail
+    const int r_first = threadIdx.x >> a.t2_shift;
+    float ctr_first = 0.f;
+    if (a.has_ctr && (threadIdx.x & (a.t2 - 1)) == 0 && r_first < n_rows)
+        ctr_first = __ldg(static_cast<const float *>(a.ctr.p[l]) + row0 + r_first);
     const int n_units = n_rows * a.units_per_row;
     const float *src = static_cast<const float *>(a.cls.p[l]) + row0 * a.C;
     float *sval = reinterpret_cast<float *>(arg_smem);
@@ -170,7 +177,8 @@ __global__ void __launch_bounds__(kArgThreads)
             float score = best;
             if (a.has_ctr) {
                 // np.sqrt(cls_scores * center_preds)  (decode.py:338): one mul, one IEEE sqrt
-                const float c = __ldg(static_cast<const float *>(a.ctr.p[l]) + row);
+                const float c = r == r_first ? ctr_first
+                                             : __ldg(static_cast<const float *>(a.ctr.p[l]) + row);
                 score = __fsqrt_rn(__fmul_rn(best, c));
             }
             const long long lm = a.row_base[l] + row;
@@ -300,22 +308,41 @@ __global__ void __launch_bounds__(kArgThreads)
     const int n_vec = n_floats >> 2;
     const float *src = static_cast<const float *>(a.cls.p[l]) + row0 * a.C;   // 16-byte aligned
 
-    float4 v[kArgLoadsVec];
+    // One TMA bulk copy global -> shared per tile (every tile but a level's last holds a multiple of
+    // 4 floats).  The register path it replaces (LDG.128 -> STS.128) sent every byte through the
+    // L1 / shared-memory data pipe three times (load, store, scan): ncu showed that pipe at 79 % and
+    // DRAM at 62 % (profiles/r01_cfg4_sweeps.txt); the bulk copy bypasses it twice.
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ float sctr[kArgThreads];
+    // FCOS centre-ness of the tile's rows: requested now, together with the tile -- as a dependent
+    // load at the end of each row pass it put a DRAM round trip on every CTA's critical path
+    if (a.has_ctr && (int)threadIdx.x < n_rows)
+        sctr[threadIdx.x] = __ldg(static_cast<const float *>(a.ctr.p[l]) + row0 + threadIdx.x);
+    const bool bulk = a.raw_bulk && (n_floats & 3) == 0;
+    if (bulk) {
+        stage_rows_begin(tile, src, n_floats, &mbar, true);
+        stage_rows_wait(&mbar, true);
+    } else {
+        // a level's last tile when it does not hold a multiple of 4 floats (or the A/B knob)
+        for (int u0 = 0; u0 < n_vec; u0 += kArgLoadsVec * kArgThreads) {
+            float4 v[kArgLoadsVec];
 #pragma unroll
-    for (int k = 0; k < kArgLoadsVec; ++k) {
-        const int u = k * kArgThreads + threadIdx.x;
-        if (u < n_vec) v[k] = __ldcs(reinterpret_cast<const float4 *>(src) + u);
-    }
+            for (int k = 0; k < kArgLoadsVec; ++k) {
+                const int u = u0 + k * kArgThreads + threadIdx.x;
+                if (u < n_vec) v[k] = __ldcs(reinterpret_cast<const float4 *>(src) + u);
+            }
 #pragma unroll
-    for (int k = 0; k < kArgLoadsVec; ++k) {
-        const int u = k * kArgThreads + threadIdx.x;
-        if (u < n_vec) reinterpret_cast<float4 *>(tile)[u] = v[k];
+            for (int k = 0; k < kArgLoadsVec; ++k) {
+                const int u = u0 + k * kArgThreads + threadIdx.x;
+                if (u < n_vec) reinterpret_cast<float4 *>(tile)[u] = v[k];
+            }
+        }
+        if (threadIdx.x < (n_floats & 3)) {
+            const int i = (n_vec << 2) + threadIdx.x;
+            tile[i] = __ldcs(src + i);
+        }
+        __syncthreads();
     }
-    if (threadIdx.x < (n_floats & 3)) {   // tail of the last tile of a level
-        const int i = (n_vec << 2) + threadIdx.x;
-        tile[i] = __ldcs(src + i);
-    }
-    __syncthreads();
 
     const int j = threadIdx.x & (a.t2 - 1);
     for (int r = threadIdx.x >> a.t2_shift; r < a.rows_per_block; r += kArgThreads >> a.t2_shift) {
@@ -323,13 +350,23 @@ __global__ void __launch_bounds__(kArgThreads)
         float best = -__int_as_float(0x7f800000);
         int best_c = 0x7fffffff;
         if (live) {
-            const float *row = tile + r * a.C;
-            for (int c = j; c < a.C; c += a.t2) {
-                const float x = row[c];
-                if (x > best) {  // strict: first maximum in class order (np.argmax)
-                    best = x;
-                    best_c = c;
-                }
+            // strict '>' in class order: first maximum (np.argmax).  Four independent loads per
+            // iteration off a walking pointer: ~5 instructions per element (the plain
+            // `for c: row[c]` loop was 20 and made this kernel issue-bound at 0.78 of the HBM peak,
+            // profiles/r01_cfg4_sweeps.txt).
+            const int T = a.t2, C = a.C;
+            const float *p = tile + r * C + j;
+            int c = j;
+            for (; c + 3 * T < C; c += 4 * T, p += 4 * T) {
+                const float x0 = p[0], x1 = p[T], x2 = p[2 * T], x3 = p[3 * T];
+                if (x0 > best) best = x0, best_c = c;
+                if (x1 > best) best = x1, best_c = c + T;
+                if (x2 > best) best = x2, best_c = c + 2 * T;
+                if (x3 > best) best = x3, best_c = c + 3 * T;
+            }
+            for (; c < C; c += T, p += T) {
+                const float x = *p;
+                if (x > best) best = x, best_c = c;
             }
         }
         for (int o = a.t2 >> 1; o > 0; o >>= 1) {
@@ -343,10 +380,7 @@ __global__ void __launch_bounds__(kArgThreads)
         if (live && j == 0) {
             const long long row_g = row0 + r;
             float score = best;
-            if (a.has_ctr) {
-                const float c = __ldg(static_cast<const float *>(a.ctr.p[l]) + row_g);
-                score = __fsqrt_rn(__fmul_rn(best, c));
-            }
+            if (a.has_ctr) score = __fsqrt_rn(__fmul_rn(best, sctr[r]));
             const long long lm = a.row_base[l] + row_g;
             keys[lm] = (score > a.min_score) ? flip_key(score) : 0u;
             classes[lm] = best_c;
@@ -1116,6 +1150,8 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     a.C = g.num_classes;
     a.min_score = min_score;
     a.has_ctr = ctr != nullptr;
+    static const bool raw_no_bulk = getenv("B200DET_RAW_NO_BULK") != nullptr;   // A/B knob
+    a.raw_bulk = raw_no_bulk ? 0 : 1;
     a.alpha = alpha;
     a.gamma = gamma;
     a.focal_slots = focal_slots;
@@ -1147,10 +1183,20 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
         if (R * units > budget) return B200DET_ERANGE;   // more than 5120 classes
         a.pitch = units | 1;
     } else {
-        // raw tile: R rows, R % 4 == 0 so that every tile starts 16-byte aligned
-        R = (int)(((long long)budget * 4 / g.num_classes) & ~3ll);
+        // raw tile: R rows, R % 4 == 0 so that every tile starts 16-byte aligned; staged by one TMA
+        // bulk copy (no register budget): one pass of the row scan (kArgThreads / t2 rows) within
+        // 40 KB of shared memory, e.g. 16 rows = 23 KB for C = 365
+        int t2 = 1, t2s = 0;
+        while (t2 < 32 && (units + t2 - 1) / t2 > 32) {
+            t2 <<= 1;
+            ++t2s;
+        }
+        R = kArgThreads >> t2s;
+        const int fit = (int)(40 * 1024 / ((long long)g.num_classes * 4));
+        if (R > fit) R = fit;
+        R &= ~3;
         if (R < 4) R = 4;
-        if ((long long)R * g.num_classes > (long long)budget * 4) return B200DET_ERANGE;  // > 1280 classes
+        if ((long long)R * g.num_classes * 4 > 47 * 1024) return B200DET_ERANGE;  // > ~3000 classes
         a.pitch = g.num_classes;
     }
     a.rows_per_block = R;
@@ -1161,6 +1207,8 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
             t2 <<= 1;
             ++t2s;
         }
+        // (a whole warp per row -- conflict-free LDS for any row pitch -- was measured slower for
+        // C = 365: 0.24 vs 0.18 ms at BASELINE configs[3]; 16 lanes x 2 rows it stays)
         a.t2 = t2;
         a.t2_shift = t2s;
     }

@@ -284,17 +284,56 @@ __device__ __noinline__ SlowUnit slow_unit4(float4 v, int tgt, float alpha, floa
     return r;
 }
 
+// A 4-float unit that straddles two rows (class counts that are not a multiple of 4, XROW below):
+// the first 4 - nx elements are classes c0.. of a row labelled lab0, the last nx elements are classes
+// 0.. of the next row, labelled lab1.  One unit in C / 4; exact-form path, out of line.
+template <bool GRAD>
+__device__ __noinline__ SlowUnit cross_unit4(float4 v, int lab0, int tgt0, int lab1, int nx,
+                                             float alpha, float gamma, bool gamma2) {
+    SlowUnit r;
+    r.pos = r.neg = 0.f;
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool first = e < 4 - nx;
+        const int lab = first ? lab0 : lab1;
+        const bool is_target = first ? (lab0 > 0 && tgt0 == e) : (lab1 - 1 == e - (4 - nx));
+        if (lab >= 0) slow_element<GRAD>(x[e], is_target, alpha, gamma, gamma2, r.pos, r.neg, g[e]);
+    }
+    r.g = make_float4(g[0], g[1], g[2], g[3]);
+    return r;
+}
+
 // Label-aware sweep: used when gradients are requested (one read of cls, one write of its
 // gradient already scaled by weight / positives), or when the caller did not let the
 // assignment kernel apply the corrections.
+// XROW (VEC == 4 only): the class count is not a multiple of 4 (Objects365: 365), but every level
+// holds a multiple of 4 floats and is 16-byte aligned, so the level is still swept as a flat stream
+// of 128-bit units; a unit's (row, first class) come from its element index, and the one unit in
+// C / 4 that straddles two rows takes cross_unit4.  The scalar kernel (VEC == 1) this replaces ran
+// 75 instructions per element, issue-bound at half the HBM peak (profiles/r01_cfg4_sweeps.txt).
 #ifndef B200DET_FOCAL_GRAD_MINB
 #define B200DET_FOCAL_GRAD_MINB 6
 #endif
-template <int VEC, bool GRAD, bool GAMMA2>
-__global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
+#ifndef B200DET_FOCAL_XROW_MINB
+#define B200DET_FOCAL_XROW_MINB 5
+#endif
+template <int VEC, bool GRAD, bool GAMMA2, bool XROW = false>
+__global__ void __launch_bounds__(kFocalThreads, XROW ? B200DET_FOCAL_XROW_MINB : B200DET_FOCAL_GRAD_MINB)
     focal_kernel(FocalArgs a, const int *__restrict__ labels, long long *__restrict__ partials) {
+    static_assert(!XROW || VEC == 4, "XROW sweeps 128-bit units");
     const int l = chunk_level(a);
     const long long chunk_start = (long long)(blockIdx.x - a.chunk_off[l]) * kChunkUnits;
+    // XROW: row and class of the chunk's first element (one 64-bit division per CTA); units_per_row
+    // and magic are those of the divisor C here
+    unsigned row_c = 0, rem_c = 0;
+    if (XROW) {
+        const unsigned long long e_chunk = (unsigned long long)chunk_start * 4ull;
+        const unsigned long long q = e_chunk / (unsigned)a.units_per_row;
+        row_c = (unsigned)q;
+        rem_c = (unsigned)(e_chunk - q * (unsigned)a.units_per_row);
+    }
     const long long n_units = a.units[l];
     const float *__restrict__ src = static_cast<const float *>(a.cls.p[l]);
     float *__restrict__ dst = GRAD ? static_cast<float *>(a.grad.p[l]) : nullptr;
@@ -323,10 +362,18 @@ __global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) v[k][e] = 0.f;
             if (u < n_units) {
-                const unsigned uu = (unsigned)u;
-                const unsigned row =
-                    a.magic_shift < 0 ? uu : (__umulhi(uu, a.magic) >> a.magic_shift);
-                const int c0 = (int)(uu - row * (unsigned)a.units_per_row) * VEC;
+                unsigned row;
+                int c0;
+                if (XROW) {
+                    const unsigned el = 4u * (unsigned)(u - chunk_start) + rem_c;
+                    const unsigned r_off = __umulhi(el, a.magic) >> a.magic_shift;
+                    c0 = (int)(el - r_off * (unsigned)a.units_per_row);
+                    row = row_c + r_off;
+                } else {
+                    const unsigned uu = (unsigned)u;
+                    row = a.magic_shift < 0 ? uu : (__umulhi(uu, a.magic) >> a.magic_shift);
+                    c0 = (int)(uu - row * (unsigned)a.units_per_row) * VEC;
+                }
                 load_unit<VEC>(src, u, v[k]);
                 const int lb = __ldg(lab_l + row);
                 lab[k] = lb;
@@ -339,7 +386,38 @@ __global__ void __launch_bounds__(kFocalThreads, B200DET_FOCAL_GRAD_MINB)
             float g[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) g[e] = 0.f;
-            if (lab[k] >= 0) {
+            // XROW: a warp's 128 elements meet a row boundary in a third of its iterations, so the
+            // straddling unit (nx > 0 of its elements belong to the next row) stays on the fast path
+            // whenever it can: both rows valid and no target class inside -> a plain background unit;
+            // both ignored -> skipped; the rest (next to a positive / an ignored row) is exact-form.
+            // The next row's label is read here, not in the load phase (registers): it is the label
+            // the neighbouring lanes have just loaded, an L1 hit.
+            int nx = 0, lb1 = -1;
+            bool cross_slow = false;
+            if (XROW) {
+                nx = (lab[k] - 1 - tgt[k]) + 4 - a.units_per_row;   // c0 + 4 - C
+                if (nx > 0) {
+                    const unsigned el = 4u * (unsigned)(u - chunk_start) + rem_c;
+                    lb1 = __ldg(lab_l + row_c + (__umulhi(el, a.magic) >> a.magic_shift) + 1);
+                    const int lb = lab[k];
+                    const bool t0 = lb > 0 && (unsigned)tgt[k] < 4u;
+                    const bool t1 = lb1 > 0 && lb1 - 1 < nx;
+                    if (lb >= 0 && lb1 >= 0 && !t0 && !t1) {
+                        lab[k] = 0;
+                        tgt[k] = -1;
+                    } else if (lb >= 0 || lb1 >= 0) {
+                        cross_slow = true;
+                    }
+                }
+            }
+            if (XROW && cross_slow) {
+                const SlowUnit r = cross_unit4<GRAD>(
+                    make_float4(v[k][0], v[k][1 % VEC], v[k][2 % VEC], v[k][3 % VEC]), lab[k], tgt[k],
+                    lb1, nx, a.alpha, a.gamma, GAMMA2);
+                acc_pos += r.pos;
+                acc_neg += r.neg;
+                g[0] = r.g.x, g[1 % VEC] = r.g.y, g[2 % VEC] = r.g.z, g[3 % VEC] = r.g.w;
+            } else if (lab[k] >= 0) {
                 float x[VEC];
                 float mx = 0.f;
 #pragma unroll
@@ -590,6 +668,22 @@ extern "C" size_t b200det_loss_workspace_bytes(const b200det_geometry *geo) {
     return loss_ws_layout(g).total;
 }
 
+static cudaError_t launch_focal_xrow(const FocalArgs &a, int chunks, bool grad, bool gamma2,
+                                     const int *labels, long long *partials, cudaStream_t st) {
+    if (grad) {
+        if (gamma2)
+            focal_kernel<4, true, true, true><<<chunks, kFocalThreads, 0, st>>>(a, labels, partials);
+        else
+            focal_kernel<4, true, false, true><<<chunks, kFocalThreads, 0, st>>>(a, labels, partials);
+    } else {
+        if (gamma2)
+            focal_kernel<4, false, true, true><<<chunks, kFocalThreads, 0, st>>>(a, labels, partials);
+        else
+            focal_kernel<4, false, false, true><<<chunks, kFocalThreads, 0, st>>>(a, labels, partials);
+    }
+    return cudaGetLastError();
+}
+
 template <int VEC>
 static cudaError_t launch_focal(const FocalArgs &a, int chunks, bool grad, bool gamma2,
                                 const int *labels, long long *partials, cudaStream_t st) {
@@ -623,14 +717,22 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     int vec = focal_vec(g);
     // the label-free sweep has no notion of rows: it can use 128-bit loads for ANY class count as
     // long as every level holds a multiple of 4 floats and is 16-byte aligned (e.g. C = 365)
-    bool flat4 = false;
-    if (vec == 1 && labels == nullptr) {
+    // ... and so can the label-aware sweep (xrow): a unit's row comes from its element index
+    bool flat4 = false, xrow = false;
+    if (vec == 1 && g.num_classes >= 4 && g.num_classes < 16384) {
         flat4 = true;
         for (int l = 0; l < g.n_levels; ++l) {
             if (((long long)g.batch * g.rows[l] * g.num_classes) & 3) flat4 = false;
             if (cls[l] && (reinterpret_cast<uintptr_t>(cls[l]) & 15)) flat4 = false;
+            if (cls_grad && cls_grad[l] && (reinterpret_cast<uintptr_t>(cls_grad[l]) & 15))
+                flat4 = false;
         }
-        if (flat4) vec = 4;
+        const bool no_xrow = getenv("B200DET_FOCAL_NO_XROW") != nullptr;   // tests compare both
+        if (labels != nullptr) {
+            xrow = flat4 && !no_xrow;
+            flat4 = false;
+        }
+        if (flat4 || xrow) vec = 4;
     }
     const uintptr_t amask = vec == 4 ? 15 : 3;
     for (int l = 0; l < kMaxLevels; ++l) {
@@ -649,7 +751,7 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
             a.grad.p[l] = cls_grad[l];
         }
     }
-    a.units_per_row = flat4 ? 1 : g.num_classes / vec;
+    a.units_per_row = flat4 ? 1 : (xrow ? g.num_classes : g.num_classes / vec);
     // row = u / d for u < 2^31 by multiply-high: s = ceil(log2 d), m = floor(2^(31+s)/d) + 1,
     // row = umulhi(u, m) >> (s - 1)   (Granlund-Montgomery, 31-bit dividends)
     if (a.units_per_row == 1) {
@@ -668,7 +770,7 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
     a.sums = sums;
     int chunks = 0;
     for (int l = 0; l < g.n_levels; ++l) {
-        a.units[l] = flat4 ? (long long)g.batch * g.rows[l] * g.num_classes / 4
+        a.units[l] = (flat4 || xrow) ? (long long)g.batch * g.rows[l] * g.num_classes / 4
                            : (long long)g.batch * g.rows[l] * a.units_per_row;
         if (a.units[l] >= (1ll << 31)) return B200DET_ERANGE;
         a.row_base[l] = (long long)g.batch * g.off[l];
@@ -697,6 +799,9 @@ extern "C" int b200det_focal_loss(const b200det_geometry *geo, const void *const
             else focal_all_kernel<1, false><<<chunks, kFocalThreads, 0, st>>>(a, partials);
         }
         e = cudaGetLastError();
+    } else if (xrow) {
+        e = launch_focal_xrow(a, chunks, cls_grad != nullptr, gamma2, labels, partials,
+                              (cudaStream_t)stream);
     } else {
         e = vec == 4 ? launch_focal<4>(a, chunks, cls_grad != nullptr, gamma2, labels, partials,
                                        (cudaStream_t)stream)

@@ -199,3 +199,61 @@ def test_fuzz_fcos(seed):
         G.assert_bit_equal(b1, b0, 'fused boxes')
         if ref['num_pos'] > 0:
             assert_close(loss_values(loss, keys), want, LOSS_RTOL, 'fused loss')
+
+
+@pytest.mark.parametrize('kind', ['retina', 'fcos'])
+@pytest.mark.parametrize('C', [5, 7, 13, 91, 365])
+def test_training_sweep_class_counts_not_multiple_of_4(kind, C, monkeypatch):
+    """Class counts that are not a multiple of 4 on levels that hold a multiple of 4 floats: the
+    label-aware sweep reads 128-bit units that straddle rows (focal.cu XROW).  Loss values and
+    gradients against the oracle's autograd, and against the scalar kernel it replaces; many
+    positives and (Retina) ignored rows so that target classes and row boundaries meet inside units."""
+    rng = np.random.RandomState(C)
+    shapes, strides = [(12, 8), (6, 4), (2, 2)], [8., 16., 32.]
+    B = 3
+    gen = torch.Generator().manual_seed(C)
+    if kind == 'retina':
+        kw = dict(areas=[[32, 32], [64, 64], [128, 128]], ratios=[0.5, 1., 2.], scales=[1., 1.5],
+                  strides=strides)
+        cls = [torch.sigmoid(torch.randn((B, h, w, 6, C), generator=gen) - 2.0) for h, w in shapes]
+        reg = [torch.randn((B, h, w, 6, 4), generator=gen) * 0.2 for h, w in shapes]
+        preds = [cls, reg]
+        crit = losses.RetinaLoss(**kw, box_loss_type='SmoothL1')
+        keys = ['cls_loss', 'reg_loss']
+    else:
+        kw = dict(strides=strides, mi=[[-1, 64], [64, 128], [128, 100000]])
+        cls = [torch.sigmoid(torch.randn((B, h, w, C), generator=gen) - 2.0) for h, w in shapes]
+        reg = [torch.randn((B, h, w, 4), generator=gen) * 0.3 + math.log(s) for (h, w), s in zip(shapes, strides)]
+        ctr = [torch.sigmoid(torch.randn((B, h, w, 1), generator=gen)) for h, w in shapes]
+        preds = [cls, reg, ctr]
+        crit = losses.FCOSLoss(**kw)
+        keys = ['cls_loss', 'reg_loss', 'center_ness_loss']
+    for t in cls:                     # some probabilities outside the clamp and above the fast range
+        flat = t.view(-1)
+        idx = torch.from_numpy(rng.randint(0, flat.numel(), size=40))
+        flat[idx[:10]] = 0.
+        flat[idx[10:20]] = 1.
+        flat[idx[20:]] = 0.6
+    ann = synth.make_annotations(B, 12, 96, C, seed=C + 1)
+    ann[..., 1] *= 64 / 96.
+    ann[..., 3] = torch.where(ann[..., 4] >= 0, torch.maximum(ann[..., 3] * (64 / 96.), ann[..., 1] + 1),
+                              ann[..., 3])
+    p_ref = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+    ref = (O.retina_loss(p_ref, ann, **kw, box_loss_type='SmoothL1') if kind == 'retina'
+           else O.fcos_loss(p_ref, ann, **kw))
+    assert ref['num_pos'] > 0
+    sum(ref[k] for k in keys).backward()
+    want = [ref[k].item() for k in keys]
+    results = []
+    for scalar in (False, True):
+        if scalar:
+            monkeypatch.setenv('B200DET_FOCAL_NO_XROW', '1')
+        p = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(preds)]
+        d = crit(p, ann.cuda())
+        assert_close(loss_values(d, keys), want, LOSS_RTOL, f'{kind} C={C} scalar={scalar}')
+        sum(d[k] for k in keys).backward()
+        for i in range(len(shapes)):
+            grads_close(p[0][i].grad, p_ref[0][i].grad, f'cls grad level {i} scalar={scalar}')
+        results.append([t.grad.clone() for t in p[0]])
+    for a, b in zip(*results):
+        grads_close(a, b, 'XROW vs scalar kernel')

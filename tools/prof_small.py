@@ -11,16 +11,19 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 from b200det import synth, losses, decode, _lib  # noqa: E402
 
 out = {}
-for name, B, fcos in (('retina_b1', 1, False), ('retina_b16', 16, False), ('fcos_b16', 16, True)):
+for name, B, fcos, S, C, G in (('retina_b1', 1, False, 800, 80, 100),
+                               ('retina_b16', 16, False, 800, 80, 100),
+                               ('fcos_b16', 16, True, 800, 80, 100),
+                               ('fcos_1024_c365_b32', 32, True, 1024, 365, 200)):
     if fcos:
-        preds = synth.make_fcos_preds(B, 800, 80, seed=1, device='cuda')
+        preds = synth.make_fcos_preds(B, S, C, seed=1, device='cuda')
         crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
         dec = decode.FCOSDecoder(strides=synth.STRIDES)
     else:
-        preds = synth.make_retina_preds(B, 800, 80, seed=1, device='cuda')
+        preds = synth.make_retina_preds(B, S, C, seed=1, device='cuda')
         crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
         dec = decode.RetinaDecoder(**synth.RETINA_KW)
-    ann = synth.make_annotations(B, 100, 800, 80, seed=2).cuda()
+    ann = synth.make_annotations(B, G, S, C, seed=2).cuda()
     res = {}
     for what, fn in (('decode', lambda: dec(preds)), ('loss', lambda: crit(preds, ann))):
         with torch.no_grad():
