@@ -348,7 +348,9 @@ __global__ void __launch_bounds__(kFocalThreads, XROW ? B200DET_FOCAL_XROW_MINB 
 
     float acc_neg = 0.f, acc_pos = 0.f;
     float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
+    // XROW: one copy of the batch body (the second copy made the kernel 95 KB of code and
+    // instruction-fetch stalls its top stall reason, profiles/r01_cfg4_sweeps.txt)
+#pragma unroll(XROW ? 1 : kFocalBatches)
     for (int bt = 0; bt < kFocalBatches; ++bt) {
         const long long u0 = chunk_start + (long long)bt * kFocalThreads * kFocalUnroll + threadIdx.x;
         float v[kFocalUnroll][VEC];
@@ -410,6 +412,18 @@ __global__ void __launch_bounds__(kFocalThreads, XROW ? B200DET_FOCAL_XROW_MINB 
                     }
                 }
             }
+            // XROW: ONE out-of-line exact-form function for straddling and ordinary units (code size)
+            if (XROW && !cross_slow && lab[k] >= 0) {
+                float mx = 0.f;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) mx = fmaxf(mx, fmax_nan(v[k][e], kClampLo));
+                const bool has_target = lab[k] > 0 && (unsigned)tgt[k] < (unsigned)VEC;
+                if (!(GAMMA2 && !has_target && mx <= kFastMax)) {
+                    cross_slow = true;
+                    nx = 0;
+                    if (!has_target) tgt[k] = -1;
+                }
+            }
             if (XROW && cross_slow) {
                 const SlowUnit r = cross_unit4<GRAD>(
                     make_float4(v[k][0], v[k][1 % VEC], v[k][2 % VEC], v[k][3 % VEC]), lab[k], tgt[k],
@@ -426,7 +440,7 @@ __global__ void __launch_bounds__(kFocalThreads, XROW ? B200DET_FOCAL_XROW_MINB 
                     mx = fmaxf(mx, x[e]);
                 }
                 const bool has_target = lab[k] > 0 && (unsigned)tgt[k] < (unsigned)VEC;
-                if (GAMMA2 && !has_target && mx <= kFastMax) {
+                if (XROW || (GAMMA2 && !has_target && mx <= kFastMax)) {   // XROW: decided above
                     if (VEC == 4) {
                         // packed FP32 (FFMA2): two elements per instruction
 #pragma unroll
