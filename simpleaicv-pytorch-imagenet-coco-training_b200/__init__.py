@@ -11,7 +11,7 @@ The numerics run in hand-written CUDA kernels (csrc/*.cu) behind a C ABI (includ
 loaded with ctypes; PyTorch only provides device memory, streams and torch.distributed.
 """
 from . import _build, _lib, geometry  # noqa: F401
-from . import losses, decode, fused, heads, evaluation  # noqa: F401
+from . import losses, decode, fused, heads, evaluation, anchor  # noqa: F401
 from .losses import RetinaLoss, FCOSLoss  # noqa: F401
 from .decode import RetinaDecoder, FCOSDecoder  # noqa: F401
 
