@@ -493,6 +493,8 @@ class IoUMethod:
         assert box_type in ['xyxy', 'xywh'], 'wrong box_type type!'
         _require_cuda(boxes1, 'boxes1')
         _require_cuda(boxes2, 'boxes2')
+        if boxes1.device != boxes2.device:
+            raise RuntimeError('boxes1 and boxes2 must be on the same CUDA device')
         if boxes1.shape[-1] != 4 or boxes2.shape[-1] != 4:
             raise RuntimeError('boxes must be [..., 4]')
         if (iou_type in ('GIoU', 'CIoU') or box_type == 'xywh') and \
