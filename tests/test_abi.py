@@ -155,3 +155,25 @@ def test_peer_exchange_needs_a_process_group():
     with pytest.raises(RuntimeError):
         peer.PeerExchange()
     assert ctypes.sizeof(_lib.PeerExchange) == 4 + 4 + 8 + 8 + 8 * _lib.MAX_PEERS
+
+
+def test_new_modules_have_no_cpu_path():
+    """anchor / evaluation / IoUMethod fail loudly without a CUDA device or with CPU tensors (the
+    product never falls back to the oracle or to torch-CPU arithmetic)."""
+    import numpy as np
+    import torch
+    from b200det import anchor, evaluation, losses
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    with pytest.raises(RuntimeError):
+        anchor.RetinaAnchors()([[4, 4], [2, 2], [1, 1], [1, 1], [1, 1]])
+    with pytest.raises(RuntimeError):
+        anchor.FCOSPositions()([[4, 4]])
+    boxes = np.array([[0, 0, 10, 10]], dtype=np.float32)
+    with pytest.raises(RuntimeError):
+        evaluation.compute_ious(boxes, boxes)
+    with pytest.raises(RuntimeError):
+        evaluation.voc_map([[boxes, np.zeros(1, np.float32), np.ones(1, np.float32)]],
+                           [[boxes, np.zeros(1, np.float32)]], [0.5], 1)
+    with pytest.raises(RuntimeError):
+        losses.IoUMethod()(torch.from_numpy(boxes), torch.from_numpy(boxes))
