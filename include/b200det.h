@@ -238,9 +238,10 @@ int b200det_scale_levels(void *const *ptrs, const long long *counts, int n_level
 int b200det_scale_f32(float *x, long long n, const float *scale_dev, void *stream);
 
 /* ---- decode ------------------------------------------------------------------------- */
-/* scratch for b200det_select_decode_nms / b200det_decode (per-image global histograms, counters
- * and candidate lists of the multi-CTA selection front end).  Optional: with workspace == NULL
- * the whole selection runs in one CTA per image (slower for small batches). */
+/* scratch for b200det_select_decode_nms / b200det_decode.  Since ABI-compatible revision r02 the
+ * selection keeps its per-image histograms and candidate lists in (distributed) shared memory of a
+ * thread-block cluster; the workspace is accepted and not touched (returns a token 256 bytes;
+ * 0 = bad geometry / topn).  workspace == NULL is allowed. */
 size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, int topn);
 
 /*
@@ -257,7 +258,8 @@ int b200det_score_argmax(const b200det_geometry *geo, const void *const *cls,
                          int32_t *classes, void *stream);
 
 /*
- * Global top-n per image (radix select + bitonic sort), box decode, NMS, max_object_num cap.
+ * Global top-n per image (histogram select + placement by histogram rank), box decode, NMS,
+ * max_object_num cap: ONE launch, a cluster of 1-8 CTAs per image.
  * Replaces DecodeMethod.__call__ (decode.py:121-172), DetNMSMethod.__call__ (:34-104),
  * RetinaDecoder.snap_txtytwth_to_x1y1x2y2 (:251-271) / FCOSDecoder.snap_ltrb_to_x1y1x2y2
  * (:350-364) incl. NumPy's float32 exp and the int32 truncation.
@@ -385,6 +387,10 @@ int b200det_rows_to_image_major(const b200det_geometry *geo, const void *src, vo
 int b200det_generate_rows(const b200det_geometry *geo, int is_fcos, float *out, void *stream);
 /* y[i] = exp(x[i]) with the NumPy float32 algorithm used by the decoders (test hook) */
 int b200det_npexp_f32(const float *x, float *y, long long n, void *stream);
+/* profiling hook (tools/prof_select.py): device int64 [B,16] receiving %globaltimer stamps of the
+ * select kernel's phases (0 start, 1 histograms, 2 candidate list, 3 order, 4 box decode, 5 NMS,
+ * 6 outputs), or NULL = off (default).  Process-wide; not for concurrent use. */
+int b200det_select_stamps(long long *stamps);
 
 /* ---- head tail: sigmoid + NCHW -> NHWC in one pass --------------------------------
  * Replaces `x = x.float(); x = self.sigmoid(x)` (models/head.py:46-50 RetinaClsHead.forward,

@@ -166,6 +166,7 @@ SIGNATURES = {
     'b200det_rows_to_image_major': (ctypes.c_int, [_geo, _vp, _vp, ctypes.c_int, _vp]),
     'b200det_generate_rows': (ctypes.c_int, [_geo, ctypes.c_int, _vp, _vp]),
     'b200det_npexp_f32': (ctypes.c_int, [_vp, _vp, ctypes.c_longlong, _vp]),
+    'b200det_select_stamps': (ctypes.c_int, [_vp]),
     'b200det_logits_sweep': (ctypes.c_int, [
         _geo, _vpp, ctypes.c_int, _vpp, _vp, ctypes.c_float, ctypes.c_float, _vp, ctypes.c_size_t,
         ctypes.c_float, _vp, _vp, _vp

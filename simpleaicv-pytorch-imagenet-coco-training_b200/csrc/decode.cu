@@ -12,7 +12,9 @@
 // Compiled with -fmad=false: box / IoU arithmetic is one IEEE float32 op per reference op.
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include "focal_terms.cuh"
 
 namespace b200det {
@@ -105,13 +107,16 @@ __global__ void __launch_bounds__(kArgThreads)
         if (u < n_units) {
             float best = v[k][0];
             int bi = 0;
+            float any = v[k][0];   // NaN iff the unit holds a NaN (max.NaN propagates)
 #pragma unroll
             for (int e = 1; e < VEC; ++e) {
                 if (v[k][e] > best) {
                     best = v[k][e];
                     bi = e;
                 }
+                any = fmax_nan(any, v[k][e]);
             }
+            if (any != any) best = any;
             const int row = (int)(((unsigned)u * a.magic) >> 24);
             const int col = u - row * a.units_per_row;
             sval[row * a.pitch + col] = best;
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(kArgThreads)
         const bool live = r < n_rows;
         float best = -__int_as_float(0x7f800000);
         int best_c = 0x7fffffff;
+        float any = 0.f;   // NaN iff a class score of the row is NaN
         if (live) {
             for (int c = j; c < a.units_per_row; c += a.t2) {
                 const float x = sval[r * a.pitch + c];
@@ -161,17 +167,22 @@ __global__ void __launch_bounds__(kArgThreads)
                     best = x;
                     best_c = sidx[r * a.pitch + c];
                 }
+                any = fmax_nan(any, x);
             }
         }
         // combine the row's lanes: larger value wins, equal values -> lower class index
         for (int o = a.t2 >> 1; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            any = fmax_nan(any, __shfl_xor_sync(0xffffffffu, any, o));
             if (ov > best || (ov == best && oc < best_c)) {
                 best = ov;
                 best_c = oc;
             }
         }
+        // np.argmax stops at the first NaN (decode.py:230-238): the row's score is NaN and fails
+        // `score > threshold`, whatever the other classes hold
+        if (any != any) best = any;
         if (live && j == 0) {
             const long long row = row0 + r;
             float score = best;
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
             if (live && (k << ts) + j < U) v[k] = __ldcs(src + (k << ts));
 
         float best = ninf;
+        float any = 0.f;   // NaN iff a class score of the row is NaN (max.NaN propagates)
         int code = 0;   // (k << 2) | e of the lane's first maximum
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -244,6 +256,7 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
                         code = (k << 2) | e;
                     }
                 }
+                any = fmax_nan(fmax_nan(any, fmax_nan(e4[0], e4[1])), fmax_nan(e4[2], e4[3]));
             }
         }
         int best_c = best > ninf ? ((((code >> 2) << ts) + j) << 2) + (code & 3) : 0x7fffffff;
@@ -271,11 +284,13 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
         for (int o = T >> 1; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            any = fmax_nan(any, __shfl_xor_sync(0xffffffffu, any, o));
             if (ov > best || (ov == best && oc < best_c)) {
                 best = ov;
                 best_c = oc;
             }
         }
+        if (any != any) best = any;   // np.argmax stops at the first NaN: the row's score is NaN
         if (live && j == 0) {
             float score = best;
             if (a.has_ctr) {
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(kArgThreads)
         const bool live = r < n_rows;
         float best = -__int_as_float(0x7f800000);
         int best_c = 0x7fffffff;
+        float any = 0.f;   // NaN iff a class score of the row is NaN
         if (live) {
             // strict '>' in class order: first maximum (np.argmax).  Four independent loads per
             // iteration off a walking pointer: ~5 instructions per element (the plain
@@ -363,20 +379,24 @@ __global__ void __launch_bounds__(kArgThreads)
                 if (x1 > best) best = x1, best_c = c + T;
                 if (x2 > best) best = x2, best_c = c + 2 * T;
                 if (x3 > best) best = x3, best_c = c + 3 * T;
+                any = fmax_nan(fmax_nan(any, fmax_nan(x0, x1)), fmax_nan(x2, x3));
             }
             for (; c < C; c += T, p += T) {
                 const float x = *p;
                 if (x > best) best = x, best_c = c;
+                any = fmax_nan(any, x);
             }
         }
         for (int o = a.t2 >> 1; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            any = fmax_nan(any, __shfl_xor_sync(0xffffffffu, any, o));
             if (ov > best || (ov == best && oc < best_c)) {
                 best = ov;
                 best_c = oc;
             }
         }
+        if (any != any) best = any;   // np.argmax stops at the first NaN: the row's score is NaN
         if (live && j == 0) {
             const long long row_g = row0 + r;
             float score = best;
@@ -391,6 +411,7 @@ __global__ void __launch_bounds__(kArgThreads)
 // ---------------------------------------------------------------------------------------
 // per-image select + decode + NMS
 // ---------------------------------------------------------------------------------------
+static long long *g_select_stamps = nullptr;   // profiling hook, see b200det_select_stamps
 constexpr int kSelThreads = 1024;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kBins = 2048;
@@ -407,6 +428,9 @@ struct SelectArgs {
     int key_shift;     // pass-A bin = min((key - key_lo) >> key_shift, kBins - 1)
     float nms_thr_f;
     double nms_thr_d;
+    int slices, rows_per_slice;   // CTAs of the image's cluster and the rows each one scans
+    int force_bitonic;            // A/B knob (B200DET_SELECT_BITONIC)
+    long long *stamps;            // NULL, or [B,16] globaltimer stamps of the leader's phases (profiling)
 };
 
 // block-wide sums; result broadcast to all threads.  `scratch` holds kSelWarps values.
@@ -434,32 +458,64 @@ __device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t *scratch)
     return ~block_max_u32(~v, scratch);
 }
 
-// visit every (key, image-major row) of image b; F(key, row)
+// visit every (key, image-major row) of image b whose image-major row lies in [r0, r1); F(key, row)
 template <typename F>
-__device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t *__restrict__ keys,
-                                             F f) {
+__device__ __forceinline__ void for_each_key_range(const Geo &g, int b,
+                                                   const uint32_t *__restrict__ keys, int r0, int r1,
+                                                   F f) {
     // 128-bit loads over the 16-byte-aligned middle of every level segment (the visiting order is
     // irrelevant to the callers): 4x the bytes in flight of a scalar loop, which is what bounds these
-    // passes (one CTA per image, keys coming from L2 / HBM).
+    // passes (keys coming from L2 / HBM).
     for (int l = 0; l < g.n_levels; ++l) {
-        const uint32_t *p = keys + lm_index(g, b, l, 0);
-        const int n = g.rows[l], off = g.off[l];
+        const int lo = max(r0, g.off[l]) - g.off[l];
+        const int hi = min(r1, g.off[l + 1]) - g.off[l];
+        if (lo >= hi) continue;
+        const uint32_t *p = keys + lm_index(g, b, l, 0) + lo;
+        const int n = hi - lo, off = g.off[l] + lo;
         const int head = min(n, (int)((4u - ((unsigned)(reinterpret_cast<uintptr_t>(p) >> 2) & 3u)) & 3u));
         if ((int)threadIdx.x < head) f(__ldg(p + threadIdx.x), off + (int)threadIdx.x);
         const uint4 *q = reinterpret_cast<const uint4 *>(p + head);
         const int nv = (n - head) >> 2;
-#pragma unroll 2
-        for (int j = threadIdx.x; j < nv; j += kSelThreads) {
-            const uint4 v = __ldg(q + j);
-            const int r = off + head + 4 * j;
-            f(v.x, r);
-            f(v.y, r + 1);
-            f(v.z, r + 2);
-            f(v.w, r + 3);
+        // four 128-bit loads in flight per thread before the first use: with two (r01) a CTA moved
+        // ~23 GB/s, i.e. one L2 round trip per 32 KB (profiles/r02_select.txt)
+        int j = threadIdx.x;
+        for (; j + 3 * kSelThreads < nv; j += 4 * kSelThreads) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(q + j + u * kSelThreads);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = off + head + 4 * (j + u * kSelThreads);
+                f(v[u].x, r);
+                f(v[u].y, r + 1);
+                f(v[u].z, r + 2);
+                f(v[u].w, r + 3);
+            }
+        }
+        {
+            uint4 v[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (j + u * kSelThreads < nv) v[u] = __ldg(q + j + u * kSelThreads);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                if (j + u * kSelThreads < nv) {
+                    const int r = off + head + 4 * (j + u * kSelThreads);
+                    f(v[u].x, r);
+                    f(v[u].y, r + 1);
+                    f(v[u].z, r + 2);
+                    f(v[u].w, r + 3);
+                }
+            }
         }
         const int t0 = head + 4 * nv + (int)threadIdx.x;
         if (t0 < n) f(__ldg(p + t0), off + t0);
     }
+}
+template <typename F>
+__device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t *__restrict__ keys,
+                                             F f) {
+    for_each_key_range(g, b, keys, 0, g.off[g.n_levels], f);
 }
 
 // Given a 2048-bin histogram in shared memory (bin index grows with the key), finds the bin where
@@ -467,7 +523,8 @@ __device__ __forceinline__ void for_each_key(const Geo &g, int b, const uint32_t
 // bin's own count and the total.  Thread t owns bins 2t, 2t+1 (kSelThreads == kBins / 2).
 __device__ __forceinline__ void find_cut(const int *hist, int topn, int *scratch, int *s_digit,
                                          int *s_above, int *s_count, int *s_total, int &cut_bin,
-                                         int &above, int &in_bin, int &total_out) {
+                                         int &above, int &in_bin, int &total_out,
+                                         int *above_of_bin = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
     const int mine = h0 + h1;
@@ -488,6 +545,10 @@ __device__ __forceinline__ void find_cut(const int *hist, int topn, int *scratch
     }
     const int need = min(topn, total);
     const int above_excl = above_warps + suf - mine;
+    if (above_of_bin) {   // number of keys in the bins above 2t+1 / above 2t
+        above_of_bin[2 * tid + 1] = above_excl;
+        above_of_bin[2 * tid] = above_excl + h1;
+    }
     if (tid == 0) {
         *s_digit = 0;      // fewer candidates than topn (or none): take everything
         *s_above = 0;
@@ -514,90 +575,8 @@ __device__ __forceinline__ void find_cut(const int *hist, int topn, int *scratch
     __syncthreads();
 }
 
-// visit the keys of image b whose image-major row lies in [r0, r1)
-template <typename F>
-__device__ __forceinline__ void for_each_key_range(const Geo &g, int b,
-                                                   const uint32_t *__restrict__ keys, int r0, int r1,
-                                                   F f) {
-    for (int l = 0; l < g.n_levels; ++l) {
-        const int lo = max(r0, g.off[l]) - g.off[l];
-        const int hi = min(r1, g.off[l + 1]) - g.off[l];
-        if (lo >= hi) continue;
-        const uint32_t *p = keys + lm_index(g, b, l, 0);
-        const int off = g.off[l];
-#pragma unroll 4
-        for (int j = lo + (int)threadIdx.x; j < hi; j += kSelThreads) f(__ldg(p + j), off + j);
-    }
-}
-
-// ---- multi-CTA front end of the selection (used when an image has enough rows to split) ----
-// select_hist_kernel   : grid (slices, B): each CTA histograms its slice of the image's keys in
-//                        shared memory and adds the non-empty bins to the image's global histogram
-// select_collect_kernel: grid (slices, B): every CTA derives the cut bin from the global
-//                        histogram and appends its slice's keys at or above it to the image's list
-// select_nms_kernel then only loads the list (<= 2*pad_n entries), sorts, decodes and runs NMS.
-struct PreArgs {
-    Geo g;
-    uint32_t key_lo;
-    int key_shift, slices, rows_per_slice, topn, cap;
-};
-
-__global__ void __launch_bounds__(kSelThreads)
-    select_hist_kernel(PreArgs a, const uint32_t *__restrict__ keys, int *__restrict__ ghist) {
-    __shared__ int hist[kBins];
-    const int b = blockIdx.y, tid = threadIdx.x;
-    for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
-    __syncthreads();
-    const int r0 = blockIdx.x * a.rows_per_slice;
-    for_each_key_range(a.g, b, keys, r0, r0 + a.rows_per_slice, [&](uint32_t k, int) {
-        if (k) atomicAdd(&hist[min((k - a.key_lo) >> a.key_shift, (uint32_t)(kBins - 1))], 1);
-    });
-    __syncthreads();
-    for (int i = tid; i < kBins; i += kSelThreads)
-        if (hist[i]) atomicAdd(ghist + (size_t)b * kBins + i, hist[i]);
-}
-
-__global__ void __launch_bounds__(kSelThreads)
-    select_collect_kernel(PreArgs a, const uint32_t *__restrict__ keys,
-                          const int *__restrict__ ghist, unsigned long long *__restrict__ glist,
-                          int *__restrict__ gcount) {
-    extern __shared__ __align__(16) unsigned char pre_smem[];
-    int *hist = reinterpret_cast<int *>(pre_smem);
-    unsigned long long *slist = reinterpret_cast<unsigned long long *>(hist + kBins);  // cap
-    __shared__ int scratch[kSelWarps];
-    __shared__ int s_digit, s_above, s_count, s_total, s_base;
-    const int b = blockIdx.y, tid = threadIdx.x;
-    for (int i = tid; i < kBins; i += kSelThreads) hist[i] = ghist[(size_t)b * kBins + i];
-    __syncthreads();
-    int cut_bin, above, in_bin, total;
-    find_cut(hist, a.topn, scratch, &s_digit, &s_above, &s_count, &s_total, cut_bin, above, in_bin,
-             total);
-    const int n_collect = total <= a.topn ? total : above + in_bin;
-    if (blockIdx.x == 0 && tid == 0) {
-        gcount[b * 4 + 0] = total;
-        gcount[b * 4 + 1] = n_collect;
-    }
-    if (n_collect > a.cap || n_collect == 0) return;   // crowded cut bin: the select kernel refines
-    uint32_t T = 1u;
-    if (total > a.topn && cut_bin > 0) T = a.key_lo + ((uint32_t)cut_bin << a.key_shift);
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    const int r0 = blockIdx.x * a.rows_per_slice;
-    for_each_key_range(a.g, b, keys, r0, r0 + a.rows_per_slice, [&](uint32_t k, int row) {
-        if (k >= T && k != 0u)
-            slist[atomicAdd(&s_count, 1)] =
-                ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
-    });
-    __syncthreads();
-    const int n_local = s_count;
-    if (tid == 0) s_base = n_local ? atomicAdd(gcount + b * 4 + 2, n_local) : 0;
-    __syncthreads();
-    for (int i = tid; i < n_local; i += kSelThreads)
-        glist[(size_t)b * a.cap + s_base + i] = slist[i];
-}
-
-constexpr int kNmsWindow = 256;
-constexpr int kNmsGroup = 8;     // candidates resolved per NMS step (28 pairwise tests = one ballot)
+constexpr int kNmsW = 128;          // NMS round: candidates resolved per bit matrix
+constexpr int kRankScanMax = 128;   // histogram-rank placement only while no bin holds more entries
 
 // does kept box kb suppress the later box ob?  (decode.py:45-100 / torchvision CPU nms)
 __device__ __forceinline__ bool nms_suppresses(const float4 kb, const float4 ob, int nms_type,
@@ -678,136 +657,197 @@ __device__ __forceinline__ bool nms_suppresses_fast(const float4 kb, const float
     return nms_suppresses_exact(kb, ob, nms_type, thr_f, thr_d);
 }
 
-__global__ void __launch_bounds__(kSelThreads, 2)
+// One CLUSTER of `slices` CTAs per image (grid = slices x B, cluster = slices x 1; slices = 1 for
+// small images).  Front end, all CTAs: each histograms its slice of the image's keys in its own
+// shared memory; after a cluster barrier every CTA sums the slices' histograms through distributed
+// shared memory, derives the cut bin, collects its slice's keys at or above it and appends them to
+// the leader's list with a DSMEM atomic + DSMEM stores.  After the second cluster barrier only the
+// leader (cluster rank 0) goes on: placement by histogram rank (or the bitonic sort when a bin is
+// crowded), box decode, bit-matrix NMS, outputs.  One launch per decode instead of a memset and
+// three kernels, and no global-memory round trip for histograms / lists.
+template <int MINB>   // 2: register-capped build (two CTAs of 1024 threads per SM) for large batches
+__global__ void __launch_bounds__(kSelThreads, MINB)
     select_nms_kernel(SelectArgs a, const uint32_t *__restrict__ keys,
                       const int *__restrict__ classes, float *__restrict__ out,
                       int *__restrict__ order_out, int *__restrict__ keep_out,
-                      int *__restrict__ counts, const unsigned long long *__restrict__ glist,
-                      const int *__restrict__ gcount) {
+                      int *__restrict__ counts) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem[];
-    // carve: hist | key64 | box | cls | keep | removed
-    int *hist = reinterpret_cast<int *>(smem);                                // kBins
-    unsigned long long *skey = reinterpret_cast<unsigned long long *>(hist + kBins);  // 2*pad_n
-    float4 *sbox = reinterpret_cast<float4 *>(skey + 2 * a.pad_n);            // pad_n
-    int *scls = reinterpret_cast<int *>(sbox + a.pad_n);                      // pad_n
-    int *skeep = scls + a.pad_n;                                              // pad_n
-    uint32_t *srem = reinterpret_cast<uint32_t *>(skeep + a.pad_n);           // max(pad_n, 256)/32
+    // carve: hist | htot | sbase | sfill | key64 | tmp64 (later: box) | cls | keep | mcol
+    const int cap = 2 * a.pad_n;  // capacity of skey / stmp
+    int *hist = reinterpret_cast<int *>(smem);                                    // kBins: own slice
+    int *htot = hist + kBins;                                                     // kBins: image
+    int *sbase = htot + kBins;                                                    // kBins
+    int *sfill = sbase + kBins;                                                   // kBins
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(sfill + kBins);  // cap
+    unsigned long long *stmp = skey + cap;                                        // cap
+    float4 *sbox = reinterpret_cast<float4 *>(stmp);                              // pad_n (aliases stmp)
+    int *scls = reinterpret_cast<int *>(stmp + cap);                              // pad_n
+    int *skeep = scls + a.pad_n;                                                  // pad_n
+    uint32_t *mcol = reinterpret_cast<uint32_t *>(skeep + a.pad_n);               // kNmsW * 4
     __shared__ int scratch[kSelWarps];
-    __shared__ int s_digit, s_above, s_count, s_total;
-    __shared__ int sgroup[kNmsGroup];
+    __shared__ int s_digit, s_above, s_count, s_total, s_list;
+    __shared__ __align__(16) uint32_t s_alive[4];
+    __shared__ __align__(16) uint32_t s_keepm[4];
 
     const Geo &g = a.g;
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
+    const int crank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int B = g.batch;
+    const int N = g.off[g.n_levels];
+    long long *stamps = a.stamps ? a.stamps + (size_t)b * 16 : nullptr;
+    auto stamp = [&](int k) {
+        if (stamps && crank == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            stamps[k] = (long long)t;
+        }
+    };
+    stamp(0);
 
     float *out_scores = out + (size_t)b * a.max_out;
     float *out_classes = out + (size_t)B * a.max_out + (size_t)b * a.max_out;
     float *out_boxes = out + (size_t)2 * B * a.max_out + (size_t)b * a.max_out * 4;
 
-    const int cap = 2 * a.pad_n;  // capacity of skey
-    int ncand, k_sel, n_got;
-    // ---- front end already done by select_hist/collect kernels? ----
-    const bool pre = glist != nullptr && gcount[b * 4 + 1] <= cap;
-    if (pre) {
-        ncand = gcount[b * 4 + 0];
-        k_sel = min(a.topn, ncand);
-        n_got = gcount[b * 4 + 1];
-        for (int i = tid; i < n_got; i += kSelThreads) skey[i] = glist[(size_t)b * cap + i];
-    } else {
-    // ---- pass A: 2048-bin histogram of the keys over the expected score range ----
+    // ---- pass A: 2048-bin histogram of the slice's keys over the expected score range ----
     // Candidate keys are > key_lo (the flipped threshold); keys above key_hi (scores > 1, not
     // produced by sigmoid heads) saturate into the top bin.  Bin D where the count from the top
-    // crosses topn bounds the selection: everything at or above D is collected and sorted.
+    // crosses topn bounds the selection: everything at or above D is collected and placed.
     const uint32_t lo = a.key_lo;
     const int shift = a.key_shift;
-    for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
+    auto bin_of = [&](uint32_t k) { return (int)min((k - lo) >> shift, (uint32_t)(kBins - 1)); };
+    for (int i = tid; i < kBins; i += kSelThreads) {
+        hist[i] = 0;
+        sfill[i] = 0;
+    }
+    if (tid == 0) s_list = 0;
     __syncthreads();
-    for_each_key(g, b, keys, [&](uint32_t k, int) {
-        if (k) atomicAdd(&hist[min((k - lo) >> shift, (uint32_t)(kBins - 1))], 1);
+    const int r0 = crank * a.rows_per_slice, r1 = min(N, r0 + a.rows_per_slice);
+    for_each_key_range(g, b, keys, r0, r1, [&](uint32_t k, int) {
+        if (k) atomicAdd(&hist[bin_of(k)], 1);
     });
-    __syncthreads();
-    int cut_bin, above, in_bin, ncand_all;
-    find_cut(hist, a.topn, scratch, &s_digit, &s_above, &s_count, &s_total, cut_bin, above, in_bin,
-             ncand_all);
-    ncand = ncand_all;
-    k_sel = min(a.topn, ncand);
-    __syncthreads();
-
-    uint32_t T = 1u;      // collect keys >= T ...
-    int tie_take = -1;    // ... or, if >= 0: keys > T plus the first `tie_take` rows with key == T
+    cluster.sync();   // every slice's histogram is complete (and visible cluster-wide)
+    stamp(1);
+    {
+        int2 t = make_int2(0, 0);   // thread t owns bins 2t, 2t+1
+        for (int r = 0; r < a.slices; ++r) {
+            const int2 v = reinterpret_cast<const int2 *>(cluster.map_shared_rank(hist, r))[tid];
+            t.x += v.x;
+            t.y += v.y;
+        }
+        reinterpret_cast<int2 *>(htot)[tid] = t;
+    }
+    int cut_bin, above, in_bin, ncand;
+    find_cut(htot, a.topn, scratch, &s_digit, &s_above, &s_count, &s_total, cut_bin, above, in_bin,
+             ncand, sbase);
+    const int k_sel = min(a.topn, ncand);
     int n_collect = ncand <= a.topn ? ncand : above + in_bin;
-    if (ncand > a.topn) {
-        T = lo + ((uint32_t)cut_bin << shift);
-        if (cut_bin == 0) T = 1u;
-        if (n_collect > cap) {
-            // The cut bin is too crowded to sort (heavy ties, or scores far outside (thr, 1]):
-            // refine inside it with an adaptive-range radix select until the bucket is exact.
-            uint32_t rlo = cut_bin == 0 ? 1u : T;
-            uint32_t rhi = cut_bin == kBins - 1
-                               ? 0xffffffffu
-                               : (uint32_t)((unsigned long long)lo + (((unsigned long long)cut_bin + 1ull) << shift) - 1ull);
-            int need = k_sel - above;
-            while (true) {
-                const unsigned long long span = (unsigned long long)rhi - rlo + 1ull;
-                int sh = 0;
-                while ((span - 1ull) >> sh >= (unsigned long long)kBins) ++sh;
-                for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
-                __syncthreads();
-                for_each_key(g, b, keys, [&](uint32_t k, int) {
-                    if (k >= rlo && k <= rhi) atomicAdd(&hist[(k - rlo) >> sh], 1);
-                });
-                __syncthreads();
-                const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
-                const int mine = h0 + h1;
-                int suf = mine;
+    // a cut bin too crowded to place (heavy ties, or scores far outside (thr, 1]): the leader
+    // refines inside it on its own, below
+    const bool crowded = n_collect > cap;
+    uint32_t T = 1u;      // collect keys >= T ...
+    if (ncand > a.topn && cut_bin > 0) T = lo + ((uint32_t)cut_bin << shift);
+    if (!crowded && n_collect > 0) {
+        // the slice's survivors: local list first, then one reservation in the leader's list
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for_each_key_range(g, b, keys, r0, r1, [&](uint32_t k, int row) {
+            // one shared-memory atomic per warp and visit (the survivors are ~1 % of the keys, so
+            // most ballots are empty), not one per survivor on the same address
+            const bool take = k >= T && k != 0u;
+            const unsigned act = __activemask();
+            const unsigned m = __ballot_sync(act, take);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int slot = 0;
+                if (lane == leader) slot = atomicAdd(&s_count, __popc(m));
+                slot = __shfl_sync(act, slot, leader);
+                if (take)
+                    stmp[slot + __popc(m & ((1u << lane) - 1u))] =
+                        ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
+            }
+        });
+        __syncthreads();
+        const int n_local = s_count;
+        unsigned long long *lead_key = cluster.map_shared_rank(skey, 0);
+        if (tid == 0) s_digit = n_local ? atomicAdd(cluster.map_shared_rank(&s_list, 0), n_local) : 0;
+        __syncthreads();
+        const int base = s_digit;
+        for (int i = tid; i < n_local; i += kSelThreads) lead_key[base + i] = stmp[i];
+    }
+    cluster.sync();   // the leader's list is complete; nobody touches another CTA's memory after this
+    if (crank != 0) return;
+    stamp(2);
+
+    int n_got = s_list;
+    bool bitonic = a.force_bitonic != 0;
+    if (crowded) {
+        // ---- adaptive-range radix select inside the cut bin until the bucket is exact ----
+        bitonic = true;
+        int tie_take = -1;    // if >= 0: keys > T plus the first `tie_take` rows with key == T
+        uint32_t rlo = cut_bin == 0 ? 1u : T;
+        uint32_t rhi = cut_bin == kBins - 1
+                           ? 0xffffffffu
+                           : (uint32_t)((unsigned long long)lo + (((unsigned long long)cut_bin + 1ull) << shift) - 1ull);
+        int need = k_sel - above;
+        while (true) {
+            const unsigned long long span = (unsigned long long)rhi - rlo + 1ull;
+            int sh = 0;
+            while ((span - 1ull) >> sh >= (unsigned long long)kBins) ++sh;
+            for (int i = tid; i < kBins; i += kSelThreads) hist[i] = 0;
+            __syncthreads();
+            for_each_key(g, b, keys, [&](uint32_t k, int) {
+                if (k >= rlo && k <= rhi) atomicAdd(&hist[(k - rlo) >> sh], 1);
+            });
+            __syncthreads();
+            const int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+            const int mine = h0 + h1;
+            int suf = mine;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_down_sync(0xffffffffu, suf, o);
-                    if (lane + o < 32) suf += t;
-                }
-                if (lane == 0) scratch[warp] = suf;
-                __syncthreads();
-                int above_warps = 0;
-                for (int w = warp + 1; w < kSelWarps; ++w) above_warps += scratch[w];
-                const int above_excl = above_warps + suf - mine;
-                if (above_excl < need && need <= above_excl + mine) {
-                    if (need <= above_excl + h1) {
-                        s_digit = 2 * tid + 1;
-                        s_above = above_excl;
-                        s_count = h1;
-                    } else {
-                        s_digit = 2 * tid;
-                        s_above = above_excl + h1;
-                        s_count = h0;
-                    }
-                }
-                __syncthreads();
-                const int digit = s_digit, cnt = s_count;
-                need -= s_above;
-                const uint32_t lo2 = rlo + ((uint32_t)digit << sh);
-                const unsigned long long hi2 = (unsigned long long)lo2 + ((1ull << sh) - 1ull);
-                rlo = lo2;
-                if (hi2 < rhi) rhi = (uint32_t)hi2;
-                __syncthreads();
-                if (cnt == need) {  // the whole bucket is needed
-                    T = rlo;
-                    break;
-                }
-                if (sh == 0) {      // one key value with more copies than needed: ties
-                    T = rlo;
-                    tie_take = need;
-                    break;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            if (lane == 0) scratch[warp] = suf;
+            __syncthreads();
+            int above_warps = 0;
+            for (int w = warp + 1; w < kSelWarps; ++w) above_warps += scratch[w];
+            const int above_excl = above_warps + suf - mine;
+            if (above_excl < need && need <= above_excl + mine) {
+                if (need <= above_excl + h1) {
+                    s_digit = 2 * tid + 1;
+                    s_above = above_excl;
+                    s_count = h1;
+                } else {
+                    s_digit = 2 * tid;
+                    s_above = above_excl + h1;
+                    s_count = h0;
                 }
             }
-            n_collect = k_sel;
+            __syncthreads();
+            const int digit = s_digit, cnt = s_count;
+            need -= s_above;
+            const uint32_t lo2 = rlo + ((uint32_t)digit << sh);
+            const unsigned long long hi2 = (unsigned long long)lo2 + ((1ull << sh) - 1ull);
+            rlo = lo2;
+            if (hi2 < rhi) rhi = (uint32_t)hi2;
+            __syncthreads();
+            if (cnt == need) {  // the whole bucket is needed
+                T = rlo;
+                break;
+            }
+            if (sh == 0) {      // one key value with more copies than needed: ties
+                T = rlo;
+                tie_take = need;
+                break;
+            }
         }
-    }
-
-    // ---- collect the selected (key,row) pairs ----
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    if (n_collect > 0) {
+        n_collect = k_sel;
+        // ---- collect the selected (key,row) pairs over the whole image ----
+        if (tid == 0) s_count = 0;
+        __syncthreads();
         for_each_key(g, b, keys, [&](uint32_t k, int row) {
             const bool take = tie_take < 0 ? (k >= T && k != 0u) : (k > T);
             if (take) {
@@ -846,33 +886,63 @@ __global__ void __launch_bounds__(kSelThreads, 2)
                 }
             }
         }
+        __syncthreads();
+        n_got = s_count;  // == n_collect
     }
-    __syncthreads();
-    n_got = s_count;  // == n_collect
-    }  // !pre
-    __syncthreads();
-    const int n_sel = min(n_got, k_sel);  // after the sort only the first k_sel entries are used
-    int sort_n = 1;
-    while (sort_n < n_got) sort_n <<= 1;
-    for (int i = n_got + tid; i < sort_n; i += kSelThreads) skey[i] = 0ull;
-    __syncthreads();
+    const int n_sel = min(n_got, k_sel);  // only the first k_sel entries of the sorted list are used
 
-    // ---- bitonic sort, descending (score desc, then row asc) ----
-    for (int size = 2; size <= sort_n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (sort_n >> 1); t += kSelThreads) {
-                const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-                const int p = i | stride;
-                const bool desc = (i & size) == 0;
-                const unsigned long long x = skey[i], y = skey[p];
-                if ((x < y) == desc) {
-                    skey[i] = y;
-                    skey[p] = x;
+    // ---- order: descending (score desc, then row asc) ----
+    {
+        // placement by histogram rank needs every bin at or above the cut to be small
+        const int h0 = htot[2 * tid], h1 = htot[2 * tid + 1];
+        const bool big = (2 * tid >= cut_bin && h0 > kRankScanMax) ||
+                         (2 * tid + 1 >= cut_bin && h1 > kRankScanMax);
+        if (__syncthreads_or(big)) bitonic = true;
+    }
+    if (!bitonic) {
+        // Every entry already knows how many entries sit in HIGHER bins (sbase, from find_cut's
+        // suffix sums over the image histogram): scatter the entries into their bin's span, then
+        // rank each inside its span (a few entries) -- 3 barriers instead of the 66 passes of a
+        // bitonic sort of 2048.
+        for (int i = tid; i < n_got; i += kSelThreads) {
+            const unsigned long long e = skey[i];
+            const int bn = bin_of((uint32_t)(e >> 32));
+            stmp[sbase[bn] + atomicAdd(&sfill[bn], 1)] = e;
+        }
+        __syncthreads();
+        for (int i = tid; i < n_got; i += kSelThreads) {
+            const unsigned long long e = stmp[i];
+            const int bn = bin_of((uint32_t)(e >> 32));
+            const int first = sbase[bn];
+            if (first >= k_sel) continue;
+            const int c = htot[bn];
+            int rank = 0;
+            for (int j = 0; j < c; ++j) rank += stmp[first + j] > e;
+            if (first + rank < k_sel) skey[first + rank] = e;
+        }
+        __syncthreads();
+    } else {
+        int sort_n = 1;
+        while (sort_n < n_got) sort_n <<= 1;
+        for (int i = n_got + tid; i < sort_n; i += kSelThreads) skey[i] = 0ull;
+        __syncthreads();
+        for (int size = 2; size <= sort_n; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (sort_n >> 1); t += kSelThreads) {
+                    const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                    const int p = i | stride;
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long x = skey[i], y = skey[p];
+                    if ((x < y) == desc) {
+                        skey[i] = y;
+                        skey[p] = x;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
+    stamp(3);
 
     // ---- decode the selected rows (reference op order, NumPy exp, x86 int32 truncation) ----
     for (int i = tid; i < n_sel; i += kSelThreads) {
@@ -918,115 +988,119 @@ __global__ void __launch_bounds__(kSelThreads, 2)
     }
     if (order_out)
         for (int i = n_sel + tid; i < a.topn; i += kSelThreads) order_out[(size_t)b * a.topn + i] = -1;
-    // bit = "not a candidate": everything at or beyond n_sel from the start
-    for (int i = tid; i < (max(a.pad_n, kNmsWindow) >> 5); i += kSelThreads) {
-        const int i0 = i << 5;
-        srem[i] = i0 >= n_sel ? 0xffffffffu : (i0 + 32 <= n_sel ? 0u : ~((1u << (n_sel - i0)) - 1u));
-    }
     __syncthreads();
+    stamp(4);
 
-    // ---- greedy NMS (decode.py:45-100), up to kNmsGroup kept boxes per step ----
-    // Greedy NMS is a chain of dependent steps, so the kernel waits for step LATENCY, not throughput
-    // (one kept box per step with a barrier measured ~750-1100 cycles per box).  Each step therefore
-    // takes the first G <= 8 candidates that are still alive, resolves the greedy order INSIDE that
-    // group from its 28 pairwise tests (every warp does that redundantly: one ballot, no exchange
-    // between warps), and lets every later candidate test itself against the group's kept members
-    // at once.  That is the reference's scan: the group members are the next candidates in order
-    // (everything between them is already dead), a member is kept iff no kept earlier member
-    // suppresses it, and later candidates are only ever tested against kept boxes.  The scan works
-    // on a window of kNmsWindow candidates (srem bit = "no longer a candidate": removed, kept, or
-    // beyond n_sel); when the window is exhausted the next kNmsWindow candidates first test themselves
-    // against ALL boxes kept so far.  Only the kNmsWindow / 32 warps of the window take part (named
-    // barrier 1); two barriers per step.
+    // ---- greedy NMS (decode.py:45-100) by bit matrix, kNmsW candidates per round ----
+    // Greedy NMS is a chain of dependent decisions; walking it box by box costs one barrier-bound
+    // step per kept box (r01: ~13 steps of ~1 us for 100 boxes).  Here a round takes the next
+    // kNmsW candidates (in score order): (1) each drops out if a box kept in an EARLIER round
+    // suppresses it (8 threads per candidate share the kept list); (2) the round's own
+    // "j suppresses i" bits, j < i, are computed by all 32 warps at once (one ballot per 32 pairs) and
+    // stored per column i; (3) 128 threads iterate keep(i) = alive(i) && no kept j < i suppresses i
+    // on the 128-bit keep mask until it stops changing.  That recurrence has exactly one solution,
+    // the reference's sequential scan (i only depends on j < i, so position i is final after i + 1
+    // sweeps at the latest; typical chains are 2-4 deep); (4) the kept ones are appended in order.
     const int limit = keep_out ? n_sel : min(a.max_out, n_sel);
-    if (tid < kNmsWindow) {
-        const NmsFast nf = nms_fast_of(a.nms_type, a.nms_thr_f);
-        // pair p = b (b - 1) / 2 + a  (a < b < 8) is tested by lane p
-        const int pb = lane >= 21 ? 7 : lane >= 15 ? 6 : lane >= 10 ? 5 : lane >= 6 ? 4
-                       : lane >= 3 ? 3 : lane >= 1 ? 2 : 1;
-        const int pa = lane - pb * (pb - 1) / 2;
-        int n_keep = 0;
-        int win_base = 0, win_end = min(n_sel, kNmsWindow);
-        while (n_keep < limit) {
-            // ---- A: rank of every alive candidate of the window (the 8 words are read by all)
-            const uint4 *wp = reinterpret_cast<const uint4 *>(srem + (win_base >> 5));
-            const uint4 w0 = wp[0], w1 = wp[1];
-            const uint32_t aw[8] = {~w0.x, ~w0.y, ~w0.z, ~w0.w, ~w1.x, ~w1.y, ~w1.z, ~w1.w};
-            int total = 0, before = 0;
-            uint32_t mine_word = 0u;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const int c = __popc(aw[w]);
-                total += c;
-                if (w < warp) before += c;
-                if (w == warp) mine_word = aw[w];
-            }
-            if (total == 0) {
-                if (win_end >= n_sel) break;
-                // slide the window: the new candidates against everything kept so far
-                const int new_end = min(n_sel, win_end + kNmsWindow);
-                const int j = win_end + tid;
-                bool suppress = false;
-                if (j < new_end) {
-                    const float4 ob = sbox[j];
-                    for (int k = 0; k < n_keep && !suppress; ++k)
-                        suppress = nms_suppresses_fast(sbox[skeep[k]], ob, a.nms_type, a.nms_thr_f,
-                                                       a.nms_thr_d, nf);
+    const NmsFast nf = nms_fast_of(a.nms_type, a.nms_thr_f);
+    int n_keep = 0;
+    if (a.nms_type == B200DET_NMS_NONE) {   // DETRDecoder(nms_type=None), decode.py:453
+        for (int i = tid; i < limit; i += kSelThreads) skeep[i] = i;
+        n_keep = limit;
+        __syncthreads();
+    } else {
+        for (int w0 = 0; w0 < n_sel && n_keep < limit; w0 += kNmsW) {
+            const int wn = min(kNmsW, n_sel - w0);
+            // (1) alive = not suppressed by a box kept in an earlier round
+            if (tid < 4) s_alive[tid] = 0u;
+            __syncthreads();
+            {
+                const int c = tid >> 3, sub = tid & 7;
+                bool sup = false;
+                if (c < wn && n_keep > 0) {
+                    const float4 ob = sbox[w0 + c];
+                    for (int k = sub; k < n_keep && !sup; k += 8)
+                        sup = nms_suppresses_fast(sbox[skeep[k]], ob, a.nms_type, a.nms_thr_f,
+                                                  a.nms_thr_d, nf);
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, suppress);
-                if (lane == 0 && bal) srem[j >> 5] |= bal;  // each word is owned by one warp
-                win_base = win_end;
-                win_end = new_end;
-                asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
-                continue;
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if (sub == 0 && c < wn && ((bal >> lane) & 0xffu) == 0u)
+                    atomicOr(&s_alive[c >> 5], 1u << (c & 31));
             }
-            const int j = win_base + tid;
-            const bool mine = (mine_word >> lane) & 1u;
-            const int rank = before + __popc(mine_word & ((1u << lane) - 1u));
-            const int G = min(kNmsGroup, total);
-            if (mine && rank < kNmsGroup) sgroup[rank] = j;
-            asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
-            // ---- B: the group's pairwise tests (lane p: does member pa suppress member pb?)
-            bool psup = false;
-            if (lane < 28 && pb < G)
-                psup = nms_suppresses_fast(sbox[sgroup[pa]], sbox[sgroup[pb]], a.nms_type,
-                                           a.nms_thr_f, a.nms_thr_d, nf);
-            const unsigned pm = __ballot_sync(0xffffffffu, psup);
-            unsigned kept = 1u;   // member 0 is always kept
+            __syncthreads();
+            const uint4 al4 = *reinterpret_cast<const uint4 *>(s_alive);
+            const uint32_t alw[4] = {al4.x, al4.y, al4.z, al4.w};
+            // (2) column i of the round's matrix: bit j = alive j < i suppresses alive i
 #pragma unroll
-            for (int m = 1; m < kNmsGroup; ++m) {
-                const unsigned by = (pm >> (m * (m - 1) / 2)) & ((1u << m) - 1u);   // who would suppress m
-                if (m < G && (by & kept) == 0u) kept |= 1u << m;
-            }
-            // never more than `limit` boxes: drop the group's last kept members (the scan ends here)
-            while (n_keep + __popc(kept) > limit) kept &= ~(0x80000000u >> __clz(kept));
-            if (tid < kNmsGroup && ((kept >> tid) & 1u))
-                skeep[n_keep + __popc(kept & ((1u << tid) - 1u))] = sgroup[tid];
-            // ---- C: group members leave the candidate set; later candidates against the kept ones
-            bool gone = false;
-            if (mine) {
-                if (rank < G) {
-                    gone = true;
-                } else {
-                    const float4 ob = sbox[j];
-                    unsigned k = kept;
-                    while (k && !gone) {
-                        const int m = __ffs(k) - 1;
-                        k &= k - 1u;
-                        gone = nms_suppresses_fast(sbox[sgroup[m]], ob, a.nms_type, a.nms_thr_f,
-                                                   a.nms_thr_d, nf);
+            for (int q = 0; q < 4; ++q) {
+                const int i = warp + 32 * q;   // uniform per warp; i >> 5 == q
+                uint32_t words[4] = {0u, 0u, 0u, 0u};
+                if (i < wn && ((alw[q] >> warp) & 1u)) {
+                    const float4 ob = sbox[w0 + i];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r <= q) {
+                            const int j = r * 32 + lane;
+                            bool p = j < i && ((alw[r] >> lane) & 1u);
+                            if (p)
+                                p = nms_suppresses_fast(sbox[w0 + j], ob, a.nms_type, a.nms_thr_f,
+                                                        a.nms_thr_d, nf);
+                            words[r] = __ballot_sync(0xffffffffu, p);
+                        }
                     }
                 }
+                if (lane == 0)
+                    *reinterpret_cast<uint4 *>(mcol + 4 * i) =
+                        make_uint4(words[0], words[1], words[2], words[3]);
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, gone);
-            if (lane == 0 && bal) srem[(win_base >> 5) + warp] |= bal;
-            n_keep += __popc(kept);
-            asm volatile("bar.sync 1, %0;" ::"n"(kNmsWindow) : "memory");
+            __syncthreads();
+            // (3) fixed point of keep(i) = alive(i) && !(keep & column(i)) on the first 4 warps
+            if (tid < kNmsW) {
+                const uint4 col = *reinterpret_cast<const uint4 *>(mcol + 4 * tid);
+                const bool ai = (alw[warp & 3] >> lane) & 1u;
+                if (lane == 0) s_keepm[warp] = alw[warp & 3];
+                asm volatile("bar.sync 1, %0;" ::"n"(kNmsW) : "memory");
+                while (true) {
+                    const uint4 km = *reinterpret_cast<const uint4 *>(s_keepm);   // (barriers clobber memory)
+                    const bool kn =
+                        ai && ((km.x & col.x) | (km.y & col.y) | (km.z & col.z) | (km.w & col.w)) == 0u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, kn);
+                    const unsigned prev = warp == 0 ? km.x : warp == 1 ? km.y : warp == 2 ? km.z : km.w;
+                    const unsigned changed = bal != prev;
+                    unsigned any;   // barrier (everyone has read km) + OR over the 128 threads
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p, q;\n"
+                        "setp.ne.u32 p, %1, 0;\n"
+                        "bar.red.or.pred q, 1, %2, p;\n"
+                        "selp.u32 %0, 1, 0, q;\n"
+                        "}\n"
+                        : "=r"(any)
+                        : "r"(changed), "n"(kNmsW)
+                        : "memory");
+                    if (lane == 0) s_keepm[warp] = bal;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kNmsW) : "memory");
+                    if (!any) break;
+                }
+            }
+            __syncthreads();
+            // (4) append the round's kept boxes in order, never more than `limit` in total
+            {
+                const uint4 km = *reinterpret_cast<const uint4 *>(s_keepm);
+                const uint32_t kw[4] = {km.x, km.y, km.z, km.w};
+                if (tid < kNmsW && ((kw[warp & 3] >> lane) & 1u)) {
+                    int before = __popc(kw[warp & 3] & ((1u << lane) - 1u));
+#pragma unroll
+                    for (int w = 0; w < 3; ++w)
+                        if (w < warp) before += __popc(kw[w]);
+                    if (n_keep + before < limit) skeep[n_keep + before] = w0 + tid;
+                }
+                n_keep = min(limit, n_keep + __popc(kw[0]) + __popc(kw[1]) + __popc(kw[2]) + __popc(kw[3]));
+            }
+            __syncthreads();
         }
-        if (tid == 0) s_total = n_keep;
     }
-    __syncthreads();
-    const int n_keep = s_total;
+    stamp(5);
 
     // ---- outputs (decode.py:123-128, :158-167) ----
     const int n_out = min(n_keep, a.max_out);
@@ -1075,6 +1149,7 @@ __global__ void __launch_bounds__(kSelThreads, 2)
         counts[b * 3 + 1] = n_sel;
         counts[b * 3 + 2] = n_keep;
     }
+    stamp(6);
 }
 
 __global__ void npexp_kernel(const float *__restrict__ x, float *__restrict__ y, long long n) {
@@ -1084,43 +1159,20 @@ __global__ void npexp_kernel(const float *__restrict__ x, float *__restrict__ y,
 }
 
 static size_t select_smem_bytes(int pad_n) {
-    const int rem_bits = pad_n > kNmsWindow ? pad_n : kNmsWindow;   // whole windows of the bitmask
-    return (size_t)kBins * 4 + (size_t)pad_n * (16 + 16 + 4 + 4) + (size_t)(rem_bits / 32) * 4 + 16;
+    // 4 histograms / offset tables | key64 + tmp64 (2 * pad_n each) | cls, keep | NMS bit matrix
+    return (size_t)4 * kBins * 4 + (size_t)pad_n * (16 + 16 + 4 + 4) + (size_t)kNmsW * 16 + 16;
 }
 
 }  // namespace b200det
 
 using namespace b200det;
 
-// decode workspace: [global histograms B*kBins int | counters B*4 int | lists B*cap uint64]
-struct DecodeWs {
-    int slices, rows_per_slice, cap;
-    size_t off_hist, off_count, off_list, zero_bytes, total;
-};
-static DecodeWs decode_ws_layout(const Geo &g, int topn) {
-    DecodeWs w;
-    int pad_n = 32;
-    while (pad_n < topn) pad_n <<= 1;
-    w.cap = 2 * pad_n;
-    const int N = g.off[g.n_levels];
-    // one slice per ~16k rows: below two slices the single-CTA front end is just as fast
-    int slices = (N + 16383) / 16384;
-    if (slices > 16) slices = 16;
-    w.slices = slices;
-    w.rows_per_slice = (N + slices - 1) / slices;
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    w.off_hist = 0;
-    w.off_count = up((size_t)g.batch * kBins * sizeof(int));
-    w.zero_bytes = w.off_count + up((size_t)g.batch * 4 * sizeof(int));
-    w.off_list = w.zero_bytes;
-    w.total = w.off_list + up((size_t)g.batch * w.cap * sizeof(unsigned long long));
-    return w;
-}
-
 extern "C" size_t b200det_decode_workspace_bytes(const b200det_geometry *geo, int topn) {
+    // The selection keeps its histograms and candidate lists in (distributed) shared memory; the
+    // workspace argument of the decode calls is accepted for ABI stability and not touched.
     Geo g;
     if (make_geo(geo, &g) || topn < 1 || topn > B200DET_MAX_TOPN) return 0;
-    return decode_ws_layout(g, topn).total;
+    return 256;
 }
 
 namespace b200det {
@@ -1306,59 +1358,66 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
         a.key_shift = sh;
     }
     const size_t smem = select_smem_bytes(pad_n);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(select_nms_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)select_smem_bytes(B200DET_MAX_TOPN));
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    static std::atomic<unsigned long long> attr_set{0};   // bit d: raised for device d
+    if (dev < 64 && !((attr_set.load(std::memory_order_relaxed) >> dev) & 1ull)) {
+        e = cudaFuncSetAttribute(select_nms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)select_smem_bytes(B200DET_MAX_TOPN));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(select_nms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)select_smem_bytes(B200DET_MAX_TOPN));
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set.fetch_or(1ull << dev, std::memory_order_relaxed);
     }
-    // multi-CTA front end (global histogram + collect) when the caller gave a workspace and an
-    // image is big enough to be worth splitting; otherwise the select kernel does it all
-    const unsigned long long *glist = nullptr;
-    const int *gcount = nullptr;
-    const DecodeWs dw = decode_ws_layout(g, topn);
+    // Cluster size = CTAs that share one image's key passes.  The front end is latency-bound, so a
+    // small batch wants every image spread over as many SMs as there are (8 slices of ~15 k rows
+    // for an 800x800 RetinaNet pyramid), a large batch one CTA per image (the SMs are busy anyway
+    // and clusters must be co-scheduled inside a GPC).
+    const int N = g.off[g.n_levels];
+    int slices = 1;
+    while (slices < 8 && slices * 2 * g.batch <= 160 && N / (slices * 2) >= 4096) slices *= 2;
+    static const int env_slices = getenv("B200DET_SELECT_SLICES") ? atoi(getenv("B200DET_SELECT_SLICES")) : 0;
+    if (env_slices == 1 || env_slices == 2 || env_slices == 4 || env_slices == 8) slices = env_slices;
+    a.slices = slices;
+    a.rows_per_slice = (N + slices - 1) / slices;
+    static const bool env_bitonic = getenv("B200DET_SELECT_BITONIC") != nullptr;
+    a.force_bitonic = env_bitonic ? 1 : 0;
+    a.stamps = g_select_stamps;
+    (void)workspace;
+    (void)workspace_bytes;
     ProfScope prof(kKernSelect, stream);
-    // (measured: at batch 256 every SM already holds two select CTAs and the extra launches cost
-    // more than they save; at batch 16 the front end is the critical path of 16 lonely CTAs)
-    if (workspace && workspace_bytes >= dw.total && dw.slices >= 2 && g.batch < 64) {
-        char *base = static_cast<char *>(workspace);
-        cudaError_t e = cudaMemsetAsync(base, 0, dw.zero_bytes, (cudaStream_t)stream);
-        if (e != cudaSuccess) return (int)e;
-        PreArgs pa;
-        pa.g = g;
-        pa.key_lo = a.key_lo;
-        pa.key_shift = a.key_shift;
-        pa.slices = dw.slices;
-        pa.rows_per_slice = dw.rows_per_slice;
-        pa.topn = topn;
-        pa.cap = dw.cap;
-        int *ghist = reinterpret_cast<int *>(base + dw.off_hist);
-        int *gc = reinterpret_cast<int *>(base + dw.off_count);
-        unsigned long long *gl = reinterpret_cast<unsigned long long *>(base + dw.off_list);
-        const dim3 grid((unsigned)dw.slices, (unsigned)g.batch);
-        select_hist_kernel<<<grid, kSelThreads, 0, (cudaStream_t)stream>>>(pa, keys, ghist);
-        count_launch();
-        const size_t pre_smem = (size_t)kBins * 4 + (size_t)dw.cap * 8;
-        static bool pre_attr = false;
-        if (!pre_attr) {
-            e = cudaFuncSetAttribute(select_collect_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)kBins * 4 + (size_t)4 * B200DET_MAX_TOPN * 8));
-            if (e != cudaSuccess) return (int)e;
-            pre_attr = true;
-        }
-        select_collect_kernel<<<grid, kSelThreads, pre_smem, (cudaStream_t)stream>>>(pa, keys, ghist,
-                                                                                  gl, gc);
-        count_launch();
-        glist = gl;
-        gcount = gc;
-    }
-    select_nms_kernel<<<g.batch, kSelThreads, smem, (cudaStream_t)stream>>>(
-        a, keys, classes, out, order, keep, counts, glist, gcount);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)slices, (unsigned)g.batch, 1);
+    cfg.blockDim = dim3(kSelThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)slices;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // more images than SMs: two CTAs per SM (32 registers) instead of two waves
+    static const int env_minb = getenv("B200DET_SELECT_MINB") ? atoi(getenv("B200DET_SELECT_MINB")) : 0;
+    const bool two = env_minb ? env_minb == 2 : (slices * g.batch > 148 && smem <= 100 * 1024);
+    e = two ? cudaLaunchKernelEx(&cfg, select_nms_kernel<2>, a, keys, (const int *)classes, out,
+                                 (int *)order, (int *)keep, (int *)counts)
+            : cudaLaunchKernelEx(&cfg, select_nms_kernel<1>, a, keys, (const int *)classes, out,
+                                 (int *)order, (int *)keep, (int *)counts);
     count_launch();
+    if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
+}
+
+// Profiling hook (tools/prof_select.py): device int64 [B,16] that receives the globaltimer stamps of
+// the select kernel's phases (0 start, 1 histograms, 2 list, 3 order, 4 decode, 5 NMS, 6 outputs), or
+// NULL to switch it off.  Not part of the product path.
+extern "C" int b200det_select_stamps(long long *stamps) {
+    g_select_stamps = stamps;
+    return 0;
 }
 
 extern "C" int b200det_npexp_f32(const float *x, float *y, long long n, void *stream) {

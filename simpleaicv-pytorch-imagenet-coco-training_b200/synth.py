@@ -85,6 +85,30 @@ def make_fcos_preds(batch, size, num_classes, seed=0, sigma=1.0, device='cpu', s
     return [cls, reg, ctr]
 
 
+def make_retina_preds_sharded(first, count, size, num_classes, seed=0, sigma=1.0, per_loc=9,
+                              device='cpu'):
+    """Images [first, first + count) of ONE global synthetic batch: every image has its own seed, so
+    the union over any sharding (1, 2, 4, 8 ranks ...) is the same batch, bit for bit.  Same
+    distributions as make_retina_preds."""
+    sizes = pyramid_sizes(size)
+    cls = [torch.empty((count, p, p, per_loc, num_classes), device=device) for p in sizes]
+    reg = [torch.empty((count, p, p, per_loc, 4), device=device) for p in sizes]
+    gen = torch.Generator(device=device)
+    for i in range(count):
+        gen.manual_seed(1000003 * (seed + 1) + first + i)
+        for l, p in enumerate(sizes):
+            c = torch.randn((p, p, per_loc, num_classes), generator=gen, device=device)
+            cls[l][i] = torch.sigmoid(c * sigma - 4.595)
+            reg[l][i] = torch.randn((p, p, per_loc, 4), generator=gen, device=device) * 0.2
+    return [cls, reg]
+
+
+def make_annotations_sharded(first, count, max_gt, size, num_classes, seed=1):
+    """Rows [first, first + count) of the global batch's annotations (per-image seeds)."""
+    return torch.cat([make_annotations(1, max_gt, size, num_classes, seed=1000003 * (seed + 1) + first + i)
+                      for i in range(count)], dim=0)
+
+
 def make_tie_free(preds, min_score=0.05, max_rounds=64):
     """Bumps the arg-max class probability of rows whose FINAL score (max prob, or
     sqrt(max prob * centre-ness) for FCOS) collides with another row of the same image, until

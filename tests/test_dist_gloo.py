@@ -80,4 +80,9 @@ def test_bench_reference_arm_prints_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'images/s' and line['value'] > 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
+    # the reference's own classes when baseline/fetch_ref.sh has vendored them, else the oracle port
+    vendored = os.path.isfile(os.path.join(ROOT, 'baseline', '_ref', 'simpleAICV', 'detection',
+                                           'losses.py'))
+    assert line['cpu_baseline']['kind'] == ('reference' if vendored else 'port')
+    assert line['e2e']['h2d_bytes_per_step'] == 0
+    assert line['scaling'] == 'strong' and line['config']['global_batch'] == 256
