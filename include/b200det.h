@@ -10,7 +10,11 @@
  * Conventions
  *  - plain C: POD structs, raw device pointers, sizes; no torch / C++ types.
  *  - the caller owns every buffer (including `workspace`); the library allocates nothing
- *    on the device and keeps no mutable global state except a launch counter.
+ *    on the device (the 4 KB peer-exchange buffers and the helper stream / events of
+ *    b200det_loss_forward_overlap are created for, and owned by, the caller through explicit
+ *    create / destroy calls).  Process-wide mutable state is limited to: a launch counter, the
+ *    optional event profiler behind b200det_profile* (off by default; a mutex-guarded record list),
+ *    the b200det_select_stamps debug pointer, and per-device "shared-memory limit raised" bits.
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
  *    and never synchronises the host.
  *  - return value: 0 = ok, negative = B200DET_E* argument error, positive = cudaError_t of
@@ -493,9 +497,15 @@ int b200det_peer_buffer_destroy(void *buffer);
 
 typedef struct b200det_peer_exchange {
     int32_t rank, world;            /* world <= B200DET_MAX_PEERS */
-    uint64_t epoch;                 /* 1, 2, 3, ...: the same value on every rank for one exchange */
-    uint64_t timeout_cycles;        /* spin budget in SM cycles (0: ~30 s); on expiry the sums become
-                                       NaN and *status = 1 -- the kernel never hangs */
+    uint64_t epoch;                 /* 0 (normal use): the exchange number is kept in device memory (in
+                                       the rank's own buffer) and advanced by the kernel, so replays of a
+                                       captured CUDA graph advance it like eager calls do; != 0: caller-
+                                       numbered exchange, the same value on every rank */
+    uint64_t timeout_cycles;        /* wait budget in NANOSECONDS of %globaltimer (the field keeps its
+                                       r01 name; 0: 120 s); on expiry the sums and losses become NaN and
+                                       *status = 1 -- the kernel never hangs.  After a timeout the ranks'
+                                       counters may disagree: re-synchronise (barrier) and recreate the
+                                       buffers before the next exchange */
     void *peer[B200DET_MAX_PEERS];  /* peer[r]: rank r's buffer as mapped here; peer[rank]: own */
 } b200det_peer_exchange;
 
@@ -516,6 +526,32 @@ int b200det_loss_forward_exchange(const b200det_geometry *geo, const b200det_los
                                   void *workspace, size_t workspace_bytes,
                                   const b200det_peer_exchange *px, double *sums, float *losses,
                                   int32_t *status, void *stream);
+
+/*
+ * b200det_loss_forward / b200det_loss_forward_exchange (px != NULL) with the assignment and the
+ * sparse losses -- which do not read what the focal sweep writes -- enqueued on `side_stream` BESIDE
+ * the HBM-bound sweep: fork (ev_fork) after the memset, join (ev_join) before the reduction, so that
+ * everything is ordered on `stream` again when the call returns; capturable in a CUDA graph.  The
+ * stream and the two events belong to the caller (one set per criterion object); NULL for any of
+ * the three = everything on `stream`.  status may be NULL without px.
+ * phase: 0 = the whole call.  A host layer that wants the HBM-bound sweep on the GPU as early as
+ * possible splits it: phase 1 = memset + fork + focal sweep only (reads geo, params, cls, workspace;
+ * the other pointers may be NULL), then -- after it has prepared the remaining arguments -- phase 2 =
+ * assignment, sparse losses, join, reduction with the same geo / cls / workspace / streams / events.
+ */
+int b200det_loss_forward_overlap(const b200det_geometry *geo, const b200det_loss_params *params,
+                                 const float *annotations, int max_gt, const void *const *cls,
+                                 const void *const *reg, const void *const *ctr, int32_t *labels,
+                                 void *workspace, size_t workspace_bytes,
+                                 const b200det_peer_exchange *px, double *sums, float *losses,
+                                 int32_t *status, void *side_stream, void *ev_fork, void *ev_join,
+                                 void *stream, int phase);
+/* caller-owned helper objects for the call above: a non-blocking stream (high_priority != 0: the
+ * device's highest priority) and timing-free events, on the current device */
+int b200det_stream_create(void **stream, int high_priority);
+int b200det_stream_destroy(void *stream);
+int b200det_event_create(void **event);
+int b200det_event_destroy(void *event);
 
 #ifdef __cplusplus
 }

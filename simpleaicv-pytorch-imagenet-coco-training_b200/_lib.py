@@ -200,6 +200,15 @@ SIGNATURES = {
         _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vp,
         ctypes.c_size_t, ctypes.POINTER(PeerExchange), _vp, _vp, _vp, _vp
     ]),
+    'b200det_loss_forward_overlap': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vp,
+        ctypes.c_size_t, ctypes.POINTER(PeerExchange), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+        ctypes.c_int
+    ]),
+    'b200det_stream_create': (ctypes.c_int, [_vpp, ctypes.c_int]),
+    'b200det_stream_destroy': (ctypes.c_int, [_vp]),
+    'b200det_event_create': (ctypes.c_int, [_vpp]),
+    'b200det_event_destroy': (ctypes.c_int, [_vp]),
     'b200det_head_sigmoid_permute': (ctypes.c_int, [
         _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, _vp, _vp]),
     'b200det_head_sigmoid_permute_backward': (ctypes.c_int, [

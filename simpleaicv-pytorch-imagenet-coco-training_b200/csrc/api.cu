@@ -6,45 +6,23 @@
 
 using namespace b200det;
 
+namespace b200det {
+int loss_forward_impl(const b200det_geometry *geo, const b200det_loss_params *p,
+                      const float *annotations, int max_gt, const void *const *cls,
+                      const void *const *reg, const void *const *ctr, int32_t *labels,
+                      void *workspace, size_t workspace_bytes, const b200det_peer_exchange *px,
+                      double *sums, float *losses, int32_t *status, void *side, void *ev_fork,
+                      void *ev_join, void *stream, int phase);   // exchange.cu
+}
+
 extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_loss_params *p,
                                     const float *annotations, int max_gt, const void *const *cls,
                                     const void *const *reg, const void *const *ctr,
                                     int32_t *labels, void *workspace, size_t workspace_bytes,
                                     double *sums, float *losses, void *stream) {
-    Geo g;
-    int rc = make_geo(geo, &g);
-    if (rc) return rc;
-    if (!p || !annotations || !cls || !labels || !workspace || !sums) return B200DET_EINVAL;
-    const LossWs ws = loss_ws_layout(g);
-    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
-    // sweep accumulators and queue counters are adjacent in the workspace: one memset
-    char *base = static_cast<char *>(workspace);
-    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
-                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
-                                    (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
-    g_skip_memset = true;
-    // the long HBM-bound sweep first: the host prepares the remaining launches behind it
-    rc = b200det_focal_loss(geo, cls, nullptr, p->alpha, p->gamma, nullptr, nullptr, 0.f,
-                            workspace, workspace_bytes, stream);
-    if (!rc) {
-        rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample,
-                                              labels, nullptr, nullptr, workspace,
-                                              workspace_bytes, stream)
-                        : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos,
-                                                labels, nullptr, workspace, workspace_bytes,
-                                                stream);
-    }
-    if (!rc)
-        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
-                                   ctr, p->box_loss, p->beta, cls, p->alpha, p->gamma, nullptr,
-                                   nullptr, workspace, workspace_bytes, stream);
-    g_skip_memset = false;
-    if (!rc)   // reduction and normalisation in one launch unless the caller all-reduces in between
-        rc = losses ? b200det_loss_reduce_finish(geo, workspace, workspace_bytes, p->w_cls, p->w_box,
-                                                 p->w_ctr, sums, losses, stream)
-                    : b200det_loss_reduce(geo, 3, workspace, workspace_bytes, sums, stream);
-    return rc;
+    return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
+                             workspace_bytes, nullptr, sums, losses, nullptr, nullptr, nullptr,
+                             nullptr, stream, 0);
 }
 
 extern "C" int b200det_loss_forward_grad(const b200det_geometry *geo, const b200det_loss_params *p,

@@ -24,6 +24,7 @@
 //      focal.cu run label-free and concurrently.  Sums are accumulated in 64-bit fixed point, so
 //      they do not depend on the order in which rows are visited (deterministic).
 #include <stdlib.h>
+#include <atomic>
 #include "common.cuh"
 #include "dual.cuh"
 #include "focal_terms.cuh"
@@ -321,7 +322,8 @@ template <int PL>
 __global__ void __launch_bounds__(kAssignThreads)
     retina_assign_kernel(Geo g, BaseAnchors ba, TileTab tt, IouThresholds thr,
                          const float *__restrict__ annots, int G, int *__restrict__ labels,
-                         int *__restrict__ matched, Queues q, int *__restrict__ npos_partials) {
+                         int *__restrict__ matched, Queues q, int *__restrict__ npos_partials,
+                         int b0) {
     constexpr int NA = PL > 0 ? PL : 1;
     constexpr int kQueue = kAssignThreads * (PL > 0 ? PL : kMaxPerLoc);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kAssignThreads)
         n_ign_s = 0;
     }
 
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + b0;
     const GtSmem s = carve(smem_raw, G);
     const float *src = annots + (size_t)b * G * 5;
     const bool bulk = (((G * 5 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(kAssignThreads)
     }
     __syncthreads();
     flush_queues(q, pos_q, n_pos_s, ign_q, n_ign_s,
-                 npos_partials + (size_t)blockIdx.y * gridDim.x + blockIdx.x, bases);
+                 npos_partials + (size_t)b * gridDim.x + blockIdx.x, bases);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(kAssignThreads)
     fcos_assign_kernel(Geo g, FcosTab ft, TileTab tt, const float *__restrict__ annots, int G,
                        int use_center_sample, int *__restrict__ labels,
                        int *__restrict__ matched, float *__restrict__ targets, Queues q,
-                       int *__restrict__ npos_partials) {
+                       int *__restrict__ npos_partials, int b0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ float red[4 * kAssignWarps];
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(kAssignThreads)
     __shared__ int n_pos_s, bases[2];
     if (threadIdx.x == 0) n_pos_s = 0;
 
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + b0;
     const GtSmem s = carve(smem_raw, G);
     const float *src = annots + (size_t)b * G * 5;
     const bool bulk = (((G * 5 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(kAssignThreads)
     }
     __syncthreads();
     flush_queues(q, pos_q, n_pos_s, nullptr, 0,
-                 npos_partials + (size_t)blockIdx.y * gridDim.x + blockIdx.x, bases);
+                 npos_partials + (size_t)b * gridDim.x + blockIdx.x, bases);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -893,13 +895,18 @@ static void copy_base(const b200det_geometry *geo, BaseAnchors *ba) {
         for (int a = 0; a < kMaxPerLoc; ++a)
             for (int k = 0; k < 4; ++k) ba->v[l][a][k] = geo->base_anchors[l][a][k];
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: `done` holds one bit per
+// device ordinal (a process that drives several GPUs raises it on each)
 template <typename K>
-static int raise_smem_limit(K kernel, bool *done) {
-    if (*done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kAssignSmemBudget);
+static int raise_smem_limit(K kernel, std::atomic<unsigned long long> *done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    *done = true;
+    if (dev < 64 && ((done->load(std::memory_order_relaxed) >> dev) & 1ull)) return 0;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kAssignSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 64) done->fetch_or(1ull << dev, std::memory_order_relaxed);
     return 0;
 }
 
@@ -923,7 +930,7 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
     copy_base(geo, &ba);
     TileTab tt = make_tiles(g);
     set_anchor_extents(&tt, g, ba);
-    static bool a9 = false, a0 = false;
+    static std::atomic<unsigned long long> a9{0}, a0{0};
     if ((rc = raise_smem_limit(retina_assign_kernel<9>, &a9))) return rc;
     if ((rc = raise_smem_limit(retina_assign_kernel<0>, &a0))) return rc;
     char *base = static_cast<char *>(workspace);
@@ -933,16 +940,21 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
         cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)g.batch);
     const size_t smem = assign_dyn_smem(max_gt);
     ProfScope prof(kKernAssign, stream);
-    if (g.per_loc == 9)
-        retina_assign_kernel<9><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
-            g, ba, tt, thr, annotations, max_gt, labels, matched, q, npos);
-    else
-        retina_assign_kernel<0><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
-            g, ba, tt, thr, annotations, max_gt, labels, matched, q, npos);
-    count_launch();
+    // g_assign_chunk > 0 (set by the overlapped forward): a few images per launch, so that the
+    // kernel's CTAs (96 registers each) displace only part of the HBM-bound sweep they run beside
+    const int chunk = g_assign_chunk > 0 ? g_assign_chunk : g.batch;
+    for (int b0 = 0; b0 < g.batch; b0 += chunk) {
+        dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)(g.batch - b0 < chunk ? g.batch - b0 : chunk));
+        if (g.per_loc == 9)
+            retina_assign_kernel<9><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
+                g, ba, tt, thr, annotations, max_gt, labels, matched, q, npos, b0);
+        else
+            retina_assign_kernel<0><<<grid, kAssignThreads, smem, (cudaStream_t)stream>>>(
+                g, ba, tt, thr, annotations, max_gt, labels, matched, q, npos, b0);
+        count_launch();
+    }
     return (int)cudaGetLastError();
 }
 
@@ -965,7 +977,7 @@ extern "C" int b200det_fcos_assign(const b200det_geometry *geo, const float *ann
         ft.radius[l] = geo->radius[l];
     }
     const TileTab tt = make_tiles(g);
-    static bool done = false;
+    static std::atomic<unsigned long long> done{0};
     if ((rc = raise_smem_limit(fcos_assign_kernel, &done))) return rc;
     char *base = static_cast<char *>(workspace);
     const Queues q = queues_of(base, ws);
@@ -973,12 +985,15 @@ extern "C" int b200det_fcos_assign(const b200det_geometry *geo, const float *ann
         cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)g.batch);
     ProfScope prof(kKernAssign, stream);
-    fcos_assign_kernel<<<grid, kAssignThreads, assign_dyn_smem(max_gt), (cudaStream_t)stream>>>(
-        g, ft, tt, annotations, max_gt, use_center_sample, labels, matched, targets, q,
-        reinterpret_cast<int *>(base + ws.off_assign));
-    count_launch();
+    const int chunk = g_assign_chunk > 0 ? g_assign_chunk : g.batch;
+    for (int b0 = 0; b0 < g.batch; b0 += chunk) {
+        dim3 grid((unsigned)ws.assign_blocks_per_image, (unsigned)(g.batch - b0 < chunk ? g.batch - b0 : chunk));
+        fcos_assign_kernel<<<grid, kAssignThreads, assign_dyn_smem(max_gt), (cudaStream_t)stream>>>(
+            g, ft, tt, annotations, max_gt, use_center_sample, labels, matched, targets, q,
+            reinterpret_cast<int *>(base + ws.off_assign), b0);
+        count_launch();
+    }
     return (int)cudaGetLastError();
 }
 

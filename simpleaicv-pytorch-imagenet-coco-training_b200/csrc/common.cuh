@@ -83,6 +83,8 @@ int score_argmax_impl(const b200det_geometry *geo, const void *const *cls, const
                       long long *focal_slots, void *stream);   // decode.cu
 // set by the fused entry points after they have cleared all accumulators with ONE memset
 extern thread_local bool g_skip_memset;
+// set by the overlapped forward: images per assignment launch (0 = the whole batch in one launch)
+extern thread_local int g_assign_chunk;
 int assign_blocks_per_image(const Geo &g);  // assign.cu
 int sparse_blocks(const Geo &g);            // assign.cu
 
@@ -148,6 +150,15 @@ __device__ __forceinline__ float4 load_reg4(const void *base, int dtype, long lo
         return make_float4(a.x, a.y, b.x, b.y);
     }
 }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start once every CTA of its predecessor has
+// executed launch_dependents (or exited); it must execute wait before touching anything the
+// predecessor wrote (wait = the predecessor grid has completed and its writes are visible).
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

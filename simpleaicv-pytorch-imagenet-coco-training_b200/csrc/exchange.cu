@@ -12,11 +12,19 @@
 // slot r of set s = {sums[4], epoch} written by rank r.  A rank can not run two epochs ahead of a
 // peer (finishing epoch e+1 needs every peer's e+1 store, which a peer issues only after it has read
 // epoch e), so two sets are enough.  Data and flag are written by the same thread, the flag with
-// st.release.sys; the reader spins with ld.acquire.sys on the flag, bounded by a cycle budget: on
-// expiry the sums become NaN and the status word is set -- the kernel never hangs.
+// st.release.sys; the reader spins with ld.acquire.sys on the flag, bounded by a wall-clock budget
+// (%globaltimer; default 120 s): on expiry the sums become NaN and the status word is set -- the
+// kernel never hangs.
+//
+// The EPOCH lives in device memory (byte 2048 of the rank's own buffer) and is advanced by the
+// kernel itself: every rank runs the same sequence of exchanges, so the counters move in lock-step,
+// and a captured CUDA graph that is replayed advances them like eager calls do (a host-side counter
+// passed by value would be frozen into the graph and a replay would match the previous replay's
+// flags).  px->epoch != 0 still selects a caller-numbered exchange (tests).
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,11 +36,19 @@ constexpr int kMaxPeers = B200DET_MAX_PEERS;
 constexpr int kSlotDoubles = 8;   // 64-byte slots
 constexpr size_t kPeerBufferBytes = 4096;
 
+constexpr size_t kEpochOffset = 2048;      // device-side epoch counter of the owning rank
+
 struct ExchangeArgs {
     double *peer[kMaxPeers];
     int rank, world;
-    unsigned long long epoch, timeout_cycles;
+    unsigned long long epoch;        // 0: take (and advance) the counter in the rank's own buffer
+    unsigned long long timeout_ns;
 };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -102,22 +118,34 @@ __device__ __forceinline__ void exchange_tail(const double *local, const Exchang
                                               float *__restrict__ losses, int *__restrict__ status) {
     __shared__ double gathered[kMaxPeers][4];
     __shared__ int failed;
-    if (threadIdx.x == 0) failed = 0;
+    __shared__ unsigned long long s_epoch;
+    if (threadIdx.x == 0) {
+        failed = 0;
+        unsigned long long e = x.epoch;
+        if (e == 0) {   // this rank's exchange number, kept on the device (graph replays advance it)
+            unsigned long long *ctr = reinterpret_cast<unsigned long long *>(
+                reinterpret_cast<char *>(x.peer[x.rank]) + kEpochOffset);
+            e = *ctr + 1ull;
+            *ctr = e;
+        }
+        s_epoch = e;
+    }
     __syncthreads();
-    const int set = (int)(x.epoch & 1ull);
+    const unsigned long long epoch = s_epoch;
+    const int set = (int)(epoch & 1ull);
     const int t = threadIdx.x;
     if (t < x.world) {
         // my contribution into slot [rank] of peer t's buffer (t == rank: my own buffer)
         double *dst = x.peer[t] + ((size_t)set * kMaxPeers + x.rank) * kSlotDoubles;
 #pragma unroll
         for (int k = 0; k < 4; ++k) st_relaxed_sys(dst + k, local[k]);
-        st_release_sys(reinterpret_cast<unsigned long long *>(dst + 4), x.epoch);
+        st_release_sys(reinterpret_cast<unsigned long long *>(dst + 4), epoch);
         // peer t's contribution from slot [t] of my own buffer
         const double *src = x.peer[x.rank] + ((size_t)set * kMaxPeers + t) * kSlotDoubles;
-        const long long t0 = clock64();
+        const unsigned long long t0 = globaltimer_ns();
         bool ok = true;
-        while (ld_acquire_sys(reinterpret_cast<const unsigned long long *>(src + 4)) != x.epoch) {
-            if ((unsigned long long)(clock64() - t0) > x.timeout_cycles) {
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long *>(src + 4)) != epoch) {
+            if (globaltimer_ns() - t0 > x.timeout_ns) {
                 ok = false;
                 break;
             }
@@ -227,7 +255,6 @@ static int fill_exchange(const b200det_peer_exchange *px, ExchangeArgs *out) {
     if (!px) return B200DET_EINVAL;
     if (px->world < 1 || px->world > kMaxPeers || px->rank < 0 || px->rank >= px->world)
         return B200DET_ERANGE;
-    if (px->epoch == 0) return B200DET_EINVAL;
     ExchangeArgs &x = *out;
     for (int r = 0; r < kMaxPeers; ++r) x.peer[r] = nullptr;
     for (int r = 0; r < px->world; ++r) {
@@ -238,7 +265,8 @@ static int fill_exchange(const b200det_peer_exchange *px, ExchangeArgs *out) {
     x.rank = px->rank;
     x.world = px->world;
     x.epoch = px->epoch;
-    x.timeout_cycles = px->timeout_cycles ? px->timeout_cycles : 60000000000ull;   // ~30 s
+    // the field keeps its r01 name; since r02 it is a wall-clock budget in nanoseconds
+    x.timeout_ns = px->timeout_cycles ? px->timeout_cycles : 120000000000ull;      // 120 s
     return 0;
 }
 
@@ -280,6 +308,84 @@ extern "C" int b200det_loss_reduce_exchange(const b200det_geometry *geo, const v
     return (int)cudaGetLastError();
 }
 
+// The whole no-grad forward.  px == NULL: reduce (+ finish when `losses`); px != NULL: reduce +
+// cross-rank exchange + finish in one kernel.  side / ev_fork / ev_join != NULL: the assignment and
+// the sparse losses -- which do not depend on the focal sweep -- run on `side` beside it
+// (fork after the memset, join before the reduction).  The caller owns the stream and the events.
+namespace b200det {
+int loss_forward_impl(const b200det_geometry *geo, const b200det_loss_params *p,
+                      const float *annotations, int max_gt, const void *const *cls,
+                      const void *const *reg, const void *const *ctr, int32_t *labels,
+                      void *workspace, size_t workspace_bytes, const b200det_peer_exchange *px,
+                      double *sums, float *losses, int32_t *status, void *side, void *ev_fork,
+                      void *ev_join, void *stream, int phase) {
+    // phase: 0 = everything; 1 = only memset + fork + focal sweep (needs geo, p, cls, workspace);
+    //        2 = the rest of a call whose phase 1 has been enqueued (same arguments)
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!p || !cls || !workspace) return B200DET_EINVAL;
+    if (phase != 1 && (!annotations || !labels || !sums)) return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    const bool fork = side && ev_fork && ev_join;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (phase != 2) {
+        // sweep accumulators and queue counters are adjacent in the workspace: one memset
+        char *base = static_cast<char *>(workspace);
+        e = cudaMemsetAsync(base + ws.off_focal, 0, ws.off_counters + 2 * sizeof(int) - ws.off_focal, st);
+        if (e != cudaSuccess) return (int)e;
+        if (fork) {
+            if ((e = cudaEventRecord((cudaEvent_t)ev_fork, st)) != cudaSuccess) return (int)e;
+            if ((e = cudaStreamWaitEvent((cudaStream_t)side, (cudaEvent_t)ev_fork, 0)) != cudaSuccess)
+                return (int)e;
+        }
+        g_skip_memset = true;
+        // the long HBM-bound sweep first: the host prepares the remaining launches behind it
+        rc = b200det_focal_loss(geo, cls, nullptr, p->alpha, p->gamma, nullptr, nullptr, 0.f, workspace,
+                                workspace_bytes, stream);
+        g_skip_memset = false;
+        if (phase == 1) return rc;
+    }
+    void *st_sparse = stream;
+    if (fork) {
+        st_sparse = side;
+        static const int env_chunk = getenv("B200DET_ASSIGN_CHUNK") ? atoi(getenv("B200DET_ASSIGN_CHUNK")) : -1;
+        g_assign_chunk = env_chunk >= 0 ? env_chunk : 0;
+    }
+    g_skip_memset = true;
+    if (!rc) {
+        rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample,
+                                              labels, nullptr, nullptr, workspace,
+                                              workspace_bytes, st_sparse)
+                        : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos,
+                                                labels, nullptr, workspace, workspace_bytes,
+                                                st_sparse);
+    }
+    if (!rc)
+        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
+                                   ctr, p->box_loss, p->beta, cls, p->alpha, p->gamma, nullptr,
+                                   nullptr, workspace, workspace_bytes, st_sparse);
+    g_skip_memset = false;
+    g_assign_chunk = 0;
+    if (fork) {
+        // always re-join, also after a failed launch: the side stream must not stay forked (capture)
+        e = cudaEventRecord((cudaEvent_t)ev_join, (cudaStream_t)side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+    }
+    if (rc) return rc;
+    if (px)
+        return b200det_loss_reduce_exchange(geo, workspace, workspace_bytes, px, p->w_cls, p->w_box,
+                                            p->w_ctr, sums, losses, status, stream);
+    // reduction and normalisation in one launch unless the caller all-reduces in between
+    return losses ? b200det_loss_reduce_finish(geo, workspace, workspace_bytes, p->w_cls, p->w_box,
+                                               p->w_ctr, sums, losses, stream)
+                  : b200det_loss_reduce(geo, 3, workspace, workspace_bytes, sums, stream);
+}
+}  // namespace b200det
+
 // b200det_loss_forward with the reduction, the cross-rank exchange and the normalisation in one
 // kernel (see above) instead of reduce -> [caller all-reduces] -> finish.
 extern "C" int b200det_loss_forward_exchange(const b200det_geometry *geo,
@@ -290,35 +396,50 @@ extern "C" int b200det_loss_forward_exchange(const b200det_geometry *geo,
                                              void *workspace, size_t workspace_bytes,
                                              const b200det_peer_exchange *px, double *sums,
                                              float *losses, int32_t *status, void *stream) {
-    Geo g;
-    int rc = make_geo(geo, &g);
-    if (rc) return rc;
-    if (!p || !annotations || !cls || !labels || !workspace || !sums || !px) return B200DET_EINVAL;
-    const LossWs ws = loss_ws_layout(g);
-    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
-    char *base = static_cast<char *>(workspace);
-    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
-                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
-                                    (cudaStream_t)stream);
+    if (!px) return B200DET_EINVAL;
+    return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
+                             workspace_bytes, px, sums, losses, status, nullptr, nullptr, nullptr,
+                             stream, 0);
+}
+
+extern "C" int b200det_loss_forward_overlap(const b200det_geometry *geo,
+                                            const b200det_loss_params *p, const float *annotations,
+                                            int max_gt, const void *const *cls,
+                                            const void *const *reg, const void *const *ctr,
+                                            int32_t *labels, void *workspace,
+                                            size_t workspace_bytes,
+                                            const b200det_peer_exchange *px, double *sums,
+                                            float *losses, int32_t *status, void *side_stream,
+                                            void *ev_fork, void *ev_join, void *stream, int phase) {
+    if (phase < 0 || phase > 2) return B200DET_EINVAL;
+    return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
+                             workspace_bytes, px, sums, losses, status, side_stream, ev_fork,
+                             ev_join, stream, phase);
+}
+
+// Caller-owned helper objects of b200det_loss_forward_overlap (the library keeps none itself).
+extern "C" int b200det_stream_create(void **stream, int high_priority) {
+    if (!stream) return B200DET_EINVAL;
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (e != cudaSuccess) return (int)e;
-    g_skip_memset = true;
-    rc = b200det_focal_loss(geo, cls, nullptr, p->alpha, p->gamma, nullptr, nullptr, 0.f, workspace,
-                            workspace_bytes, stream);
-    if (!rc) {
-        rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample,
-                                              labels, nullptr, nullptr, workspace,
-                                              workspace_bytes, stream)
-                        : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos,
-                                                labels, nullptr, workspace, workspace_bytes,
-                                                stream);
-    }
-    if (!rc)
-        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
-                                   ctr, p->box_loss, p->beta, cls, p->alpha, p->gamma, nullptr,
-                                   nullptr, workspace, workspace_bytes, stream);
-    g_skip_memset = false;
-    if (!rc)
-        rc = b200det_loss_reduce_exchange(geo, workspace, workspace_bytes, px, p->w_cls, p->w_box,
-                                          p->w_ctr, sums, losses, status, stream);
-    return rc;
+    cudaStream_t s = nullptr;
+    e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo);
+    if (e != cudaSuccess) return (int)e;
+    *stream = s;
+    return 0;
+}
+extern "C" int b200det_stream_destroy(void *stream) {
+    return stream ? (int)cudaStreamDestroy((cudaStream_t)stream) : B200DET_EINVAL;
+}
+extern "C" int b200det_event_create(void **event) {
+    if (!event) return B200DET_EINVAL;
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+    *event = ev;
+    return 0;
+}
+extern "C" int b200det_event_destroy(void *event) {
+    return event ? (int)cudaEventDestroy((cudaEvent_t)event) : B200DET_EINVAL;
 }

@@ -26,6 +26,7 @@ namespace b200det {
 // ---------------------------------------------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
 thread_local bool g_skip_memset = false;
+thread_local int g_assign_chunk = 0;
 
 // ---- per-kernel event profiler -------------------------------------------------------------
 struct ProfRec {
@@ -342,7 +343,8 @@ __global__ void __launch_bounds__(kFocalThreads, XROW ? B200DET_FOCAL_XROW_MINB 
     float gs = 0.f;
     if (GRAD) {
         const double npos = a.sums[0];
-        gs = npos > 0.0 ? (float)((double)a.grad_scale / npos) : 0.f;
+        // a NaN count (failed cross-rank exchange) must poison the gradient, not zero it
+        gs = npos > 0.0 ? (float)((double)a.grad_scale / npos) : (npos != npos ? (float)npos : 0.f);
     }
     const float one_m_alpha = 1.f - a.alpha;
 
@@ -578,6 +580,7 @@ __global__ void loss_finish_kernel(const double *__restrict__ sums, float w_cls,
             float v = 0.f;
             // float32 sum / count, then * weight  (losses.py:259, :293, :318, :210-211)
             if (npos > 0.0) v = w[i] * ((float)sums[1 + i] / (float)npos);
+            if (npos != npos) v = (float)npos;   // failed cross-rank exchange: NaN, never a silent 0
             losses[i] = v;
         }
     }
@@ -593,7 +596,7 @@ __global__ void scale_levels_kernel(ScaleArgs a, const float *__restrict__ g,
     float k = *g;
     if (sums) {
         const double npos = sums[0];
-        k = npos > 0.0 ? (float)((double)k * (double)weight / npos) : 0.f;
+        k = npos > 0.0 ? (float)((double)k * (double)weight / npos) : (npos != npos ? (float)npos : 0.f);
     }
     if (k == 1.f) return;
     float *x = a.ptr[blockIdx.y];

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from . import geometry as _geom
-from .losses import _prep_f32, _prep_reg
+from .losses import _on_device, _prep_f32, _prep_reg, _require_cuda
 
 _ZERO_COPY = os.environ.get('B200DET_ZERO_COPY', '1') != '0'
 # the returned arrays are views of the call's own pinned buffer (no host memcpy); '1' hands out
@@ -112,6 +112,11 @@ class _DecoderBase:
         return [scores, out_classes, boxes]
 
     def _run(self, preds, details=False, scales=None, sizes=None, to_xywh=False):
+        _require_cuda(preds[0][0], 'cls_preds')
+        with _on_device(preds[0][0].device):
+            return self._run_on(preds, details, scales, sizes, to_xywh)
+
+    def _run_on(self, preds, details, scales, sizes, to_xywh):
         lib = _lib.load()
         if self._is_fcos:
             cls_preds, reg_preds, center_preds = preds
@@ -268,7 +273,8 @@ class _FlatDecoder(_DecoderBase):
         if details:
             order = torch.empty(batch * topn, dtype=torch.int32, device=device)
             keep = torch.empty(batch * topn, dtype=torch.int32, device=device)
-        _lib.check(
+        with _on_device(device):
+            rc = (
             lib.b200det_select_decode_nms(
                 ctypes.byref(geo), keys.data_ptr(), classes.data_ptr(), _lib.ptr_array([boxes]),
                 _lib.F32, _lib.DECODE_BOXES, float(np.float32(min_score)), int(topn), int(max_out),
@@ -276,8 +282,8 @@ class _FlatDecoder(_DecoderBase):
                 float(self.nms_threshold if self.nms_threshold is not None else 0.5), None, None, 0,
                 out.data_ptr(), order.data_ptr() if details else None,
                 keep.data_ptr() if details else None, None, ws.data_ptr(), ws_bytes,
-                _lib.raw_stream(device)),
-            'b200det_select_decode_nms')
+                _lib.raw_stream(device)))
+        _lib.check(rc, 'b200det_select_decode_nms')
         result = self._to_host(out, batch, max_out, device)
         if not details:
             return result
@@ -294,14 +300,14 @@ class _FlatDecoder(_DecoderBase):
         xyxy = torch.empty((batch, queries, 4), dtype=torch.float32, device=device) \
             if boxes is not None else None
         dtype = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}[cls.dtype]
-        _lib.check(
-            lib.b200det_query_scores(
+        with _on_device(device):
+            rc = lib.b200det_query_scores(
                 cls.data_ptr(), dtype, mode, boxes.data_ptr() if boxes is not None else None,
                 sizes.data_ptr() if sizes is not None else None, batch, queries, channels,
                 int(num_classes), float(np.float32(min_score)), keys.data_ptr(), classes.data_ptr(),
                 xyxy.data_ptr() if xyxy is not None else None,
-                _lib.raw_stream(device)),
-            'b200det_query_scores')
+                _lib.raw_stream(device))
+        _lib.check(rc, 'b200det_query_scores')
         return keys, classes, xyxy
 
 

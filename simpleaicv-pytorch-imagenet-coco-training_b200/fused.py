@@ -21,8 +21,8 @@ import torch
 
 from . import _lib
 from . import geometry as _geom
-from .losses import (_DTYPES, _Plan, _loss_params, _plan_for, _prep_annotations, _prep_f32,
-                     _prep_reg, _sync_sums)
+from .losses import (_DTYPES, _Plan, _loss_params, _on_device, _plan_for, _prep_annotations,
+                     _prep_f32, _prep_reg, _require_cuda, _sync_sums)
 
 __all__ = ['EvalStep', 'LogitsEvalStep']
 
@@ -36,6 +36,11 @@ class EvalStep:
         self.decoder = decoder
 
     def __call__(self, preds, annotations, scales=None, sizes=None, to_xywh=False):
+        _require_cuda(preds[0][0], 'cls_preds')
+        with _on_device(preds[0][0].device):
+            return self._call_on(preds, annotations, scales, sizes, to_xywh)
+
+    def _call_on(self, preds, annotations, scales, sizes, to_xywh):
         lib = _lib.load()
         crit, dec = self.criterion, self.decoder
         is_fcos = crit._is_fcos
@@ -132,6 +137,11 @@ class LogitsEvalStep:
         return plan
 
     def __call__(self, preds, annotations, scales=None, sizes=None, to_xywh=False):
+        _require_cuda(preds[0][0], 'cls_preds')
+        with _on_device(preds[0][0].device):
+            return self._call_on(preds, annotations, scales, sizes, to_xywh)
+
+    def _call_on(self, preds, annotations, scales, sizes, to_xywh):
         lib = _lib.load()
         crit, dec = self.criterion, self.decoder
         cls = [t.detach() for t in preds[0]]

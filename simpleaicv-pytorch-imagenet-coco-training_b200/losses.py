@@ -25,6 +25,7 @@ Extra, keyword-only constructor arguments (defaults keep reference behaviour):
         exchange their sums with the stand-alone b200det_sums_exchange kernel.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -39,6 +40,29 @@ _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _li
 
 def _stream(device=None):
     return _lib.raw_stream(device)
+
+
+class _on_device:
+    """`with _on_device(t.device):` makes that GPU current for the C calls inside (kernel launches
+    go to the CURRENT device; a process may drive several).  A no-op when it already is."""
+
+    __slots__ = ('index', 'prev')
+
+    def __init__(self, device):
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.index:
+            self.prev = cur
+            torch.cuda.set_device(self.index)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _require_cuda(t, what):
@@ -128,6 +152,60 @@ def _peer_exchange(owner, device):
     return px
 
 
+class _SideStream:
+    """The helper stream + fork / join events of b200det_loss_forward_overlap for one device,
+    owned by the criterion object that uses them (the library keeps no streams itself)."""
+
+    def __init__(self, device):
+        lib = _lib.load()
+        self._lib = lib
+        self.stream, self.fork, self.join = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.b200det_stream_create(ctypes.byref(self.stream), _SIDE_HIGH), 'b200det_stream_create')
+            _lib.check(lib.b200det_event_create(ctypes.byref(self.fork)), 'b200det_event_create')
+            _lib.check(lib.b200det_event_create(ctypes.byref(self.join)), 'b200det_event_create')
+
+    def __del__(self):
+        try:
+            for ev in (self.fork, self.join):
+                if ev:
+                    self._lib.b200det_event_destroy(ev)
+            if self.stream:
+                self._lib.b200det_stream_destroy(self.stream)
+        except Exception:   # interpreter shutdown
+            pass
+
+
+_OVERLAP = os.environ.get('B200DET_LOSS_OVERLAP', '1') != '0'
+_SIDE_HIGH = int(os.environ.get('B200DET_SIDE_PRIORITY', '1') != '0')
+
+
+def _side_stream(owner, device):
+    """The owner's side stream for `device` (created on first use), or None when switched off."""
+    if not _OVERLAP:
+        return None
+    sides = owner.__dict__.get('_sides')
+    if sides is None:
+        sides = owner.__dict__['_sides'] = {}
+    side = sides.get(device.index)
+    if side is None:
+        side = sides[device.index] = _SideStream(device)
+    return side
+
+
+class _Stateless:
+    """Copy / pickle support: CUDA handles, peer mappings and cached plans are per-process runtime
+    state and are rebuilt on first use."""
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for key in ('_sides', '_peer', '_params_cache'):
+            state.pop(key, None)
+        state['_plans'] = {}
+        state['last_stats'] = None
+        return state
+
+
 def _wants_grad(tensors):
     if not torch.is_grad_enabled():
         return False
@@ -188,46 +266,62 @@ def _loss_params(owner, reg_dtype):
 
 
 def _forward_eval(owner, annotations, cls_in, reg_in, ctr_in):
-    """No-grad forward: one C call (b200det_loss_forward)."""
+    """No-grad forward: one C call (b200det_loss_forward_overlap)."""
+    _require_cuda(cls_in[0], 'cls_preds')
+    with _on_device(cls_in[0].device):
+        return _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in)
+
+
+def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
     lib = _lib.load()
+    # Phase 1 as early as possible: the sweep only needs the classification tensors, so it is on the
+    # GPU while the host still checks / marshals the other arguments (the eval loop calls this right
+    # after the decoder's host sync: every microsecond before the first launch is GPU idle time).
     cls = _prep_f32(cls_in, 'cls_preds')
-    reg, reg_dtype = _prep_reg(reg_in)
-    ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
-    annotations = _prep_annotations(annotations)
     plan = _plan_for(owner, cls)
-    if annotations.shape[0] != plan.batch:
-        raise ValueError('annotations and predictions disagree on the batch size')
     device = cls[0].device
     # scratch = workspace | labels ; out = sums (4 doubles) | losses (3 floats, 8 reserved)
     scratch = torch.empty(plan.ws_bytes + 4 * plan.batch * plan.n_rows, dtype=torch.uint8,
                           device=device)
-    out = torch.empty(8, dtype=torch.float64, device=device)
     ws_ptr = scratch.data_ptr()
+    st = _stream(device)
+    # assignment + sparse losses run on the criterion's side stream beside the HBM-bound sweep
+    side = _side_stream(owner, device)
+    side_args = (side.stream, side.fork, side.join) if side is not None else (None, None, None)
+    params = _loss_params(owner, _lib.F32)
+    cls_ptrs = _lib.ptr_array(cls)
+    _lib.check(
+        lib.b200det_loss_forward_overlap(plan.geo_ref, ctypes.byref(params), None, 0, cls_ptrs, None,
+                                         None, None, ws_ptr, plan.ws_bytes, None, None, None, None,
+                                         *side_args, st, 1), 'b200det_loss_forward_overlap')
+    reg, reg_dtype = _prep_reg(reg_in)
+    ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
+    annotations = _prep_annotations(annotations)
+    if annotations.shape[0] != plan.batch:
+        raise ValueError('annotations and predictions disagree on the batch size')
+    out = torch.empty(8, dtype=torch.float64, device=device)
     sums_ptr = out.data_ptr()
     sync = owner.sync_normalizer and torch.distributed.is_available() \
         and torch.distributed.is_initialized()
-    st = _stream(device)
-    params = _loss_params(owner, reg_dtype)
-    if sync and owner.sync_normalizer == 'p2p':
+    if reg_dtype != _lib.F32:
+        params = _loss_params(owner, reg_dtype)
+    p2p = sync and owner.sync_normalizer == 'p2p'
+    px = status = None
+    if p2p:
         # reduce + exchange over NVLink peer memory + normalisation in ONE kernel (csrc/exchange.cu)
-        px = _peer_exchange(owner, device)
+        px = _peer_exchange(owner, device).next()
         status = out[6:7].view(torch.int32)[0:1]   # written by the kernel on every call
-        _lib.check(
-            lib.b200det_loss_forward_exchange(plan.geo_ref, ctypes.byref(params),
-                                              annotations.data_ptr(), int(annotations.shape[1]),
-                                              _lib.ptr_array(cls), _lib.ptr_array(reg),
-                                              _lib.ptr_array(ctr), ws_ptr + plan.ws_bytes, ws_ptr,
-                                              plan.ws_bytes, px.next(), sums_ptr, sums_ptr + 32,
-                                              status.data_ptr(), st),
-            'b200det_loss_forward_exchange')
+    _lib.check(
+        lib.b200det_loss_forward_overlap(plan.geo_ref, ctypes.byref(params), annotations.data_ptr(),
+                                         int(annotations.shape[1]), cls_ptrs,
+                                         _lib.ptr_array(reg), _lib.ptr_array(ctr),
+                                         ws_ptr + plan.ws_bytes, ws_ptr, plan.ws_bytes, px, sums_ptr,
+                                         None if (sync and not p2p) else sums_ptr + 32,
+                                         status.data_ptr() if p2p else None, *side_args, st, 2),
+        'b200det_loss_forward_overlap')
+    if p2p:
         owner.__dict__['last_stats'] = {'sums': out[0:4], 'exchange_status': status}
         return out[4:8].view(torch.float32)
-    _lib.check(
-        lib.b200det_loss_forward(plan.geo_ref, ctypes.byref(params), annotations.data_ptr(),
-                                 int(annotations.shape[1]), _lib.ptr_array(cls),
-                                 _lib.ptr_array(reg), _lib.ptr_array(ctr),
-                                 ws_ptr + plan.ws_bytes, ws_ptr, plan.ws_bytes, sums_ptr,
-                                 None if sync else sums_ptr + 32, st), 'b200det_loss_forward')
     if sync:
         _maybe_all_reduce(out[0:4], True, owner.process_group)
         _lib.check(
@@ -245,6 +339,12 @@ class _DetLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, owner, annotations, n_levels, *heads):
+        _require_cuda(heads[0], 'cls_preds')
+        with _on_device(heads[0].device):
+            return _DetLossFunction._forward(ctx, owner, annotations, n_levels, *heads)
+
+    @staticmethod
+    def _forward(ctx, owner, annotations, n_levels, *heads):
         lib = _lib.load()
         is_fcos = owner._is_fcos
         cls = _prep_f32(heads[0:n_levels], 'cls_preds')
@@ -257,7 +357,7 @@ class _DetLossFunction(torch.autograd.Function):
             raise ValueError('annotations and predictions disagree on the batch size')
         device = cls[0].device
         geo, ws_bytes = plan.geo_ref, plan.ws_bytes
-        st = _stream()
+        st = _stream(device)
         max_gt = int(annotations.shape[1])
         alpha, gamma = float(owner.alpha), float(owner.gamma)
         w_cls = float(owner.cls_loss_weight)
@@ -341,22 +441,46 @@ class _DetLossFunction(torch.autograd.Function):
         ctx.want = (any(need[0:n_levels]), any(need[n_levels:2 * n_levels]),
                     is_fcos and any(need[2 * n_levels:3 * n_levels]))
         ctx.weights = (w_box, w_ctr)
+        ctx.consumed = False
+        ctx.set_materialize_grads(False)   # an unused loss term arrives as None, not as zeros
         ctx.save_for_backward(sums, *cls_grad, *reg_grad, *(ctr_grad or []))
         owner.last_stats = {'sums': sums}
         return (losses[0], losses[1], losses[2]) if is_fcos else (losses[0], losses[1])
 
     @staticmethod
     def backward(ctx, *grad_out):
+        # The stored gradients are scaled IN PLACE by the upstream scalars (no second copy of a
+        # cls-sized tensor): a second pass over the same node would scale them twice, or resurrect
+        # terms a first pass multiplied by an upstream zero.  Refuse instead of returning wrong
+        # gradients (torch does the same for a freed graph); call backward once on the summed loss,
+        # as tools/scripts.py:918-945 does, or re-run the forward.
+        if ctx.consumed:
+            raise RuntimeError(
+                'b200det: backward through this loss call a second time is not supported (its '
+                'gradients are produced by the forward kernels and scaled in place once); sum the '
+                'loss terms and call backward once, or run the forward again')
+        ctx.consumed = True
+        saved = ctx.saved_tensors
+        with _on_device(saved[0].device):
+            return _DetLossFunction._backward(ctx, saved, *grad_out)
+
+    @staticmethod
+    def _backward(ctx, saved, *grad_out):
         lib = _lib.load()
         n = ctx.n_levels
-        saved = ctx.saved_tensors
         sums = saved[0]
         cls_grad = saved[1:1 + n]
         reg_grad = saved[1 + n:1 + 2 * n]
         ctr_grad = saved[1 + 2 * n:1 + 3 * n]
         want_cls, want_reg, want_ctr = ctx.want
-        st = _stream()
+        st = _stream(sums.device)
         grads = [None] * (3 * n if ctx.is_fcos else 2 * n)
+        # a loss term nobody differentiated (grad None): its head gets no gradient from this node
+        # unless another term feeds it -- cls only feeds cls_loss, ctr only centre-ness; reg feeds
+        # reg_loss only
+        want_cls = want_cls and grad_out[0] is not None
+        want_reg = want_reg and grad_out[1] is not None
+        want_ctr = want_ctr and len(grad_out) > 2 and grad_out[2] is not None
 
         def scale(levels, g, with_norm, weight):
             """levels[l] *= g * (weight / positives if with_norm else 1): one launch"""
@@ -390,6 +514,11 @@ def _debug_assign(owner, preds, annotations, exact=True):
     the image's filtered GT list; -1 = none) and, for FCOS, targets [B,N,6] float32.
     exact=False runs the production scan (no `matched` output: pairs that cannot reach IoU 0.38
     are dropped early) and returns the labels only."""
+    with _on_device(preds[0][0].device):
+        return _debug_assign_on(owner, preds, annotations, exact)
+
+
+def _debug_assign_on(owner, preds, annotations, exact):
     lib = _lib.load()
     is_fcos = owner._is_fcos
     cls = _prep_f32(preds[0], 'cls_preds')
@@ -397,7 +526,7 @@ def _debug_assign(owner, preds, annotations, exact=True):
     plan = _plan_for(owner, cls)
     device = cls[0].device
     batch, n_rows, geo, ws_bytes = plan.batch, plan.n_rows, plan.geo_ref, plan.ws_bytes
-    st = _stream()
+    st = _stream(device)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     labels = torch.empty(batch * n_rows, dtype=torch.int32, device=device)
     matched = torch.empty(batch * n_rows, dtype=torch.int32, device=device) if exact else None
@@ -521,7 +650,7 @@ class IoUMethod:
         return out.view(out_shape)
 
 
-class RetinaLoss(nn.Module):
+class RetinaLoss(_Stateless, nn.Module):
     """Drop-in for simpleAICV.detection.losses.RetinaLoss (losses.py:126-429)."""
 
     _is_fcos = False
@@ -597,7 +726,7 @@ class RetinaLoss(nn.Module):
         return loss_dict
 
 
-class FCOSLoss(nn.Module):
+class FCOSLoss(_Stateless, nn.Module):
     """Drop-in for simpleAICV.detection.losses.FCOSLoss (losses.py:432-833)."""
 
     _is_fcos = True

@@ -52,13 +52,14 @@ class PeerExchange:
                 if r == self.rank:
                     px.peer[r] = self._own.value
                     continue
-                if not torch.cuda.can_device_access_peer(self.device.index, dev_index):
-                    self.close()
-                    raise RuntimeError(f'GPU {self.device.index} cannot access GPU {dev_index} '
-                                       'as a peer')
+                # (no can_device_access_peer(local index) test: the other process's device index
+                # means nothing here when CUDA_VISIBLE_DEVICES differs per rank; mapping the IPC
+                # handle enables peer access and fails if the two GPUs are not peers)
                 ptr = ctypes.c_void_p()
-                _lib.check(lib.b200det_peer_buffer_open(raw, ctypes.byref(ptr)),
-                           'b200det_peer_buffer_open')
+                rc = lib.b200det_peer_buffer_open(raw, ctypes.byref(ptr))
+                if rc != 0:
+                    self.close()
+                    _lib.check(rc, f'b200det_peer_buffer_open (rank {r}: not a peer of this GPU?)')
                 self._mapped.append(ptr)
                 px.peer[r] = ptr.value
         self.params = px
@@ -66,8 +67,9 @@ class PeerExchange:
         dist.barrier(group=group)
 
     def next(self):
-        """The struct for the next exchange (epochs count up in lock-step on every rank)."""
-        self.params.epoch += 1
+        """The struct for the next exchange.  epoch = 0: the exchange number lives in device memory
+        and the kernel advances it, in lock-step on every rank (every rank runs the same sequence
+        of exchanges) -- so a captured CUDA graph that is replayed advances it like eager calls."""
         return ctypes.byref(self.params)
 
     def close(self):
