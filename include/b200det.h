@@ -58,6 +58,13 @@ extern "C" {
 #define B200DET_F32 0
 #define B200DET_F16 1
 #define B200DET_BF16 2
+/* OR into a half-precision `reg_dtype`: exp() of a regression value is ROUNDED to that precision
+ * before it is used, as the reference's eager half arithmetic does (torch.exp on a float16 tensor,
+ * losses.py:417-426 / :568; np.exp on a float16 array, decode.py:257-268 / :356: the result of exp
+ * is float16 and only the following multiply / subtract promote to float32).  Without the flag exp
+ * runs on the upcast value -- what the reference computes under CUDA autocast, where exp is on the
+ * float32 list (tools/scripts.py:886-893 calls the criterion inside `with autocast()`). */
+#define B200DET_REG_EXP_ROUNDED 0x10
 
 /* box loss: RetinaLoss box_loss_type (losses.py:139-148) / FCOSLoss box_loss_iou_type (:443-448) */
 #define B200DET_BOX_NONE 0 /* assignment only */
@@ -331,6 +338,13 @@ typedef struct b200det_decode_params {
     const float *scales;  /* device [B] or NULL, see b200det_select_decode_nms */
     const float *sizes;   /* device [B,2] (h,w) or NULL */
     int32_t to_xywh;
+    /* float16 regression head (reg_dtype = B200DET_F16 | B200DET_REG_EXP_ROUNDED) only: device
+     * uint16[65536] = the float16 bits of np.exp for every float16 input as the HOST's NumPy
+     * computes it, or NULL = half(expf(float(x))), NumPy's generic half loop.  np.exp on float16 is
+     * CPU-dependent (hosts with AVX512-FP16 take an SVML kernel that differs from the correctly
+     * rounded value for 17 % of the inputs); the Python layer passes the table that matches the
+     * host it runs on (tools/make_half_exp_table.py). */
+    const uint16_t *half_exp_table;
 } b200det_decode_params;
 
 /*

@@ -556,11 +556,27 @@ def query_decode(cls_logits, reg_preds, scaled_sizes, activation, num_classes=No
     return result, {'per_image': extras, 'scores': scores, 'classes': classes, 'boxes': boxes}
 
 
-def _to_np_rows(level_tensors):
-    return np.concatenate([
-        t.cpu().detach().float().numpy().reshape(t.shape[0], -1, t.shape[-1])
-        for t in level_tensors
-    ], axis=1)
+def _to_np_rows(level_tensors, keep_half=False):
+    """decode.py:208-219: `.cpu().detach().numpy()` keeps the tensor's dtype, so a float16 head stays
+    float16 in NumPy (keep_half).  bfloat16 has no NumPy dtype -- the reference raises there -- and is
+    upcast."""
+    def one(t):
+        t = t.cpu().detach()
+        if not (keep_half and t.dtype == torch.float16):
+            t = t.float()
+        return t.numpy().reshape(t.shape[0], -1, t.shape[-1])
+    return np.concatenate([one(t) for t in level_tensors], axis=1)
+
+
+def _decoder_exp(reg, exp_fn):
+    """np.exp as the decoders see it (decode.py:260, :356): float32 arrays go through NumPy's SIMD
+    float32 kernel (restated in oracle/npexp.c); float16 arrays through NumPy's half loop (float
+    conversion, the C library's expf, rounding to half) -- the result IS float16 and only the
+    following multiply / subtract promotes to float32."""
+    if reg.dtype == np.float16:
+        with np.errstate(over='ignore'):
+            return np.exp(reg)
+    return exp_fn(reg)
 
 
 def retina_decode(preds, areas, ratios, scales, strides, max_object_num=100,
@@ -573,13 +589,13 @@ def retina_decode(preds, areas, ratios, scales, strides, max_object_num=100,
         level_anchors = retina_anchors(feature_sizes_of(cls_levels), areas, ratios, scales,
                                        strides)
     cls = _to_np_rows(cls_levels)
-    reg = _to_np_rows(reg_levels)
+    reg = _to_np_rows(reg_levels, keep_half=True)
     anchors = np.concatenate([a.reshape(-1, 4) for a in level_anchors], axis=0)[None]
     classes = np.argmax(cls, axis=2)
     scores = np.take_along_axis(cls, classes[:, :, None], axis=2)[:, :, 0]
     a_wh = anchors[:, :, 2:4] - anchors[:, :, 0:2]
     a_ctr = anchors[:, :, 0:2] + 0.5 * a_wh
-    wh = exp_fn(reg[:, :, 2:4]) * a_wh
+    wh = _decoder_exp(reg[:, :, 2:4], exp_fn) * a_wh
     ctr = reg[:, :, :2] * a_wh + a_ctr
     boxes = np.concatenate([ctr - 0.5 * wh, ctr + 0.5 * wh], axis=2)
     with np.errstate(invalid='ignore'):
@@ -596,13 +612,13 @@ def fcos_decode(preds, strides, max_object_num=100, min_score_threshold=0.05, to
     cls_levels, reg_levels, ctr_levels = preds
     positions = fcos_positions(feature_sizes_of(cls_levels), strides)
     cls = _to_np_rows(cls_levels)
-    reg = _to_np_rows(reg_levels)
+    reg = _to_np_rows(reg_levels, keep_half=True)
     ctr = _to_np_rows(ctr_levels)
     pts = np.concatenate([p.reshape(-1, 2) for p in positions], axis=0)[None]
     classes = np.argmax(cls, axis=2)
     scores = np.take_along_axis(cls, classes[:, :, None], axis=2)[:, :, 0]
     scores = np.sqrt(scores * ctr[:, :, 0])
-    dist = exp_fn(reg)
+    dist = _decoder_exp(reg, exp_fn)
     boxes = np.concatenate([pts - dist[:, :, 0:2], pts + dist[:, :, 2:4]], axis=2)
     with np.errstate(invalid='ignore'):
         boxes = boxes.astype(np.int32)

@@ -14,6 +14,7 @@ MAX_GT = 2048
 MAX_TOPN = 2048
 
 F32, F16, BF16 = 0, 1, 2
+REG_EXP_ROUNDED = 0x10   # see include/b200det.h: eager half arithmetic rounds exp() to half
 BOX_NONE, BOX_SMOOTHL1, BOX_IOU, BOX_GIOU, BOX_DIOU, BOX_CIOU, BOX_EIOU = range(7)
 NMS_PYTHON, NMS_DIOU_PYTHON, NMS_TORCH, NMS_NONE = range(4)
 DECODE_ANCHORS, DECODE_POINTS, DECODE_BOXES = range(3)
@@ -93,6 +94,7 @@ class DecodeParams(ctypes.Structure):
         ('scales', ctypes.c_void_p),
         ('sizes', ctypes.c_void_p),
         ('to_xywh', ctypes.c_int32),
+        ('half_exp_table', ctypes.c_void_p),
     ]
 
 

@@ -74,10 +74,10 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
     int rc = b200det_score_argmax(geo, cls, p->is_fcos ? ctr : nullptr, p->min_score, keys,
                                   classes, stream);
     if (!rc)
-        rc = b200det_select_decode_nms(geo, keys, classes, reg, p->reg_dtype, p->is_fcos,
-                                       p->min_score, p->topn, p->max_out, p->nms_type,
-                                       p->nms_threshold, p->scales, p->sizes, p->to_xywh, out,
-                                       order, keep, counts, workspace, workspace_bytes, stream);
+        rc = select_decode_nms_impl(geo, keys, classes, reg, p->reg_dtype, p->is_fcos, p->min_score,
+                                    p->topn, p->max_out, p->nms_type, p->nms_threshold, p->scales,
+                                    p->sizes, p->to_xywh, out, order, keep, counts,
+                                    p->half_exp_table, stream);
     return rc;
 }
 
@@ -130,11 +130,10 @@ extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss
                                                  lp->w_box, lp->w_ctr, sums, losses, stream)
                     : b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
     if (!rc)
-        rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, dp->is_fcos,
-                                       dp->min_score, dp->topn, dp->max_out, dp->nms_type,
-                                       dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
-                                       nullptr, nullptr, nullptr, decode_workspace,
-                                       decode_workspace_bytes, stream);
+        rc = select_decode_nms_impl(geo, keys, classes, reg, dp->reg_dtype, dp->is_fcos,
+                                    dp->min_score, dp->topn, dp->max_out, dp->nms_type,
+                                    dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
+                                    nullptr, nullptr, nullptr, dp->half_exp_table, stream);
     return rc;
 }
 

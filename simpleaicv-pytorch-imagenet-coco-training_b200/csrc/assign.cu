@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(kAssignThreads)
 // ---------------------------------------------------------------------------------------
 // Box loss of one positive anchor (losses.py:263-320) and d(loss)/d(reg row).
 __device__ __forceinline__ float retina_box_term(const float4 a, const float4 gt, const float4 t,
-                                                 int box_loss, float beta, float4 &grad) {
+                                                 int box_loss, float beta, float4 &grad,
+                                                 int exp_mode) {
     const float awx = __fsub_rn(a.z, a.x), awy = __fsub_rn(a.w, a.y);
     const float acx = __fadd_rn(a.x, __fmul_rn(0.5f, awx));
     const float acy = __fadd_rn(a.y, __fmul_rn(0.5f, awy));
@@ -565,7 +566,7 @@ __device__ __forceinline__ float retina_box_term(const float4 a, const float4 gt
     } else {
         // decode (losses.py:411-429) then 1 - IoU-family (losses.py:286-293)
         const Dual tx = dvar(t.x, 0), ty = dvar(t.y, 1), tw = dvar(t.z, 2), th = dvar(t.w, 3);
-        const Dual bw = dexp(tw) * awx, bh = dexp(th) * awy;
+        const Dual bw = dexp(tw, exp_mode) * awx, bh = dexp(th, exp_mode) * awy;
         const Dual cx = tx * awx + acx, cy = ty * awy + acy;
         const Dual hw = bw * 0.5f, hh = bh * 0.5f;
         const Dual p[4] = {cx - hw, cy - hh, cx + hw, cy + hh};
@@ -649,15 +650,16 @@ __global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
             float4 grad = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!a.is_fcos) {
                 const float4 an = anchor_of(g, a.ba, l, local);
-                box_fx += to_fx(retina_box_term(an, gt, t, a.box_loss, a.beta, grad), kFxBox, bad, 1u);
+                box_fx += to_fx(retina_box_term(an, gt, t, a.box_loss, a.beta, grad, a.reg_dtype),
+                                kFxBox, bad, 1u);
             } else {
                 // IoU loss, losses.py:550-586: boxes rebuilt around the point from l,t,r,b
                 const float2 pt = point_of(g, l, local);
                 const float bl = __fsub_rn(pt.x, gt.x), bt = __fsub_rn(pt.y, gt.y);
                 const float br = __fsub_rn(gt.z, pt.x), bb = __fsub_rn(gt.w, pt.y);
                 const float ctr_t = fcos_centerness(bl, bt, br, bb);
-                const Dual e0 = dexp(dvar(t.x, 0)), e1 = dexp(dvar(t.y, 1));
-                const Dual e2 = dexp(dvar(t.z, 2)), e3 = dexp(dvar(t.w, 3));
+                const Dual e0 = dexp(dvar(t.x, 0), a.reg_dtype), e1 = dexp(dvar(t.y, 1), a.reg_dtype);
+                const Dual e2 = dexp(dvar(t.z, 2), a.reg_dtype), e3 = dexp(dvar(t.w, 3), a.reg_dtype);
                 const Dual p[4] = {pt.x - e0, pt.y - e1, e2 + pt.x, e3 + pt.y};
                 const float gg[4] = {__fsub_rn(pt.x, bl), __fsub_rn(pt.y, bt), __fadd_rn(pt.x, br),
                                      __fadd_rn(pt.y, bb)};
@@ -1016,13 +1018,15 @@ extern "C" int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos,
     if (is_fcos && (box_loss == B200DET_BOX_SMOOTHL1 || g.per_loc != 1)) return B200DET_EINVAL;
     const bool with_loss = box_loss != B200DET_BOX_NONE;
     if (with_loss && (!reg || (is_fcos && !ctr))) return B200DET_EINVAL;
-    if (reg_dtype != B200DET_F32 && reg_dtype != B200DET_F16 && reg_dtype != B200DET_BF16)
+    const int reg_base = reg_dtype & 0xf;
+    if ((reg_dtype & ~(0xf | B200DET_REG_EXP_ROUNDED)) ||
+        (reg_base != B200DET_F32 && reg_base != B200DET_F16 && reg_base != B200DET_BF16))
         return B200DET_EINVAL;
     SparseArgs a;
     a.g = g;
     copy_base(geo, &a.ba);
     if ((rc = fill_ptrs(with_loss ? reg : nullptr, g.n_levels, &a.reg,
-                        reg_dtype == B200DET_F32 ? 15 : 7)))
+                        reg_base == B200DET_F32 ? 15 : 7)))
         return rc;
     if ((rc = fill_ptrs(with_loss && is_fcos ? ctr : nullptr, g.n_levels, &a.ctr, 3))) return rc;
     if ((rc = fill_ptrs(cls, g.n_levels, &a.cls, 3))) return rc;

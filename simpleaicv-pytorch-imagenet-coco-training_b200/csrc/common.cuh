@@ -81,6 +81,12 @@ LossWs loss_ws_layout(const Geo &g);
 int score_argmax_impl(const b200det_geometry *geo, const void *const *cls, const void *const *ctr,
                       float min_score, uint32_t *keys, int32_t *classes, float alpha, float gamma,
                       long long *focal_slots, void *stream);   // decode.cu
+int select_decode_nms_impl(const b200det_geometry *geo, const uint32_t *keys, const int32_t *classes,
+                           const void *const *reg, int reg_dtype, int is_fcos, float min_score,
+                           int topn, int max_out, int nms_type, double nms_threshold,
+                           const float *scales, const float *sizes, int to_xywh, float *out,
+                           int32_t *order, int32_t *keep, int32_t *counts,
+                           const uint16_t *half_exp_table, void *stream);   // decode.cu
 // set by the fused entry points after they have cleared all accumulators with ONE memset
 extern thread_local bool g_skip_memset;
 // set by the overlapped forward: images per assignment launch (0 = the whole batch in one launch)
@@ -134,6 +140,7 @@ __device__ __forceinline__ float2 point_of(const Geo &g, int l, int local) {
 
 // regression head element loader: 4 values of row `row` of a [rows,4] tensor, upcast to f32
 __device__ __forceinline__ float4 load_reg4(const void *base, int dtype, long long row) {
+    dtype &= 0xf;   // (B200DET_REG_EXP_ROUNDED rides in the high bits)
     if (dtype == B200DET_F32) {
         return __ldg(reinterpret_cast<const float4 *>(base) + row);
     } else if (dtype == B200DET_F16) {
@@ -159,6 +166,15 @@ __device__ __forceinline__ void pdl_launch_dependents() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// exp() of a regression value as eager half arithmetic sees it: computed in float32, then rounded to
+// the tensor's own precision (B200DET_REG_EXP_ROUNDED); mode = reg_dtype incl. the flag
+__device__ __forceinline__ float round_like(float v, int mode) {
+    if (!(mode & B200DET_REG_EXP_ROUNDED)) return v;
+    if ((mode & 0xf) == B200DET_F16) return __half2float(__float2half_rn(v));
+    if ((mode & 0xf) == B200DET_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    return v;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

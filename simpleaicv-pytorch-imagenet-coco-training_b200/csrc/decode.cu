@@ -432,6 +432,7 @@ struct SelectArgs {
     float nms_thr_f;
     double nms_thr_d;
     int slices, rows_per_slice;   // CTAs of the image's cluster and the rows each one scans
+    const uint16_t *half_exp;     // NULL, or np.exp over all float16 inputs (host-specific, see header)
     int force_bitonic;            // A/B knob (B200DET_SELECT_BITONIC)
     long long *stamps;            // NULL, or [B,16] globaltimer stamps of the leader's phases (profiling)
 };
@@ -576,6 +577,17 @@ __device__ __forceinline__ void find_cut(const int *hist, int topn, int *scratch
     in_bin = *s_count;
     total_out = *s_total;
     __syncthreads();
+}
+
+// exp() of a regression value in the decoders.  float32 head: NumPy's float32 SIMD exp, op for op
+// (npexp).  float16 head (B200DET_REG_EXP_ROUNDED): NumPy's HALF loop, which converts to float, calls
+// the C library's expf (glibc: correctly rounded for all but a handful of inputs) and rounds the
+// result to half -- restated as exp in float64, rounded to float32, rounded to float16.
+__device__ __forceinline__ float decoder_exp(float x, int mode, const uint16_t *half_tab) {
+    if (!(mode & B200DET_REG_EXP_ROUNDED)) return npexp(x);
+    if (half_tab && (mode & 0xf) == B200DET_F16)   // the host NumPy's own float16 exp, entry by entry
+        return __half2float(__ushort_as_half(__ldg(half_tab + __half_as_ushort(__float2half_rn(x)))));
+    return round_like((float)exp((double)x), mode);
 }
 
 constexpr int kNmsW = 128;          // NMS round: candidates resolved per bit matrix
@@ -964,17 +976,18 @@ __global__ void __launch_bounds__(kSelThreads, 1)
         if (a.is_fcos) {
             // decode.py:356-361
             const float2 p = point_of(g, l, local);
-            x1 = __fsub_rn(p.x, npexp(t.x));
-            y1 = __fsub_rn(p.y, npexp(t.y));
-            x2 = __fadd_rn(p.x, npexp(t.z));
-            y2 = __fadd_rn(p.y, npexp(t.w));
+            x1 = __fsub_rn(p.x, decoder_exp(t.x, a.reg_dtype, a.half_exp));
+            y1 = __fsub_rn(p.y, decoder_exp(t.y, a.reg_dtype, a.half_exp));
+            x2 = __fadd_rn(p.x, decoder_exp(t.z, a.reg_dtype, a.half_exp));
+            y2 = __fadd_rn(p.y, decoder_exp(t.w, a.reg_dtype, a.half_exp));
         } else {
             // decode.py:257-268
             const float4 an = anchor_of(g, a.ba, l, local);
             const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
             const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw));
             const float acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
-            const float bw = __fmul_rn(npexp(t.z), aw), bh = __fmul_rn(npexp(t.w), ah);
+            const float bw = __fmul_rn(decoder_exp(t.z, a.reg_dtype, a.half_exp), aw);
+            const float bh = __fmul_rn(decoder_exp(t.w, a.reg_dtype, a.half_exp), ah);
             const float cx = __fadd_rn(__fmul_rn(t.x, aw), acx);
             const float cy = __fadd_rn(__fmul_rn(t.y, ah), acy);
             const float hw = __fmul_rn(0.5f, bw), hh = __fmul_rn(0.5f, bh);
@@ -1307,13 +1320,29 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
                                          float *out,
                                          int32_t *order, int32_t *keep, int32_t *counts,
                                          void *workspace, size_t workspace_bytes, void *stream) {
+    (void)workspace;   // r02: the selection lives in (distributed) shared memory
+    (void)workspace_bytes;
+    return select_decode_nms_impl(geo, keys, classes, reg, reg_dtype, is_fcos, min_score, topn,
+                                  max_out, nms_type, nms_threshold, scales, sizes, to_xywh, out,
+                                  order, keep, counts, nullptr, stream);
+}
+
+int b200det::select_decode_nms_impl(const b200det_geometry *geo, const uint32_t *keys,
+                                    const int32_t *classes, const void *const *reg, int reg_dtype,
+                                    int is_fcos, float min_score, int topn, int max_out,
+                                    int nms_type, double nms_threshold, const float *scales,
+                                    const float *sizes, int to_xywh, float *out, int32_t *order,
+                                    int32_t *keep, int32_t *counts, const uint16_t *half_exp_table,
+                                    void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
     if (!keys || !classes || !reg || !out) return B200DET_EINVAL;
     if (topn < 1 || topn > B200DET_MAX_TOPN || max_out < 1) return B200DET_ERANGE;
     if (nms_type < B200DET_NMS_PYTHON || nms_type > B200DET_NMS_NONE) return B200DET_EINVAL;
-    if (reg_dtype != B200DET_F32 && reg_dtype != B200DET_F16 && reg_dtype != B200DET_BF16)
+    const int reg_base = reg_dtype & 0xf;
+    if ((reg_dtype & ~(0xf | B200DET_REG_EXP_ROUNDED)) ||
+        (reg_base != B200DET_F32 && reg_base != B200DET_F16 && reg_base != B200DET_BF16))
         return B200DET_EINVAL;
     if (is_fcos < 0 || is_fcos > B200DET_DECODE_BOXES) return B200DET_EINVAL;
     if (is_fcos == B200DET_DECODE_BOXES && reg_dtype != B200DET_F32) return B200DET_EINVAL;
@@ -1325,7 +1354,7 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
         for (int q = 0; q < kMaxPerLoc; ++q)
             for (int k = 0; k < 4; ++k) a.ba.v[l][q][k] = geo->base_anchors[l][q][k];
     }
-    const uintptr_t rmask = reg_dtype == B200DET_F32 ? 15 : 7;
+    const uintptr_t rmask = reg_base == B200DET_F32 ? 15 : 7;
     for (int l = 0; l < g.n_levels; ++l) {
         if (!reg[l]) return B200DET_EINVAL;
         if (reinterpret_cast<uintptr_t>(reg[l]) & rmask) return B200DET_EALIGN;
@@ -1383,8 +1412,7 @@ extern "C" int b200det_select_decode_nms(const b200det_geometry *geo, const uint
     static const bool env_bitonic = getenv("B200DET_SELECT_BITONIC") != nullptr;
     a.force_bitonic = env_bitonic ? 1 : 0;
     a.stamps = g_select_stamps;
-    (void)workspace;
-    (void)workspace_bytes;
+    a.half_exp = half_exp_table;
     ProfScope prof(kKernSelect, stream);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)slices, (unsigned)g.batch, 1);

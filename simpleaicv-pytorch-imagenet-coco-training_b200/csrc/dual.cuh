@@ -97,9 +97,11 @@ __device__ __forceinline__ Dual dsq(const Dual &a) {
     for (int i = 0; i < 4; ++i) r.d[i] = 2.f * a.v * a.d[i];
     return r;
 }
-__device__ __forceinline__ Dual dexp(const Dual &a) {
+// mode: reg_dtype incl. B200DET_REG_EXP_ROUNDED (eager half arithmetic: the result of exp is rounded
+// to the tensor's precision and autograd multiplies by that rounded result)
+__device__ __forceinline__ Dual dexp(const Dual &a, int mode = 0) {
     Dual r;
-    r.v = expf(a.v);
+    r.v = round_like(expf(a.v), mode);
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.d[i] = r.v * a.d[i];
     return r;

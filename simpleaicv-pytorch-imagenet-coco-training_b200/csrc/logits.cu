@@ -457,10 +457,9 @@ extern "C" int b200det_logits_eval_step(const b200det_geometry *geo, const b200d
                                                  lp->w_box, lp->w_ctr, sums, losses, stream)
                     : b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
     if (!rc)
-        rc = b200det_select_decode_nms(geo, keys, classes, reg, dp->reg_dtype, fcos ? 1 : 0,
-                                       dp->min_score, dp->topn, dp->max_out, dp->nms_type,
-                                       dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
-                                       nullptr, nullptr, nullptr, decode_workspace,
-                                       decode_workspace_bytes, stream);
+        rc = select_decode_nms_impl(geo, keys, classes, reg, dp->reg_dtype, fcos ? 1 : 0,
+                                    dp->min_score, dp->topn, dp->max_out, dp->nms_type,
+                                    dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
+                                    nullptr, nullptr, nullptr, dp->half_exp_table, stream);
     return rc;
 }

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from . import geometry as _geom
-from .losses import _on_device, _prep_f32, _prep_reg, _require_cuda
+from .losses import _decode_reg_mode, _on_device, _prep_f32, _prep_reg, _require_cuda
 
 _ZERO_COPY = os.environ.get('B200DET_ZERO_COPY', '1') != '0'
 # the returned arrays are views of the call's own pinned buffer (no host memcpy); '1' hands out
@@ -28,6 +28,34 @@ _RESULT_COPY = os.environ.get('B200DET_RESULT_COPY', '0') != '0'
 
 __all__ = ['RetinaDecoder', 'FCOSDecoder', 'DETRDecoder', 'DINODETRDecoder', 'DecodeMethod',
            'DetNMSMethod']
+
+
+_HALF_EXP_TABLES = {}
+
+
+def _half_exp_table(device):
+    """Device copy of np.exp over all 65536 float16 inputs AS THIS HOST'S NumPy computes it, or None.
+    The reference's decoders run np.exp on the float16 regression array (decode.py:260, :356) and
+    NumPy's float16 exp depends on the CPU: with AVX512-FP16 ("AVX512_SPR" in NumPy's dispatch) it is
+    an SVML kernel whose result differs from the correctly rounded one for 17 % of the inputs;
+    elsewhere it is half(expf(float(x))), which the kernel computes itself (table = None)."""
+    key = device.index
+    if key not in _HALF_EXP_TABLES:
+        table = None
+        try:
+            try:
+                from numpy._core._multiarray_umath import __cpu_features__ as feats
+            except ImportError:   # numpy < 2
+                from numpy.core._multiarray_umath import __cpu_features__ as feats
+            if feats.get('AVX512_SPR'):
+                path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data',
+                                    'np_exp_f16_avx512spr.npy')
+                host = np.load(path).astype(np.int16)
+                table = torch.from_numpy(host).to(device)
+        except Exception:   # no dispatch info: the generic half loop
+            table = None
+        _HALF_EXP_TABLES[key] = table
+    return _HALF_EXP_TABLES[key]
 
 
 class _DecoderBase:
@@ -151,7 +179,11 @@ class _DecoderBase:
             keep = torch.empty(batch * self.topn, dtype=torch.int32, device=device)
             counts = torch.empty(batch * 3, dtype=torch.int32, device=device)
         params = self._params
-        params.reg_dtype = reg_dtype
+        params.reg_dtype = _decode_reg_mode(reg_dtype)
+        params.half_exp_table = None
+        if reg_dtype == _lib.F16:
+            table = _half_exp_table(device)
+            params.half_exp_table = table.data_ptr() if table is not None else None
         glue = self._set_glue(params, batch, device, scales, sizes, to_xywh)
         keys_ptr = scratch.data_ptr()
         _lib.check(

@@ -21,8 +21,8 @@ import torch
 
 from . import _lib
 from . import geometry as _geom
-from .losses import (_DTYPES, _Plan, _loss_params, _on_device, _plan_for, _prep_annotations,
-                     _prep_f32, _prep_reg, _require_cuda, _sync_sums)
+from .losses import (_DTYPES, _Plan, _decode_reg_mode, _loss_params, _loss_reg_mode, _on_device,
+                     _plan_for, _prep_annotations, _prep_f32, _prep_reg, _require_cuda, _sync_sums)
 
 __all__ = ['EvalStep', 'LogitsEvalStep']
 
@@ -67,9 +67,14 @@ class EvalStep:
         dws_ptr = classes_ptr + rows_bytes
         small = torch.empty(8, dtype=torch.float64, device=device)   # sums | losses
         out = dec._out_buffer(6 * batch * m, device)
-        lp = _loss_params(crit, reg_dtype)
+        lp = _loss_params(crit, _loss_reg_mode(reg_dtype))
         dp = dec._params
-        dp.reg_dtype = reg_dtype
+        dp.reg_dtype = _decode_reg_mode(reg_dtype)
+        dp.half_exp_table = None
+        if reg_dtype == _lib.F16:
+            from .decode import _half_exp_table
+            table = _half_exp_table(device)
+            dp.half_exp_table = table.data_ptr() if table is not None else None
         glue = dec._set_glue(dp, batch, device, scales, sizes, to_xywh)
         sync = crit.sync_normalizer and torch.distributed.is_available() \
             and torch.distributed.is_initialized()
@@ -178,9 +183,14 @@ class LogitsEvalStep:
         dws_ptr = classes_ptr + rows_bytes
         small = torch.empty(8, dtype=torch.float64, device=device)   # sums | losses
         out = dec._out_buffer(6 * batch * m, device)
-        lp = _loss_params(crit, reg_dtype)
+        lp = _loss_params(crit, _loss_reg_mode(reg_dtype))
         dp = dec._params
-        dp.reg_dtype = reg_dtype
+        dp.reg_dtype = _decode_reg_mode(reg_dtype)
+        dp.half_exp_table = None
+        if reg_dtype == _lib.F16:
+            from .decode import _half_exp_table
+            table = _half_exp_table(device)
+            dp.half_exp_table = table.data_ptr() if table is not None else None
         glue = dec._set_glue(dp, batch, device, scales, sizes, to_xywh)
         sync = crit.sync_normalizer and torch.distributed.is_available() \
             and torch.distributed.is_initialized()

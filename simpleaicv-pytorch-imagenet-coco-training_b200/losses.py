@@ -104,6 +104,22 @@ def _prep_reg(levels):
     return out, _DTYPES[dtype]
 
 
+def _loss_reg_mode(reg_dtype):
+    """reg_dtype code for the LOSS kernels.  A half-precision regression head reaches the criterion
+    in two ways in the reference: inside `with autocast()` (tools/scripts.py:886-893), where CUDA
+    autocast runs torch.exp in float32 on the upcast value; or as plain half tensors (model.half()),
+    where torch.exp rounds its result to half (losses.py:417-426, :568).  Both are reproduced."""
+    if reg_dtype != _lib.F32 and not torch.is_autocast_enabled():
+        return reg_dtype | _lib.REG_EXP_ROUNDED
+    return reg_dtype
+
+
+def _decode_reg_mode(reg_dtype):
+    """reg_dtype code for the DECODERS: they leave torch (`.cpu().numpy()`, decode.py:208-219), so
+    np.exp runs on the float16 array whatever the autocast state and rounds to half."""
+    return reg_dtype | _lib.REG_EXP_ROUNDED if reg_dtype != _lib.F32 else reg_dtype
+
+
 def _prep_annotations(annotations):
     _require_cuda(annotations, 'annotations')
     if annotations.dim() != 3 or annotations.shape[-1] != 5:
@@ -295,6 +311,7 @@ def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
                                          None, None, ws_ptr, plan.ws_bytes, None, None, None, None,
                                          *side_args, st, 1), 'b200det_loss_forward_overlap')
     reg, reg_dtype = _prep_reg(reg_in)
+    reg_dtype = _loss_reg_mode(reg_dtype)
     ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
     annotations = _prep_annotations(annotations)
     if annotations.shape[0] != plan.batch:
@@ -349,6 +366,7 @@ class _DetLossFunction(torch.autograd.Function):
         is_fcos = owner._is_fcos
         cls = _prep_f32(heads[0:n_levels], 'cls_preds')
         reg, reg_dtype = _prep_reg(heads[n_levels:2 * n_levels])
+        reg_dtype = _loss_reg_mode(reg_dtype)
         ctr = _prep_f32(heads[2 * n_levels:3 * n_levels], 'center_preds') if is_fcos else None
         need = ctx.needs_input_grad[3:]
         annotations = _prep_annotations(annotations)

@@ -455,8 +455,109 @@ def make_heads(path):
                         y=y.detach().numpy(), wgt=wgt.numpy(), gx=captured['x'].grad.numpy())
 
 
+def make_half_nan(path):
+    """(1) Half-precision regression heads WITHOUT autocast (model.half()-style eager arithmetic): the
+    reference then runs torch.exp / np.exp on float16 and rounds the result to half
+    (losses.py:417-426, :568; decode.py:257-268, :356).  Loss values, gradients and decoder outputs
+    of the unmodified classes for float16 `reg` (and bfloat16 for the losses; the decoders cannot
+    take bfloat16: `.numpy()` raises).
+    (2) NaN class / centre-ness scores in the decoders: np.argmax stops at the first NaN
+    (decode.py:230-238, :319-338), the row's score is NaN and fails `score > threshold`."""
+    L, D, _ = refload.load()
+    out = {'versions': versions()}
+    # ---- Retina ----
+    size, C, B, G = 128, 8, 3, 12
+    preds = synth.make_tie_free(synth.make_retina_preds(B, size, C, seed=40))
+    ann = edge_annotations(synth.make_annotations(B, G, size, C, seed=41), size)
+    out['r_annotations'] = ann.numpy()
+    for i, (c, r) in enumerate(zip(*preds)):
+        out[f'r_cls{i}'] = c.numpy()
+        out[f'r_reg{i}_f16'] = r.half().numpy()
+        out[f'r_reg{i}_bf16_bits'] = r.bfloat16().view(torch.int16).numpy()
+    for tag, cast in (('f16', torch.float16), ('bf16', torch.bfloat16)):
+        hp = [preds[0], [r.to(cast) for r in preds[1]]]
+        for box_type in ('SmoothL1', 'GIoU', 'CIoU'):
+            crit = L.RetinaLoss(**synth.RETINA_KW, box_loss_type=box_type)
+            with torch.no_grad():
+                d = crit(hp, ann)
+            out[f'r_loss_{tag}_{box_type}'] = np.array(
+                [d['cls_loss'].float().item(), d['reg_loss'].float().item()], dtype=np.float32)
+        crit = L.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+        p = [[t.clone().requires_grad_(True) for t in grp] for grp in hp]
+        d = crit(p, ann)
+        (d['cls_loss'] + 2.0 * d['reg_loss']).backward()
+        for i in range(len(p[0])):
+            out[f'r_greg_{tag}_{i}'] = p[1][i].grad.float().numpy()
+    hp = [preds[0], [r.half() for r in preds[1]]]
+    s_, c_, b_ = D.RetinaDecoder(**synth.RETINA_KW)(hp)
+    out['r_dec_f16_scores'], out['r_dec_f16_classes'], out['r_dec_f16_boxes'] = s_, c_, b_
+    # ---- FCOS ----
+    size = 256
+    fp = synth.make_tie_free(synth.make_fcos_preds(B, size, C, seed=42))
+    fann = edge_annotations(synth.make_annotations(B, G, size, C, seed=43), size)
+    out['f_annotations'] = fann.numpy()
+    for i, (c, r, t) in enumerate(zip(*fp)):
+        out[f'f_cls{i}'] = c.numpy()
+        out[f'f_reg{i}_f16'] = r.half().numpy()
+        out[f'f_ctr{i}'] = t.numpy()
+    hp = [fp[0], [r.half() for r in fp[1]], fp[2]]
+    for iou_type in ('GIoU', 'DIoU'):
+        crit = L.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, box_loss_iou_type=iou_type)
+        with torch.no_grad():
+            d = crit(hp, fann)
+        out[f'f_loss_f16_{iou_type}'] = np.array(
+            [d['cls_loss'].float().item(), d['reg_loss'].float().item(),
+             d['center_ness_loss'].float().item()], dtype=np.float32)
+    crit = L.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in hp]
+    d = crit(p, fann)
+    (d['cls_loss'] + 2.0 * d['reg_loss'] + 3.0 * d['center_ness_loss']).backward()
+    for i in range(len(p[0])):
+        out[f'f_greg_f16_{i}'] = p[1][i].grad.float().numpy()
+    s_, c_, b_ = D.FCOSDecoder(strides=synth.STRIDES)(hp)
+    out['f_dec_f16_scores'], out['f_dec_f16_classes'], out['f_dec_f16_boxes'] = s_, c_, b_
+
+    # ---- NaN scores in the decoders ----
+    nan = float('nan')
+    npreds = [[t.clone() for t in grp] for grp in preds]
+    c0 = npreds[0][0].view(B, -1, C)
+    top = c0[0].max(dim=1).values.argsort(descending=True)
+    c0[0, top[0], 0] = nan                 # best row of image 0: NaN in the first class
+    c0[0, top[1], C - 1] = nan             # second best: NaN in the last class, real maximum before it
+    c0[0, top[2], :] = nan                 # third: all NaN
+    c0[1, top[0], 3] = nan
+    npreds[0][2].view(B, -1, C)[2, 5, 1] = nan
+    for i, c in enumerate(npreds[0]):
+        out[f'rn_cls{i}'] = c.numpy()
+        out[f'rn_reg{i}'] = npreds[1][i].numpy()
+    for nms in ('python_nms', 'torch_nms'):
+        s_, c_, b_ = D.RetinaDecoder(**synth.RETINA_KW, nms_type=nms)(npreds)
+        out[f'rn_dec_{nms}_scores'], out[f'rn_dec_{nms}_classes'], out[f'rn_dec_{nms}_boxes'] = s_, c_, b_
+    fpn = [[t.clone() for t in grp] for grp in fp]
+    c0 = fpn[0][0].view(B, -1, C)
+    t0 = fpn[2][0].view(B, -1)
+    score = (c0.max(dim=2).values * t0).sqrt()
+    top = score[0].argsort(descending=True)
+    c0[0, top[0], 2] = nan                 # NaN class score
+    t0[0, top[1]] = nan                    # NaN centre-ness
+    c0[0, top[2], C - 1] = nan
+    t0[1, top[0]] = nan
+    for i in range(len(fpn[0])):
+        out[f'fn_cls{i}'] = fpn[0][i].numpy()
+        out[f'fn_reg{i}'] = fpn[1][i].numpy()
+        out[f'fn_ctr{i}'] = fpn[2][i].numpy()
+    with np.errstate(invalid='ignore'):
+        s_, c_, b_ = D.FCOSDecoder(strides=synth.STRIDES)(fpn)
+    out['fn_dec_scores'], out['fn_dec_classes'], out['fn_dec_boxes'] = s_, c_, b_
+    np.savez_compressed(path, **out)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'half':
+        make_half_nan(os.path.join(HERE, 'half_nan.npz'))
+        print('half_nan.npz', os.path.getsize(os.path.join(HERE, 'half_nan.npz')))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'heads':
         make_heads(os.path.join(HERE, 'head_tail.npz'))
         print('head_tail.npz', os.path.getsize(os.path.join(HERE, 'head_tail.npz')))
@@ -485,5 +586,6 @@ if __name__ == '__main__':
     make_queries(os.path.join(HERE, 'queries.npz'))
     make_voc(os.path.join(HERE, 'voc_eval.npz'))
     make_iou_method(os.path.join(HERE, 'iou_method.npz'))
+    make_half_nan(os.path.join(HERE, 'half_nan.npz'))
     for f in ('retina_small.npz', 'fcos_small.npz', 'tables.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)))

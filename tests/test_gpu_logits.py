@@ -38,7 +38,37 @@ def both_paths(cls_logits, reg, ann, kw, num_classes, loss_kw=None, dec_kw=None)
         want_loss = crit([probs, reg], ann)
         want_det = dec([probs, reg])
         got_loss, got_det = fused.LogitsEvalStep(crit, dec)([cls_logits, reg], ann)
+    oracle_leg([p.cpu() for p in probs], [r.cpu() for r in reg], ann.cpu(), kw, loss_kw, dec_kw,
+               got_loss, got_det)
     return want_loss, want_det, got_loss, got_det
+
+
+def oracle_leg(probs, reg, ann, kw, loss_kw, dec_kw, got_loss, got_det):
+    """Third leg: the ORACLE (pinned to the unmodified reference) on the same probabilities -- the
+    logits path is compared with the reference's arithmetic directly, not only through this
+    repo's probability path.  Scores can tie on these inputs, where the reference's unstable
+    argsort leaves the order undefined: detections are compared when the oracle's candidate
+    scores are unique, the loss always."""
+    with torch.no_grad():
+        ref = O.retina_loss([probs, reg], ann, **kw, **(loss_kw or {}))
+    w = np.array([ref['cls_loss'].item(), ref['reg_loss'].item()])
+    g = loss_values(got_loss, ['cls_loss', 'reg_loss'])
+    if not np.isfinite(w).all():
+        assert (np.isfinite(g) == np.isfinite(w)).all()
+    elif (w == 0).all():
+        assert (g == 0).all()
+    else:
+        assert_close(g, w, LOSS_RTOL, 'logits path vs oracle: loss')
+    (s0, c0, b0), extra = O.retina_decode([probs, reg], **kw, **(dec_kw or {}))
+    thr = (dec_kw or {}).get('min_score_threshold', 0.05)
+    for b in range(s0.shape[0]):
+        sc = extra['scores'][b]
+        cand = sc[sc > np.float32(thr)]
+        if np.unique(cand).size != cand.size:
+            continue   # ties among the candidates: order undefined in the reference
+        G.assert_bit_equal(got_det[0][b], s0[b], f'logits path vs oracle: scores, image {b}')
+        G.assert_bit_equal(got_det[1][b], c0[b], f'logits path vs oracle: classes, image {b}')
+        G.assert_bit_equal(got_det[2][b], b0[b], f'logits path vs oracle: boxes, image {b}')
 
 
 def check(want_loss, want_det, got_loss, got_det, what=''):
@@ -165,6 +195,29 @@ def fcos_both_paths(cls, reg, ctr, ann, strides, mi, loss_kw=None, dec_kw=None):
         want_loss = crit([probs, reg, cprobs], ann)
         want_det = dec([probs, reg, cprobs])
         got_loss, got_det = fused.LogitsEvalStep(crit, dec)([cls, reg, ctr], ann)
+    # third leg: the oracle on the same probabilities (see oracle_leg)
+    cpu = [[t.cpu() for t in grp] for grp in (probs, reg, cprobs)]
+    with torch.no_grad():
+        ref = O.fcos_loss(cpu, ann.cpu(), strides, mi, **(loss_kw or {}))
+    keys = ['cls_loss', 'reg_loss', 'center_ness_loss']
+    w = np.array([ref[k].item() for k in keys])
+    g = loss_values(got_loss, keys)
+    if (w == 0).all():
+        assert (g == 0).all()
+    else:
+        assert_close(g, w, LOSS_RTOL, 'FCOS logits path vs oracle: loss')
+    (s0, c0, b0), extra = O.fcos_decode(cpu, strides, **(dec_kw or {}))
+    thr = (dec_kw or {}).get('min_score_threshold', 0.05)
+    for b in range(s0.shape[0]):
+        sc = extra['scores'][b]
+        cand = sc[sc > np.float32(thr)]
+        if np.unique(cand).size != cand.size:
+            continue
+        # torch-CPU sqrt (MKL) may be 1 ulp off the IEEE value the GPU computes (see
+        # test_gpu_parity.assert_targets_equal); scores come from NumPy's sqrt here, which is IEEE
+        G.assert_bit_equal(got_det[0][b], s0[b], f'FCOS logits path vs oracle: scores, image {b}')
+        G.assert_bit_equal(got_det[1][b], c0[b], f'FCOS logits path vs oracle: classes, image {b}')
+        G.assert_bit_equal(got_det[2][b], b0[b], f'FCOS logits path vs oracle: boxes, image {b}')
     return want_loss, want_det, got_loss, got_det
 
 

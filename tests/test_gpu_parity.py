@@ -407,21 +407,151 @@ def test_extreme_regression_values_truncate_like_x86():
 
 
 def test_half_precision_regression_head():
-    """Under autocast the Retina reg head is fp16: accepted and upcast."""
+    """A half-precision regression head reaches the path in two ways (both reproduced):
+    inside `with autocast()` (tools/scripts.py:886-893): CUDA autocast runs torch.exp in float32 on
+    the upcast value -> equals the oracle fed the upcast tensors; as plain half tensors: torch.exp /
+    np.exp round to half (losses.py:417-426, decode.py:257-268) -> equals the oracle fed the half
+    tensors (SmoothL1 has no exp: both coincide)."""
     preds = synth.make_tie_free(synth.make_retina_preds(2, 128, 8, seed=6))
     ann = synth.make_annotations(2, 12, 128, 8, seed=7)
     for dt in (torch.float16, torch.bfloat16):
         half = [preds[0], [r.to(dt) for r in preds[1]]]
         up = [preds[0], [r.float() for r in half[1]]]
-        crit = losses.RetinaLoss(**synth.RETINA_KW)
+        for box in ('SmoothL1', 'GIoU'):
+            crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type=box)
+            with torch.no_grad():
+                eager = crit(dev(half), ann.cuda())
+                with torch.autocast('cuda', dtype=dt):
+                    amp = crit(dev(half), ann.cuda())
+                ref_half = O.retina_loss(half, ann, **synth.RETINA_KW, box_loss_type=box)
+                ref_up = O.retina_loss(up, ann, **synth.RETINA_KW, box_loss_type=box)
+            keys = ['cls_loss', 'reg_loss']
+            assert_close(loss_values(eager, keys), [ref_half[k].float().item() for k in keys],
+                         LOSS_RTOL, f'eager {dt} {box}')
+            assert_close(loss_values(amp, keys), [ref_up[k].item() for k in keys], LOSS_RTOL,
+                         f'autocast {dt} {box}')
+        if dt == torch.float16:   # the reference's decoders cannot take bfloat16 (`.numpy()` raises)
+            s, c, b = decode.RetinaDecoder(**synth.RETINA_KW)(dev(half))
+            (s0, c0, b0), _ = O.retina_decode(half, **synth.RETINA_KW)
+            G.assert_bit_equal(b, b0, 'boxes')
+            G.assert_bit_equal(s, s0, 'scores')
+
+
+def host_numpy_half_exp_is_svml():
+    """np.exp on float16 is CPU-dependent (AVX512-FP16 hosts take an SVML kernel); the golden
+    vectors were made on such a host."""
+    try:
+        from numpy._core._multiarray_umath import __cpu_features__ as feats
+    except ImportError:
+        from numpy.core._multiarray_umath import __cpu_features__ as feats
+    return bool(feats.get('AVX512_SPR'))
+
+
+def half_grad_close(got, want, what):
+    """Gradients w.r.t. a half tensor are half values.  The reference's autograd casts the upstream
+    gradient of exp() to float16 BEFORE multiplying by exp(t) (the exp node lives in half), which
+    loses bits -- all of them below 6e-8, most of them below the 6e-5 subnormal limit -- while the
+    kernel keeps float32 up to the final cast: equal within 2 ulp of half precision plus an absolute
+    2e-5 for the subnormal upstream values (measured worst case 7.6e-6)."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    tol = np.abs(want) * 2.0 ** -9 + 2e-5
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), f'{what}: {int(bad.sum())} of {bad.size} differ, max ' \
+                          f'{np.abs(got - want).max()}'
+
+
+@pytest.mark.parametrize('reg', ['f16', 'bf16'])
+def test_half_reg_golden_retina(reg):
+    """tests/golden/half_nan.npz: the unmodified reference on float16 / bfloat16 regression heads
+    without autocast (exp rounded to half)."""
+    d = G.load('half_nan.npz')
+    preds, ann = G.half_nan_inputs(d, 'r', reg)
+    for box in ('SmoothL1', 'GIoU', 'CIoU'):
+        crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type=box)
         with torch.no_grad():
-            d = crit(dev(half), ann.cuda())
-            ref = O.retina_loss(up, ann, **synth.RETINA_KW)
-        assert_close(loss_values(d, ['cls_loss', 'reg_loss']),
-                     [ref['cls_loss'].item(), ref['reg_loss'].item()], LOSS_RTOL, str(dt))
-        s, c, b = decode.RetinaDecoder(**synth.RETINA_KW)(dev(half))
-        (s0, c0, b0), _ = O.retina_decode(up, **synth.RETINA_KW)
+            got = crit(dev(preds), ann.cuda())
+        assert_close(loss_values(got, ['cls_loss', 'reg_loss']), d[f'r_loss_{reg}_{box}'],
+                     2e-6 if box == 'CIoU' else LOSS_RTOL, f'{reg} {box}')
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(preds)]
+    out = crit(p, ann.cuda())
+    (out['cls_loss'] + 2.0 * out['reg_loss']).backward()
+    for i in range(len(p[0])):
+        assert p[1][i].grad.dtype == preds[1][i].dtype
+        if reg == 'f16':
+            half_grad_close(p[1][i].grad.float().cpu().numpy(), d[f'r_greg_{reg}_{i}'], f'greg {i}')
+    if reg == 'f16':
+        s, c, b = decode.RetinaDecoder(**synth.RETINA_KW)(dev(preds))
+        (s0, c0, b0), _ = O.retina_decode(preds, **synth.RETINA_KW)    # np.exp of THIS host
+        G.assert_bit_equal(s, s0, 'scores')
         G.assert_bit_equal(b, b0, 'boxes')
+        if host_numpy_half_exp_is_svml():   # ... which is the golden's when the CPUs match
+            G.assert_bit_equal(s, d['r_dec_f16_scores'], 'scores')
+            G.assert_bit_equal(c, d['r_dec_f16_classes'], 'classes')
+            G.assert_bit_equal(b, d['r_dec_f16_boxes'], 'boxes')
+
+
+def test_half_reg_golden_fcos():
+    d = G.load('half_nan.npz')
+    preds, ann = G.half_nan_inputs(d, 'f', 'f16')
+    for iou in ('GIoU', 'DIoU'):
+        crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI, box_loss_iou_type=iou)
+        with torch.no_grad():
+            got = crit(dev(preds), ann.cuda())
+        assert_close(loss_values(got, ['cls_loss', 'reg_loss', 'center_ness_loss']),
+                     d[f'f_loss_f16_{iou}'], LOSS_RTOL, f'fcos f16 {iou}')
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in dev(preds)]
+    out = crit(p, ann.cuda())
+    (out['cls_loss'] + 2.0 * out['reg_loss'] + 3.0 * out['center_ness_loss']).backward()
+    for i in range(len(p[0])):
+        half_grad_close(p[1][i].grad.float().cpu().numpy(), d[f'f_greg_f16_{i}'], f'greg {i}')
+    s, c, b = decode.FCOSDecoder(strides=synth.STRIDES)(dev(preds))
+    (s0, c0, b0), _ = O.fcos_decode(preds, synth.STRIDES)
+    G.assert_bit_equal(s, s0, 'scores')
+    G.assert_bit_equal(b, b0, 'boxes')
+    if host_numpy_half_exp_is_svml():
+        G.assert_bit_equal(s, d['f_dec_f16_scores'], 'scores')
+        G.assert_bit_equal(c, d['f_dec_f16_classes'], 'classes')
+        G.assert_bit_equal(b, d['f_dec_f16_boxes'], 'boxes')
+
+
+def test_decoder_nan_scores_golden():
+    """np.argmax stops at the first NaN (decode.py:230-238): a row with a NaN class score (or NaN
+    centre-ness) has a NaN score and never passes `score > threshold`, whatever its other classes."""
+    d = G.load('half_nan.npz')
+    preds, _ = G.half_nan_inputs(d, 'rn')
+    for nms in ('python_nms', 'torch_nms'):
+        s, c, b = decode.RetinaDecoder(**synth.RETINA_KW, nms_type=nms)(dev(preds))
+        G.assert_bit_equal(s, d[f'rn_dec_{nms}_scores'], 'scores')
+        G.assert_bit_equal(c, d[f'rn_dec_{nms}_classes'], 'classes')
+        G.assert_bit_equal(b, d[f'rn_dec_{nms}_boxes'], 'boxes')
+    (s0, c0, b0), extra = O.retina_decode(preds, **synth.RETINA_KW)
+    (s, c, b), info = decode.RetinaDecoder(**synth.RETINA_KW).decode_with_details(dev(preds))
+    check_decode_details(info, extra['per_image'], 1000)
+    preds, _ = G.half_nan_inputs(d, 'fn')
+    s, c, b = decode.FCOSDecoder(strides=synth.STRIDES)(dev(preds))
+    G.assert_bit_equal(s, d['fn_dec_scores'], 'scores')
+    G.assert_bit_equal(c, d['fn_dec_classes'], 'classes')
+    G.assert_bit_equal(b, d['fn_dec_boxes'], 'boxes')
+    # the fused sweep (row-group kernel) and a class count that is not a multiple of 4 (raw-tile kernel)
+    from b200det import fused
+    preds, ann = G.half_nan_inputs(d, 'rn')
+    crit = losses.RetinaLoss(**synth.RETINA_KW)
+    _, (s, c, b) = fused.EvalStep(crit, decode.RetinaDecoder(**synth.RETINA_KW))(dev(preds), ann.cuda())
+    G.assert_bit_equal(s, d['rn_dec_python_nms_scores'], 'fused scores')
+    G.assert_bit_equal(b, d['rn_dec_python_nms_boxes'], 'fused boxes')
+    odd = synth.make_tie_free(synth.make_fcos_preds(2, 128, 7, seed=50))
+    flat = odd[0][0].view(2, -1, 7)
+    best = flat[0].max(dim=1).values.argsort(descending=True)
+    flat[0, best[0], 6] = float('nan')
+    flat[0, best[1], 0] = float('nan')
+    with np.errstate(invalid='ignore'):
+        (s0, c0, b0), _ = O.fcos_decode(odd, synth.STRIDES)
+    s, c, b = decode.FCOSDecoder(strides=synth.STRIDES)(dev(odd))
+    G.assert_bit_equal(s, s0, 'C=7 scores')
+    G.assert_bit_equal(b, b0, 'C=7 boxes')
 
 
 def test_non_default_focal_parameters_and_weights():
