@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
         // group that holds the maximum; the winning group is rescanned after the loop
         float m1 = ninf, m2 = ninf;
         int ig = 0;
+        bool any_nan = false;   // a NaN logit: np.argmax stops there, the row's score is NaN
         float2 acc2 = make_float2(0.f, 0.f);
         float acc_slow = 0.f;   // exact-form background terms, without (1 - alpha)
 
@@ -199,10 +200,14 @@ __global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
                 if (FULL || c0 + k < C) x[k] = lg_load<T>(lg_plane(ptr, plane_bytes, k));
             }
             ptr = lg_plane(ptr, plane_bytes, kLgUnroll);
-            float g = x[0];   // largest logit of the group
+            float g = x[0];   // largest logit of the group; NaN if the group holds one (max.NaN)
 #pragma unroll
-            for (int k = 1; k < kLgUnroll; ++k) g = fmaxf(g, x[k]);
+            for (int k = 1; k < kLgUnroll; ++k) g = fmax_nan(g, x[k]);
             if (ARGMAX) {
+                if (g != g) {
+                    any_nan = true;
+                    g = ninf;
+                }
                 m2 = fmaxf(m2, fminf(m1, g));
                 if (g > m1) {   // strict: the first group that reaches the maximum; park its logits
                     ig = c0;
@@ -303,6 +308,9 @@ __global__ void __launch_bounds__(kLgThreads, kLgMinCtas)
             float score = p1;
             // np.sqrt(cls_scores * center_preds)  (decode.py:338) on the exact probabilities
             if (a.ctr.p[l]) score = __fsqrt_rn(__fmul_rn(p1, cp));
+            // sigmoid(NaN) is NaN and np.argmax returns the first NaN (decode.py:230-238): the
+            // row's score is NaN and fails the threshold whatever the other classes hold
+            if (any_nan) score = __int_as_float(0x7fc00000);
             s_key[slot] = (int)((score > a.min_score) ? ((__float_as_uint(score) & 0x80000000u)
                                                              ? ~__float_as_uint(score)
                                                              : (__float_as_uint(score) | 0x80000000u))

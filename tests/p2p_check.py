@@ -104,13 +104,43 @@ def main():
         fused_same = all(fa[k].item() == fb[k].item() for k in keys) and all(
             np.array_equal(x_, y_) for x_, y_ in zip(da, db))
         good = good and train_same and fused_same and rel_train <= 1e-5
+        # CUDA-graph replays of the p2p forward: the exchange number lives in device memory and the
+        # kernel advances it, so every replay is a NEW exchange (a host-side epoch would be frozen
+        # into the graph and a replay would match the previous replay's flags and read stale sums).
+        # Replays on fresh inputs must give the fresh batch's loss on every rank.
+        static = [[t.clone() for t in grp] for grp in shard]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                c_p2p(static, ann_s)
+        torch.cuda.current_stream().wait_stream(side)
+        dist.barrier()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            gout = c_p2p(static, ann_s)
+        graph_ok = True
+        for it in range(4):
+            scale = 1.0 - 0.1 * it     # a different batch every replay, the same on every rank
+            for dst, src in zip(static[0], shard[0]):
+                dst.copy_(src * scale)
+            graph.replay()
+            with torch.no_grad():
+                eager = c_nccl([[t * scale for t in shard[0]]] + shard[1:], ann_s)
+            g = np.array([gout[k].item() for k in keys], dtype=np.float32)
+            e = np.array([eager[k].item() for k in keys], dtype=np.float32)
+            graph_ok = graph_ok and bool(np.max(np.abs(g - e) / np.maximum(np.abs(e), 1e-12)) <= 1e-6)
+            graph_ok = graph_ok and int(c_p2p.last_stats['exchange_status'].item()) == 0
+        good = good and graph_ok
         ok = ok and good
         report[name] = dict(p2p=va.tolist(), nccl=vb.tolist(), oracle_unsharded=want.tolist(),
                             identical_on_all_ranks=same_everywhere, status=status,
                             rel_vs_nccl=rel_nccl, rel_vs_oracle=rel_ref,
                             ms_per_call_p2p=round(t_p2p, 4), ms_per_call_nccl=round(t_nccl, 4),
                             training_identical_to_nccl=train_same, training_rel_vs_oracle=rel_train,
-                            fused_step_identical_to_nccl=fused_same)
+                            fused_step_identical_to_nccl=fused_same,
+                            graph_replays_match_eager=graph_ok)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -295,3 +295,30 @@ def test_logits_step_rejects_unsupported_inputs():
     step = fused.LogitsEvalStep(rc, decode.RetinaDecoder(**synth.RETINA_KW))
     with pytest.raises(RuntimeError):
         step([[torch.zeros(1, 72, 4, 4)], [torch.zeros(1, 4, 4, 9, 4)]], torch.zeros(1, 1, 5))
+
+
+def test_logits_nan_rows_are_dropped_like_np_argmax():
+    """A NaN logit makes sigmoid NaN; np.argmax returns the first NaN (decode.py:230-238), the row's
+    score is NaN and fails `score > threshold` -- even when another class of the row is confident."""
+    C = 8
+    sizes = [(p, p) for p in synth.pyramid_sizes(128)]
+    cls, reg = make_logits(2, sizes, 9, C, seed=41, mean=-3.0)
+    x = cls[0].view(2, 9, C, -1)                    # [B, A, C, HW]
+    best = x[0].max(dim=1).values.flatten().argsort(descending=True)
+    hw = x.shape[-1]
+    for n, (cpos, val) in enumerate(((0, 6.0), (C - 1, 7.0), (3, 8.0))):
+        a_i, p_i = int(best[n]) // hw, int(best[n]) % hw
+        x[0, a_i, (cpos + 1) % C, p_i] = val        # a confident class ...
+        x[0, a_i, cpos, p_i] = float('nan')         # ... and a NaN beside it
+    ann = synth.make_annotations(2, 12, 128, C, seed=42).cuda()
+    crit = losses.RetinaLoss(**synth.RETINA_KW)
+    dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    probs = [O.head_tail(t, C) for t in cls]
+    _, got = fused.LogitsEvalStep(crit, dec)([cls, reg], ann)
+    want = dec([probs, reg])
+    (s0, c0, b0), _ = O.retina_decode([[p.cpu() for p in probs], [r.cpu() for r in reg]],
+                                      **synth.RETINA_KW)
+    for name, a, b, c in zip(('scores', 'classes', 'boxes'), got, want, (s0, c0, b0)):
+        G.assert_bit_equal(a, b, f'NaN rows, probability path: {name}')
+        G.assert_bit_equal(a[1], c[1], f'NaN rows, oracle (image without ties): {name}')
+    assert not np.isnan(got[0]).any() and (got[0][0] < 0.99).all()   # the planted rows are gone

@@ -554,6 +554,25 @@ def test_decoder_nan_scores_golden():
     G.assert_bit_equal(b, b0, 'C=7 boxes')
 
 
+def test_second_backward_is_refused_not_wrong():
+    """The gradients are produced by the forward kernels and scaled in place by the upstream scalars:
+    a second pass over the same autograd node would return wrong values, so it raises (as torch does
+    for a freed graph); unused loss terms arrive as None and leave their head's gradient alone."""
+    preds = dev(synth.make_retina_preds(2, 128, 8, seed=90))
+    ann = synth.make_annotations(2, 12, 128, 8, seed=91).cuda()
+    crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+    p = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+    d = crit(p, ann)
+    d['cls_loss'].backward(retain_graph=True)
+    assert p[0][0].grad is not None and p[1][0].grad is None     # reg untouched by cls_loss alone
+    with pytest.raises(RuntimeError, match='second time'):
+        d['reg_loss'].backward()
+    # the supported pattern (tools/scripts.py:918-945): one backward on the summed loss
+    q = [[t.clone().requires_grad_(True) for t in grp] for grp in preds]
+    sum(crit(q, ann).values()).backward()
+    assert torch.equal(q[0][0].grad, p[0][0].grad) and q[1][0].grad.abs().sum() > 0
+
+
 def test_non_default_focal_parameters_and_weights():
     preds = synth.make_retina_preds(2, 128, 8, seed=8)
     ann = synth.make_annotations(2, 12, 128, 8, seed=9)
