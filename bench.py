@@ -30,8 +30,8 @@ training step of configs[4].
 import argparse
 import json
 import os
+import gc
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -81,61 +81,80 @@ def ncu_traffic():
         return {}
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+_PROBE_SRC = r"""
+import json, sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+period = float(sys.argv[2])
+names = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+         'sw_power_cap': 0x4, 'hw_power_brake': 0x80}
+samples, reasons = [], set()
+max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+sys.stdout.write('ready\n'); sys.stdout.flush()
+import select
+while True:
+    samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+    try:
+        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    for k, bit in names.items():
+        if mask & bit:
+            reasons.add(k)
+    if select.select([sys.stdin], [], [], period)[0]:
+        break
+s = sorted(samples)
+print(json.dumps({'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': max_mhz,
+                  'reasons': sorted(reasons), 'samples': len(s)}))
+"""
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs -- in a
+    separate PROCESS: a sampling thread inside the benchmark process takes the GIL every few
+    milliseconds, and with one process per GPU every such hiccup stalls ALL ranks at the next
+    exchange of the loss normaliser (measured at 8 GPUs, 32 images per rank)."""
 
     def __init__(self, index, period=0.005):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.reasons = [], set()
-        self.max_mhz = None
-        self._stop_evt = threading.Event()
-        self.ok = False
+        import subprocess
+        self.proc = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
-            self.ok = True
+            # NVML indexes physical GPUs: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    index = int(ids[index])
+            self.proc = subprocess.Popen([sys.executable, '-c', _PROBE_SRC, str(index), str(period)],
+                                         stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.ok = False
+            self.proc = None
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        names = {
-            'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
-            'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
-            'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
-            'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4),
-            'hw_power_brake': getattr(nv, 'nvmlClocksEventReasonHwPowerBrakeSlowdown', 0x80),
-        }
-        while not self._stop_evt.is_set():
+    def start(self):
+        """Blocks until the probe has initialised NVML and taken up sampling."""
+        if self.proc is not None:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
+                if self.proc.stdout.readline().strip() != 'ready':
+                    self.proc.kill()
+                    self.proc = None
             except Exception:
-                pass
-            self._stop_evt.wait(self.period)
+                self.proc = None
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        s = sorted(self.samples)
-        return {
-            'sm_mhz': s[len(s) // 2] if s else None,
-            'sm_max_mhz': self.max_mhz,
-            'reasons': sorted(self.reasons),
-            'samples': len(s),
-        }
+        none = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return none
+        try:
+            out, _ = self.proc.communicate('stop\n', timeout=10)
+            return json.loads(out.strip().splitlines()[-1])
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+            return none
 
 
 # --------------------------------------------------------------------------------------------
@@ -317,6 +336,19 @@ class Runner:
             dist.init_process_group('nccl', device_id=self.dev)
         _lib.load()
         self.exchange = 'none'
+        self.cpus = None
+        if self.distributed and not args.no_pin:
+            # one disjoint slice of the allowed CPUs per rank: the launcher starts all ranks on the
+            # same cpuset, and a migrating / preempted main thread on one rank delays all of them
+            try:
+                allowed = sorted(os.sched_getaffinity(0))
+                per = max(1, len(allowed) // self.world)
+                mine = allowed[self.local_rank * per:(self.local_rank + 1) * per]
+                if mine:
+                    os.sched_setaffinity(0, mine)
+                    self.cpus = len(mine)
+            except Exception as exc:   # noqa: BLE001
+                print(f'[bench] CPU pinning skipped: {exc}', file=sys.stderr)
 
     def barrier(self):
         if self.distributed:
@@ -365,13 +397,18 @@ class Runner:
             last = step()
         self.barrier()
         sampler = None
-        if sample_clocks:
+        if sample_clocks and self.rank == 0:   # the line reports rank 0's GPU
             sampler = ClockSampler(self.local_rank)
             sampler.start()
         if profile_every:
             lib.profile_start()
         launches0 = lib.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # no garbage-collector pauses inside the timed region: with one process per GPU a pause on
+        # ANY rank stalls every rank at the next exchange
+        gc.collect()
+        gc_was = gc.isenabled()
+        gc.disable()
         self.barrier()
         start.record()
         for i in range(steps):
@@ -382,6 +419,8 @@ class Runner:
             last = step()
         stop.record()
         self.barrier()
+        if gc_was:
+            gc.enable()
         elapsed_ms = start.elapsed_time(stop)
         launches = lib.launch_count() - launches0
         kernels = lib.profile_stop() if profile_every else {}
@@ -496,6 +535,7 @@ def run_b200(args, out):
                      'p2p': '4 doubles per step over NVLink peer memory inside the reduction kernel',
                      'none': 'single GPU: no exchange'}[R.exchange],
         'exchange_status': exchange_status,
+        'host_cpus_per_rank': R.cpus,
         'roofline': {
             'bound': 'hbm',
             'kernel': dom,
@@ -806,6 +846,7 @@ def main():
                     help='N > 1: how the loss normaliser crosses GPUs')
     ap.add_argument('--no-fused', action='store_true')
     ap.add_argument('--no-weak', action='store_true')
+    ap.add_argument('--no-pin', action='store_true', help='N > 1: do not give every rank its own CPUs')
     ap.add_argument('--no-configs', action='store_true')
     ap.add_argument('--profile-every', type=int, default=0)
     ap.add_argument('--no-e2e', action='store_true')

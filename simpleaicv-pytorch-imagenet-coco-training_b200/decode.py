@@ -30,6 +30,13 @@ __all__ = ['RetinaDecoder', 'FCOSDecoder', 'DETRDecoder', 'DINODETRDecoder', 'De
            'DetNMSMethod']
 
 
+def _detached(levels):
+    """The level tensors without autograd history (the decoders never differentiate); tensors that
+    do not require grad are passed through -- `.detach()` costs a microsecond per tensor of the host
+    time in front of the decoder's first launch."""
+    return [t.detach() if t.requires_grad else t for t in levels]
+
+
 _HALF_EXP_TABLES = {}
 
 
@@ -151,27 +158,35 @@ class _DecoderBase:
         else:
             cls_preds, reg_preds = preds
             center_preds = None
-        cls = _prep_f32([t.detach() for t in cls_preds], 'cls_preds')
-        reg, reg_dtype = _prep_reg([t.detach() for t in reg_preds])
-        ctr = _prep_f32([t.detach() for t in center_preds], 'center_preds') \
+        cls = _prep_f32(_detached(cls_preds), 'cls_preds')
+        reg, reg_dtype = _prep_reg(_detached(reg_preds))
+        ctr = _prep_f32(_detached(center_preds), 'center_preds') \
             if center_preds is not None else None
         device = cls[0].device
         shape0 = cls[0].shape
-        key = (tuple(t.shape[1:3] for t in cls), shape0[0], shape0[-1])
+        key = tuple([t.shape for t in cls])
         plan = self._geo_cache.get(key)
         if plan is None:
             shapes = _geom.level_shapes(cls)
             geo = self._geometry(shapes, int(shape0[0]), int(shape0[-1]))
             ws_bytes = int(lib.b200det_decode_workspace_bytes(ctypes.byref(geo), int(self.topn)))
             plan = (geo, ctypes.byref(geo), int(shape0[0]),
-                    _geom.rows_per_image(shapes, geo.per_loc), ws_bytes)
+                    _geom.rows_per_image(shapes, geo.per_loc), ws_bytes, {})
             self._geo_cache = {key: plan}
-        _, geo_ref, batch, n_rows, ws_bytes = plan
+        _, geo_ref, batch, n_rows, ws_bytes, scratch_by_stream = plan
         m = int(self.max_object_num)
 
         # scratch = keys | classes (int32 each) | selection workspace ; out = scores|classes|boxes
+        # (kept per (device, stream), like the criterion's: every call rewrites all of it)
         rows_bytes = (8 * batch * n_rows + 255) & ~255
-        scratch = torch.empty(rows_bytes + ws_bytes, dtype=torch.uint8, device=device)
+        st = _lib.raw_stream(device)
+        skey = (device.index, st.value)
+        scratch = scratch_by_stream.get(skey)
+        if scratch is None:
+            if len(scratch_by_stream) >= 4:
+                scratch_by_stream.clear()
+            scratch = scratch_by_stream[skey] = torch.empty(rows_bytes + ws_bytes, dtype=torch.uint8,
+                                                            device=device)
         out = self._out_buffer(6 * batch * m, device)
         order = keep = counts = None
         if details:
@@ -193,8 +208,7 @@ class _DecoderBase:
                                order.data_ptr() if details else None,
                                keep.data_ptr() if details else None,
                                counts.data_ptr() if details else None,
-                               keys_ptr + rows_bytes, ws_bytes,
-                               _lib.raw_stream(device)),
+                               keys_ptr + rows_bytes, ws_bytes, st),
             'b200det_decode')
 
         del glue

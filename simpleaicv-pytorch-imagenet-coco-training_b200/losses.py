@@ -235,7 +235,7 @@ class _Plan:
     """Everything about one (pyramid shapes, batch, classes) combination that does not change
     between calls: geometry struct, workspace size, row count."""
 
-    __slots__ = ('geo', 'geo_ref', 'ws_bytes', 'n_rows', 'batch')
+    __slots__ = ('geo', 'geo_ref', 'ws_bytes', 'n_rows', 'batch', 'scratch')
 
     def __init__(self, geo, batch, n_rows):
         self.geo = geo
@@ -243,11 +243,26 @@ class _Plan:
         self.batch = batch
         self.n_rows = n_rows
         self.ws_bytes = int(_lib.load().b200det_loss_workspace_bytes(self.geo_ref))
+        self.scratch = {}   # (device, raw stream) -> workspace | labels of the no-grad forward
+
+    def eval_scratch(self, device, stream):
+        """Workspace + labels of the no-grad forward, kept per (device, stream): every call
+        re-initialises what it reads, reuse on one stream is stream-ordered, and calls on different
+        streams get different buffers.  (A fresh torch.empty per call cost ~3.5 us of the host time
+        between the decoder's sync and the first launch of the next step.)"""
+        key = (device.index, stream.value)
+        buf = self.scratch.get(key)
+        if buf is None:
+            if len(self.scratch) >= 4:
+                self.scratch.clear()
+            buf = self.scratch[key] = torch.empty(self.ws_bytes + 4 * self.batch * self.n_rows,
+                                                  dtype=torch.uint8, device=device)
+        return buf
 
 
 def _plan_for(owner, cls):
     shape0 = cls[0].shape
-    key = (tuple(t.shape[1:3] for t in cls), shape0[0], shape0[-1])
+    key = tuple([t.shape for t in cls])
     plan = owner._plans.get(key)
     if plan is None:
         shapes = _geom.level_shapes(cls)
@@ -297,19 +312,27 @@ def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
     plan = _plan_for(owner, cls)
     device = cls[0].device
     # scratch = workspace | labels ; out = sums (4 doubles) | losses (3 floats, 8 reserved)
-    scratch = torch.empty(plan.ws_bytes + 4 * plan.batch * plan.n_rows, dtype=torch.uint8,
-                          device=device)
-    ws_ptr = scratch.data_ptr()
     st = _stream(device)
-    # assignment + sparse losses run on the criterion's side stream beside the HBM-bound sweep
-    side = _side_stream(owner, device)
+    if torch.cuda.is_current_stream_capturing():
+        scratch = torch.empty(plan.ws_bytes + 4 * plan.batch * plan.n_rows, dtype=torch.uint8,
+                              device=device)   # from the graph's private pool
+    else:
+        scratch = plan.eval_scratch(device, st)
+    ws_ptr = scratch.data_ptr()
+    # assignment + sparse losses run on the criterion's side stream beside the HBM-bound sweep --
+    # when there is a sweep worth hiding behind: below ~50 us of sweep (256 MB of class scores) the
+    # call is bound by its host work, and the fork / join (4 more stream operations) and the second
+    # C call only add to it
+    big = plan.batch * plan.n_rows * int(cls[0].shape[-1]) >= (64 << 20)
+    side = _side_stream(owner, device) if big else None
     side_args = (side.stream, side.fork, side.join) if side is not None else (None, None, None)
     params = _loss_params(owner, _lib.F32)
     cls_ptrs = _lib.ptr_array(cls)
-    _lib.check(
-        lib.b200det_loss_forward_overlap(plan.geo_ref, ctypes.byref(params), None, 0, cls_ptrs, None,
-                                         None, None, ws_ptr, plan.ws_bytes, None, None, None, None,
-                                         *side_args, st, 1), 'b200det_loss_forward_overlap')
+    if big:
+        _lib.check(
+            lib.b200det_loss_forward_overlap(plan.geo_ref, ctypes.byref(params), None, 0, cls_ptrs,
+                                             None, None, None, ws_ptr, plan.ws_bytes, None, None, None,
+                                             None, *side_args, st, 1), 'b200det_loss_forward_overlap')
     reg, reg_dtype = _prep_reg(reg_in)
     reg_dtype = _loss_reg_mode(reg_dtype)
     ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
@@ -334,7 +357,8 @@ def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
                                          _lib.ptr_array(reg), _lib.ptr_array(ctr),
                                          ws_ptr + plan.ws_bytes, ws_ptr, plan.ws_bytes, px, sums_ptr,
                                          None if (sync and not p2p) else sums_ptr + 32,
-                                         status.data_ptr() if p2p else None, *side_args, st, 2),
+                                         status.data_ptr() if p2p else None, *side_args, st,
+                                         2 if big else 0),
         'b200det_loss_forward_overlap')
     if p2p:
         owner.__dict__['last_stats'] = {'sums': out[0:4], 'exchange_status': status}
