@@ -1403,8 +1403,14 @@ int b200det::select_decode_nms_impl(const b200det_geometry *geo, const uint32_t 
     // for an 800x800 RetinaNet pyramid), a large batch one CTA per image (the SMs are busy anyway
     // and clusters must be co-scheduled inside a GPC).
     const int N = g.off[g.n_levels];
+    // Measured (tools/prof_select.py, RetinaNet 800x800, select kernel in us, slices 1 / 2 / 4 / 8):
+    // batch 1: 41 / - / - / 27; 16: 46 / 38 / 34 / 44; 32: 47 / - / 34 / 58; 64: 48 / 42 / 59 / 86;
+    // 128: 50 / 69 / 99 / 152.  Up to 128 CTAs in all; clusters of 8 only while they fit one per GPC.
     int slices = 1;
-    while (slices < 8 && slices * 2 * g.batch <= 160 && N / (slices * 2) >= 4096) slices *= 2;
+    if (8 * g.batch <= 64) slices = 8;
+    else if (4 * g.batch <= 128) slices = 4;
+    else if (2 * g.batch <= 128) slices = 2;
+    while (slices > 1 && N / slices < 4096) slices >>= 1;
     static const int env_slices = getenv("B200DET_SELECT_SLICES") ? atoi(getenv("B200DET_SELECT_SLICES")) : 0;
     if (env_slices == 1 || env_slices == 2 || env_slices == 4 || env_slices == 8) slices = env_slices;
     a.slices = slices;

@@ -30,7 +30,8 @@ def main():
     ap.add_argument('--only', default='')
     args = ap.parse_args()
     for name, B, fcos, S, C in (('retina_b1', 1, False, 800, 80), ('retina_b16', 16, False, 800, 80),
-                                ('retina_b32', 32, False, 800, 80), ('retina_b256', 256, False, 800, 80),
+                                ('retina_b32', 32, False, 800, 80), ('retina_b64', 64, False, 800, 80),
+                                ('retina_b128', 128, False, 800, 80), ('retina_b256', 256, False, 800, 80),
                                 ('fcos_b16', 16, True, 800, 80), ('fcos_1024_c365_b32', 32, True, 1024, 365)):
         if args.only and name not in args.only.split(','):
             continue
