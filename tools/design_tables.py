@@ -1,0 +1,92 @@
+"""Regenerates the measured tables of DESIGN.md from bench.py's own JSON lines (so the document
+quotes what the bench printed, not hand-copied numbers):
+
+    python tools/design_tables.py profiles/r02_bench_line.json [profiles/r02_scale_n{1,2,4,8}.json ...]
+
+Replaces the text between `<!-- BEGIN:name -->` / `<!-- END:name -->` markers in DESIGN.md."""
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load(path):
+    return json.loads(open(path).read().strip().splitlines()[-1])
+
+
+def kernel_table(d):
+    B = d['config']['images_per_gpu']
+    n, c = d['config']['rows_per_image'], 80
+    sweep = B * 4 * n * c
+    alg = {'focal_loss': sweep, 'score_argmax': sweep}
+    peak = d['roofline']['peak']
+    rows = ['| Kernel (1 launch / step) | Bound | Alg. bytes / launch | Time (CUDA events in the timed region) | Achieved |',
+            '|---|---|---|---|---|']
+    names = {'focal_loss': '`focal_all_kernel<4,γ=2>` (beside it on the helper stream: assignment + sparse losses)',
+             'assign': '`retina_assign_kernel<9>` (helper stream, overlapped)',
+             'sparse_losses': '`sparse_loss_kernel` (helper stream, overlapped)',
+             'loss_reduce': '`loss_reduce` (+ finish / peer exchange)',
+             'score_argmax': '`score_argmax_kernel<4>`',
+             'select_decode_nms': '`select_nms_kernel` (cluster per image)'}
+    bound = {'focal_loss': 'HBM', 'score_argmax': 'HBM', 'assign': 'ALU (issue)', 'sparse_losses': 'latency / issue',
+             'loss_reduce': '—', 'select_decode_nms': 'latency (L2-resident keys)'}
+    for k, ms in d['kernels_ms'].items():
+        a = alg.get(k)
+        ach = f'{a / (ms / 1e3) / 1e12:.2f} TB/s = **{a / (ms / 1e3) / 1e9 / peak:.2f} × measured peak**' if a else '—'
+        rows.append(f'| {names.get(k, k)} | {bound.get(k, "—")} | {a / 1e9:.3f} GB |' if a else
+                    f'| {names.get(k, k)} | {bound.get(k, "—")} | — |')
+        rows[-1] += f' {ms:.4f} ms | {ach} |'
+    step_b = B * d['config']['algorithmic_bytes_per_image']
+    rows.append(f'| **step** (criterion + decoder, 2 calls) | HBM | {step_b / 1e9:.2f} GB | **{d["ms_per_step"]:.3f} ms** | '
+                f'**{d["step_roofline"]["algorithmic_GBps"] / 1e3:.2f} TB/s = {d["step_roofline"]["frac_of_hbm_peak"]:.3f} × measured peak** |')
+    return '\n'.join(rows)
+
+
+def configs_table(d):
+    rows = ['| Config | loss fwd | loss fwd+bwd | decode+NMS | reference on the host CPU (bounded sample) |', '|---|---|---|---|---|']
+    for c in d.get('configs', []):
+        def cell(k):
+            if k not in c:
+                return '—'
+            v = c[k]
+            return f'{v["ms"]:.3f} ms = {v["frac_of_hbm_peak"]:.2f}' if v['frac_of_hbm_peak'] >= 0.3 else f'{v["ms"]:.3f} ms (latency-bound, {v["frac_of_hbm_peak"]:.2f})'
+        cpu = c.get('cpu_baseline')
+        rows.append(f'| {c["name"]} | {cell("loss_fwd")} | {cell("loss_fwd_bwd")} | {cell("decode_nms")} | '
+                    + (f'{cpu["value"]:.1f} images/s ({cpu["sample"].split(", stages")[0]}, {cpu["cores"]} cores)' if cpu else '—') + ' |')
+    return '\n'.join(rows)
+
+
+def scale_table(lines):
+    rows = ['| N GPUs | images / GPU | ms / step | images/s | speed-up | efficiency | exchange | sharded == unsharded |', '|---|---|---|---|---|---|---|---|']
+    base = None
+    for d in sorted(lines, key=lambda x: x['n_gpus']):
+        if base is None:
+            base = d['value'] / d['n_gpus']
+        pc = d.get('parity_check')
+        rows.append(f'| {d["n_gpus"]} | {d["config"]["images_per_gpu"]} | {d["ms_per_step"]:.4f} | {d["value"]:,.0f} | '
+                    f'{d["value"] / base:.2f}× | {d["value"] / base / d["n_gpus"]:.3f} | {d["exchange"].split(" per step")[0] if d["n_gpus"] > 1 else "—"} | '
+                    + (f'rel {pc["sharded_vs_unsharded_rel"]:.1e}, labels {"equal" if pc["labels_equal"] else "DIFFER"}' if pc else '—') + ' |')
+    return '\n'.join(rows)
+
+
+def main():
+    lines = [load(p) for p in sys.argv[1:]]
+    main_line = next(d for d in lines if d['n_gpus'] == 1)
+    blocks = {'kernels': kernel_table(main_line), 'configs': configs_table(main_line)}
+    if len(lines) > 1:
+        blocks['scaling'] = scale_table(lines)
+    path = os.path.join(ROOT, 'DESIGN.md')
+    text = open(path).read()
+    for name, body in blocks.items():
+        pat = re.compile(rf'(<!-- BEGIN:{name} -->\n).*?(<!-- END:{name} -->)', re.S)
+        if not pat.search(text):
+            print(f'marker {name} not found', file=sys.stderr)
+            continue
+        text = pat.sub(lambda m: m.group(1) + body + '\n' + m.group(2), text)
+    open(path, 'w').write(text)
+
+
+if __name__ == '__main__':
+    main()
