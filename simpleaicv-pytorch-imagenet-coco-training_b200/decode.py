@@ -136,15 +136,23 @@ class _DecoderBase:
         if out.is_cuda:
             staging = self._staging(out.numel())
             staging.copy_(out, non_blocking=True)
+        copy = _RESULT_COPY or staging is self._pinned
+        result = None
+        if not copy:
+            # the views are built while the GPU is still working: nothing but the return is left
+            # between the end of the synchronisation and the caller's next launch
+            host = staging.numpy()
+            result = [host[0:batch * m].reshape(batch, m),
+                      host[batch * m:2 * batch * m].reshape(batch, m),
+                      host[2 * batch * m:].reshape(batch, m, 4)]
         _lib.check(_lib.load().b200det_stream_synchronize(_lib.raw_stream(device)),
                    'b200det_stream_synchronize')
-        host = staging.numpy()
-        if _RESULT_COPY or staging is self._pinned:
-            host = host.copy()
-        scores = host[0:batch * m].reshape(batch, m)
-        out_classes = host[batch * m:2 * batch * m].reshape(batch, m)
-        boxes = host[2 * batch * m:].reshape(batch, m, 4)
-        return [scores, out_classes, boxes]
+        if result is None:
+            host = staging.numpy().copy()
+            result = [host[0:batch * m].reshape(batch, m),
+                      host[batch * m:2 * batch * m].reshape(batch, m),
+                      host[2 * batch * m:].reshape(batch, m, 4)]
+        return result
 
     def _run(self, preds, details=False, scales=None, sizes=None, to_xywh=False):
         _require_cuda(preds[0][0], 'cls_preds')
