@@ -69,5 +69,46 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def fastpath_path():
+    import sysconfig
+    return os.path.join(PKG_DIR, '_fastpath' + sysconfig.get_config_var('EXT_SUFFIX'))
+
+
+def build_fastpath(force=False, verbose=False):
+    """Compiles csrc/fastpath.cpp -- the optional host-side marshalling fast path (pybind11 + ATen,
+    no CUDA code; it calls the C ABI through function pointers) -- in-tree with g++.  Returns the
+    path, or None when it cannot be built here (no compiler / torch headers): the Python layer then
+    simply keeps doing the marshalling itself."""
+    src = os.path.join(CSRC, 'fastpath.cpp')
+    out = fastpath_path()
+    hdr = os.path.join(PKG_DIR, '..', 'include', 'b200det.h')
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src),
+                                                                          os.path.getmtime(hdr)):
+        return out
+    try:
+        import sysconfig
+        import torch
+        from torch.utils import cpp_extension as ce
+        gxx = shutil.which('g++')
+        if gxx is None:
+            raise RuntimeError('g++ not found')
+        tlib = os.path.join(os.path.dirname(torch.__file__), 'lib')
+        cmd = [gxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fvisibility=hidden',
+               '-DTORCH_EXTENSION_NAME=_fastpath', '-DTORCH_API_INCLUDE_EXTENSION_H',
+               f'-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}']
+        cmd += [f'-I{p}' for p in ce.include_paths()] + [f'-I{sysconfig.get_paths()["include"]}']
+        cmd += [src, '-o', out, f'-L{tlib}', '-ltorch_python', '-ltorch', '-ltorch_cpu', '-lc10',
+                f'-Wl,-rpath,{tlib}']
+        if verbose:
+            print(' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        return out
+    except Exception as exc:   # noqa: BLE001 -- optional component
+        print(f'[b200det] host fast path not built ({exc}); the Python marshalling path is used',
+              file=sys.stderr)
+        return None
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_fastpath(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -245,6 +245,28 @@ def load():
     return lib
 
 
+_FAST = None
+
+
+def fastpath():
+    """The optional host-side marshalling fast path (csrc/fastpath.cpp, built by
+    _build.build_fastpath) bound to the loaded library's entry points, or None (not built, or
+    B200DET_FASTPATH=0).  It is not a compute path: it calls the same C-ABI functions."""
+    global _FAST
+    if _FAST is None:
+        _FAST = False
+        if os.environ.get('B200DET_FASTPATH', '1') != '0':
+            try:
+                from . import _fastpath as mod
+                lib = load()
+                mod.bind(ctypes.cast(lib.b200det_loss_forward_overlap, ctypes.c_void_p).value,
+                         ctypes.cast(lib.b200det_decode, ctypes.c_void_p).value)
+                _FAST = mod
+            except Exception:   # noqa: BLE001 -- optional
+                _FAST = False
+    return _FAST or None
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().b200det_error_string(rc).decode()

@@ -159,6 +159,42 @@ class _DecoderBase:
         with _on_device(preds[0][0].device):
             return self._run_on(preds, details, scales, sizes, to_xywh)
 
+    def _run_fast(self, fast, cls_preds, reg_preds, center_preds):
+        """The plain decoder(preds) call through csrc/fastpath.cpp (same checks / marshalling / C-ABI
+        call as _run_on, in C++); None when the inputs need the Python path."""
+        try:
+            key = tuple([t.shape for t in cls_preds])
+            plan = self._geo_cache.get(key)
+            if plan is None:
+                return None   # first call with these shapes: the Python path builds the plan
+            geo, _, batch, n_rows, ws_bytes, scratch_by_stream = plan
+            device = cls_preds[0].device
+        except Exception:   # noqa: BLE001
+            return None
+        if device.type != 'cuda':
+            return None
+        st = _lib.raw_stream(device)
+        rows_bytes = (8 * batch * n_rows + 255) & ~255
+        skey = (device.index, st.value)
+        scratch = scratch_by_stream.get(skey)
+        if scratch is None:
+            return None
+        table = 0
+        if reg_preds[0].dtype == torch.float16:
+            t = _half_exp_table(device)
+            table = t.data_ptr() if t is not None else 0
+        p = self._params
+        res = fast.decode_run(ctypes.addressof(geo), list(cls_preds), list(reg_preds),
+                              list(center_preds) if center_preds is not None else None,
+                              (p.is_fcos, p.topn, p.max_out, p.nms_type, p.min_score, p.nms_threshold),
+                              scratch.data_ptr(), 4 * batch * n_rows, rows_bytes, ws_bytes, table,
+                              st.value or 0)
+        if res is None:
+            return None
+        if isinstance(res, int):
+            _lib.check(res, 'b200det_decode')
+        return self._to_host(res, batch, int(self.max_object_num), device)
+
     def _run_on(self, preds, details, scales, sizes, to_xywh):
         lib = _lib.load()
         if self._is_fcos:
@@ -166,6 +202,13 @@ class _DecoderBase:
         else:
             cls_preds, reg_preds = preds
             center_preds = None
+        if not details and scales is None and sizes is None and not to_xywh and _ZERO_COPY \
+                and not _RESULT_COPY:
+            fast = _lib.fastpath()
+            if fast is not None:
+                res = self._run_fast(fast, cls_preds, reg_preds, center_preds)
+                if res is not None:
+                    return res
         cls = _prep_f32(_detached(cls_preds), 'cls_preds')
         reg, reg_dtype = _prep_reg(_detached(reg_preds))
         ctr = _prep_f32(_detached(center_preds), 'center_preds') \

@@ -303,7 +303,63 @@ def _forward_eval(owner, annotations, cls_in, reg_in, ctr_in):
         return _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in)
 
 
+def _forward_eval_fast(fast, owner, annotations, cls_in, reg_in, ctr_in):
+    """The common case through csrc/fastpath.cpp: the same checks, pointer marshalling and C-ABI call
+    as _forward_eval_on below, done in C++ (the host time in front of the first launch is GPU idle
+    time in an eval loop).  Returns the losses tensor, or None when the inputs need the Python path."""
+    if not (isinstance(annotations, torch.Tensor) and annotations.dim() == 3):
+        return None
+    try:
+        plan = _plan_for(owner, cls_in)
+    except Exception:   # noqa: BLE001 -- unusual inputs: let the Python path report them
+        return None
+    device = cls_in[0].device
+    if device.type != 'cuda' or torch.cuda.is_current_stream_capturing():
+        return None
+    st = _stream(device)
+    scratch = plan.eval_scratch(device, st)
+    big = plan.batch * plan.n_rows * int(cls_in[0].shape[-1]) >= (64 << 20)
+    side = _side_stream(owner, device) if big else None
+    sync = owner.sync_normalizer and torch.distributed.is_available() \
+        and torch.distributed.is_initialized()
+    p2p = sync and owner.sync_normalizer == 'p2p'
+    px = ctypes.addressof(_peer_exchange(owner, device).params) if p2p else 0
+    params = (int(owner._is_fcos), owner._box_code, int(getattr(owner, 'use_center_sample', 0)),
+              float(owner.alpha), float(owner.gamma), float(owner.beta), float(owner.cls_loss_weight),
+              float(owner.box_loss_weight), float(getattr(owner, 'center_ness_loss_weight', 0.)),
+              owner._iou_thresholds[0], owner._iou_thresholds[1])
+    res = fast.loss_eval(ctypes.addressof(plan.geo), list(cls_in), list(reg_in),
+                         list(ctr_in) if ctr_in is not None else None, annotations, params,
+                         torch.is_autocast_enabled(), scratch.data_ptr(), plan.ws_bytes,
+                         2 if p2p else (1 if sync else 0), px,
+                         side.stream.value if side is not None else 0,
+                         side.fork.value if side is not None else 0,
+                         side.join.value if side is not None else 0, st.value or 0)
+    if res is None:
+        return None
+    if isinstance(res, int):
+        _lib.check(res, 'b200det_loss_forward_overlap')
+    out = res
+    if p2p:
+        owner.__dict__['last_stats'] = {'sums': out[0:4],
+                                        'exchange_status': out[6:7].view(torch.int32)[0:1]}
+        return out[4:8].view(torch.float32)
+    if sync:
+        _maybe_all_reduce(out[0:4], True, owner.process_group)
+        sums_ptr = out.data_ptr()
+        _lib.check(
+            _lib.load().b200det_loss_finish(sums_ptr, params[6], params[7], params[8], sums_ptr + 32,
+                                            st), 'b200det_loss_finish')
+    owner.__dict__['last_stats'] = {'sums': out[0:4]}
+    return out[4:8].view(torch.float32)
+
+
 def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
+    fast = _lib.fastpath()
+    if fast is not None:
+        res = _forward_eval_fast(fast, owner, annotations, cls_in, reg_in, ctr_in)
+        if res is not None:
+            return res
     lib = _lib.load()
     # Phase 1 as early as possible: the sweep only needs the classification tensors, so it is on the
     # GPU while the host still checks / marshals the other arguments (the eval loop calls this right

@@ -554,6 +554,46 @@ def test_decoder_nan_scores_golden():
     G.assert_bit_equal(b, b0, 'C=7 boxes')
 
 
+def test_host_fast_path_and_python_path_agree():
+    """csrc/fastpath.cpp only replaces the Python argument marshalling: both host paths must enqueue
+    the same work (bit-identical losses and detections), and inputs outside the fast path's common
+    case (non-contiguous / double tensors, a glue call) must fall through to the Python path."""
+    from b200det import _lib
+    preds = dev(synth.make_tie_free(synth.make_fcos_preds(2, 256, 8, seed=92)))
+    ann = synth.make_annotations(2, 12, 256, 8, seed=93).cuda()
+    crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+    dec = decode.FCOSDecoder(strides=synth.STRIDES)
+
+    def run(p):
+        with torch.no_grad():
+            d = crit(p, ann)
+        return [d[k].item() for k in ('cls_loss', 'reg_loss', 'center_ness_loss')], dec(p)
+
+    saved = _lib._FAST
+    try:
+        _lib._FAST = None
+        fast_loss, fast_det = run(preds)          # second call: plans exist, the fast path runs
+        fast_loss, fast_det = run(preds)
+        had_fast = _lib.fastpath() is not None
+        _lib._FAST = False
+        slow_loss, slow_det = run(preds)
+    finally:
+        _lib._FAST = saved
+    assert fast_loss == slow_loss
+    for a, b in zip(fast_det, slow_det):
+        assert np.array_equal(a, b)
+    # not the common case: permuted (non-contiguous) class tensors and float64 annotations
+    odd = [[t.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3) for t in preds[0]], preds[1], preds[2]]
+    assert not odd[0][0].is_contiguous()
+    with torch.no_grad():
+        d = crit(odd, ann.double())
+    assert [d[k].item() for k in ('cls_loss', 'reg_loss', 'center_ness_loss')] == slow_loss
+    for a, b in zip(dec(odd), slow_det):
+        assert np.array_equal(a, b)
+    if not had_fast:
+        pytest.skip('host fast path not built on this box (Python path verified)')
+
+
 def test_second_backward_is_refused_not_wrong():
     """The gradients are produced by the forward kernels and scaled in place by the upstream scalars:
     a second pass over the same autograd node would return wrong values, so it raises (as torch does
