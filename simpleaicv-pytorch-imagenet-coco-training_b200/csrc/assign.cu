@@ -401,8 +401,16 @@ __global__ void __launch_bounds__(kAssignThreads)
                 const int row = (int)(lm0 + a0 + a);
                 labels[row] = label;
                 if (matched) matched[row] = match;
-                if (label > 0) pos_q[atomicAdd(&n_pos_s, 1)] = make_int2(row, grow);
-                if (label < 0) ign_q[atomicAdd(&n_ign_s, 1)] = row;
+                if (label > 0) {
+                    const int slot = atomicAdd(&n_pos_s, 1);
+                    B200DET_ASSERT(slot < kQueue);   // one slot per (thread, anchor)
+                    pos_q[slot] = make_int2(row, grow);
+                }
+                if (label < 0) {
+                    const int slot = atomicAdd(&n_ign_s, 1);
+                    B200DET_ASSERT(slot < kQueue);
+                    ign_q[slot] = row;
+                }
             }
         }
     }

@@ -10,6 +10,16 @@
 #error "libb200det is written for sm_100a (B200) only"
 #endif
 
+// Debug builds (B200DET_NVCC_EXTRA=-DB200DET_DEBUG python -m b200det._build --force) check the
+// capacities of the shared-memory lists / queues on the device (compute-sanitizer is not available on
+// the GPU pool); release builds compile the checks away.
+#ifdef B200DET_DEBUG
+#include <assert.h>
+#define B200DET_ASSERT(cond) assert(cond)
+#else
+#define B200DET_ASSERT(cond) ((void)0)
+#endif
+
 namespace b200det {
 
 constexpr int kMaxLevels = B200DET_MAX_LEVELS;

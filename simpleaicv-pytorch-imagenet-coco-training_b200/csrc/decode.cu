@@ -751,10 +751,15 @@ __global__ void __launch_bounds__(kSelThreads, 1)
     stamp(1);
     {
         int2 t = make_int2(0, 0);   // thread t owns bins 2t, 2t+1
-        for (int r = 0; r < a.slices; ++r) {
-            const int2 v = reinterpret_cast<const int2 *>(cluster.map_shared_rank(hist, r))[tid];
-            t.x += v.x;
-            t.y += v.y;
+        int2 v[8];                  // all remote loads in flight before the first add
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            v[r] = r < a.slices ? reinterpret_cast<const int2 *>(cluster.map_shared_rank(hist, r))[tid]
+                                : make_int2(0, 0);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            t.x += v[r].x;
+            t.y += v[r].y;
         }
         reinterpret_cast<int2 *>(htot)[tid] = t;
     }
@@ -777,9 +782,11 @@ __global__ void __launch_bounds__(kSelThreads, 1)
         // (one atomic per survivor: they are ~1 % of the keys; a warp-aggregated version -- ballot,
         // one atomic per warp -- was measured SLOWER, 7.4 -> 8.7 us for this phase at batch 1)
         for_each_key_range(g, b, keys, r0, r1, [&](uint32_t k, int row) {
-            if (k >= T && k != 0u)
-                stmp[atomicAdd(&s_count, 1)] =
-                    ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
+            if (k >= T && k != 0u) {
+                const int slot = atomicAdd(&s_count, 1);
+                B200DET_ASSERT(slot < cap);   // n_collect <= cap was checked on the histogram
+                stmp[slot] = ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
+            }
         });
         __syncthreads();
         stamp(9);
@@ -788,6 +795,7 @@ __global__ void __launch_bounds__(kSelThreads, 1)
         if (tid == 0) s_digit = n_local ? atomicAdd(cluster.map_shared_rank(&s_list, 0), n_local) : 0;
         __syncthreads();
         const int base = s_digit;
+        B200DET_ASSERT(base + n_local <= cap);
         for (int i = tid; i < n_local; i += kSelThreads) lead_key[base + i] = stmp[i];
     }
     cluster.sync();   // the leader's list is complete; nobody touches another CTA's memory after this
@@ -865,6 +873,7 @@ __global__ void __launch_bounds__(kSelThreads, 1)
             const bool take = tie_take < 0 ? (k >= T && k != 0u) : (k > T);
             if (take) {
                 const int slot = atomicAdd(&s_count, 1);
+                B200DET_ASSERT(slot < cap);   // the refinement ends with exactly k_sel <= cap keys
                 skey[slot] = ((unsigned long long)k << 32) | (0xffffffffu - (uint32_t)row);
             }
         });
@@ -920,7 +929,9 @@ __global__ void __launch_bounds__(kSelThreads, 1)
         for (int i = tid; i < n_got; i += kSelThreads) {
             const unsigned long long e = skey[i];
             const int bn = bin_of((uint32_t)(e >> 32));
-            stmp[sbase[bn] + atomicAdd(&sfill[bn], 1)] = e;
+            const int pos = sbase[bn] + atomicAdd(&sfill[bn], 1);
+            B200DET_ASSERT(pos >= 0 && pos < cap);
+            stmp[pos] = e;
         }
         __syncthreads();
         for (int i = tid; i < n_got; i += kSelThreads) {
