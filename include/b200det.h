@@ -397,6 +397,17 @@ int b200det_eval_step(const b200det_geometry *geo, const b200det_loss_params *lo
                       int32_t *classes, float *out, void *decode_workspace,
                       size_t decode_workspace_bytes, void *stream);
 
+/* b200det_eval_step with the assignment and the sparse losses on a caller-owned helper stream beside
+ * the sweep and the selection (fork after the memset, join before the reduction; see
+ * b200det_loss_forward_overlap for the stream / event contract).  No decode workspace. */
+int b200det_eval_step_overlap(const b200det_geometry *geo, const b200det_loss_params *loss_params,
+                              const b200det_decode_params *decode_params, const float *annotations,
+                              int max_gt, const void *const *cls, const void *const *reg,
+                              const void *const *ctr, int32_t *labels, void *loss_workspace,
+                              size_t loss_workspace_bytes, double *sums, float *losses,
+                              uint32_t *keys, int32_t *classes, float *out, void *side_stream,
+                              void *ev_fork, void *ev_join, void *stream);
+
 /* ---- utilities (tests / parity outputs) ---------------------------------------------- */
 /* dst[b*N + off_l + i] = src[B*off_l + b*n_l + i] for `width` int32/float32 words per row */
 int b200det_rows_to_image_major(const b200det_geometry *geo, const void *src, void *dst,

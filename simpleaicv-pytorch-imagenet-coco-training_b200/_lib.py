@@ -126,6 +126,10 @@ SIGNATURES = {
         _geo, ctypes.POINTER(LossParams), ctypes.POINTER(DecodeParams), _vp, ctypes.c_int, _vpp,
         _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp
     ]),
+    'b200det_eval_step_overlap': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), ctypes.POINTER(DecodeParams), _vp, ctypes.c_int, _vpp,
+        _vpp, _vpp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp
+    ]),
     'b200det_decode': (ctypes.c_int, [
         _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp

@@ -85,14 +85,12 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
 // the score/arg-max sweep also accumulates the label-free focal sum.  Not part of the reference's
 // call structure (criterion and decoder are separate calls there, tools/scripts.py:733-740); an
 // optional extension for eval loops that are willing to make one call instead of two.
-extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss_params *lp,
-                                 const b200det_decode_params *dp, const float *annotations,
-                                 int max_gt, const void *const *cls, const void *const *reg,
-                                 const void *const *ctr, int32_t *labels, void *loss_workspace,
-                                 size_t loss_workspace_bytes, double *sums, float *losses,
-                                 uint32_t *keys, int32_t *classes, float *out,
-                                 void *decode_workspace, size_t decode_workspace_bytes,
-                                 void *stream) {
+static int eval_step_impl(const b200det_geometry *geo, const b200det_loss_params *lp,
+                          const b200det_decode_params *dp, const float *annotations, int max_gt,
+                          const void *const *cls, const void *const *reg, const void *const *ctr,
+                          int32_t *labels, void *loss_workspace, size_t loss_workspace_bytes,
+                          double *sums, float *losses, uint32_t *keys, int32_t *classes, float *out,
+                          void *side, void *ev_fork, void *ev_join, void *stream) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
@@ -102,11 +100,20 @@ extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss
     if (g.num_classes % 4) return B200DET_EINVAL;
     const LossWs ws = loss_ws_layout(g);
     if (loss_workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    const bool fork = side && ev_fork && ev_join;
+    cudaStream_t st = (cudaStream_t)stream;
     char *base = static_cast<char *>(loss_workspace);
     cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
-                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
-                                    (cudaStream_t)stream);
+                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal, st);
     if (e != cudaSuccess) return (int)e;
+    void *st_sparse = stream;
+    if (fork) {
+        // assignment + sparse losses beside the sweep AND the selection (neither reads their output)
+        if ((e = cudaEventRecord((cudaEvent_t)ev_fork, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent((cudaStream_t)side, (cudaEvent_t)ev_fork, 0)) != cudaSuccess)
+            return (int)e;
+        st_sparse = side;
+    }
     g_skip_memset = true;
     rc = score_argmax_impl(geo, cls, dp->is_fcos ? ctr : nullptr, dp->min_score, keys, classes,
                            lp->alpha, lp->gamma, reinterpret_cast<long long *>(base + ws.off_focal),
@@ -114,27 +121,65 @@ extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss
     if (!rc) {
         rc = lp->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, lp->use_center_sample,
                                                labels, nullptr, nullptr, loss_workspace,
-                                               loss_workspace_bytes, stream)
+                                               loss_workspace_bytes, st_sparse)
                          : b200det_retina_assign(geo, annotations, max_gt, lp->iou_neg, lp->iou_pos,
                                                  labels, nullptr, loss_workspace,
-                                                 loss_workspace_bytes, stream);
+                                                 loss_workspace_bytes, st_sparse);
     }
     if (!rc)
         rc = b200det_sparse_losses(geo, lp->is_fcos, annotations, max_gt, labels, reg,
                                    lp->reg_dtype, ctr, lp->box_loss, lp->beta, cls, lp->alpha,
                                    lp->gamma, nullptr, nullptr, loss_workspace,
-                                   loss_workspace_bytes, stream);
+                                   loss_workspace_bytes, st_sparse);
     g_skip_memset = false;
+    if (!rc && fork)   // the selection only needs the sweep's keys: it goes in front of the join
+        rc = select_decode_nms_impl(geo, keys, classes, reg, dp->reg_dtype, dp->is_fcos,
+                                    dp->min_score, dp->topn, dp->max_out, dp->nms_type,
+                                    dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
+                                    nullptr, nullptr, nullptr, dp->half_exp_table, stream);
+    if (fork) {
+        e = cudaEventRecord((cudaEvent_t)ev_join, (cudaStream_t)side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+    }
     if (!rc)   // reduction and normalisation in one launch unless the caller all-reduces in between
         rc = losses ? b200det_loss_reduce_finish(geo, loss_workspace, loss_workspace_bytes, lp->w_cls,
                                                  lp->w_box, lp->w_ctr, sums, losses, stream)
                     : b200det_loss_reduce(geo, 3, loss_workspace, loss_workspace_bytes, sums, stream);
-    if (!rc)
+    if (!rc && !fork)
         rc = select_decode_nms_impl(geo, keys, classes, reg, dp->reg_dtype, dp->is_fcos,
                                     dp->min_score, dp->topn, dp->max_out, dp->nms_type,
                                     dp->nms_threshold, dp->scales, dp->sizes, dp->to_xywh, out,
                                     nullptr, nullptr, nullptr, dp->half_exp_table, stream);
     return rc;
+}
+
+extern "C" int b200det_eval_step(const b200det_geometry *geo, const b200det_loss_params *lp,
+                                 const b200det_decode_params *dp, const float *annotations,
+                                 int max_gt, const void *const *cls, const void *const *reg,
+                                 const void *const *ctr, int32_t *labels, void *loss_workspace,
+                                 size_t loss_workspace_bytes, double *sums, float *losses,
+                                 uint32_t *keys, int32_t *classes, float *out,
+                                 void *decode_workspace, size_t decode_workspace_bytes,
+                                 void *stream) {
+    (void)decode_workspace;
+    (void)decode_workspace_bytes;
+    return eval_step_impl(geo, lp, dp, annotations, max_gt, cls, reg, ctr, labels, loss_workspace,
+                          loss_workspace_bytes, sums, losses, keys, classes, out, nullptr, nullptr,
+                          nullptr, stream);
+}
+
+extern "C" int b200det_eval_step_overlap(const b200det_geometry *geo, const b200det_loss_params *lp,
+                                         const b200det_decode_params *dp, const float *annotations,
+                                         int max_gt, const void *const *cls, const void *const *reg,
+                                         const void *const *ctr, int32_t *labels,
+                                         void *loss_workspace, size_t loss_workspace_bytes,
+                                         double *sums, float *losses, uint32_t *keys,
+                                         int32_t *classes, float *out, void *side_stream,
+                                         void *ev_fork, void *ev_join, void *stream) {
+    return eval_step_impl(geo, lp, dp, annotations, max_gt, cls, reg, ctr, labels, loss_workspace,
+                          loss_workspace_bytes, sums, losses, keys, classes, out, side_stream, ev_fork,
+                          ev_join, stream);
 }
 
 // cudaStreamSynchronize for the host layer (the decoder's only host wait): avoids building a

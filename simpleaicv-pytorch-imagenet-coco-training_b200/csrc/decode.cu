@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
                         code = (k << 2) | e;
                     }
                 }
-                any = fmax_nan(fmax_nan(any, fmax_nan(e4[0], e4[1])), fmax_nan(e4[2], e4[3]));
+                // (with the focal terms fused in, their clamp tree below doubles as the NaN tracker)
+                if (!FOCAL)
+                    any = fmax_nan(fmax_nan(any, fmax_nan(e4[0], e4[1])), fmax_nan(e4[2], e4[3]));
             }
         }
         int best_c = best > ninf ? ((((code >> 2) << ts) + j) << 2) + (code & 3) : 0x7fffffff;
@@ -270,7 +272,10 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
                 if (live && (k << ts) + j < U) {
                     const float x0 = fmax_nan(v[k].x, kClampLo), x1 = fmax_nan(v[k].y, kClampLo);
                     const float x2 = fmax_nan(v[k].z, kClampLo), x3 = fmax_nan(v[k].w, kClampLo);
-                    const float mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+                    // max.NaN: a NaN score makes mx NaN -> exact-form terms (NaN, poisoning the sum
+                    // like the reference's) AND marks the row for the arg-max's "first NaN wins"
+                    const float mx = fmax_nan(fmax_nan(x0, x1), fmax_nan(x2, x3));
+                    any = fmax_nan(any, mx);
                     if (gamma2 && mx <= kFastMax) {
                         float2 xr, xs;
                         acc2 = neg_term_fast2_acc(make_float2(x0, x1), acc2, xr, xs);

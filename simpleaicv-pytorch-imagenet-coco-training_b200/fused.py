@@ -22,7 +22,8 @@ import torch
 from . import _lib
 from . import geometry as _geom
 from .losses import (_DTYPES, _Plan, _decode_reg_mode, _loss_params, _loss_reg_mode, _on_device,
-                     _plan_for, _prep_annotations, _prep_f32, _prep_reg, _require_cuda, _sync_sums)
+                     _plan_for, _prep_annotations, _prep_f32, _prep_reg, _require_cuda, _side_stream,
+                     _sync_sums)
 
 __all__ = ['EvalStep', 'LogitsEvalStep']
 
@@ -80,13 +81,17 @@ class EvalStep:
             and torch.distributed.is_initialized()
         st = _lib.raw_stream(device)
         sums_ptr = small.data_ptr()
+        # assignment + sparse losses on the criterion's helper stream beside the sweep and the selection
+        side = _side_stream(crit, device) if not torch.cuda.is_current_stream_capturing() else None
+        side_args = (side.stream, side.fork, side.join) if side is not None else (None, None, None)
         _lib.check(
-            lib.b200det_eval_step(plan.geo_ref, ctypes.byref(lp), ctypes.byref(dp),
-                                  annotations.data_ptr(), int(annotations.shape[1]),
-                                  _lib.ptr_array(cls), _lib.ptr_array(reg), _lib.ptr_array(ctr),
-                                  labels_ptr, base, plan.ws_bytes, sums_ptr,
-                                  None if sync else sums_ptr + 32, keys_ptr, classes_ptr,
-                                  out.data_ptr(), dws_ptr, dws_bytes, st), 'b200det_eval_step')
+            lib.b200det_eval_step_overlap(plan.geo_ref, ctypes.byref(lp), ctypes.byref(dp),
+                                          annotations.data_ptr(), int(annotations.shape[1]),
+                                          _lib.ptr_array(cls), _lib.ptr_array(reg),
+                                          _lib.ptr_array(ctr), labels_ptr, base, plan.ws_bytes,
+                                          sums_ptr, None if sync else sums_ptr + 32, keys_ptr,
+                                          classes_ptr, out.data_ptr(), *side_args, st),
+            'b200det_eval_step_overlap')
         if sync:
             _sync_sums(crit, small[0:4], crit.process_group, st,
                        finish=(lp.w_cls, lp.w_box, lp.w_ctr, sums_ptr + 32))
