@@ -632,6 +632,44 @@ def parity_check(R, crit):
     }
 
 
+def _set_mempolicy(mode, node):
+    """set_mempolicy(2) through libc's syscall(): page placement of what this thread touches next."""
+    import ctypes
+    libc = ctypes.CDLL(None, use_errno=True)
+    if node is None:
+        return libc.syscall(238, 0, None, 0)                     # MPOL_DEFAULT
+    mask = ctypes.c_ulong(1 << node)
+    return libc.syscall(238, mode, ctypes.byref(mask), 64)
+
+
+def prefer_numa_node_of(bus_id):
+    """Prefers the NUMA node the GPU hangs off for the pinned staging buffers allocated next (a
+    cpuset that confines all ranks to one socket's CPUs would otherwise first-touch every rank's
+    buffers on that socket, and half of the GPUs would read them across the socket link).  Returns
+    the node, or None when it is unknown or the policy cannot be set."""
+    try:
+        bus = bus_id.decode() if isinstance(bus_id, bytes) else str(bus_id)
+        bus = bus.lower()
+        if len(bus.split(':')[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs has 4
+            bus = bus[4:]
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        if _set_mempolicy(1, node) != 0:          # MPOL_PREFERRED
+            return None
+        return node
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def set_mempolicy_default():
+    try:
+        _set_mempolicy(0, None)
+    except Exception:   # noqa: BLE001
+        pass
+
+
 def run_e2e(R, args, preds, ann, crit, dec):
     """Same step through the public classes, but starting from pinned host buffers every step."""
     torch = R.torch
@@ -648,18 +686,26 @@ def run_e2e(R, args, preds, ann, crit, dec):
     # give the thread its old CPU mask back (the CPU baseline must keep all host cores)
     old_mask = os.sched_getaffinity(0)
     cpus = None
+    numa = None
     try:
         import pynvml
         pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0))
-        cpus = len(os.sched_getaffinity(0))
-    except Exception as e:  # restricted cpuset, no NVML: keep the default placement
+        handle = pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)
+        try:
+            pynvml.nvmlDeviceSetCpuAffinity(handle)
+            cpus = len(os.sched_getaffinity(0))
+        except Exception as e:  # restricted cpuset: keep the CPU placement
+            print(f'[bench] CPU affinity to the GPU skipped: {e}', file=sys.stderr)
+        numa = prefer_numa_node_of(pynvml.nvmlDeviceGetPciInfo(handle).busId)
+    except Exception as e:  # no NVML: keep the default placement
         print(f'[bench] NUMA binding skipped: {e}', file=sys.stderr)
     try:
         host = [[t[:B].cpu().pin_memory() for t in grp] for grp in preds]
         host_ann = ann[:B].cpu().pin_memory()
     finally:
         os.sched_setaffinity(0, old_mask)
+        if numa is not None:
+            set_mempolicy_default()
     h2d = sum(t.numel() * t.element_size() for grp in host for t in grp)
     h2d += host_ann.numel() * host_ann.element_size()
     d2h = 6 * B * 100 * 4 + 2 * 4
@@ -703,6 +749,7 @@ def run_e2e(R, args, preds, ann, crit, dec):
         },
         'frac_of_h2d_only': (dt_copy / dt),
         'pinned_alloc_cpus': cpus,
+        'pinned_alloc_numa_node': numa,
         'note': 'pinned host -> HBM copy of all head outputs + annotations, loss, decode+NMS, D2H '
                 'of losses and detections, every step; PCIe-bound (129 kB of input per image-level '
                 'row block: 40.3 MB per image against 80.7 MB of HBM traffic)',

@@ -72,7 +72,11 @@ def scale_table(lines):
 
 
 def main():
-    lines = [load(p) for p in sys.argv[1:]]
+    args = sys.argv[1:]
+    only = None
+    if args and args[0].startswith('--only='):
+        only = args.pop(0).split('=', 1)[1].split(',')
+    lines = [load(p) for p in args]
     main_line = next(d for d in lines if d['n_gpus'] == 1)
     blocks = {'kernels': kernel_table(main_line), 'configs': configs_table(main_line)}
     if len(lines) > 1:
@@ -80,6 +84,8 @@ def main():
     path = os.path.join(ROOT, 'DESIGN.md')
     text = open(path).read()
     for name, body in blocks.items():
+        if only and name not in only:
+            continue
         pat = re.compile(rf'(<!-- BEGIN:{name} -->\n).*?(<!-- END:{name} -->)', re.S)
         if not pat.search(text):
             print(f'marker {name} not found', file=sys.stderr)
