@@ -56,7 +56,7 @@ __device__ __forceinline__ GtSmem carve(unsigned char *base, int G) {
     s.ridx = s.fidx + G;
     return s;
 }
-static size_t gt_smem_bytes(int G) {
+__host__ __device__ static inline size_t gt_smem_bytes(int G) {
     const int raw_floats = (G * 5 + 3) & ~3;
     return (size_t)raw_floats * 4 + (size_t)G * (16 + 4 + 4 + 2 + 2);
 }
@@ -70,9 +70,11 @@ enum CullMode { kCullNone = 0, kCullOverlap = 1, kCullContain = 2 };
 //   kCullContain : the box can strictly contain a point of the region (FCOS min(l,t,r,b) > 0)
 // Returns {#kept, #valid}.  Order is preserved, which keeps the reference's "first maximum /
 // first minimum" tie rules exact.
+template <int THREADS = kAssignThreads>
 __device__ __forceinline__ int2 compact_gt(const GtSmem &s, int G, int mode, float rx1, float ry1,
                                            float rx2, float ry2, bool fcos_area,
-                                           int *warp_cnt /* [2*kAssignWarps] smem */) {
+                                           int *warp_cnt /* [2 * THREADS / 32] smem */) {
+    constexpr int kAssignThreads = THREADS, kAssignWarps = THREADS / 32;   // of THIS instantiation
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int base_valid = 0, base_keep = 0;
     for (int j0 = 0; j0 < G; j0 += kAssignThreads) {
@@ -417,6 +419,240 @@ __global__ void __launch_bounds__(kAssignThreads)
     __syncthreads();
     flush_queues(q, pos_q, n_pos_s, ign_q, n_ign_s,
                  npos_partials + (size_t)b * gridDim.x + blockIdx.x, bases);
+}
+
+// ---------------------------------------------------------------------------------------
+// Retina, production scan (no `matched` output), r02: one CTA per TILE of one level, GT-centric.
+//
+// The anchor-centric kernel above costs ~100 thread instructions per anchor whatever the image holds
+// (anchor generation, per-CTA staging + compaction of the GT rows repeated by 114 CTAs per image,
+// per-warp culling): 1 us per image of ALU time that the HBM-bound sweep running beside it has to
+// absorb.  Only anchors that reach the IoU floor (0.38) with some GT can end up anything but
+// background, and those are ~1 % of the 120 087: so here a CTA owns a tile of <= 32 x 32 locations of
+// one level, keeps one 64-bit key (IoU bits | ~candidate index) per anchor of the tile in shared
+// memory, lets every WARP take GT boxes and visit only the (anchor shape, location) pairs that can
+// reach the floor with it -- area ratio within the floor, overlap per axis >= floor * max(area) /
+// min(height) -- and atomicMax the pair's exact IoU into the anchor's key (largest IoU wins, equal
+// IoUs -> lowest GT index: the reference's first maximum, losses.py:357).  A final pass turns the keys
+// into labels, two anchors per thread, and queues the few positive / ignored rows.  The IoU itself is
+// the same float32 op sequence as in scan_candidates; the candidate ranges are conservative supersets
+// (0.5 % slack on the floor, one location of slack per side), so labels are bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr int kTileWarps = kTileThreads / 32;
+#ifndef B200DET_TILE_SIDE
+#define B200DET_TILE_SIDE 32
+#endif
+constexpr int kTileSide = B200DET_TILE_SIDE;   // largest tile side in locations
+constexpr int kTileItems = 1024;   // (GT box, anchor shape) work items per round
+
+struct BigTiles {
+    int tile_off[kMaxLevels + 1];        // tiles of one image before level l
+    int nx[kMaxLevels];                  // tiles per row of level l
+    int tw[kMaxLevels], th[kMaxLevels];  // tile size in locations
+    float ext[kMaxLevels][4];            // extent of the level's base anchors (see TileTab)
+    int max_anchors;                     // largest tw * th * per_loc
+};
+
+__device__ __forceinline__ float shift_f32(int i, float stride) {
+    // (i + 0.5) * stride rounded once: i + 0.5 is exact in float32 and so is the product in float64,
+    // hence this equals shift_of()'s float64 product rounded to float32
+    return __fmul_rn(__fadd_rn(__int2float_rn(i), 0.5f), stride);
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+    retina_assign_tile_kernel(Geo g, BaseAnchors ba, BigTiles bt, IouThresholds thr,
+                              const float *__restrict__ annots, int G, int *__restrict__ labels,
+                              Queues q, int *__restrict__ npos_partials, int blocks_per_image) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int warp_cnt[2 * kTileWarps];
+    __shared__ int s_npos, s_items;
+    __shared__ int2 items[kTileItems];
+    __shared__ int touched[kTileSide * ((kTileSide * kMaxPerLoc + 127) / 128)];   // per 128-anchor run of a row
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < g.n_levels && (int)blockIdx.x >= bt.tile_off[i]) l = i;
+    const int t = blockIdx.x - bt.tile_off[l];
+    const int tyi = t / bt.nx[l], txi = t - tyi * bt.nx[l];
+    const int x0 = txi * bt.tw[l], y0 = tyi * bt.th[l];
+    const int tw = min(bt.tw[l], g.W[l] - x0), th = min(bt.th[l], g.H[l] - y0);
+    const int per_loc = g.per_loc;
+    const int row_len = tw * per_loc, n_anch = row_len * th;
+    const float stride = g.stride[l];
+
+    const GtSmem s = carve(smem_raw, G);
+    unsigned long long *keys =
+        reinterpret_cast<unsigned long long *>(smem_raw + ((gt_smem_bytes(G) + 15) & ~(size_t)15));
+    const float *src = annots + (size_t)b * G * 5;
+    const bool bulk = (((G * 5 * 4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    stage_rows_begin(s.raw, src, G * 5, &mbar, bulk);
+    for (int i = tid; i < n_anch; i += kTileThreads) keys[i] = 0ull;
+    const int runs_per_row = (row_len + 127) >> 7;
+    for (int i = tid; i < th * runs_per_row; i += kTileThreads) touched[i] = 0;
+    if (tid == 0) s_npos = 0;
+    // exact bounding box of the tile's anchors (rounding is monotonic, see TileTab::ext)
+    const float rx1 = __fadd_rn(bt.ext[l][0], shift_f32(x0, stride));
+    const float ry1 = __fadd_rn(bt.ext[l][1], shift_f32(y0, stride));
+    const float rx2 = __fadd_rn(bt.ext[l][2], shift_f32(x0 + tw - 1, stride));
+    const float ry2 = __fadd_rn(bt.ext[l][3], shift_f32(y0 + th - 1, stride));
+    stage_rows_wait(&mbar, bulk);   // contains a __syncthreads()
+    const int2 cnt = compact_gt<kTileThreads>(s, G, kCullOverlap, rx1, ry1, rx2, ry2, false, warp_cnt);
+    const int n_cand = cnt.x;
+    const bool has_gt = cnt.y > 0;
+
+    // ---- scatter, step 1: one THREAD per (GT box, anchor shape) works out the range of locations
+    // that can reach the floor and queues the non-empty ones; step 2: one WARP per queued item,
+    // lanes over the item's locations ----
+    const float fl = thr.floor, fs = 0.995f * thr.floor;   // exact floor / floor with slack
+    const float inv_stride = 1.f / stride;
+    const int chunk = kTileItems / per_loc;                 // GT boxes per round
+    for (int c0 = 0; c0 < n_cand; c0 += chunk) {
+        const int nc = min(chunk, n_cand - c0);
+        if (tid == 0) s_items = 0;
+        __syncthreads();
+        for (int idx = tid; idx < nc * per_loc; idx += kTileThreads) {
+            const int ci = idx / per_loc, a = idx - ci * per_loc, c = c0 + ci;
+            const float4 gt = s.box[c];
+            const float garea = s.area[c];
+            if (!(garea > 0.f)) continue;   // IoU is exactly 0 with everything
+            const float gw = gt.z - gt.x, gh = gt.w - gt.y;
+            const float bx = ba.v[l][a][0], by = ba.v[l][a][1], bz = ba.v[l][a][2], bw = ba.v[l][a][3];
+            const float aw = bz - bx, ah = bw - by, aarea = aw * ah;   // (shifted anchors: same up to ulps)
+            // IoU <= min(area) / max(area)
+            if (garea < fs * aarea || fs * garea > aarea) continue;
+            // ox * oy >= floor * max(area) with oy <= min(ah, gh)  =>  ox >= need / min(ah, gh)
+            const float need = fs * fmaxf(aarea, garea);
+            const float oxmin = need / fminf(ah, gh), oymin = need / fminf(aw, gw);
+            // anchor at location x spans [sx + bx, sx + bz], sx = (x + 0.5) * stride
+            const float sxl = (gt.x + oxmin - bz) * inv_stride - 0.5f, sxh = (gt.z - oxmin - bx) * inv_stride - 0.5f;
+            const float syl = (gt.y + oymin - bw) * inv_stride - 0.5f, syh = (gt.w - oymin - by) * inv_stride - 0.5f;
+            if (!(sxl <= sxh) || !(syl <= syh)) continue;   // also catches NaN boxes
+            const int xlo = max(x0, (int)fminf(fmaxf(ceilf(sxl) - 1.f, -1.f), 2.0e6f));
+            const int xhi = min(x0 + tw - 1, (int)fmaxf(fminf(floorf(sxh) + 1.f, 2.0e6f), -2.f));
+            const int ylo = max(y0, (int)fminf(fmaxf(ceilf(syl) - 1.f, -1.f), 2.0e6f));
+            const int yhi = min(y0 + th - 1, (int)fmaxf(fminf(floorf(syh) + 1.f, 2.0e6f), -2.f));
+            if (xlo > xhi || ylo > yhi) continue;
+            items[atomicAdd(&s_items, 1)] =
+                make_int2(c | (a << 16), (xlo - x0) | ((xhi - x0) << 8) | ((ylo - y0) << 16) | ((yhi - y0) << 24));
+        }
+        __syncthreads();
+        const int n_items = s_items;
+        for (int it = warp; it < n_items; it += kTileWarps) {
+            const int2 e = items[it];
+            const int c = e.x & 0xffff, a = e.x >> 16;
+            const int xlo = x0 + (e.y & 0xff), xhi = x0 + ((e.y >> 8) & 0xff);
+            const int ylo = y0 + ((e.y >> 16) & 0xff), yhi = y0 + ((e.y >> 24) & 0xff);
+            const float4 gt = s.box[c];
+            const float garea = s.area[c];
+            const float bx = ba.v[l][a][0], by = ba.v[l][a][1], bz = ba.v[l][a][2], bw = ba.v[l][a][3];
+            const unsigned long long key_lo = 0xffffffffull - (unsigned long long)c;
+            const int nx = xhi - xlo + 1, np = nx * (yhi - ylo + 1);
+            const float rnx = 1.f / (float)nx;
+            for (int p = lane; p < np; p += 32) {
+                const int py = (int)(((float)p + 0.5f) * rnx);   // p / nx for these small integers
+                const int xx = xlo + p - py * nx, yy = ylo + py;
+                const float sx = shift_f32(xx, stride), sy = shift_f32(yy, stride);
+                const float ax1 = __fadd_rn(bx, sx), ax2 = __fadd_rn(bz, sx);   // anchor.py:80
+                const float ay1 = __fadd_rn(by, sy), ay2 = __fadd_rn(bw, sy);
+                // IoU exactly as scan_candidates (losses.py:54-70)
+                const float area_a = __fmul_rn(fmaxf(__fsub_rn(ax2, ax1), 0.f),
+                                               fmaxf(__fsub_rn(ay2, ay1), 0.f));
+                if (garea < fl * area_a || fl * garea > area_a) continue;
+                const float mnx = fminf(ax2, gt.z), mxx = fmaxf(ax1, gt.x);
+                const float mny = fminf(ay2, gt.w), mxy = fmaxf(ay1, gt.y);
+                if (mnx > mxx && mny > mxy) {
+                    const float ov = __fmul_rn(__fsub_rn(mnx, mxx), __fsub_rn(mny, mxy));
+                    const float un = fmaxf(__fsub_rn(__fadd_rn(area_a, garea), ov), 1e-4f);
+                    if (ov < fl * un) continue;
+                    const float iou = __fdiv_rn(ov, un);
+                    const int j = (xx - x0) * per_loc + a;
+                    atomicMax(keys + (yy - y0) * row_len + j,
+                              ((unsigned long long)__float_as_uint(iou) << 32) | key_lo);
+                    touched[(yy - y0) * runs_per_row + (j >> 7)] = 1;   // (benign race: all write 1)
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- labels (losses.py:358-365): a warp per tile row, 4 x 32 anchors per lane round ----
+    int n_pos_mine = 0;
+    for (int r = warp; r < th; r += kTileWarps) {
+        const long long grow0 = lm_index(g, b, l, ((y0 + r) * g.W[l] + x0) * per_loc);
+        const unsigned long long *krow = keys + r * row_len;
+        for (int j0 = 0; j0 < row_len; j0 += 128) {
+            if (has_gt && !touched[r * runs_per_row + (j0 >> 7)]) {
+                // no pair of this run reached the floor: background (the common case by far)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    if (j < row_len) labels[grow0 + j] = 0;
+                }
+                continue;
+            }
+            int label[4], grow[4];
+            bool quiet = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                label[u] = 0;
+                grow[u] = -1;
+                if (j < row_len) {
+                    if (has_gt) {
+                        const unsigned long long k = krow[j];
+                        if (k != 0ull) {
+                            const float best = __uint_as_float((uint32_t)(k >> 32));
+                            if (!(best < thr.neg)) label[u] = -1;
+                            if (best >= thr.pos) {
+                                const uint32_t slot = 0xffffffffu - (uint32_t)k;
+                                label[u] = s.label[slot];
+                                grow[u] = s.ridx[slot];
+                            }
+                        }
+                    } else {
+                        label[u] = -1;   // image without GT: every anchor ignored (losses.py:341-345)
+                    }
+                    labels[grow0 + j] = label[u];
+                    quiet = quiet && label[u] == 0;
+                }
+            }
+            if (__all_sync(0xffffffffu, quiet)) continue;   // background only: the common case
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                const bool valid = j < row_len;
+                const bool is_pos = valid && label[u] > 0, is_ign = valid && label[u] < 0;
+                const unsigned mp = __ballot_sync(0xffffffffu, is_pos);
+                const unsigned mi = __ballot_sync(0xffffffffu, is_ign);
+                const unsigned lower = (1u << lane) - 1u;
+                if (mp) {   // one global atomic per warp and visit
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(q.counters + 0, __popc(mp));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (is_pos) q.pos[base + __popc(mp & lower)] = make_int2((int)(grow0 + j), grow[u]);
+                    n_pos_mine += is_pos;
+                }
+                if (mi) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(q.counters + 1, __popc(mi));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (is_ign) q.ign[base + __popc(mi & lower)] = (int)(grow0 + j);
+                }
+            }
+        }
+    }
+    n_pos_mine = warp_sum_int(n_pos_mine);
+    if (lane == 0 && n_pos_mine) atomicAdd(&s_npos, n_pos_mine);
+    __syncthreads();
+    int *part = npos_partials + (size_t)b * blocks_per_image;
+    if (tid == 0) part[blockIdx.x] = s_npos;
+    // the workspace has one slot per CTA of the anchor-centric kernel: clear the ones this grid lacks
+    if (blockIdx.x == 0)
+        for (int i = gridDim.x + tid; i < blocks_per_image; i += kTileThreads) part[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -834,6 +1070,29 @@ static void set_anchor_extents(TileTab *t, const Geo &g, const BaseAnchors &ba) 
     }
 }
 
+static BigTiles make_big_tiles(const Geo &g) {
+    BigTiles t;
+    int off = 0;
+    t.max_anchors = 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        t.tile_off[l] = off;
+        t.nx[l] = t.tw[l] = t.th[l] = 1;
+        for (int k = 0; k < 4; ++k) t.ext[l][k] = 0.f;
+        if (l < g.n_levels) {
+            // balanced tiles of at most kTileSide x kTileSide locations (100 -> 4 x 25, 50 -> 2 x 25)
+            const int nx = (g.W[l] + kTileSide - 1) / kTileSide, ny = (g.H[l] + kTileSide - 1) / kTileSide;
+            t.nx[l] = nx;
+            t.tw[l] = (g.W[l] + nx - 1) / nx;
+            t.th[l] = (g.H[l] + ny - 1) / ny;
+            off += nx * ((g.H[l] + t.th[l] - 1) / t.th[l]);
+            const int anchors = t.tw[l] * t.th[l] * g.per_loc;
+            if (anchors > t.max_anchors) t.max_anchors = anchors;
+        }
+    }
+    for (int l = g.n_levels; l <= kMaxLevels; ++l) t.tile_off[l] = off;
+    return t;
+}
+
 static Queues queues_of(char *base, const LossWs &ws) {
     Queues q;
     q.counters = reinterpret_cast<int *>(base + ws.off_counters);
@@ -863,8 +1122,12 @@ static size_t assign_dyn_smem(int max_gt) {
 
 // CTAs per image of the assignment kernels / CTAs of the sparse kernel (workspace layout)
 int assign_blocks_per_image(const Geo &g) {
+    // one positive-count slot per CTA of whichever assignment kernel runs (the tile kernel clears
+    // the slots it does not use)
     const TileTab t = make_tiles(g);
-    return (t.tile_off[g.n_levels] + kAssignWarps - 1) / kAssignWarps;
+    const int anchor_centric = (t.tile_off[g.n_levels] + kAssignWarps - 1) / kAssignWarps;
+    const int tiles = make_big_tiles(g).tile_off[g.n_levels];
+    return anchor_centric > tiles ? anchor_centric : tiles;
 }
 int sparse_blocks(const Geo &g) {
     const long long total = (long long)g.batch * g.off[g.n_levels];
@@ -950,8 +1213,25 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
         cudaError_t e = cudaMemsetAsync(q.counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
         if (e != cudaSuccess) return (int)e;
     }
-    const size_t smem = assign_dyn_smem(max_gt);
     ProfScope prof(kKernAssign, stream);
+    // production scan (labels + queues only): the GT-centric tile kernel
+    static const bool no_tiles = getenv("B200DET_ASSIGN_ANCHOR_CENTRIC") != nullptr;   // A/B knob
+    if (!matched && !no_tiles) {
+        BigTiles bt = make_big_tiles(g);
+        for (int l = 0; l < g.n_levels; ++l)
+            for (int k = 0; k < 4; ++k) bt.ext[l][k] = tt.ext[l][k];
+        const size_t tile_smem = ((gt_smem_bytes(max_gt) + 15) & ~(size_t)15) + (size_t)bt.max_anchors * 8;
+        if (tile_smem <= kAssignSmemBudget) {
+            static std::atomic<unsigned long long> at{0};
+            if ((rc = raise_smem_limit(retina_assign_tile_kernel, &at))) return rc;
+            dim3 grid((unsigned)bt.tile_off[g.n_levels], (unsigned)g.batch);
+            retina_assign_tile_kernel<<<grid, kTileThreads, tile_smem, (cudaStream_t)stream>>>(
+                g, ba, bt, thr, annotations, max_gt, labels, q, npos, (int)ws.assign_blocks_per_image);
+            count_launch();
+            return (int)cudaGetLastError();
+        }
+    }
+    const size_t smem = assign_dyn_smem(max_gt);
     // g_assign_chunk > 0 (set by the overlapped forward): a few images per launch, so that the
     // kernel's CTAs (96 registers each) displace only part of the HBM-bound sweep they run beside
     const int chunk = g_assign_chunk > 0 ? g_assign_chunk : g.batch;
