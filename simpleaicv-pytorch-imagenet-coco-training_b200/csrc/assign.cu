@@ -852,12 +852,18 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 
 // level-major row -> level and row inside that level's [B*rows_l] tensor
+// (batch * off[k] < 2^31 is checked by make_geo: 32-bit products and compares)
 __device__ __forceinline__ int split_row(const Geo &g, int i, long long &rrow) {
-    int l = 0;
+    int l = 0, base = 0;
 #pragma unroll
-    for (int k = 1; k < kMaxLevels; ++k)
-        if (k < g.n_levels && (long long)i >= (long long)g.batch * g.off[k]) l = k;
-    rrow = (long long)i - (long long)g.batch * g.off[l];
+    for (int k = 1; k < kMaxLevels; ++k) {
+        const int bk = g.batch * g.off[k];
+        if (k < g.n_levels && i >= bk) {
+            l = k;
+            base = bk;
+        }
+    }
+    rrow = (long long)(i - base);
     return l;
 }
 
@@ -947,6 +953,12 @@ __global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
         const long long n_pairs = (long long)n_ign * U;
         const float one_m_alpha = 1.f - a.alpha;
         constexpr int kInFlight = 4;
+        // p / U by multiply-high while the pair index fits 31 bits (it does up to ~100 M ignored
+        // class scores; the 64-bit division was 10 % of this kernel's instructions)
+        const bool small = n_pairs < (1ll << 31);
+        int sft = 0;
+        while ((1u << sft) < (unsigned)U) ++sft;
+        const unsigned magic = U > 1 ? (unsigned)(((1ull << (31 + sft)) / (unsigned long long)U) + 1ull) : 0u;
         for (long long p0 = gtid; p0 < n_pairs; p0 += (long long)kInFlight * gsize) {
             float4 v[kInFlight];
             bool live[kInFlight];
@@ -956,7 +968,9 @@ __global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
                 live[t] = p < n_pairs;
                 v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (live[t]) {
-                    const int r = (int)(p / U), u = (int)(p - (long long)r * U);
+                    const int r = U == 1 ? (int)p
+                                         : (small ? (int)(__umulhi((unsigned)p, magic) >> (sft - 1)) : (int)(p / U));
+                    const int u = (int)(p - (long long)r * U);
                     long long rr;
                     const int l = split_row(g, __ldg(q.ign + r), rr);
                     const float *row = static_cast<const float *>(a.cls.p[l]) + rr * a.C;
