@@ -222,7 +222,8 @@ int b200det_focal_loss(const b200det_geometry *geo, const void *const *cls,
 /*
  * Deterministic (fixed-order, fp64) reduction of the block partials.
  *   which : bit 0 = assignment + sparse partials (positives, box, ctr, focal corrections),
- *           bit 1 = focal sweep partials
+ *           bit 1 = focal sweep partials,
+ *           bit 2 = the positive count alone (sums[0]; complete once the assignment has run)
  *   sums  : device double[4] {positives, cls_sum, box_sum, ctr_sum}; only selected fields written
  * Replaces the `.sum()` / `positive_anchors_num` bookkeeping of losses.py:231-259, :277-293.
  */
@@ -245,6 +246,16 @@ int b200det_loss_reduce_finish(const b200det_geometry *geo, const void *workspac
  * (autograd backward: upstream scalar, loss weight, positive count); no-op when the factor is 1 */
 int b200det_scale_levels(void *const *ptrs, const long long *counts, int n_levels,
                          const float *g_dev, const double *sums, float weight, void *stream);
+/* Autograd backward of the box / centre-ness losses without a pass over the whole gradient tensors:
+ * b200det_sparse_losses wrote d(loss sum)/d(input) at the rows of the positives only, and the
+ * assignment left those rows in the workspace's positive queue, so
+ *   reg_grad[row] *= *g_box * w_box / sums[0],  ctr_grad[row] *= *g_ctr * w_ctr / sums[0]
+ * for the queued rows is all there is to do (0 without positives, NaN after a failed exchange).
+ * `workspace` must be the one the forward used, untouched since.  g_box / g_ctr NULL: head skipped. */
+int b200det_scale_pos_rows(const b200det_geometry *geo, const void *workspace, size_t workspace_bytes,
+                           void *const *reg_grad, void *const *ctr_grad, const float *g_box,
+                           const float *g_ctr, const double *sums, float w_box, float w_ctr,
+                           void *stream);
 /* x[i] *= *scale for n float32 values unless *scale == 1 (autograd backward helper) */
 int b200det_scale_f32(float *x, long long n, const float *scale_dev, void *stream);
 
@@ -373,6 +384,16 @@ int b200det_loss_forward_grad(const b200det_geometry *geo, const b200det_loss_pa
                               void *const *cls_grad, void *const *reg_grad,
                               void *const *ctr_grad, void *workspace, size_t workspace_bytes,
                               double *sums, float *losses, void *stream);
+
+/* b200det_loss_forward_grad with the sparse losses on a caller-owned helper stream beside the
+ * gradient-writing sweep (see b200det_loss_forward_overlap for the stream / event contract) */
+int b200det_loss_forward_grad_overlap(const b200det_geometry *geo, const b200det_loss_params *params,
+                                      const float *annotations, int max_gt, const void *const *cls,
+                                      const void *const *reg, const void *const *ctr, int32_t *labels,
+                                      void *const *cls_grad, void *const *reg_grad,
+                                      void *const *ctr_grad, void *workspace, size_t workspace_bytes,
+                                      double *sums, float *losses, void *side_stream, void *ev_fork,
+                                      void *ev_join, void *stream);
 
 /*
  * Whole RetinaDecoder.__call__ / FCOSDecoder.__call__ (decode.py:201-249, :293-348) up to the

@@ -119,6 +119,10 @@ SIGNATURES = {
         _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vpp, _vpp,
         _vpp, _vp, ctypes.c_size_t, _vp, _vp, _vp
     ]),
+    'b200det_loss_forward_grad_overlap': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vpp, _vpp,
+        _vpp, _vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp
+    ]),
     'b200det_scale_levels': (ctypes.c_int, [
         _vpp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp, _vp, ctypes.c_float, _vp
     ]),
@@ -158,6 +162,9 @@ SIGNATURES = {
     'b200det_loss_finish': (ctypes.c_int,
                             [_vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp]),
     'b200det_scale_f32': (ctypes.c_int, [_vp, ctypes.c_longlong, _vp, _vp]),
+    'b200det_scale_pos_rows': (ctypes.c_int, [
+        _geo, _vp, ctypes.c_size_t, _vpp, _vpp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp
+    ]),
     'b200det_decode_workspace_bytes': (ctypes.c_size_t, [_geo, ctypes.c_int]),
     'b200det_score_argmax': (ctypes.c_int, [_geo, _vpp, _vpp, ctypes.c_float, _vp, _vp, _vp]),
     'b200det_select_decode_nms': (ctypes.c_int, [

@@ -25,6 +25,61 @@ extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_l
                              nullptr, stream, 0);
 }
 
+static int loss_forward_grad_impl(const b200det_geometry *geo, const b200det_loss_params *p,
+                                  const float *annotations, int max_gt, const void *const *cls,
+                                  const void *const *reg, const void *const *ctr, int32_t *labels,
+                                  void *const *cls_grad, void *const *reg_grad,
+                                  void *const *ctr_grad, void *workspace, size_t workspace_bytes,
+                                  double *sums, float *losses, void *side, void *ev_fork,
+                                  void *ev_join, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!p || !annotations || !cls || !labels || !workspace || !sums || !cls_grad || !losses)
+        return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    const bool fork = side && ev_fork && ev_join;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = static_cast<char *>(workspace);
+    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
+                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal, st);
+    if (e != cudaSuccess) return (int)e;
+    g_skip_memset = true;
+    rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample, labels,
+                                          nullptr, nullptr, workspace, workspace_bytes, stream)
+                    : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos, labels,
+                                            nullptr, workspace, workspace_bytes, stream);
+    // the positive count must exist before the sweep (it scales the gradient the sweep writes); it
+    // is complete as soon as the assignment is, so the sparse losses (box / centre-ness terms and
+    // their gradients) can run beside the sweep on the helper stream
+    if (!rc) rc = b200det_loss_reduce(geo, 4, workspace, workspace_bytes, sums, stream);
+    void *st_sparse = stream;
+    if (!rc && fork) {
+        if ((e = cudaEventRecord((cudaEvent_t)ev_fork, st)) != cudaSuccess) rc = (int)e;
+        if (!rc && (e = cudaStreamWaitEvent((cudaStream_t)side, (cudaEvent_t)ev_fork, 0)) != cudaSuccess)
+            rc = (int)e;
+        if (!rc) st_sparse = side;
+    }
+    if (!rc)
+        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
+                                   ctr, p->box_loss, p->beta, nullptr, p->alpha, p->gamma,
+                                   reg_grad, ctr_grad, workspace, workspace_bytes, st_sparse);
+    if (!rc)
+        rc = b200det_focal_loss(geo, cls, labels, p->alpha, p->gamma, cls_grad, sums, p->w_cls,
+                                workspace, workspace_bytes, stream);
+    g_skip_memset = false;
+    if (st_sparse != stream) {
+        e = cudaEventRecord((cudaEvent_t)ev_join, (cudaStream_t)side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+    }
+    if (!rc)
+        rc = b200det_loss_reduce_finish(geo, workspace, workspace_bytes, p->w_cls, p->w_box, p->w_ctr,
+                                        sums, losses, stream);
+    return rc;
+}
+
 extern "C" int b200det_loss_forward_grad(const b200det_geometry *geo, const b200det_loss_params *p,
                                          const float *annotations, int max_gt,
                                          const void *const *cls, const void *const *reg,
@@ -33,36 +88,24 @@ extern "C" int b200det_loss_forward_grad(const b200det_geometry *geo, const b200
                                          void *const *ctr_grad, void *workspace,
                                          size_t workspace_bytes, double *sums, float *losses,
                                          void *stream) {
-    Geo g;
-    int rc = make_geo(geo, &g);
-    if (rc) return rc;
-    if (!p || !annotations || !cls || !labels || !workspace || !sums || !cls_grad || !losses)
-        return B200DET_EINVAL;
-    const LossWs ws = loss_ws_layout(g);
-    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
-    char *base = static_cast<char *>(workspace);
-    cudaError_t e = cudaMemsetAsync(base + ws.off_focal, 0,
-                                    ws.off_counters + 2 * sizeof(int) - ws.off_focal,
-                                    (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
-    g_skip_memset = true;
-    rc = p->is_fcos ? b200det_fcos_assign(geo, annotations, max_gt, p->use_center_sample, labels,
-                                          nullptr, nullptr, workspace, workspace_bytes, stream)
-                    : b200det_retina_assign(geo, annotations, max_gt, p->iou_neg, p->iou_pos, labels,
-                                            nullptr, workspace, workspace_bytes, stream);
-    if (!rc)
-        rc = b200det_sparse_losses(geo, p->is_fcos, annotations, max_gt, labels, reg, p->reg_dtype,
-                                   ctr, p->box_loss, p->beta, nullptr, p->alpha, p->gamma,
-                                   reg_grad, ctr_grad, workspace, workspace_bytes, stream);
-    // the positive count must exist before the sweep: it scales the gradient it writes
-    if (!rc) rc = b200det_loss_reduce(geo, 1, workspace, workspace_bytes, sums, stream);
-    if (!rc)
-        rc = b200det_focal_loss(geo, cls, labels, p->alpha, p->gamma, cls_grad, sums, p->w_cls,
-                                workspace, workspace_bytes, stream);
-    g_skip_memset = false;
-    if (!rc) rc = b200det_loss_reduce(geo, 2, workspace, workspace_bytes, sums, stream);
-    if (!rc) rc = b200det_loss_finish(sums, p->w_cls, p->w_box, p->w_ctr, losses, stream);
-    return rc;
+    return loss_forward_grad_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, cls_grad,
+                                  reg_grad, ctr_grad, workspace, workspace_bytes, sums, losses, nullptr,
+                                  nullptr, nullptr, stream);
+}
+
+extern "C" int b200det_loss_forward_grad_overlap(const b200det_geometry *geo,
+                                                 const b200det_loss_params *p,
+                                                 const float *annotations, int max_gt,
+                                                 const void *const *cls, const void *const *reg,
+                                                 const void *const *ctr, int32_t *labels,
+                                                 void *const *cls_grad, void *const *reg_grad,
+                                                 void *const *ctr_grad, void *workspace,
+                                                 size_t workspace_bytes, double *sums, float *losses,
+                                                 void *side_stream, void *ev_fork, void *ev_join,
+                                                 void *stream) {
+    return loss_forward_grad_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, cls_grad,
+                                  reg_grad, ctr_grad, workspace, workspace_bytes, sums, losses,
+                                  side_stream, ev_fork, ev_join, stream);
 }
 
 extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *p,

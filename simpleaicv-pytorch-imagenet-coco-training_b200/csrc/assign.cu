@@ -1028,6 +1028,40 @@ __global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
 // ---------------------------------------------------------------------------------------
 // utilities: materialise rows (tests), level-major -> image-major
 // ---------------------------------------------------------------------------------------
+// Autograd backward of the box / centre-ness losses: the forward wrote their gradients at the rows of
+// the positives only (into zeroed buffers); scaling them by upstream * weight / positives therefore
+// only has to visit the positive-row queue the assignment left in the workspace -- a few thousand
+// rows instead of a pass over the whole [B*N, 4] tensor (492 MB read + written at batch 256).
+struct ScaleRowsArgs {
+    Geo g;
+    MutPtrTab reg_grad, ctr_grad;
+    const float *g_box, *g_ctr;   // upstream scalars (device), NULL: that head is not scaled
+    const double *sums;           // sums[0] = positives
+    float w_box, w_ctr;
+};
+__global__ void scale_pos_rows_kernel(ScaleRowsArgs a, Queues q) {
+    const double npos = a.sums[0];
+    // as scale_levels_kernel: 0 without positives, NaN after a failed cross-rank exchange
+    const float kb = a.g_box ? (npos > 0.0 ? (float)((double)*a.g_box * (double)a.w_box / npos)
+                                           : (npos != npos ? (float)npos : 0.f))
+                             : 1.f;
+    const float kc = a.g_ctr ? (npos > 0.0 ? (float)((double)*a.g_ctr * (double)a.w_ctr / npos)
+                                           : (npos != npos ? (float)npos : 0.f))
+                             : 1.f;
+    const int n_pos = q.counters[0];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pos; k += gridDim.x * blockDim.x) {
+        long long rrow;
+        const int l = split_row(a.g, q.pos[k].x, rrow);
+        if (a.g_box) {
+            float4 *p = reinterpret_cast<float4 *>(a.reg_grad.p[l]) + rrow;
+            float4 v = *p;
+            v.x *= kb, v.y *= kb, v.z *= kb, v.w *= kb;
+            *p = v;
+        }
+        if (a.g_ctr) static_cast<float *>(a.ctr_grad.p[l])[rrow] *= kc;
+    }
+}
+
 __global__ void generate_rows_kernel(Geo g, BaseAnchors ba, int is_fcos, float *out) {
     const int N = g.off[g.n_levels];
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1351,6 +1385,33 @@ extern "C" int b200det_sparse_losses(const b200det_geometry *geo, int is_fcos,
     sparse_loss_kernel<<<(unsigned)ws.sparse_blocks, kSparseThreads, 0, (cudaStream_t)stream>>>(
         a, annotations, labels, queues_of(base, ws),
         reinterpret_cast<SparsePartial *>(base + ws.off_sparse));
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200det_scale_pos_rows(const b200det_geometry *geo, const void *workspace,
+                                      size_t workspace_bytes, void *const *reg_grad,
+                                      void *const *ctr_grad, const float *g_box, const float *g_ctr,
+                                      const double *sums, float w_box, float w_ctr, void *stream) {
+    Geo g;
+    int rc = make_geo(geo, &g);
+    if (rc) return rc;
+    if (!workspace || !sums || (!g_box && !g_ctr)) return B200DET_EINVAL;
+    if ((g_box && !reg_grad) || (g_ctr && !ctr_grad)) return B200DET_EINVAL;
+    const LossWs ws = loss_ws_layout(g);
+    if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
+    ScaleRowsArgs a;
+    a.g = g;
+    if ((rc = fill_mut_ptrs(g_box ? reg_grad : nullptr, g.n_levels, &a.reg_grad, 15))) return rc;
+    if ((rc = fill_mut_ptrs(g_ctr ? ctr_grad : nullptr, g.n_levels, &a.ctr_grad, 3))) return rc;
+    a.g_box = g_box;
+    a.g_ctr = g_ctr;
+    a.sums = sums;
+    a.w_box = w_box;
+    a.w_ctr = w_ctr;
+    char *base = const_cast<char *>(static_cast<const char *>(workspace));
+    ProfScope prof(kKernOther, stream);
+    scale_pos_rows_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(a, queues_of(base, ws));
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -509,8 +509,9 @@ __global__ void __launch_bounds__(1024)
                        float *__restrict__ losses) {
     __shared__ double red[4][32];
     double s_pos = 0.0, s_cls = 0.0, s_box = 0.0, s_ctr = 0.0;
-    if (which & 1) {
+    if (which & 5)   // bit 2: the positive count alone (it is complete as soon as the assignment is)
         for (long long i = threadIdx.x; i < n_assign; i += blockDim.x) s_pos += (double)npos[i];
+    if (which & 1) {
         for (long long i = threadIdx.x; i < n_sparse; i += blockDim.x) {
             const SparsePartial p = sp[i];
             s_box += p.box;
@@ -549,12 +550,12 @@ __global__ void __launch_bounds__(1024)
             d += __shfl_xor_sync(0xffffffffu, d, o);
         }
         if (lane == 0) {
+            if (which & 5) sums[0] = a;
             if (which & 1) {
-                sums[0] = a;
                 sums[2] = c;
                 sums[3] = d;
             }
-            sums[1] = b;  // focal partials (bit 1) + the sparse kernel's corrections (bit 0)
+            if (which & 3) sums[1] = b;  // focal partials (bit 1) + the sparse kernel's corrections (bit 0)
             if (losses) {
                 // loss_finish_kernel fused (which == 3): float32 sum / count, then * weight
                 const float w[3] = {w_cls, w_box, w_ctr};
@@ -834,7 +835,7 @@ extern "C" int b200det_loss_reduce(const b200det_geometry *geo, int which, const
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
-    if (!workspace || !sums || (which & 3) == 0) return B200DET_EINVAL;
+    if (!workspace || !sums || (which & 7) == 0 || (which & ~7)) return B200DET_EINVAL;
     const LossWs ws = loss_ws_layout(g);
     if (workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     const char *base = static_cast<const char *>(workspace);

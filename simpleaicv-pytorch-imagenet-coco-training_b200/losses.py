@@ -489,14 +489,18 @@ class _DetLossFunction(torch.autograd.Function):
             and torch.distributed.is_initialized()
         if not sync:
             params = _loss_params(owner, reg_dtype)
+            # the sparse losses (box / centre-ness terms + their gradients) beside the sweep
+            big = plan.batch * plan.n_rows * int(cls[0].shape[-1]) >= (64 << 20)
+            side = _side_stream(owner, device) if big else None
+            side_args = (side.stream, side.fork, side.join) if side is not None else (None, None, None)
             _lib.check(
-                lib.b200det_loss_forward_grad(geo, ctypes.byref(params), annotations.data_ptr(),
-                                              max_gt, _lib.ptr_array(cls), _lib.ptr_array(reg),
-                                              _lib.ptr_array(ctr), labels_ptr,
-                                              _lib.ptr_array(cls_grad), _lib.ptr_array(reg_grad),
-                                              _lib.ptr_array(ctr_grad), ws_ptr, ws_bytes,
-                                              sums.data_ptr(), losses.data_ptr(), st),
-                'b200det_loss_forward_grad')
+                lib.b200det_loss_forward_grad_overlap(geo, ctypes.byref(params), annotations.data_ptr(),
+                                                      max_gt, _lib.ptr_array(cls), _lib.ptr_array(reg),
+                                                      _lib.ptr_array(ctr), labels_ptr,
+                                                      _lib.ptr_array(cls_grad), _lib.ptr_array(reg_grad),
+                                                      _lib.ptr_array(ctr_grad), ws_ptr, ws_bytes,
+                                                      sums.data_ptr(), losses.data_ptr(), *side_args, st),
+                'b200det_loss_forward_grad_overlap')
         else:
             group = owner.process_group
             if is_fcos:
@@ -539,6 +543,8 @@ class _DetLossFunction(torch.autograd.Function):
         ctx.want = (any(need[0:n_levels]), any(need[n_levels:2 * n_levels]),
                     is_fcos and any(need[2 * n_levels:3 * n_levels]))
         ctx.weights = (w_box, w_ctr)
+        ctx.plan = plan
+        ctx.scratch = scratch   # keeps the positive-row queue alive for backward
         ctx.consumed = False
         ctx.set_materialize_grads(False)   # an unused loss term arrives as None, not as zeros
         ctx.save_for_backward(sums, *cls_grad, *reg_grad, *(ctr_grad or []))
@@ -594,12 +600,23 @@ class _DetLossFunction(torch.autograd.Function):
             scale(cls_grad, grad_out[0], False, 1.0)
             for i in range(n):
                 grads[i] = cls_grad[i].view(ctx.in_shapes[i]).to(ctx.in_dtypes[i])
+        if want_reg or want_ctr:
+            # only the positives' rows hold gradients: scale those rows (the assignment's queue is
+            # still in the forward's workspace), not the whole [B*N, 4] tensors
+            g_box = grad_out[1].detach().float().contiguous() if want_reg else None
+            g_ctr = grad_out[2].detach().float().contiguous() if want_ctr else None
+            _lib.check(
+                lib.b200det_scale_pos_rows(ctx.plan.geo_ref, ctx.scratch.data_ptr(), ctx.plan.ws_bytes,
+                                           _lib.ptr_array(list(reg_grad)) if want_reg else None,
+                                           _lib.ptr_array(list(ctr_grad)) if want_ctr else None,
+                                           g_box.data_ptr() if want_reg else None,
+                                           g_ctr.data_ptr() if want_ctr else None, sums.data_ptr(),
+                                           ctx.weights[0], ctx.weights[1], st),
+                'b200det_scale_pos_rows')
         if want_reg:
-            scale(reg_grad, grad_out[1], True, ctx.weights[0])
             for i in range(n):
                 grads[n + i] = reg_grad[i].view(ctx.in_shapes[n + i]).to(ctx.in_dtypes[n + i])
         if want_ctr:
-            scale(ctr_grad, grad_out[2], True, ctx.weights[1])
             for i in range(n):
                 grads[2 * n + i] = ctr_grad[i].view(ctx.in_shapes[2 * n + i]).to(
                     ctx.in_dtypes[2 * n + i])

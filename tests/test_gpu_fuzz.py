@@ -257,3 +257,67 @@ def test_training_sweep_class_counts_not_multiple_of_4(kind, C, monkeypatch):
         results.append([t.grad.clone() for t in p[0]])
     for a, b in zip(*results):
         grads_close(a, b, 'XROW vs scalar kernel')
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_tile_assignment_stress(seed):
+    """The production assignment (GT-centric tile kernel: candidate ranges derived from conservative
+    bounds) against the exhaustive anchor-centric scan, on inputs built to sit on its edges: GT boxes
+    that are jittered copies of actual anchors (IoU around the 0.4 / 0.5 thresholds and the 0.38 floor),
+    boxes straddling tile borders (tiles are <= 32 locations wide: the pyramids here are up to 70 wide),
+    duplicated / degenerate / huge / sub-pixel boxes, odd strides, 1-12 anchors per location, and more
+    annotation rows than one work-item round holds."""
+    rng = np.random.RandomState(7000 + seed)
+    n_levels = int(rng.randint(1, 5))
+    h, w = int(rng.randint(5, 71)), int(rng.randint(5, 71))
+    s0 = float(rng.choice([4, 6, 8]))
+    shapes, strides = [], []
+    for l in range(n_levels):
+        shapes.append((h, w))
+        strides.append(s0 * 2**l)
+        h, w = (h + 1) // 2, (w + 1) // 2
+    ratios = [float(r) for r in rng.choice([0.33, 0.5, 1, 2, 3], size=int(rng.randint(1, 5)), replace=False)]
+    scales = [float(s) for s in rng.choice([1, 1.26, 1.59], size=int(rng.randint(1, 4)), replace=False)]
+    per_loc = len(ratios) * len(scales)
+    kw = dict(areas=[[4 * s, 4 * s] for s in strides], ratios=ratios, scales=scales, strides=strides)
+    B, C = int(rng.randint(1, 4)), 5
+    G_rows = int(rng.choice([8, 40, 150, 300]))
+    crit = losses.RetinaLoss(**kw)
+    cls = [torch.full((B, hh, ww, per_loc, C), 0.01) for hh, ww in shapes]
+    reg = [torch.zeros((B, hh, ww, per_loc, 4)) for hh, ww in shapes]
+    from b200det import anchor as A
+    tables = A.RetinaAnchors(**kw)([[ww, hh] for hh, ww in shapes])
+    flat = np.concatenate([t.reshape(-1, 4) for t in tables], axis=0)
+    width, height = shapes[0][1] * strides[0], shapes[0][0] * strides[0]
+    ann = np.full((B, G_rows, 5), -1, dtype=np.float32)
+    for b in range(B):
+        n = int(rng.randint(0, G_rows + 1))
+        rows = np.sort(rng.permutation(G_rows)[:n])
+        for j, r in enumerate(rows):
+            kind = rng.randint(0, 10)
+            a = flat[rng.randint(0, flat.shape[0])]
+            if kind < 6:      # jittered copy of an anchor: IoU anywhere between 0.2 and 1
+                aw, ah = a[2] - a[0], a[3] - a[1]
+                jit = rng.uniform(-0.35, 0.35, size=4) * np.array([aw, ah, aw, ah])
+                box = a + jit
+            elif kind == 6:   # exact anchor (IoU 1) -- and sometimes a duplicate of the previous row
+                box = a.copy() if j == 0 or rng.rand() < 0.5 else ann[b, rows[j - 1], :4].copy()
+            elif kind == 7:   # huge box
+                box = np.array([-5., -7., width + 3., height + 9.])
+            elif kind == 8:   # sub-pixel / degenerate
+                x, y = rng.uniform(0, width), rng.uniform(0, height)
+                box = np.array([x, y, x + rng.choice([0., 0.3, 1.]), y + rng.choice([0., 0.5, 2.])])
+            else:             # random box
+                x1, y1 = rng.uniform(-10, width), rng.uniform(-10, height)
+                box = np.array([x1, y1, x1 + rng.uniform(1, width), y1 + rng.uniform(1, height)])
+            ann[b, r, :4] = box.astype(np.float32)
+            ann[b, r, 4] = rng.randint(0, C)
+    ann_t = torch.from_numpy(ann).cuda()
+    preds = dev([cls, reg])
+    exact = crit.debug_assign(preds, ann_t, exact=True)['labels']
+    fast = crit.debug_assign(preds, ann_t, exact=False)['labels']
+    assert torch.equal(exact, fast), f'{int((exact != fast).sum())} labels differ'
+    # ... and the queues the sparse kernel consumes agree with the labels: same losses either way
+    with torch.no_grad():
+        d = crit(preds, ann_t)
+    assert np.isfinite(d['cls_loss'].item()) and np.isfinite(d['reg_loss'].item())
