@@ -150,10 +150,28 @@ __device__ __forceinline__ int chunk_level(const FocalArgs &a) {
     return l;
 }
 
+#ifndef B200DET_FOCAL_LOAD
+// 0: ld.global.cs; 1: ld.global.nc.L1::no_allocate -- measured identical (tools/tune_loads.sh: 3.285 vs
+// 3.314 ms per batch-256 step with the assignment running beside the sweep, 0.457 vs 0.461 at batch
+// 32): what the co-running kernels cost the sweep is issue slots, not L1 capacity
+#define B200DET_FOCAL_LOAD 0
+#endif
+__device__ __forceinline__ float4 sweep_ld4(const float4 *p) {
+#if B200DET_FOCAL_LOAD == 1
+    float4 t;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                 : "l"(p));
+    return t;
+#else
+    return __ldcs(p);
+#endif
+}
+
 template <int VEC>
 __device__ __forceinline__ void load_unit(const float *__restrict__ src, long long u, float (&v)[VEC]) {
     if (VEC == 4) {
-        const float4 t = __ldcs(reinterpret_cast<const float4 *>(src) + u);
+        const float4 t = sweep_ld4(reinterpret_cast<const float4 *>(src) + u);
         v[0] = t.x;
         v[1 % VEC] = t.y;
         v[2 % VEC] = t.z;

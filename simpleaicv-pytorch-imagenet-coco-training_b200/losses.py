@@ -474,10 +474,7 @@ class _DetLossFunction(torch.autograd.Function):
             """one allocation for all levels' gradients; returns (flat, per-level views)"""
             sizes = [t.numel() for t in levels]
             flat = (torch.zeros if zero else torch.empty)(sum(sizes), dtype=dtype, device=device)
-            views, o = [], 0
-            for t, n_el in zip(levels, sizes):
-                views.append(flat[o:o + n_el].view(t.shape))
-                o += n_el
+            views = [v.view(t.shape) for v, t in zip(flat.split(sizes), levels)]
             return flat, views
 
         # the sparse kernel writes the rows of the positives only -> zero-initialised
@@ -595,11 +592,17 @@ class _DetLossFunction(torch.autograd.Function):
                                          sums.data_ptr() if with_norm else None, weight, st),
                 'b200det_scale_levels')
 
+        def as_input(t, k):
+            """gradient in the input's shape / dtype (no-ops for the usual float32 heads)"""
+            if t.shape != ctx.in_shapes[k]:
+                t = t.view(ctx.in_shapes[k])
+            return t if t.dtype == ctx.in_dtypes[k] else t.to(ctx.in_dtypes[k])
+
         if want_cls:
             # already scaled by cls_loss_weight / positives; only the upstream scalar is left
             scale(cls_grad, grad_out[0], False, 1.0)
             for i in range(n):
-                grads[i] = cls_grad[i].view(ctx.in_shapes[i]).to(ctx.in_dtypes[i])
+                grads[i] = as_input(cls_grad[i], i)
         if want_reg or want_ctr:
             # only the positives' rows hold gradients: scale those rows (the assignment's queue is
             # still in the forward's workspace), not the whole [B*N, 4] tensors
@@ -615,11 +618,10 @@ class _DetLossFunction(torch.autograd.Function):
                 'b200det_scale_pos_rows')
         if want_reg:
             for i in range(n):
-                grads[n + i] = reg_grad[i].view(ctx.in_shapes[n + i]).to(ctx.in_dtypes[n + i])
+                grads[n + i] = as_input(reg_grad[i], n + i)
         if want_ctr:
             for i in range(n):
-                grads[2 * n + i] = ctr_grad[i].view(ctx.in_shapes[2 * n + i]).to(
-                    ctx.in_dtypes[2 * n + i])
+                grads[2 * n + i] = as_input(ctr_grad[i], 2 * n + i)
         return (None, None, None, *grads)
 
 
