@@ -307,6 +307,9 @@ def workload_config(batch_per_gpu, n_gpus, scaling):
                        'global positive count (4 doubles exchanged per step)'
                        if scaling == 'strong' else f'{batch_per_gpu} images per GPU x{n_gpus}',
         'l2_policy': 'per-GPU inputs (>= 1.29 GB at 32 images) far exceed the 126 MB L2',
+        'call_structure': 'the reference\'s two calls per step, criterion(preds, annots) then '
+                          'decoder(preds), on the same tensors; the criterion\'s sweep also writes the '
+                          'decoder\'s keys (computed every step, verified on the device; b200det/_handoff.py)',
     }
 
 
@@ -450,8 +453,25 @@ def run_b200(args, out):
         return d, r
 
     profile_every = args.profile_every or (1 if B >= 128 else 4)
+    # The two calls share one sweep over cls when the decoder is called on the tensors the criterion
+    # just read (b200det/_handoff.py; the library's default).  First the same loop with the hand-over
+    # switched off -- every call sweeps for itself, r01 / early-r02 behaviour -- as `separate_sweeps`.
+    from b200det import _handoff
+    separate = None
+    if _handoff.ENABLED and not args.no_separate:
+        _handoff.ENABLED = False
+        sms, sk, _, _, _ = R.timed(step, args.steps, args.warmup, profile_every=profile_every)
+        _handoff.ENABLED = True
+        _handoff.reset()
+        separate = {
+            'value': B * world / (sms / 1e3), 'unit': 'images/s', 'ms_per_step': sms,
+            'kernels_ms': {k: round(v[1], 4) for k, v in sk.items()},
+            'note': 'B200DET_HANDOFF=0: criterion and decoder each stream cls (2 x 4NC bytes per image)',
+        }
+    handoff0 = dict(_handoff.stats)
     ms_per_step, kernels, launches, clocks, (d, r) = R.timed(
         step, args.steps, args.warmup, profile_every=profile_every, sample_clocks=True)
+    handoff = {k: _handoff.stats[k] - handoff0[k] for k in handoff0} if _handoff.ENABLED else None
     value = B * world / (ms_per_step / 1e3)
     status = crit.last_stats.get('exchange_status') if crit.last_stats else None
     exchange_status = int(status.item()) if status is not None else 0
@@ -512,7 +532,10 @@ def run_b200(args, out):
     # also covers their ALU work); the arg-max sweep has the GPU to itself: it is the one whose launch
     # duration is a clean kernel time, and the one reported as `roofline`.  The focal sweep's window
     # is in `roofline_focal_window`.
+    # With the hand-over there is ONE sweep per step: the fused one (focal sum + arg-max keys), timed
+    # under the arg-max sweep's id, with the assignment + sparse kernels beside it on the helper stream.
     dom = 'score_argmax' if 'score_argmax' in kernels else 'focal_loss'
+    fused_sweep = 'focal_loss' not in kernels
     dom_ms = kernels[dom][1]
     achieved = alg[dom] / (dom_ms / 1e3) / 1e9
     loss_b, dec_b = algorithmic_bytes_per_image()
@@ -543,28 +566,29 @@ def run_b200(args, out):
         'host_cpus_per_rank': R.cpus,
         'roofline': {
             'bound': 'hbm',
-            'kernel': dom,
+            'kernel': 'fused_sweep (fused_rows_kernel: focal sum + arg-max keys from one read of cls; '
+                      'assignment + sparse losses beside it on the helper stream)' if fused_sweep else dom,
             'achieved': achieved,
             'peak': peak,
             'unit': 'GB/s',
             'frac': achieved / peak,
-            'traffic': traffic.get(dom) * B / 256 if traffic.get(dom) else None,
+            'traffic': (traffic.get('fused_sweep' if fused_sweep else dom) or 0) * B / 256 or None,
             'peak_source': peak_src,
             'algorithmic_bytes_per_launch': alg[dom],
             'kernel_ms': dom_ms,
         },
-        'roofline_focal_window': {
-            'kernel': 'focal_loss',
-            'kernel_ms': kernels['focal_loss'][1],
-            'frac': alg['focal_loss'] / (kernels['focal_loss'][1] / 1e3) / 1e9 / peak,
-            'note': 'window of the focal sweep with assignment + sparse losses running beside it on '
-                    'the helper stream (B200DET_LOSS_OVERLAP=0: the sweep alone reaches ~1.08 x peak)',
-        },
         'step_roofline': {
             'algorithmic_GBps': step_gbs,
             'frac_of_hbm_peak': step_gbs / peak,
-            'note': 'whole step (loss fwd + decode + NMS, 80.70 MB/image) against the HBM peak',
+            'note': 'whole step against the HBM peak for SURVEY 8d\'s algorithmic bytes (80.70 MB/image: '
+                    'cls counted once per call, i.e. twice per step).  With the hand-over the step reads '
+                    'cls once, so this fraction may exceed 1; see single_read_*',
+            'single_read_bytes_per_image': loss_b + dec_b - 4 * n * c,
+            'single_read_GBps': B * (loss_b + dec_b - 4 * n * c) / (ms_per_step / 1e3) / 1e9,
+            'single_read_frac_of_hbm_peak': B * (loss_b + dec_b - 4 * n * c) / (ms_per_step / 1e3) / 1e9 / peak,
         },
+        'handoff': handoff,
+        'separate_sweeps': separate,
         'kernels_ms': {k: round(v[1], 4) for k, v in kernels.items()},
         'outside_kernels_ms': round(ms_per_step - kernel_sum, 4),
         'clocks': clocks,
@@ -905,6 +929,8 @@ def main():
                     help='N > 1: how the loss normaliser crosses GPUs')
     ap.add_argument('--no-fused', action='store_true')
     ap.add_argument('--no-weak', action='store_true')
+    ap.add_argument('--no-separate', action='store_true',
+                    help='skip the extra timed loop with the sweep hand-over switched off')
     ap.add_argument('--no-pin', action='store_true', help='N > 1: do not give every rank its own CPUs')
     ap.add_argument('--no-configs', action='store_true')
     ap.add_argument('--profile-every', type=int, default=0)

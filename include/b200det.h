@@ -405,6 +405,21 @@ int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *par
                    int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * b200det_decode without its sweep: selection, box decode and NMS on `keys` / `classes` that
+ * b200det_loss_forward_keys left behind for the same head outputs (decode.py:133-167 on the rows the
+ * criterion's sweep scored).  cls (and ctr for FCOS) are only read to VERIFY the hand-over: for every
+ * selected row the kernel recomputes the key from the class score it names; if one differs -- the head
+ * outputs were modified after the criterion read them -- it sets *stale = 1 and the caller must decode
+ * again with b200det_decode.  stale: caller-zeroed int32 the device can write (device or mapped pinned
+ * host memory), or NULL (then cls / ctr may be NULL).
+ */
+int b200det_decode_from_keys(const b200det_geometry *geo, const b200det_decode_params *params,
+                             const void *const *cls, const void *const *ctr, const void *const *reg,
+                             const uint32_t *keys, const int32_t *classes, float *out,
+                             int32_t *order, int32_t *keep, int32_t *counts, int32_t *stale,
+                             void *stream);
+
+/*
  * OPTIONAL extension (not in the reference's call structure): loss forward + decode of one
  * evaluation step with a SINGLE sweep over the classification tensors -- the score / arg-max
  * sweep also accumulates the label-free focal sum.  Same results as b200det_loss_forward followed
@@ -592,6 +607,25 @@ int b200det_loss_forward_overlap(const b200det_geometry *geo, const b200det_loss
                                  const b200det_peer_exchange *px, double *sums, float *losses,
                                  int32_t *status, void *side_stream, void *ev_fork, void *ev_join,
                                  void *stream, int phase);
+/*
+ * b200det_loss_forward_overlap whose sweep ALSO does the decoder's: the fused sweep of b200det_eval_step
+ * (focal sum + first-maximum class and score key of every row, thresholded with `min_score` like
+ * b200det_score_argmax) instead of the focal-only one.  The reference's evaluation loop calls
+ * criterion(outs, annots) and then decoder(outs) on the SAME head outputs (tools/scripts.py:733-740);
+ * after this call the decoder only needs b200det_select_decode_nms on `keys` / `classes`, so the
+ * classification tensors -- 98 % of the step's HBM traffic -- are read once per step while the caller
+ * keeps the reference's two calls.  The host layer (b200det._handoff) decides when that is safe.
+ * Same arguments as b200det_loss_forward_overlap plus min_score / keys / classes as
+ * b200det_score_argmax.  num_classes % 4 == 0; FCOS needs `ctr` in phase 1 too.
+ */
+int b200det_loss_forward_keys(const b200det_geometry *geo, const b200det_loss_params *params,
+                              const float *annotations, int max_gt, const void *const *cls,
+                              const void *const *reg, const void *const *ctr, int32_t *labels,
+                              void *workspace, size_t workspace_bytes,
+                              const b200det_peer_exchange *px, double *sums, float *losses,
+                              int32_t *status, void *side_stream, void *ev_fork, void *ev_join,
+                              void *stream, int phase, float min_score, uint32_t *keys,
+                              int32_t *classes);
 /* caller-owned helper objects for the call above: a non-blocking stream (high_priority != 0: the
  * device's highest priority) and timing-free events, on the current device */
 int b200det_stream_create(void **stream, int high_priority);

@@ -138,6 +138,9 @@ SIGNATURES = {
         _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_size_t, _vp
     ]),
+    'b200det_decode_from_keys': (ctypes.c_int, [
+        _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp
+    ]),
     'b200det_stream_synchronize': (ctypes.c_int, [_vp]),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),
     'b200det_loss_workspace_bytes': (ctypes.c_size_t, [_geo]),
@@ -218,6 +221,11 @@ SIGNATURES = {
         ctypes.c_size_t, ctypes.POINTER(PeerExchange), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
         ctypes.c_int
     ]),
+    'b200det_loss_forward_keys': (ctypes.c_int, [
+        _geo, ctypes.POINTER(LossParams), _vp, ctypes.c_int, _vpp, _vpp, _vpp, _vp, _vp,
+        ctypes.c_size_t, ctypes.POINTER(PeerExchange), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+        ctypes.c_int, ctypes.c_float, _vp, _vp
+    ]),
     'b200det_stream_create': (ctypes.c_int, [_vpp, ctypes.c_int]),
     'b200det_stream_destroy': (ctypes.c_int, [_vp]),
     'b200det_event_create': (ctypes.c_int, [_vpp]),
@@ -271,7 +279,9 @@ def fastpath():
                 from . import _fastpath as mod
                 lib = load()
                 mod.bind(ctypes.cast(lib.b200det_loss_forward_overlap, ctypes.c_void_p).value,
-                         ctypes.cast(lib.b200det_decode, ctypes.c_void_p).value)
+                         ctypes.cast(lib.b200det_decode, ctypes.c_void_p).value,
+                         ctypes.cast(lib.b200det_loss_forward_keys, ctypes.c_void_p).value,
+                         ctypes.cast(lib.b200det_decode_from_keys, ctypes.c_void_p).value)
                 _FAST = mod
             except Exception:   # noqa: BLE001 -- optional
                 _FAST = False

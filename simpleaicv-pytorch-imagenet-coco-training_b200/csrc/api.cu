@@ -12,7 +12,8 @@ int loss_forward_impl(const b200det_geometry *geo, const b200det_loss_params *p,
                       const void *const *reg, const void *const *ctr, int32_t *labels,
                       void *workspace, size_t workspace_bytes, const b200det_peer_exchange *px,
                       double *sums, float *losses, int32_t *status, void *side, void *ev_fork,
-                      void *ev_join, void *stream, int phase);   // exchange.cu
+                      void *ev_join, void *stream, int phase, float keys_min_score, uint32_t *keys,
+                      int32_t *classes);   // exchange.cu
 }
 
 extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_loss_params *p,
@@ -22,7 +23,7 @@ extern "C" int b200det_loss_forward(const b200det_geometry *geo, const b200det_l
                                     double *sums, float *losses, void *stream) {
     return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
                              workspace_bytes, nullptr, sums, losses, nullptr, nullptr, nullptr,
-                             nullptr, stream, 0);
+                             nullptr, stream, 0, 0.f, nullptr, nullptr);
 }
 
 static int loss_forward_grad_impl(const b200det_geometry *geo, const b200det_loss_params *p,
@@ -122,6 +123,23 @@ extern "C" int b200det_decode(const b200det_geometry *geo, const b200det_decode_
                                     p->sizes, p->to_xywh, out, order, keep, counts,
                                     p->half_exp_table, stream);
     return rc;
+}
+
+// The decoder's tail alone, on keys / classes that the criterion's sweep left behind
+// (b200det_loss_forward_keys): selection, box decode, NMS.  cls (+ ctr for FCOS) are only used to
+// VERIFY the hand-over: the select kernel re-derives the key of every selected row from the class
+// score it names and sets *stale (caller-zeroed, may be mapped host memory) on a mismatch.
+extern "C" int b200det_decode_from_keys(const b200det_geometry *geo, const b200det_decode_params *p,
+                                        const void *const *cls, const void *const *ctr,
+                                        const void *const *reg, const uint32_t *keys,
+                                        const int32_t *classes, float *out, int32_t *order,
+                                        int32_t *keep, int32_t *counts, int32_t *stale,
+                                        void *stream) {
+    if (!p) return B200DET_EINVAL;
+    return select_decode_nms_impl(geo, keys, classes, reg, p->reg_dtype, p->is_fcos, p->min_score,
+                                  p->topn, p->max_out, p->nms_type, p->nms_threshold, p->scales,
+                                  p->sizes, p->to_xywh, out, order, keep, counts, p->half_exp_table,
+                                  stream, cls, p->is_fcos ? ctr : nullptr, stale);
 }
 
 // Loss forward + decode of one evaluation step with ONE sweep over the classification tensors:

@@ -312,6 +312,348 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
         sweep_accumulate<kArgThreads>((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
 }
 
+// The fused sweep of the evaluation step (loss + decode from ONE read of cls), r02b.  Same work split
+// as score_argmax_rows_kernel<K, true> -- T lanes per row, K 128-bit units per lane, everything in
+// registers -- with the instruction count cut from ~19 to ~10 per element (the r02 kernel was
+// issue-bound at 0.83 of the HBM peak, profiles/r02_kernels.json):
+//  * the focal term's clamp tree IS the arg-max's max: x = max.NaN(v, 1e-4) per element, then
+//    3-input max.NaN (FMNMX3) down to the lane maximum M; a row maximum above the clamp is the true
+//    maximum, bit for bit (max returns one of its operands).  The compare/select chain per element
+//    (FSETP + FSEL + SEL) is gone;
+//  * the first-maximum INDEX is found afterwards, and only if some row of the warp can pass the score
+//    threshold: equality scan v == M in reverse class order (FSETP + SEL), lowest class over the lanes;
+//    rows whose (upper bound of the) score fails the threshold get key 0 and no class -- the select
+//    kernel reads classes of selected rows only.  Real heads have ~1 % candidate rows;
+//  * rows whose maximum was clamped (<= 1e-4) or NaN while they could still pass (threshold below the
+//    clamp, FCOS centre-ness > 1, NaN scores) take the r02 exact scan, warp-uniformly;
+//  * ONE fast/slow decision per lane and row (M <= 0.25) instead of one per unit, gamma == 2 and
+//    "every lane holds K units" (C = 4*K*T, e.g. 80) are template parameters.
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+static __device__ __noinline__ float neg_unit_exact(float4 v, float gamma, bool gamma2) {
+    return (neg_term(v.x, gamma, gamma2) + neg_term(v.y, gamma, gamma2)) +
+           (neg_term(v.z, gamma, gamma2) + neg_term(v.w, gamma, gamma2));
+}
+// One row group of the fused sweep: v = the lane's K units of the row (raw scores), `src` = where they
+// came from (re-read by the rare exact scan).  Accumulates the focal terms into acc / acc2 and stores
+// the row's key (and class, if the row can pass the threshold).
+// xor-butterfly over the T = 2^ts lanes of a row; TS >= 0: compile-time lane count (fully unrolled --
+// a `for (o = 16; o > 0; o >>= 1) if (o < T)` loop is compiled into a jump-table loop of 6 trips)
+template <int TS, class Op>
+__device__ __forceinline__ void row_butterfly(int T, Op op) {
+    if (TS >= 0) {
+        if (TS >= 1) op(1);
+        if (TS >= 2) op(2);
+        if (TS >= 3) op(4);
+        if (TS >= 4) op(8);
+        if (TS >= 5) op(16);
+    } else {
+        for (int o = T >> 1; o > 0; o >>= 1) op(o);
+    }
+}
+
+template <int K, bool FULL, bool GAMMA2, int TS, class AfterReads>
+__device__ __forceinline__ void fused_rows_step(float4 (&v)[K], const bool (&has)[K], bool live, float ctrv,
+                                                int j, int ts, int T, long long row,
+                                                const float4 *__restrict__ src, const ArgmaxArgs &a,
+                                                uint32_t *__restrict__ kout, int *__restrict__ cout,
+                                                float &acc, float2 &acc2, AfterReads after_reads) {
+    const float ninf = -__int_as_float(0x7f800000);
+    // Clamp IN PLACE (losses.py:196: the focal term's lower clamp; max.NaN keeps a NaN): from here
+    // on only the clamped values are alive -- one array of 4K registers, not two -- and the few
+    // rows that need the raw scores again (below) re-read them.
+    float M = kClampLo;   // lane maximum of the clamped scores, NaN if any score is NaN
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        v[k].x = fmax_nan(v[k].x, kClampLo);
+        v[k].y = fmax_nan(v[k].y, kClampLo);
+        v[k].z = fmax_nan(v[k].z, kClampLo);
+        v[k].w = fmax_nan(v[k].w, kClampLo);
+        M = fmax3_nan(fmax3_nan(v[k].x, v[k].y, v[k].z), v[k].w, M);
+    }
+    // every value the caller handed over has been consumed (M depends on all of them): a caller that
+    // staged them in shared memory may refill the stage now
+    asm volatile("" ::"f"(M) : "memory");
+    after_reads();
+    // label-free focal terms (focal.cu: focal_all_kernel): one fast / slow decision per lane and row
+    if (GAMMA2 && M <= kFastMax) {
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (has[k]) {
+                    float2 xr, xs;
+                    acc2 = neg_term_fast2_acc(make_float2(v[k].x, v[k].y), acc2, xr, xs);
+                    acc2 = neg_term_fast2_acc(make_float2(v[k].z, v[k].w), acc2, xr, xs);
+                }
+            }
+        }
+    } else if (live) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (has[k]) {
+                const float mx = fmax_nan(fmax_nan(v[k].x, v[k].y), fmax_nan(v[k].z, v[k].w));
+                if (GAMMA2 && mx <= kFastMax) {
+                    float2 xr, xs;
+                    acc2 = neg_term_fast2_acc(make_float2(v[k].x, v[k].y), acc2, xr, xs);
+                    acc2 = neg_term_fast2_acc(make_float2(v[k].z, v[k].w), acc2, xr, xs);
+                } else {
+                    acc += neg_unit_exact(v[k], a.gamma, GAMMA2);   // (clamping is idempotent)
+                }
+            }
+        }
+    }
+
+    // row maximum over the T lanes; sM = the score it would give (an upper bound when clamped)
+    float Mr = M;
+    row_butterfly<TS>(T, [&](int o) { Mr = fmax_nan(Mr, __shfl_xor_sync(0xffffffffu, Mr, o)); });
+    float sM = Mr;
+    if (a.has_ctr) sM = __fsqrt_rn(__fmul_rn(Mr, ctrv));   // decode.py:338
+    const bool trig = live && !(sM <= a.min_score);        // NaN: may not be skipped
+    if (!__any_sync(0xffffffffu, trig)) {
+        if (live && j == 0) kout[row] = 0u;
+        return;
+    }
+    float score;
+    int best_c;
+    if (__any_sync(0xffffffffu, trig && !(Mr > kClampLo))) {
+        // clamped or NaN maximum on a row that may still pass (threshold below the clamp, centre-ness
+        // above 1, NaN scores): the exact scan over the RAW scores, re-read (strict '>' in class
+        // order = np.argmax's first maximum; a NaN score makes the row's score NaN)
+        float best = ninf, any = 0.f;
+        int code = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (has[k]) {
+                const float4 r = __ldg(src + (k << ts));
+                const float e4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e4[e] > best) {
+                        best = e4[e];
+                        code = (k << 2) | e;
+                    }
+                }
+                any = fmax_nan(fmax_nan(any, fmax_nan(e4[0], e4[1])), fmax_nan(e4[2], e4[3]));
+            }
+        }
+        best_c = best > ninf ? ((((code >> 2) << ts) + j) << 2) + (code & 3) : 0x7fffffff;
+        row_butterfly<TS>(T, [&](int o) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            any = fmax_nan(any, __shfl_xor_sync(0xffffffffu, any, o));
+            if (ov > best || (ov == best && oc < best_c)) {
+                best = ov;
+                best_c = oc;
+            }
+        });
+        if (any != any) best = any;
+        score = a.has_ctr ? __fsqrt_rn(__fmul_rn(best, ctrv)) : best;
+    } else {
+        // Mr (> the clamp) is the true maximum of every row that can pass, and a clamped value
+        // equals it exactly where the raw one does.  First class that holds it: the sign bits of
+        // v - Mr (packed subtraction; +0 exactly where v == Mr, negative elsewhere) are
+        // funnel-shifted into a mask in class order, one ALU instruction per element
+        const float2 nm = make_float2(-Mr, -Mr);
+        constexpr int KA = K < 8 ? K : 8, KB = K - KA;   // two 32-bit masks: units [0, KA) and [KA, K)
+        uint32_t na = 0u, nb = 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 d01 = __fadd2_rn(make_float2(v[k].x, v[k].y), nm);
+            const float2 d23 = __fadd2_rn(make_float2(v[k].z, v[k].w), nm);
+            uint32_t &n = k < KA ? na : nb;
+            n = __funnelshift_l(__float_as_uint(d01.x), n, 1);
+            n = __funnelshift_l(__float_as_uint(d01.y), n, 1);
+            n = __funnelshift_l(__float_as_uint(d23.x), n, 1);
+            n = __funnelshift_l(__float_as_uint(d23.y), n, 1);
+        }
+        // bit (4 KA - 1 - i) of eqa: element i == Mr; eqb likewise for elements 4 KA + i
+        const uint32_t eqa = ~na & (KA == 8 ? 0xffffffffu : ((1u << (4 * KA % 32)) - 1u));
+        const uint32_t eqb = KB > 0 ? (~nb & ((1u << (4 * KB % 32)) - 1u)) : 0u;
+        const int i = eqa ? __clz(eqa) - (32 - 4 * KA) : 4 * KA + __clz(eqb) - (32 - 4 * KB);   // first one
+        best_c = (eqa | eqb) ? ((((i >> 2) << ts) + j) << 2) + (i & 3) : 0x7fffffff;
+        row_butterfly<TS>(T, [&](int o) { best_c = min(best_c, __shfl_xor_sync(0xffffffffu, best_c, o)); });
+        score = sM;
+    }
+    if (live && j == 0) {
+        kout[row] = (score > a.min_score) ? flip_key(score) : 0u;  // strict '>' (decode.py:133-138)
+        cout[row] = best_c;
+    }
+}
+
+template <int K, bool FULL, int TS /* log2(lanes per row), or -1: run-time */, bool GAMMA2, int MINB>
+__global__ void __launch_bounds__(kArgThreads, MINB)
+    fused_rows_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
+    pdl_launch_dependents();
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
+    const int ts = TS >= 0 ? TS : a.t2_shift, T = 1 << ts;
+    const int j = threadIdx.x & (T - 1);
+    const int rows_per_iter = kArgThreads >> ts;
+    const int U = FULL ? K * T : a.units_per_row;
+    const long long n_rows = a.rows[l];
+    long long row = (long long)(blockIdx.x - a.block_off[l]) * (rows_per_iter * kRowIters) +
+                    (threadIdx.x >> ts);
+    const float4 *__restrict__ base = reinterpret_cast<const float4 *>(a.cls.p[l]) + j;
+    const float *__restrict__ ctr = static_cast<const float *>(a.ctr.p[l]);
+    uint32_t *__restrict__ kout = keys + a.row_base[l];
+    int *__restrict__ cout = classes + a.row_base[l];
+    const float ninf = -__int_as_float(0x7f800000);
+    float acc = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+    for (int it = 0; it < kRowIters; ++it, row += rows_per_iter) {
+        const bool live = row < n_rows;
+        // rows past the level's end re-read its last row (and discard it): no predicates on the loads
+        const float4 *__restrict__ src = base + (live ? row : n_rows - 1) * U;
+        float4 v[K];
+        bool has[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            has[k] = FULL ? true : ((k << ts) + j < U);
+            if (FULL) {
+                v[k] = __ldcs(src + (k << ts));
+            } else {
+                v[k] = make_float4(ninf, ninf, ninf, ninf);
+                if (has[k]) v[k] = __ldcs(src + (k << ts));
+            }
+        }
+        float ctrv = 1.f;
+        if (a.has_ctr && live) ctrv = __ldg(ctr + row);
+        fused_rows_step<K, FULL, GAMMA2, TS>(v, has, live, ctrv, j, ts, T, row, src, a, kout, cout, acc, acc2,
+                                         [] {});
+    }
+    sweep_accumulate_warp((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
+}
+
+// The same sweep fed by TMA: every WARP streams its own rows through a private two-stage ring in
+// shared memory with bulk copies (cp.async.bulk + one mbarrier per stage; a warp's 32 / T rows of one
+// row group are 512 * K contiguous bytes), so the bytes in flight no longer depend on registers or
+// on how many warps happen to be waiting: while a warp computes row group i, groups i + 1 and i + 2
+// are on their way (5 KB per warp, 160 KB per SM at 4 CTAs).  The register-fed kernel above has
+// loads in flight only while a warp waits for them: ncu showed it latency-bound (long-scoreboard
+// stalls 4.1 per issued instruction, 60 % issue utilisation, 0.87 of the HBM peak alone;
+// profiles/r02b_fused_sweep.txt).  No CTA-wide barrier anywhere: warps only meet their own mbarriers.
+// Needs every lane to hold K units (C = 4 * K * T).
+#ifndef B200DET_TMA_ITERS
+#define B200DET_TMA_ITERS 8
+#endif
+constexpr int kTmaIters = B200DET_TMA_ITERS;   // row groups per warp
+__device__ __forceinline__ void warp_bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                               uint32_t mbar_smem, uint64_t policy) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_smem), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(dst_smem),
+        "l"(src), "r"(bytes), "r"(mbar_smem), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_smem, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar_smem), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr)
+                 : "memory");
+    return v;
+}
+template <int K, int TS, bool GAMMA2, int MINB>
+__global__ void __launch_bounds__(kArgThreads, MINB)
+    fused_rows_tma_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
+    constexpr int T = 1 << TS;
+    constexpr int U = K * T;                          // 128-bit units per row
+    constexpr int kRowsPerWarp = 32 >> TS;            // rows of one row group a warp owns
+    constexpr uint32_t kStageBytes = kRowsPerWarp * U * 16;   // = 512 K bytes per warp and row group
+    constexpr int kWarps = kArgThreads / 32;
+    extern __shared__ __align__(16) unsigned char arg_smem[];
+    pdl_launch_dependents();
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane & (T - 1), r = lane >> TS;
+    // the warp's rows: kTmaIters consecutive row groups of kRowsPerWarp rows, `rem` of them exist
+    const long long row0 = ((long long)(blockIdx.x - a.block_off[l]) * kWarps + warp) * (kRowsPerWarp * kTmaIters);
+    const long long left = a.rows[l] - row0;
+    const int rem = left < (long long)(kRowsPerWarp * kTmaIters) ? (int)left : kRowsPerWarp * kTmaIters;
+    const char *__restrict__ gsrc = reinterpret_cast<const char *>(a.cls.p[l]) + row0 * (U * 16);
+    const float *__restrict__ ctr = static_cast<const float *>(a.ctr.p[l]) + row0;
+    uint32_t *__restrict__ kout = keys + a.row_base[l] + row0;
+    int *__restrict__ cout = classes + a.row_base[l] + row0;
+    // shared memory: [warp] stages of 512 K bytes, then [warp] mbarriers
+    const uint32_t stage = smem_u32(arg_smem) + warp * kStageBytes;
+    const uint32_t bar = smem_u32(arg_smem) + kWarps * kStageBytes + warp * 8;
+    uint64_t policy;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    // lane 0: fetch row group `it` (the rows of it that exist) into the warp's stage
+    auto issue = [&](int it) {
+        int nr = rem - it * kRowsPerWarp;
+        nr = nr < kRowsPerWarp ? nr : kRowsPerWarp;
+        if (nr > 0) warp_bulk_load(stage, gsrc + (size_t)it * kStageBytes, (uint32_t)nr * (U * 16), bar, policy);
+    };
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(0);
+    }
+    __syncwarp();
+    float acc = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
+    const uint32_t my = stage + (r * U + j) * 16;   // (rows past the end read stale bytes and discard them)
+
+#pragma unroll 1
+    for (int it = 0; it < kTmaIters; ++it) {
+        const int nr = rem - it * kRowsPerWarp;
+        if (nr <= 0) break;   // warp-uniform: the level has no more rows for this warp
+        const bool live = r < nr;
+        const int lr = it * kRowsPerWarp + r;   // row within the warp's span
+        float ctrv = 1.f;
+        if (a.has_ctr && live) ctrv = __ldg(ctr + lr);
+        mbar_wait(bar, (uint32_t)it & 1u);
+        float4 v[K];
+        bool has[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            has[k] = true;
+            v[k] = lds128(my + (k << TS) * 16);
+        }
+        // One stage per warp is enough: the row group lives in registers from here on, so the stage
+        // is free as soon as every lane's reads have returned -- the step calls back after it has
+        // consumed them all -- and the bulk copy of row group it + 1 is in flight during the ~500
+        // instructions that process row group it.  (The refill lands ~1 us after lane 0 issues it; the
+        // __syncwarp orders the other lanes' reads before the issue.)
+        fused_rows_step<K, true, GAMMA2, TS>(
+            v, has, live, ctrv, j, TS, T, (long long)lr,
+            reinterpret_cast<const float4 *>(gsrc) + (live ? lr : it * kRowsPerWarp) * U + j, a, kout, cout, acc,
+            acc2, [&] {
+                __syncwarp();
+                if (lane == 0 && it + 1 < kTmaIters) issue(it + 1);
+            });
+    }
+    sweep_accumulate_warp((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
+}
+
 // Variant for class counts that are not a multiple of 4 (e.g. Objects365's 365): rows are not
 // 16-byte aligned, but a tile of R rows with R % 4 == 0 is, so the tile is still read as one flat
 // stream of 128-bit loads, parked RAW in shared memory, and each row is scanned from there by
@@ -440,6 +782,11 @@ struct SelectArgs {
     const uint16_t *half_exp;     // NULL, or np.exp over all float16 inputs (host-specific, see header)
     int force_bitonic;            // A/B knob (B200DET_SELECT_BITONIC)
     long long *stamps;            // NULL, or [B,16] globaltimer stamps of the leader's phases (profiling)
+    // keys handed over by the criterion's sweep (b200det_decode_from_keys): every selected row's key
+    // is re-derived from the class score it names; a mismatch (the head outputs changed since the
+    // sweep) sets *stale and the host layer decodes again from scratch
+    PtrTab vcls, vctr;
+    int32_t *stale;               // NULL = no verification
 };
 
 // block-wide sums; result broadcast to all threads.  `scratch` holds kSelWarps values.
@@ -980,6 +1327,17 @@ __global__ void __launch_bounds__(kSelThreads, 1)
         const int l = level_of_row(g, row);
         const int local = row - g.off[l];
         scls[i] = __ldg(classes + lm_index(g, b, l, local));
+        if (a.stale) {
+            const int c = scls[i];
+            bool ok = c >= 0 && c < g.num_classes;
+            if (ok) {
+                const long long r = (long long)b * g.rows[l] + local;
+                float s = __ldg(static_cast<const float *>(a.vcls.p[l]) + r * g.num_classes + c);
+                if (a.vctr.p[l]) s = __fsqrt_rn(__fmul_rn(s, __ldg(static_cast<const float *>(a.vctr.p[l]) + r)));
+                ok = flip_key(s) == (uint32_t)(kk >> 32);
+            }
+            if (!ok) *a.stale = 1;
+        }
         const float4 t = load_reg4(a.reg.p[l], a.reg_dtype, (long long)b * g.rows[l] + local);
         float x1, y1, x2, y2;
         if (a.is_fcos == B200DET_DECODE_BOXES) {
@@ -1248,6 +1606,8 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     static const bool force_rows = getenv("B200DET_ARGMAX_ROWS") != nullptr;
     const bool row_groups = vec == 4 && units <= kRowsK * 32 && (focal_slots != nullptr || force_rows);
     int R;
+    bool use_tma = false;
+    int tma_k = 0;
     if (row_groups) {
         int t = 1, tsft = 0;
         while (t * kRowsK < units) {
@@ -1257,6 +1617,21 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
         a.t2 = t;
         a.t2_shift = tsft;
         R = (kArgThreads >> tsft) * kRowIters;
+        // the TMA-fed fused sweep: every lane holds tma_k units (C = 4 * tma_k * T)
+        static const bool no_tma = getenv("B200DET_FUSED_NO_TMA") != nullptr;   // A/B knob
+        if (focal_slots != nullptr && !no_tma && !getenv("B200DET_FUSED_OLD")) {
+            int tt = -1;
+            if (units == 5) tma_k = 5, tt = 0;
+            else if (units == 10) tma_k = 10, tt = 0;
+            else if (units == 20) tma_k = 10, tt = 1;
+            else if (units == 40) tma_k = 10, tt = 2;
+            if (tt >= 0) {
+                use_tma = true;
+                a.t2 = 1 << tt;
+                a.t2_shift = tt;
+                R = (kArgThreads / 32) * (32 >> tt) * kTmaIters;
+            }
+        }
         a.pitch = 0;
     } else if (vec == 4) {
         R = budget / units;
@@ -1314,7 +1689,46 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     const size_t smem = vec == 4 ? (size_t)R * a.pitch * 8 : (size_t)R * a.C * 4 + 16;
     if (smem > 48 * 1024) return B200DET_ERANGE;
     ProfScope prof(kKernArgmax, stream);
-    if (row_groups && focal_slots)
+    static const bool fused_old = getenv("B200DET_FUSED_OLD") != nullptr;                       // A/B knobs
+    static const int fused_minb = getenv("B200DET_FUSED_MINB") ? atoi(getenv("B200DET_FUSED_MINB")) : 4;
+    if (use_tma) {
+        const bool g2 = gamma == 2.f;
+        void (*kern)(ArgmaxArgs, uint32_t *, int *);
+        // (K units per lane, T = 2^TS lanes per row): 10 x 2 for C = 80, 5 x 1 for C = 20, 10 x 1 / 10 x 4
+        // for C = 40 / 160
+#define B200DET_TMA_PICK(KK, TS) (g2 ? fused_rows_tma_kernel<KK, TS, true, 3> : fused_rows_tma_kernel<KK, TS, false, 3>)
+        kern = tma_k == 5 ? B200DET_TMA_PICK(5, 0)
+                          : a.t2_shift == 0 ? B200DET_TMA_PICK(10, 0)
+                                            : a.t2_shift == 1 ? B200DET_TMA_PICK(10, 1) : B200DET_TMA_PICK(10, 2);
+#undef B200DET_TMA_PICK
+        const size_t tma_smem = (size_t)(kArgThreads / 32) * (32 * tma_k * 16 + 8);
+        static std::atomic<unsigned long long> carve_set{0};   // per device: prefer shared memory over L1
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev < 64 &&
+            !((carve_set.load(std::memory_order_relaxed) >> dev) & 1ull)) {
+            cudaFuncSetAttribute(fused_rows_tma_kernel<5, 0, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<5, 0, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<10, 0, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<10, 0, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<10, 1, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<10, 1, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<10, 2, true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(fused_rows_tma_kernel<10, 2, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carve_set.fetch_or(1ull << dev, std::memory_order_relaxed);
+        }
+        kern<<<blocks, kArgThreads, tma_smem, (cudaStream_t)stream>>>(a, keys, classes);
+    } else if (row_groups && focal_slots && !fused_old) {
+        const bool full = units == kRowsK * a.t2, g2 = gamma == 2.f;
+        void (*kern)(ArgmaxArgs, uint32_t *, int *);
+#define B200DET_FUSED_PICK(MINB)                                                                      \
+    (full && a.t2_shift == 2                                                                          \
+         ? (g2 ? fused_rows_kernel<kRowsK, true, 2, true, MINB> : fused_rows_kernel<kRowsK, true, 2, false, MINB>)   \
+         : full ? (g2 ? fused_rows_kernel<kRowsK, true, -1, true, MINB> : fused_rows_kernel<kRowsK, true, -1, false, MINB>)   \
+                : (g2 ? fused_rows_kernel<kRowsK, false, -1, true, MINB> : fused_rows_kernel<kRowsK, false, -1, false, MINB>))
+        kern = fused_minb == 5 ? B200DET_FUSED_PICK(5) : B200DET_FUSED_PICK(4);
+#undef B200DET_FUSED_PICK
+        kern<<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+    } else if (row_groups && focal_slots)
         score_argmax_rows_kernel<kRowsK, true><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
     else if (row_groups)
         score_argmax_rows_kernel<kRowsK, false><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
@@ -1349,11 +1763,13 @@ int b200det::select_decode_nms_impl(const b200det_geometry *geo, const uint32_t 
                                     int nms_type, double nms_threshold, const float *scales,
                                     const float *sizes, int to_xywh, float *out, int32_t *order,
                                     int32_t *keep, int32_t *counts, const uint16_t *half_exp_table,
-                                    void *stream) {
+                                    void *stream, const void *const *verify_cls,
+                                    const void *const *verify_ctr, int32_t *stale) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
     if (!keys || !classes || !reg || !out) return B200DET_EINVAL;
+    if (stale && !verify_cls) return B200DET_EINVAL;
     if (topn < 1 || topn > B200DET_MAX_TOPN || max_out < 1) return B200DET_ERANGE;
     if (nms_type < B200DET_NMS_PYTHON || nms_type > B200DET_NMS_NONE) return B200DET_EINVAL;
     const int reg_base = reg_dtype & 0xf;
@@ -1435,6 +1851,12 @@ int b200det::select_decode_nms_impl(const b200det_geometry *geo, const uint32_t 
     a.force_bitonic = env_bitonic ? 1 : 0;
     a.stamps = g_select_stamps;
     a.half_exp = half_exp_table;
+    a.stale = stale;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        a.vcls.p[l] = stale && l < g.n_levels ? verify_cls[l] : nullptr;
+        a.vctr.p[l] = stale && verify_ctr && l < g.n_levels ? verify_ctr[l] : nullptr;
+        if (stale && l < g.n_levels && !a.vcls.p[l]) return B200DET_EINVAL;
+    }
     ProfScope prof(kKernSelect, stream);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)slices, (unsigned)g.batch, 1);

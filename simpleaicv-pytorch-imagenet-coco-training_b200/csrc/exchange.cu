@@ -318,7 +318,10 @@ int loss_forward_impl(const b200det_geometry *geo, const b200det_loss_params *p,
                       const void *const *reg, const void *const *ctr, int32_t *labels,
                       void *workspace, size_t workspace_bytes, const b200det_peer_exchange *px,
                       double *sums, float *losses, int32_t *status, void *side, void *ev_fork,
-                      void *ev_join, void *stream, int phase) {
+                      void *ev_join, void *stream, int phase, float keys_min_score, uint32_t *keys,
+                      int32_t *classes) {
+    // keys != NULL (b200det_loss_forward_keys): the sweep is the fused one, which also writes the
+    // decoder's keys / classes.
     // phase: 0 = everything; 1 = only memset + fork + focal sweep (needs geo, p, cls, workspace);
     //        2 = the rest of a call whose phase 1 has been enqueued (same arguments)
     Geo g;
@@ -343,8 +346,16 @@ int loss_forward_impl(const b200det_geometry *geo, const b200det_loss_params *p,
         }
         g_skip_memset = true;
         // the long HBM-bound sweep first: the host prepares the remaining launches behind it
-        rc = b200det_focal_loss(geo, cls, nullptr, p->alpha, p->gamma, nullptr, nullptr, 0.f, workspace,
-                                workspace_bytes, stream);
+        if (keys) {
+            if (!classes || g.num_classes % 4 || (p->is_fcos && !ctr)) rc = B200DET_EINVAL;
+            else
+                rc = score_argmax_impl(geo, cls, p->is_fcos ? ctr : nullptr, keys_min_score, keys, classes,
+                                       p->alpha, p->gamma,
+                                       reinterpret_cast<long long *>(base + ws.off_focal), stream);
+        } else {
+            rc = b200det_focal_loss(geo, cls, nullptr, p->alpha, p->gamma, nullptr, nullptr, 0.f, workspace,
+                                    workspace_bytes, stream);
+        }
         g_skip_memset = false;
         if (phase == 1) return rc;
     }
@@ -399,7 +410,7 @@ extern "C" int b200det_loss_forward_exchange(const b200det_geometry *geo,
     if (!px) return B200DET_EINVAL;
     return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
                              workspace_bytes, px, sums, losses, status, nullptr, nullptr, nullptr,
-                             stream, 0);
+                             stream, 0, 0.f, nullptr, nullptr);
 }
 
 extern "C" int b200det_loss_forward_overlap(const b200det_geometry *geo,
@@ -414,7 +425,27 @@ extern "C" int b200det_loss_forward_overlap(const b200det_geometry *geo,
     if (phase < 0 || phase > 2) return B200DET_EINVAL;
     return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
                              workspace_bytes, px, sums, losses, status, side_stream, ev_fork,
-                             ev_join, stream, phase);
+                             ev_join, stream, phase, 0.f, nullptr, nullptr);
+}
+
+// b200det_loss_forward_overlap whose sweep ALSO produces what the decoder's sweep would: the fused
+// sweep of b200det_eval_step (focal sum + first-maximum class / score key per row) instead of the
+// focal-only one.  A decoder call on the same head outputs then only needs b200det_select_decode_nms
+// on these keys -- cls is read once per evaluation step inside the reference's two-call structure
+// (tools/scripts.py:733-740).  num_classes % 4 == 0; FCOS: ctr is needed in phase 1 as well.
+extern "C" int b200det_loss_forward_keys(const b200det_geometry *geo, const b200det_loss_params *p,
+                                         const float *annotations, int max_gt,
+                                         const void *const *cls, const void *const *reg,
+                                         const void *const *ctr, int32_t *labels, void *workspace,
+                                         size_t workspace_bytes, const b200det_peer_exchange *px,
+                                         double *sums, float *losses, int32_t *status,
+                                         void *side_stream, void *ev_fork, void *ev_join,
+                                         void *stream, int phase, float min_score, uint32_t *keys,
+                                         int32_t *classes) {
+    if (phase < 0 || phase > 2 || !keys || !classes) return B200DET_EINVAL;
+    return loss_forward_impl(geo, p, annotations, max_gt, cls, reg, ctr, labels, workspace,
+                             workspace_bytes, px, sums, losses, status, side_stream, ev_fork,
+                             ev_join, stream, phase, min_score, keys, classes);
 }
 
 // Caller-owned helper objects of b200det_loss_forward_overlap (the library keeps none itself).

@@ -24,12 +24,27 @@ using DecodeFn = int (*)(const b200det_geometry *, const b200det_decode_params *
                          const void *const *, const void *const *, const void *const *, uint32_t *,
                          int32_t *, float *, int32_t *, int32_t *, int32_t *, void *, size_t, void *);
 
+// b200det_loss_forward_keys / b200det_decode_from_keys: the sweep hand-over (b200det/_handoff.py)
+using LossKeysFn = int (*)(const b200det_geometry *, const b200det_loss_params *, const float *, int,
+                           const void *const *, const void *const *, const void *const *, int32_t *,
+                           void *, size_t, const b200det_peer_exchange *, double *, float *, int32_t *,
+                           void *, void *, void *, void *, int, float, uint32_t *, int32_t *);
+using FromKeysFn = int (*)(const b200det_geometry *, const b200det_decode_params *,
+                           const void *const *, const void *const *, const void *const *,
+                           const uint32_t *, const int32_t *, float *, int32_t *, int32_t *, int32_t *,
+                           int32_t *, void *);
+
 LossFn g_loss = nullptr;
 DecodeFn g_decode = nullptr;
+LossKeysFn g_loss_keys = nullptr;
+FromKeysFn g_from_keys = nullptr;
 
-void bind(uintptr_t loss_forward_overlap, uintptr_t decode) {
+void bind(uintptr_t loss_forward_overlap, uintptr_t decode, uintptr_t loss_forward_keys,
+          uintptr_t decode_from_keys) {
     g_loss = reinterpret_cast<LossFn>(loss_forward_overlap);
     g_decode = reinterpret_cast<DecodeFn>(decode);
+    g_loss_keys = reinterpret_cast<LossKeysFn>(loss_forward_keys);
+    g_from_keys = reinterpret_cast<FromKeysFn>(decode_from_keys);
 }
 
 // per-level tensors -> device pointers; false when a tensor is not the common case
@@ -88,13 +103,15 @@ bool marshal(const b200det_geometry *geo, const py::list &cls, const py::list &r
 
 // RetinaLoss / FCOSLoss no-grad forward.  p = (is_fcos, box_loss, use_center_sample, alpha, gamma,
 // beta, w_cls, w_box, w_ctr, iou_neg, iou_pos).  sync: 0 = single process, 1 = the caller
-// all-reduces the sums (no finish here), 2 = peer exchange (px).  Returns the 8-double result tensor
+// all-reduces the sums (no finish here), 2 = peer exchange (px).  keys != 0: the sweep also writes the
+// decoder's keys / classes (thresholded with min_score).  Returns the 8-double result tensor
 // (sums | losses | status word) or None.
 py::object loss_eval(uintptr_t geo_addr, const py::list &cls, const py::list &reg, const py::object &ctr,
                      const py::object &ann_obj, const py::tuple &p, bool autocast,
                      uintptr_t scratch, size_t ws_bytes, int sync, uintptr_t px, uintptr_t side,
-                     uintptr_t fork, uintptr_t join, uintptr_t stream) {
-    if (!g_loss) return py::none();
+                     uintptr_t fork, uintptr_t join, uintptr_t stream, float min_score, uintptr_t keys,
+                     uintptr_t classes) {
+    if (!g_loss || !g_loss_keys) return py::none();
     const b200det_geometry *geo = reinterpret_cast<const b200det_geometry *>(geo_addr);
     if (cls.size() == 0 || !THPVariable_Check(cls[0].ptr()) || !THPVariable_Check(ann_obj.ptr()))
         return py::none();
@@ -129,23 +146,33 @@ py::object loss_eval(uintptr_t geo_addr, const py::list &cls, const py::list &re
     float *losses = sync == 1 ? nullptr : reinterpret_cast<float *>(sums + 4);
     int32_t *status = sync == 2 ? reinterpret_cast<int32_t *>(sums + 6) : nullptr;
     char *ws = reinterpret_cast<char *>(scratch);
-    const int rc = g_loss(geo, &lp, ann.data_ptr<float>(), (int)ann.size(1), lv.cls, lv.reg,
-                          lv.has_ctr ? lv.ctr : nullptr, reinterpret_cast<int32_t *>(ws + ws_bytes), ws,
-                          ws_bytes, sync == 2 ? reinterpret_cast<const b200det_peer_exchange *>(px) : nullptr,
-                          sums, losses, status, reinterpret_cast<void *>(side),
-                          reinterpret_cast<void *>(fork), reinterpret_cast<void *>(join),
-                          reinterpret_cast<void *>(stream), 0);
+    const b200det_peer_exchange *pxp =
+        sync == 2 ? reinterpret_cast<const b200det_peer_exchange *>(px) : nullptr;
+    int32_t *labels = reinterpret_cast<int32_t *>(ws + ws_bytes);
+    const void *const *ctrp = lv.has_ctr ? lv.ctr : nullptr;
+    const int rc =
+        keys ? g_loss_keys(geo, &lp, ann.data_ptr<float>(), (int)ann.size(1), lv.cls, lv.reg, ctrp, labels,
+                           ws, ws_bytes, pxp, sums, losses, status, reinterpret_cast<void *>(side),
+                           reinterpret_cast<void *>(fork), reinterpret_cast<void *>(join),
+                           reinterpret_cast<void *>(stream), 0, min_score,
+                           reinterpret_cast<uint32_t *>(keys), reinterpret_cast<int32_t *>(classes))
+             : g_loss(geo, &lp, ann.data_ptr<float>(), (int)ann.size(1), lv.cls, lv.reg, ctrp, labels, ws,
+                      ws_bytes, pxp, sums, losses, status, reinterpret_cast<void *>(side),
+                      reinterpret_cast<void *>(fork), reinterpret_cast<void *>(join),
+                      reinterpret_cast<void *>(stream), 0);
     if (rc != 0) return py::int_(rc);
     return py::cast(out);
 }
 
 // RetinaDecoder / FCOSDecoder: arg-max sweep + select kernel writing into a fresh pinned host block.
-// p = (is_fcos, topn, max_out, nms_type, min_score, nms_threshold).  Returns the pinned float32
-// tensor [6 * B * max_out] (scores | classes | boxes), an int error code, or None.
+// p = (is_fcos, topn, max_out, nms_type, min_score, nms_threshold).  from_keys: the scratch already
+// holds this call's keys / classes (hand-over): selection only, with the device-side `stale` check.
+// Returns the pinned float32 tensor [6 * B * max_out + 4] (scores | classes | boxes | stale word), an
+// int error code, or None.
 py::object decode_run(uintptr_t geo_addr, const py::list &cls, const py::list &reg, const py::object &ctr,
                       const py::tuple &p, uintptr_t scratch, size_t classes_off, size_t ws_off,
-                      size_t ws_bytes, uintptr_t half_table_f16, uintptr_t stream) {
-    if (!g_decode) return py::none();
+                      size_t ws_bytes, uintptr_t half_table_f16, uintptr_t stream, bool from_keys) {
+    if (!g_decode || !g_from_keys) return py::none();
     const b200det_geometry *geo = reinterpret_cast<const b200det_geometry *>(geo_addr);
     if (cls.size() == 0 || !THPVariable_Check(cls[0].ptr())) return py::none();
     const at::Tensor &first = THPVariable_Unpack(cls[0].ptr());
@@ -167,14 +194,23 @@ py::object decode_run(uintptr_t geo_addr, const py::list &cls, const py::list &r
     dp.reg_dtype = lv.reg_dtype == B200DET_F32 ? lv.reg_dtype : (lv.reg_dtype | B200DET_REG_EXP_ROUNDED);
     dp.half_exp_table = lv.reg_dtype == B200DET_F16 ? reinterpret_cast<const uint16_t *>(half_table_f16)
                                                     : nullptr;
-    at::Tensor out = at::empty({(long long)6 * geo->batch * dp.max_out},
-                               at::TensorOptions().dtype(at::kFloat).pinned_memory(true));
+    const long long n_out = (long long)6 * geo->batch * dp.max_out;
+    at::Tensor out = at::empty({n_out + 4}, at::TensorOptions().dtype(at::kFloat).pinned_memory(true));
     char *base = reinterpret_cast<char *>(scratch);
-    const int rc = g_decode(geo, &dp, lv.cls, lv.has_ctr ? lv.ctr : nullptr, lv.reg,
-                            reinterpret_cast<uint32_t *>(base),
-                            reinterpret_cast<int32_t *>(base + classes_off), out.data_ptr<float>(),
-                            nullptr, nullptr, nullptr, base + ws_off, ws_bytes,
-                            reinterpret_cast<void *>(stream));
+    int rc;
+    if (from_keys) {
+        int32_t *stale = reinterpret_cast<int32_t *>(out.data_ptr<float>() + n_out);
+        *stale = 0;
+        rc = g_from_keys(geo, &dp, lv.cls, lv.has_ctr ? lv.ctr : nullptr, lv.reg,
+                         reinterpret_cast<const uint32_t *>(base),
+                         reinterpret_cast<const int32_t *>(base + classes_off), out.data_ptr<float>(),
+                         nullptr, nullptr, nullptr, stale, reinterpret_cast<void *>(stream));
+    } else {
+        rc = g_decode(geo, &dp, lv.cls, lv.has_ctr ? lv.ctr : nullptr, lv.reg,
+                      reinterpret_cast<uint32_t *>(base), reinterpret_cast<int32_t *>(base + classes_off),
+                      out.data_ptr<float>(), nullptr, nullptr, nullptr, base + ws_off, ws_bytes,
+                      reinterpret_cast<void *>(stream));
+    }
     if (rc != 0) return py::int_(rc);
     return py::cast(out);
 }

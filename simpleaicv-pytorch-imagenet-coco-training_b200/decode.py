@@ -17,6 +17,7 @@ import os
 import numpy as np
 import torch
 
+from . import _handoff
 from . import _lib
 from . import geometry as _geom
 from .losses import _decode_reg_mode, _on_device, _prep_f32, _prep_reg, _require_cuda
@@ -129,6 +130,19 @@ class _DecoderBase:
             return torch.empty(numel, dtype=torch.float32, pin_memory=True)
         return torch.empty(numel, dtype=torch.float32, device=device)
 
+    def _handoff_target(self, shapes, device, stream):
+        """Where a criterion's fused sweep may leave this decoder's keys / classes (b200det._handoff):
+        the scratch of the plan for these level shapes on (device, stream), or None before the
+        decoder's first own call there."""
+        plan = self._geo_cache.get(shapes)
+        if plan is None or not _ZERO_COPY:
+            return None
+        scratch = plan[5].get((device.index, stream.value))
+        if scratch is None:
+            return None
+        base = scratch.data_ptr()
+        return base, base + 4 * plan[2] * plan[3]
+
     def _to_host(self, out, batch, m, device):
         """The only device->host traffic: 24*M bytes per image into a cached pinned buffer; the
         caller gets fresh, writable arrays (tools/scripts.py:742-758 mutates them in place)."""
@@ -144,20 +158,39 @@ class _DecoderBase:
             host = staging.numpy()
             result = [host[0:batch * m].reshape(batch, m),
                       host[batch * m:2 * batch * m].reshape(batch, m),
-                      host[2 * batch * m:].reshape(batch, m, 4)]
+                      host[2 * batch * m:6 * batch * m].reshape(batch, m, 4)]
         _lib.check(_lib.load().b200det_stream_synchronize(_lib.raw_stream(device)),
                    'b200det_stream_synchronize')
         if result is None:
             host = staging.numpy().copy()
             result = [host[0:batch * m].reshape(batch, m),
                       host[batch * m:2 * batch * m].reshape(batch, m),
-                      host[2 * batch * m:].reshape(batch, m, 4)]
+                      host[2 * batch * m:6 * batch * m].reshape(batch, m, 4)]
         return result
 
     def _run(self, preds, details=False, scales=None, sizes=None, to_xywh=False):
         _require_cuda(preds[0][0], 'cls_preds')
         with _on_device(preds[0][0].device):
             return self._run_on(preds, details, scales, sizes, to_xywh)
+
+    def _handed_over(self, cls_preds, center_preds, device, st):
+        """True when the criterion's sweep already left this call's keys in the scratch
+        (b200det._handoff); otherwise asks the next criterion call for them."""
+        if not (_handoff.ENABLED and _ZERO_COPY):
+            return False
+        tensors = list(cls_preds) + (list(center_preds) if center_preds is not None else [])
+        if _handoff.take(self, device, st, tensors, float(self._params.min_score)):
+            return True
+        _handoff.wish(self, device, st, tuple([t.shape for t in cls_preds]),
+                      int(cls_preds[0].shape[-1]))
+        return False
+
+    @staticmethod
+    def _stale(out, index):
+        """After a hand-over (and the stream sync): did the select kernel find a selected row whose
+        key no longer matches the class score it names (head outputs modified behind torch's back)?
+        `out` is the call's pinned result block, `index` the position of its flag word."""
+        return bool(out.numpy()[index] != 0.0)
 
     def _run_fast(self, fast, cls_preds, reg_preds, center_preds):
         """The plain decoder(preds) call through csrc/fastpath.cpp (same checks / marshalling / C-ABI
@@ -184,16 +217,22 @@ class _DecoderBase:
             t = _half_exp_table(device)
             table = t.data_ptr() if t is not None else 0
         p = self._params
-        res = fast.decode_run(ctypes.addressof(geo), list(cls_preds), list(reg_preds),
-                              list(center_preds) if center_preds is not None else None,
-                              (p.is_fcos, p.topn, p.max_out, p.nms_type, p.min_score, p.nms_threshold),
-                              scratch.data_ptr(), 4 * batch * n_rows, rows_bytes, ws_bytes, table,
-                              st.value or 0)
-        if res is None:
-            return None
-        if isinstance(res, int):
-            _lib.check(res, 'b200det_decode')
-        return self._to_host(res, batch, int(self.max_object_num), device)
+        handed = self._handed_over(cls_preds, center_preds, device, st)
+        while True:
+            res = fast.decode_run(ctypes.addressof(geo), list(cls_preds), list(reg_preds),
+                                  list(center_preds) if center_preds is not None else None,
+                                  (p.is_fcos, p.topn, p.max_out, p.nms_type, p.min_score,
+                                   p.nms_threshold), scratch.data_ptr(), 4 * batch * n_rows, rows_bytes,
+                                  ws_bytes, table, st.value or 0, handed)
+            if res is None:
+                return None
+            if isinstance(res, int):
+                _lib.check(res, 'b200det_decode')
+            result = self._to_host(res, batch, int(self.max_object_num), device)
+            if not handed or not self._stale(res, 6 * batch * int(self.max_object_num)):
+                return result
+            _handoff.stats['stale'] += 1   # the head outputs changed after the criterion's sweep
+            handed = False
 
     def _run_on(self, preds, details, scales, sizes, to_xywh):
         lib = _lib.load()
@@ -238,7 +277,8 @@ class _DecoderBase:
                 scratch_by_stream.clear()
             scratch = scratch_by_stream[skey] = torch.empty(rows_bytes + ws_bytes, dtype=torch.uint8,
                                                             device=device)
-        out = self._out_buffer(6 * batch * m, device)
+        handed = self._handed_over(cls_preds, center_preds, device, st)
+        out = self._out_buffer(6 * batch * m + 4, device)   # + the hand-over's `stale` word
         order = keep = counts = None
         if details:
             order = torch.empty(batch * self.topn, dtype=torch.int32, device=device)
@@ -252,18 +292,37 @@ class _DecoderBase:
             params.half_exp_table = table.data_ptr() if table is not None else None
         glue = self._set_glue(params, batch, device, scales, sizes, to_xywh)
         keys_ptr = scratch.data_ptr()
-        _lib.check(
-            lib.b200det_decode(geo_ref, ctypes.byref(params), _lib.ptr_array(cls),
-                               _lib.ptr_array(ctr), _lib.ptr_array(reg), keys_ptr,
-                               keys_ptr + 4 * batch * n_rows, out.data_ptr(),
-                               order.data_ptr() if details else None,
-                               keep.data_ptr() if details else None,
-                               counts.data_ptr() if details else None,
-                               keys_ptr + rows_bytes, ws_bytes, st),
-            'b200det_decode')
-
+        while True:
+            if handed:
+                # keys / classes are in the scratch already (b200det_loss_forward_keys): select only,
+                # verifying on the device that the selected rows still match the head outputs
+                out[6 * batch * m:].zero_()
+                _lib.check(
+                    lib.b200det_decode_from_keys(geo_ref, ctypes.byref(params), _lib.ptr_array(cls),
+                                                 _lib.ptr_array(ctr), _lib.ptr_array(reg), keys_ptr,
+                                                 keys_ptr + 4 * batch * n_rows, out.data_ptr(),
+                                                 order.data_ptr() if details else None,
+                                                 keep.data_ptr() if details else None,
+                                                 counts.data_ptr() if details else None,
+                                                 out.data_ptr() + 24 * batch * m, st),
+                    'b200det_decode_from_keys')
+            else:
+                _lib.check(
+                    lib.b200det_decode(geo_ref, ctypes.byref(params), _lib.ptr_array(cls),
+                                       _lib.ptr_array(ctr), _lib.ptr_array(reg), keys_ptr,
+                                       keys_ptr + 4 * batch * n_rows, out.data_ptr(),
+                                       order.data_ptr() if details else None,
+                                       keep.data_ptr() if details else None,
+                                       counts.data_ptr() if details else None,
+                                       keys_ptr + rows_bytes, ws_bytes, st),
+                    'b200det_decode')
+            result = self._to_host(out, batch, m, device)
+            if not handed or not self._stale(out, 6 * batch * m):
+                break
+            _handoff.stats['stale'] += 1   # the head outputs changed after the criterion's sweep
+            handed = False
+            out = self._out_buffer(6 * batch * m + 4, device)
         del glue
-        result = self._to_host(out, batch, m, device)
         if not details:
             return result
         info = {

@@ -30,6 +30,7 @@ import os
 import torch
 import torch.nn as nn
 
+from . import _handoff
 from . import _lib
 from . import geometry as _geom
 
@@ -296,6 +297,20 @@ def _loss_params(owner, reg_dtype):
     return p
 
 
+def _handoff_for(owner, cls_in, ctr_in, device, st):
+    """The decoder that asked for its keys (b200det._handoff): (decoder, keys pointer, classes
+    pointer, its score threshold, the tensors the keys will be derived from), or None."""
+    shapes = tuple([t.shape for t in cls_in])
+    dec = _handoff.offer(owner, device, st, shapes)
+    if dec is None:
+        return None
+    target = dec._handoff_target(shapes, device, st)
+    if target is None:
+        return None
+    tensors = list(cls_in) + (list(ctr_in) if ctr_in is not None else [])
+    return dec, target[0], target[1], float(dec._params.min_score), tensors
+
+
 def _forward_eval(owner, annotations, cls_in, reg_in, ctr_in):
     """No-grad forward: one C call (b200det_loss_forward_overlap)."""
     _require_cuda(cls_in[0], 'cls_preds')
@@ -324,6 +339,7 @@ def _forward_eval_fast(fast, owner, annotations, cls_in, reg_in, ctr_in):
         and torch.distributed.is_initialized()
     p2p = sync and owner.sync_normalizer == 'p2p'
     px = ctypes.addressof(_peer_exchange(owner, device).params) if p2p else 0
+    hand = _handoff_for(owner, cls_in, ctr_in, device, st) if _handoff.ENABLED else None
     params = (int(owner._is_fcos), owner._box_code, int(getattr(owner, 'use_center_sample', 0)),
               float(owner.alpha), float(owner.gamma), float(owner.beta), float(owner.cls_loss_weight),
               float(owner.box_loss_weight), float(getattr(owner, 'center_ness_loss_weight', 0.)),
@@ -334,11 +350,14 @@ def _forward_eval_fast(fast, owner, annotations, cls_in, reg_in, ctr_in):
                          2 if p2p else (1 if sync else 0), px,
                          side.stream.value if side is not None else 0,
                          side.fork.value if side is not None else 0,
-                         side.join.value if side is not None else 0, st.value or 0)
+                         side.join.value if side is not None else 0, st.value or 0,
+                         hand[3] if hand else 0., hand[1] if hand else 0, hand[2] if hand else 0)
     if res is None:
         return None
     if isinstance(res, int):
         _lib.check(res, 'b200det_loss_forward_overlap')
+    if hand:
+        _handoff.produced(hand[0], device, st, hand[4], hand[3])
     out = res
     if p2p:
         owner.__dict__['last_stats'] = {'sums': out[0:4],
@@ -384,14 +403,27 @@ def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
     side_args = (side.stream, side.fork, side.join) if side is not None else (None, None, None)
     params = _loss_params(owner, _lib.F32)
     cls_ptrs = _lib.ptr_array(cls)
+    # a decoder waiting for keys of these head outputs: the sweep does its work as well (_handoff.py)
+    hand = None
+    if _handoff.ENABLED and not torch.cuda.is_current_stream_capturing():
+        hand = _handoff_for(owner, cls_in, ctr_in, device, st)
+    ctr = None
+    if hand:
+        ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
+        forward = lib.b200det_loss_forward_keys
+        keys_args = (hand[3], hand[1], hand[2])
+    else:
+        forward = lib.b200det_loss_forward_overlap
+        keys_args = ()
     if big:
         _lib.check(
-            lib.b200det_loss_forward_overlap(plan.geo_ref, ctypes.byref(params), None, 0, cls_ptrs,
-                                             None, None, None, ws_ptr, plan.ws_bytes, None, None, None,
-                                             None, *side_args, st, 1), 'b200det_loss_forward_overlap')
+            forward(plan.geo_ref, ctypes.byref(params), None, 0, cls_ptrs, None,
+                    _lib.ptr_array(ctr) if hand else None, None, ws_ptr, plan.ws_bytes, None, None, None,
+                    None, *side_args, st, 1, *keys_args), 'b200det_loss_forward_overlap')
     reg, reg_dtype = _prep_reg(reg_in)
     reg_dtype = _loss_reg_mode(reg_dtype)
-    ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
+    if ctr is None:
+        ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
     annotations = _prep_annotations(annotations)
     if annotations.shape[0] != plan.batch:
         raise ValueError('annotations and predictions disagree on the batch size')
@@ -408,14 +440,14 @@ def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
         px = _peer_exchange(owner, device).next()
         status = out[6:7].view(torch.int32)[0:1]   # written by the kernel on every call
     _lib.check(
-        lib.b200det_loss_forward_overlap(plan.geo_ref, ctypes.byref(params), annotations.data_ptr(),
-                                         int(annotations.shape[1]), cls_ptrs,
-                                         _lib.ptr_array(reg), _lib.ptr_array(ctr),
-                                         ws_ptr + plan.ws_bytes, ws_ptr, plan.ws_bytes, px, sums_ptr,
-                                         None if (sync and not p2p) else sums_ptr + 32,
-                                         status.data_ptr() if p2p else None, *side_args, st,
-                                         2 if big else 0),
+        forward(plan.geo_ref, ctypes.byref(params), annotations.data_ptr(),
+                int(annotations.shape[1]), cls_ptrs, _lib.ptr_array(reg), _lib.ptr_array(ctr),
+                ws_ptr + plan.ws_bytes, ws_ptr, plan.ws_bytes, px, sums_ptr,
+                None if (sync and not p2p) else sums_ptr + 32,
+                status.data_ptr() if p2p else None, *side_args, st, 2 if big else 0, *keys_args),
         'b200det_loss_forward_overlap')
+    if hand:
+        _handoff.produced(hand[0], device, st, hand[4], hand[3])
     if p2p:
         owner.__dict__['last_stats'] = {'sums': out[0:4], 'exchange_status': status}
         return out[4:8].view(torch.float32)
