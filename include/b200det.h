@@ -412,12 +412,17 @@ int b200det_decode(const b200det_geometry *geo, const b200det_decode_params *par
  * outputs were modified after the criterion read them -- it sets *stale = 1 and the caller must decode
  * again with b200det_decode.  stale: caller-zeroed int32 the device can write (device or mapped pinned
  * host memory), or NULL (then cls / ctr may be NULL).
+ * inputs_complete != 0: the caller guarantees that everything this call reads (keys, classes, cls, ctr,
+ * reg, params' device arrays) was complete before the kernel that precedes it on `stream` STARTED --
+ * true for handed-over keys, whose predecessor is the criterion's reduction / peer-exchange kernel.
+ * The select kernel is launched programmatically and then skips its griddepcontrol.wait, i.e. it runs
+ * BESIDE that one-CTA kernel (and its wait for the other ranks) instead of after it.  0 = stream order.
  */
 int b200det_decode_from_keys(const b200det_geometry *geo, const b200det_decode_params *params,
                              const void *const *cls, const void *const *ctr, const void *const *reg,
                              const uint32_t *keys, const int32_t *classes, float *out,
                              int32_t *order, int32_t *keep, int32_t *counts, int32_t *stale,
-                             void *stream);
+                             int inputs_complete, void *stream);
 
 /*
  * OPTIONAL extension (not in the reference's call structure): loss forward + decode of one

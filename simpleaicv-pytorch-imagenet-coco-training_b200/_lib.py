@@ -139,7 +139,8 @@ SIGNATURES = {
         ctypes.c_size_t, _vp
     ]),
     'b200det_decode_from_keys': (ctypes.c_int, [
-        _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp
+        _geo, ctypes.POINTER(DecodeParams), _vpp, _vpp, _vpp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+        ctypes.c_int, _vp
     ]),
     'b200det_stream_synchronize': (ctypes.c_int, [_vp]),
     'b200det_rows_per_image': (ctypes.c_longlong, [_geo]),

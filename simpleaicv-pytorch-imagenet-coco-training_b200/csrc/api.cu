@@ -134,12 +134,12 @@ extern "C" int b200det_decode_from_keys(const b200det_geometry *geo, const b200d
                                         const void *const *reg, const uint32_t *keys,
                                         const int32_t *classes, float *out, int32_t *order,
                                         int32_t *keep, int32_t *counts, int32_t *stale,
-                                        void *stream) {
+                                        int inputs_complete, void *stream) {
     if (!p) return B200DET_EINVAL;
     return select_decode_nms_impl(geo, keys, classes, reg, p->reg_dtype, p->is_fcos, p->min_score,
                                   p->topn, p->max_out, p->nms_type, p->nms_threshold, p->scales,
                                   p->sizes, p->to_xywh, out, order, keep, counts, p->half_exp_table,
-                                  stream, cls, p->is_fcos ? ctr : nullptr, stale);
+                                  stream, cls, p->is_fcos ? ctr : nullptr, stale, inputs_complete != 0);
 }
 
 // Loss forward + decode of one evaluation step with ONE sweep over the classification tensors:

@@ -98,7 +98,7 @@ int select_decode_nms_impl(const b200det_geometry *geo, const uint32_t *keys, co
                            int32_t *order, int32_t *keep, int32_t *counts,
                            const uint16_t *half_exp_table, void *stream,
                            const void *const *verify_cls = nullptr, const void *const *verify_ctr = nullptr,
-                           int32_t *stale = nullptr);   // decode.cu
+                           int32_t *stale = nullptr, bool inputs_complete = false);   // decode.cu
 // set by the fused entry points after they have cleared all accumulators with ONE memset
 extern thread_local bool g_skip_memset;
 // set by the overlapped forward: images per assignment launch (0 = the whole batch in one launch)

@@ -210,11 +210,8 @@ __global__ void __launch_bounds__(kArgThreads)
 #define B200DET_ROWS_ITERS 4
 #endif
 constexpr int kRowIters = B200DET_ROWS_ITERS;   // row groups per thread: amortises the set-up
-#ifndef B200DET_ROWS_MINB
-#define B200DET_ROWS_MINB 6
-#endif
-template <int K, bool FOCAL>
-__global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
+template <int K>
+__global__ void __launch_bounds__(kArgThreads)
     score_argmax_rows_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
     pdl_launch_dependents();
     int l = 0;
@@ -233,9 +230,6 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
     uint32_t *__restrict__ kout = keys + a.row_base[l];
     int *__restrict__ cout = classes + a.row_base[l];
     const float ninf = -__int_as_float(0x7f800000);
-    float acc = 0.f;
-    float2 acc2 = make_float2(0.f, 0.f);
-
 #pragma unroll 1
     for (int it = 0; it < kRowIters; ++it, row += rows_per_iter, src += (size_t)rows_per_iter * U) {
         const bool live = row < n_rows;
@@ -258,35 +252,10 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
                         code = (k << 2) | e;
                     }
                 }
-                // (with the focal terms fused in, their clamp tree below doubles as the NaN tracker)
-                if (!FOCAL)
-                    any = fmax_nan(fmax_nan(any, fmax_nan(e4[0], e4[1])), fmax_nan(e4[2], e4[3]));
+                any = fmax_nan(fmax_nan(any, fmax_nan(e4[0], e4[1])), fmax_nan(e4[2], e4[3]));
             }
         }
         int best_c = best > ninf ? ((((code >> 2) << ts) + j) << 2) + (code & 3) : 0x7fffffff;
-        if (FOCAL) {
-            // label-free focal terms of the same registers (see focal.cu: focal_all_kernel)
-            const bool gamma2 = a.gamma == 2.f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (live && (k << ts) + j < U) {
-                    const float x0 = fmax_nan(v[k].x, kClampLo), x1 = fmax_nan(v[k].y, kClampLo);
-                    const float x2 = fmax_nan(v[k].z, kClampLo), x3 = fmax_nan(v[k].w, kClampLo);
-                    // max.NaN: a NaN score makes mx NaN -> exact-form terms (NaN, poisoning the sum
-                    // like the reference's) AND marks the row for the arg-max's "first NaN wins"
-                    const float mx = fmax_nan(fmax_nan(x0, x1), fmax_nan(x2, x3));
-                    any = fmax_nan(any, mx);
-                    if (gamma2 && mx <= kFastMax) {
-                        float2 xr, xs;
-                        acc2 = neg_term_fast2_acc(make_float2(x0, x1), acc2, xr, xs);
-                        acc2 = neg_term_fast2_acc(make_float2(x2, x3), acc2, xr, xs);
-                    } else {
-                        acc += neg_term(v[k].x, a.gamma, gamma2) + neg_term(v[k].y, a.gamma, gamma2) +
-                               neg_term(v[k].z, a.gamma, gamma2) + neg_term(v[k].w, a.gamma, gamma2);
-                    }
-                }
-            }
-        }
         // combine the row's lanes: larger value wins, equal values -> lower class index
         for (int o = T >> 1; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -308,26 +277,32 @@ __global__ void __launch_bounds__(kArgThreads, FOCAL ? B200DET_ROWS_MINB : 1)
             cout[row] = best_c;
         }
     }
-    if (FOCAL)
-        sweep_accumulate<kArgThreads>((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
 }
 
-// The fused sweep of the evaluation step (loss + decode from ONE read of cls), r02b.  Same work split
-// as score_argmax_rows_kernel<K, true> -- T lanes per row, K 128-bit units per lane, everything in
-// registers -- with the instruction count cut from ~19 to ~10 per element (the r02 kernel was
-// issue-bound at 0.83 of the HBM peak, profiles/r02_kernels.json):
-//  * the focal term's clamp tree IS the arg-max's max: x = max.NaN(v, 1e-4) per element, then
-//    3-input max.NaN (FMNMX3) down to the lane maximum M; a row maximum above the clamp is the true
-//    maximum, bit for bit (max returns one of its operands).  The compare/select chain per element
-//    (FSETP + FSEL + SEL) is gone;
+// The fused sweep of the evaluation step (loss + decode from ONE read of cls), r02b: T lanes per row,
+// K 128-bit units per lane, everything in registers.  The r02 version (the arg-max kernel above with
+// the focal terms appended) needed ~19 instructions per element and was issue-bound at 0.83 of the HBM
+// peak (profiles/r02_kernels.json); this one needs ~12-14:
+//  * the focal term's clamp tree IS the arg-max's max: x = max.NaN(v, 1e-4) per element, in place,
+//    then 3-input max.NaN (FMNMX3) down to the lane maximum M.  A row maximum above the clamp is the
+//    true maximum, bit for bit (max returns one of its operands), and a clamped value equals it exactly
+//    where the raw one does; the compare / select chain per element (FSETP + FSEL + SEL) is gone and
+//    only ONE array of 4K registers is alive;
 //  * the first-maximum INDEX is found afterwards, and only if some row of the warp can pass the score
-//    threshold: equality scan v == M in reverse class order (FSETP + SEL), lowest class over the lanes;
-//    rows whose (upper bound of the) score fails the threshold get key 0 and no class -- the select
-//    kernel reads classes of selected rows only.  Real heads have ~1 % candidate rows;
+//    threshold: the sign bits of v - M (packed subtraction: +0 exactly where v == M) are funnel-shifted
+//    into a bit mask in class order (one ALU instruction per element), count-leading-zeros gives the
+//    first class, a min over the row's lanes the row's.  Rows whose (upper bound of the) score fails
+//    the threshold get key 0 and no class -- the select kernel reads classes of selected rows only;
+//    real heads have ~1 % candidate rows (the benchmark's synthetic ones 98 %);
 //  * rows whose maximum was clamped (<= 1e-4) or NaN while they could still pass (threshold below the
-//    clamp, FCOS centre-ness > 1, NaN scores) take the r02 exact scan, warp-uniformly;
-//  * ONE fast/slow decision per lane and row (M <= 0.25) instead of one per unit, gamma == 2 and
-//    "every lane holds K units" (C = 4*K*T, e.g. 80) are template parameters.
+//    clamp, FCOS centre-ness > 1, NaN scores) re-read their raw scores and take the exact scan,
+//    warp-uniformly;
+//  * ONE fast / slow decision per lane and row (M <= 0.25) instead of one per unit; gamma == 2, the
+//    lane count and "every lane holds K units" are template parameters; no CTA barrier (one
+//    fixed-point atomic per warp).
+// Measured alone at batch 256 (profiles/r02b_fused_sweep.txt): r02 kernel 1.81 ms -> register-fed
+// 1.73 ms (latency-bound: loads are in flight only while a warp waits for them) -> TMA-fed (below)
+// 1.50 ms = 6.6 TB/s.
 __device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
     float r;
     asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -787,6 +762,10 @@ struct SelectArgs {
     // sweep) sets *stale and the host layer decodes again from scratch
     PtrTab vcls, vctr;
     int32_t *stale;               // NULL = no verification
+    // every input was complete before the kernel that precedes this launch on the stream STARTED (the
+    // host layer proves it for handed-over keys): no griddepcontrol.wait -- the kernel runs beside
+    // that predecessor (the criterion's one-CTA reduction / peer exchange) instead of after it
+    int skip_wait;
 };
 
 // block-wide sums; result broadcast to all threads.  `scratch` holds kSelWarps values.
@@ -1092,7 +1071,7 @@ __global__ void __launch_bounds__(kSelThreads, 1)
     // Launched with programmatic stream serialization: everything above ran while the arg-max sweep
     // (or whatever precedes this kernel on the stream) was still draining; its results are
     // complete and visible from here on.
-    pdl_wait();
+    if (!a.skip_wait) pdl_wait();
     stamp(10);
     __syncthreads();
     const int r0 = crank * a.rows_per_slice, r1 = min(N, r0 + a.rows_per_slice);
@@ -1619,7 +1598,7 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
         R = (kArgThreads >> tsft) * kRowIters;
         // the TMA-fed fused sweep: every lane holds tma_k units (C = 4 * tma_k * T)
         static const bool no_tma = getenv("B200DET_FUSED_NO_TMA") != nullptr;   // A/B knob
-        if (focal_slots != nullptr && !no_tma && !getenv("B200DET_FUSED_OLD")) {
+        if (focal_slots != nullptr && !no_tma) {
             int tt = -1;
             if (units == 5) tma_k = 5, tt = 0;
             else if (units == 10) tma_k = 10, tt = 0;
@@ -1689,8 +1668,6 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     const size_t smem = vec == 4 ? (size_t)R * a.pitch * 8 : (size_t)R * a.C * 4 + 16;
     if (smem > 48 * 1024) return B200DET_ERANGE;
     ProfScope prof(kKernArgmax, stream);
-    static const bool fused_old = getenv("B200DET_FUSED_OLD") != nullptr;                       // A/B knobs
-    static const int fused_minb = getenv("B200DET_FUSED_MINB") ? atoi(getenv("B200DET_FUSED_MINB")) : 4;
     if (use_tma) {
         const bool g2 = gamma == 2.f;
         void (*kern)(ArgmaxArgs, uint32_t *, int *);
@@ -1717,21 +1694,19 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
             carve_set.fetch_or(1ull << dev, std::memory_order_relaxed);
         }
         kern<<<blocks, kArgThreads, tma_smem, (cudaStream_t)stream>>>(a, keys, classes);
-    } else if (row_groups && focal_slots && !fused_old) {
+    } else if (row_groups && focal_slots) {
+        // class counts the TMA-fed kernel does not cover: the register-fed fused sweep
         const bool full = units == kRowsK * a.t2, g2 = gamma == 2.f;
         void (*kern)(ArgmaxArgs, uint32_t *, int *);
-#define B200DET_FUSED_PICK(MINB)                                                                      \
-    (full && a.t2_shift == 2                                                                          \
-         ? (g2 ? fused_rows_kernel<kRowsK, true, 2, true, MINB> : fused_rows_kernel<kRowsK, true, 2, false, MINB>)   \
-         : full ? (g2 ? fused_rows_kernel<kRowsK, true, -1, true, MINB> : fused_rows_kernel<kRowsK, true, -1, false, MINB>)   \
-                : (g2 ? fused_rows_kernel<kRowsK, false, -1, true, MINB> : fused_rows_kernel<kRowsK, false, -1, false, MINB>))
-        kern = fused_minb == 5 ? B200DET_FUSED_PICK(5) : B200DET_FUSED_PICK(4);
-#undef B200DET_FUSED_PICK
+        if (full && a.t2_shift == 2)
+            kern = g2 ? fused_rows_kernel<kRowsK, true, 2, true, 4> : fused_rows_kernel<kRowsK, true, 2, false, 4>;
+        else if (full)
+            kern = g2 ? fused_rows_kernel<kRowsK, true, -1, true, 4> : fused_rows_kernel<kRowsK, true, -1, false, 4>;
+        else
+            kern = g2 ? fused_rows_kernel<kRowsK, false, -1, true, 4> : fused_rows_kernel<kRowsK, false, -1, false, 4>;
         kern<<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
-    } else if (row_groups && focal_slots)
-        score_argmax_rows_kernel<kRowsK, true><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
-    else if (row_groups)
-        score_argmax_rows_kernel<kRowsK, false><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
+    } else if (row_groups)
+        score_argmax_rows_kernel<kRowsK><<<blocks, kArgThreads, 0, (cudaStream_t)stream>>>(a, keys, classes);
     else if (vec == 4 && focal_slots)
         score_argmax_kernel<4, true><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else if (vec == 4)
@@ -1764,7 +1739,7 @@ int b200det::select_decode_nms_impl(const b200det_geometry *geo, const uint32_t 
                                     const float *sizes, int to_xywh, float *out, int32_t *order,
                                     int32_t *keep, int32_t *counts, const uint16_t *half_exp_table,
                                     void *stream, const void *const *verify_cls,
-                                    const void *const *verify_ctr, int32_t *stale) {
+                                    const void *const *verify_ctr, int32_t *stale, bool inputs_complete) {
     Geo g;
     int rc = make_geo(geo, &g);
     if (rc) return rc;
@@ -1852,6 +1827,7 @@ int b200det::select_decode_nms_impl(const b200det_geometry *geo, const uint32_t 
     a.stamps = g_select_stamps;
     a.half_exp = half_exp_table;
     a.stale = stale;
+    a.skip_wait = inputs_complete ? 1 : 0;
     for (int l = 0; l < kMaxLevels; ++l) {
         a.vcls.p[l] = stale && l < g.n_levels ? verify_cls[l] : nullptr;
         a.vctr.p[l] = stale && verify_ctr && l < g.n_levels ? verify_ctr[l] : nullptr;

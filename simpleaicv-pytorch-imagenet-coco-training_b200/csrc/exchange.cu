@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(1024)
                                 float w_cls, float w_box, float w_ctr, double *__restrict__ sums,
                                 float *__restrict__ losses, int *__restrict__ status) {
     __shared__ double local[4];
+    // the wait for the peers below may take a while: a dependent launched programmatically (the
+    // decoder's select kernel on handed-over keys, which reads nothing this kernel writes) runs beside it
+    pdl_launch_dependents();
     double mine[4] = {0.0, 0.0, 0.0, 0.0};
     reduce_partials(npos, n_assign, sp, n_sparse, fp, n_focal, mine);
     if (threadIdx.x == 0) local[0] = mine[0], local[1] = mine[1], local[2] = mine[2], local[3] = mine[3];

@@ -32,7 +32,7 @@ using LossKeysFn = int (*)(const b200det_geometry *, const b200det_loss_params *
 using FromKeysFn = int (*)(const b200det_geometry *, const b200det_decode_params *,
                            const void *const *, const void *const *, const void *const *,
                            const uint32_t *, const int32_t *, float *, int32_t *, int32_t *, int32_t *,
-                           int32_t *, void *);
+                           int32_t *, int, void *);
 
 LossFn g_loss = nullptr;
 DecodeFn g_decode = nullptr;
@@ -204,7 +204,7 @@ py::object decode_run(uintptr_t geo_addr, const py::list &cls, const py::list &r
         rc = g_from_keys(geo, &dp, lv.cls, lv.has_ctr ? lv.ctr : nullptr, lv.reg,
                          reinterpret_cast<const uint32_t *>(base),
                          reinterpret_cast<const int32_t *>(base + classes_off), out.data_ptr<float>(),
-                         nullptr, nullptr, nullptr, stale, reinterpret_cast<void *>(stream));
+                         nullptr, nullptr, nullptr, stale, 1, reinterpret_cast<void *>(stream));
     } else {
         rc = g_decode(geo, &dp, lv.cls, lv.has_ctr ? lv.ctr : nullptr, lv.reg,
                       reinterpret_cast<uint32_t *>(base), reinterpret_cast<int32_t *>(base + classes_off),

@@ -526,6 +526,9 @@ __global__ void __launch_bounds__(1024)
                        double *__restrict__ sums, float w_cls, float w_box, float w_ctr,
                        float *__restrict__ losses) {
     __shared__ double red[4][32];
+    // a dependent launched programmatically (the decoder's select kernel on handed-over keys, which
+    // reads nothing this kernel writes) may run beside this one-CTA kernel
+    pdl_launch_dependents();
     double s_pos = 0.0, s_cls = 0.0, s_box = 0.0, s_ctr = 0.0;
     if (which & 5)   // bit 2: the positive count alone (it is complete as soon as the assignment is)
         for (long long i = threadIdx.x; i < n_assign; i += blockDim.x) s_pos += (double)npos[i];

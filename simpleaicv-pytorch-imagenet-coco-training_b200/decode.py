@@ -60,6 +60,9 @@ def _half_exp_table(device):
                                     'np_exp_f16_avx512spr.npy')
                 host = np.load(path).astype(np.int16)
                 table = torch.from_numpy(host).to(device)
+                # complete before anything uses it: a select kernel on handed-over keys does not wait
+                # for what precedes it on the stream (b200det_decode_from_keys: inputs_complete)
+                torch.cuda.synchronize(device)
         except Exception:   # no dispatch info: the generic half loop
             table = None
         _HALF_EXP_TABLES[key] = table
@@ -173,12 +176,13 @@ class _DecoderBase:
         with _on_device(preds[0][0].device):
             return self._run_on(preds, details, scales, sizes, to_xywh)
 
-    def _handed_over(self, cls_preds, center_preds, device, st):
+    def _handed_over(self, cls_preds, reg_preds, center_preds, device, st):
         """True when the criterion's sweep already left this call's keys in the scratch
         (b200det._handoff); otherwise asks the next criterion call for them."""
         if not (_handoff.ENABLED and _ZERO_COPY):
             return False
-        tensors = list(cls_preds) + (list(center_preds) if center_preds is not None else [])
+        tensors = list(cls_preds) + (list(center_preds) if center_preds is not None else []) + \
+            list(reg_preds)
         if _handoff.take(self, device, st, tensors, float(self._params.min_score)):
             return True
         _handoff.wish(self, device, st, tuple([t.shape for t in cls_preds]),
@@ -217,7 +221,7 @@ class _DecoderBase:
             t = _half_exp_table(device)
             table = t.data_ptr() if t is not None else 0
         p = self._params
-        handed = self._handed_over(cls_preds, center_preds, device, st)
+        handed = self._handed_over(cls_preds, reg_preds, center_preds, device, st)
         while True:
             res = fast.decode_run(ctypes.addressof(geo), list(cls_preds), list(reg_preds),
                                   list(center_preds) if center_preds is not None else None,
@@ -277,7 +281,7 @@ class _DecoderBase:
                 scratch_by_stream.clear()
             scratch = scratch_by_stream[skey] = torch.empty(rows_bytes + ws_bytes, dtype=torch.uint8,
                                                             device=device)
-        handed = self._handed_over(cls_preds, center_preds, device, st)
+        handed = self._handed_over(cls_preds, reg_preds, center_preds, device, st)
         out = self._out_buffer(6 * batch * m + 4, device)   # + the hand-over's `stale` word
         order = keep = counts = None
         if details:
@@ -304,7 +308,8 @@ class _DecoderBase:
                                                  order.data_ptr() if details else None,
                                                  keep.data_ptr() if details else None,
                                                  counts.data_ptr() if details else None,
-                                                 out.data_ptr() + 24 * batch * m, st),
+                                                 out.data_ptr() + 24 * batch * m,
+                                                 0 if glue else 1, st),
                     'b200det_decode_from_keys')
             else:
                 _lib.check(

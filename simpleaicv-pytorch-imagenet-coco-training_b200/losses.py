@@ -297,7 +297,7 @@ def _loss_params(owner, reg_dtype):
     return p
 
 
-def _handoff_for(owner, cls_in, ctr_in, device, st):
+def _handoff_for(owner, cls_in, reg_in, ctr_in, device, st):
     """The decoder that asked for its keys (b200det._handoff): (decoder, keys pointer, classes
     pointer, its score threshold, the tensors the keys will be derived from), or None."""
     shapes = tuple([t.shape for t in cls_in])
@@ -307,7 +307,7 @@ def _handoff_for(owner, cls_in, ctr_in, device, st):
     target = dec._handoff_target(shapes, device, st)
     if target is None:
         return None
-    tensors = list(cls_in) + (list(ctr_in) if ctr_in is not None else [])
+    tensors = list(cls_in) + (list(ctr_in) if ctr_in is not None else []) + list(reg_in)
     return dec, target[0], target[1], float(dec._params.min_score), tensors
 
 
@@ -339,7 +339,7 @@ def _forward_eval_fast(fast, owner, annotations, cls_in, reg_in, ctr_in):
         and torch.distributed.is_initialized()
     p2p = sync and owner.sync_normalizer == 'p2p'
     px = ctypes.addressof(_peer_exchange(owner, device).params) if p2p else 0
-    hand = _handoff_for(owner, cls_in, ctr_in, device, st) if _handoff.ENABLED else None
+    hand = _handoff_for(owner, cls_in, reg_in, ctr_in, device, st) if _handoff.ENABLED else None
     params = (int(owner._is_fcos), owner._box_code, int(getattr(owner, 'use_center_sample', 0)),
               float(owner.alpha), float(owner.gamma), float(owner.beta), float(owner.cls_loss_weight),
               float(owner.box_loss_weight), float(getattr(owner, 'center_ness_loss_weight', 0.)),
@@ -406,7 +406,7 @@ def _forward_eval_on(owner, annotations, cls_in, reg_in, ctr_in):
     # a decoder waiting for keys of these head outputs: the sweep does its work as well (_handoff.py)
     hand = None
     if _handoff.ENABLED and not torch.cuda.is_current_stream_capturing():
-        hand = _handoff_for(owner, cls_in, ctr_in, device, st)
+        hand = _handoff_for(owner, cls_in, reg_in, ctr_in, device, st)
     ctr = None
     if hand:
         ctr = _prep_f32(ctr_in, 'center_preds') if ctr_in is not None else None
