@@ -12,13 +12,15 @@ $CMD > $OUT/${TAG}_plain.json 2> $OUT/${TAG}_plain.err || { echo "plain run fail
 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 $CMD > /dev/null 2>&1 || exit 1
-# skip the 3 warm-up + first timed step (6 matching kernels per step), then take one step
+# bench.py first times the loop with the hand-over off (6 kernels per step: 6 x 6 = 36 launches),
+# then with it on (5 per step).  Skip into the last separate-sweeps step and take it plus one hand-over step.
 ncu --set full --clock-control none --import-source on \
-    -k regex:"focal_all_kernel|retina_assign_kernel|sparse_loss_kernel|score_argmax_kernel|select_nms_kernel|loss_reduce_kernel" \
-    -s 24 -c 6 -o $OUT/${TAG}_full $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+    -k regex:"fused_rows|focal_all_kernel|retina_assign|sparse_loss_kernel|score_argmax_kernel|select_nms_kernel|loss_reduce" \
+    -s ${SKIP:-30} -c ${COUNT:-11} -o $OUT/${TAG}_full $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 tail -2 $OUT/${TAG}_ncu_full.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,clocks_event_reasons.active --format=csv > $OUT/${TAG}_smi.csv
 
+[ -n "${SKIP_SELECT:-}" ] && exit 0
 # 4) the select kernel at batch 1 (BASELINE configs[0], latency-bound): launch list of one decoder
 #    call and a full capture of the cluster kernel
 cat > /tmp/dec1.py <<'PY'

@@ -21,11 +21,14 @@ NAMES = {
     'focal_all_kernel': 'focal_loss',
     'focal_kernel': 'focal_loss_labelled',
     'retina_assign_kernel': 'retina_assign',
+    'retina_assign_tile_kernel': 'retina_assign',
+    'fused_rows': 'fused_sweep',
     'fcos_assign_kernel': 'fcos_assign',
     'sparse_loss_kernel': 'sparse_losses',
     'score_argmax_kernel': 'score_argmax',
     'select_nms_kernel': 'select_decode_nms',
     'loss_reduce_kernel': 'loss_reduce',
+    'loss_reduce_exchange_kernel': 'loss_reduce',
     'loss_finish_kernel': 'loss_finish',
 }
 

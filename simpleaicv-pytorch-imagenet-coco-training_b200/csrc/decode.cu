@@ -550,8 +550,15 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
                  : "memory");
     return v;
 }
+// B200DET_FUSED_MAXNREG: cap the registers instead of asking for MINB resident CTAs (experiment: 3 CTAs
+// of 72 registers leave room for one 40-register assignment CTA beside them)
+#ifdef B200DET_FUSED_MAXNREG
+#define B200DET_FUSED_BOUNDS __maxnreg__(B200DET_FUSED_MAXNREG)
+#else
+#define B200DET_FUSED_BOUNDS __launch_bounds__(kArgThreads, MINB)
+#endif
 template <int K, int TS, bool GAMMA2, int MINB>
-__global__ void __launch_bounds__(kArgThreads, MINB)
+__global__ void B200DET_FUSED_BOUNDS
     fused_rows_tma_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
     constexpr int T = 1 << TS;
     constexpr int U = K * T;                          // 128-bit units per row

@@ -17,30 +17,45 @@ def load(path):
 
 
 def kernel_table(d):
+    """Two blocks: the step as the library runs it (sweep hand-over: ONE read of cls per step) and the
+    same loop with the hand-over off (`separate_sweeps`: every call sweeps for itself)."""
     B = d['config']['images_per_gpu']
     n, c = d['config']['rows_per_image'], 80
     sweep = B * 4 * n * c
-    alg = {'focal_loss': sweep, 'score_argmax': sweep}
     peak = d['roofline']['peak']
-    rows = ['| Kernel (1 launch / step) | Bound | Alg. bytes / launch | Time (CUDA events in the timed region) | Achieved |',
-            '|---|---|---|---|---|']
-    names = {'focal_loss': '`focal_all_kernel<4,γ=2>` (beside it on the helper stream: assignment + sparse losses)',
-             'assign': '`retina_assign_kernel<9>` (helper stream, overlapped)',
-             'sparse_losses': '`sparse_loss_kernel` (helper stream, overlapped)',
-             'loss_reduce': '`loss_reduce` (+ finish / peer exchange)',
-             'score_argmax': '`score_argmax_kernel<4>`',
-             'select_decode_nms': '`select_nms_kernel` (cluster per image)'}
     bound = {'focal_loss': 'HBM', 'score_argmax': 'HBM', 'assign': 'ALU (issue)', 'sparse_losses': 'latency / issue',
              'loss_reduce': '—', 'select_decode_nms': 'latency (L2-resident keys)'}
-    for k, ms in d['kernels_ms'].items():
-        a = alg.get(k)
-        ach = f'{a / (ms / 1e3) / 1e12:.2f} TB/s = **{a / (ms / 1e3) / 1e9 / peak:.2f} × measured peak**' if a else '—'
-        rows.append(f'| {names.get(k, k)} | {bound.get(k, "—")} | {a / 1e9:.3f} GB |' if a else
-                    f'| {names.get(k, k)} | {bound.get(k, "—")} | — |')
-        rows[-1] += f' {ms:.4f} ms | {ach} |'
-    step_b = B * d['config']['algorithmic_bytes_per_image']
-    rows.append(f'| **step** (criterion + decoder, 2 calls) | HBM | {step_b / 1e9:.2f} GB | **{d["ms_per_step"]:.3f} ms** | '
-                f'**{d["step_roofline"]["algorithmic_GBps"] / 1e3:.2f} TB/s = {d["step_roofline"]["frac_of_hbm_peak"]:.3f} × measured peak** |')
+    head = ['| Kernel (1 launch / step) | Bound | Alg. bytes / launch | Time (CUDA events in the timed region) | Achieved |',
+            '|---|---|---|---|---|']
+
+    def block(kernels, handed, ms_step, step_bytes, label):
+        names = {'focal_loss': '`focal_all_kernel<4,γ=2>` (beside it on the helper stream: assignment + sparse losses)',
+                 'assign': '`retina_assign_tile_kernel` (helper stream, inside the sweep\'s window)',
+                 'sparse_losses': '`sparse_loss_kernel` (helper stream, inside the sweep\'s window)',
+                 'loss_reduce': '`loss_reduce` (+ finish / peer exchange)',
+                 'score_argmax': '`fused_rows_tma_kernel` (focal sum + decoder keys from ONE read of cls; beside it '
+                                 'on the helper stream: assignment + sparse losses)' if handed else '`score_argmax_kernel<4>`',
+                 'select_decode_nms': '`select_nms_kernel` (cluster per image)'}
+        rows = []
+        for k, ms in kernels.items():
+            a = sweep if k in ('focal_loss', 'score_argmax') else None
+            ach = f'{a / (ms / 1e3) / 1e12:.2f} TB/s = **{a / (ms / 1e3) / 1e9 / peak:.2f} × measured peak**' if a else '—'
+            rows.append((f'| {names.get(k, k)} | {bound.get(k, "—")} | {a / 1e9:.3f} GB |' if a else
+                         f'| {names.get(k, k)} | {bound.get(k, "—")} | — |') + f' {ms:.4f} ms | {ach} |')
+        gbs = step_bytes / (ms_step / 1e3) / 1e9
+        rows.append(f'| **step: {label}** | HBM | {step_bytes / 1e9:.2f} GB | **{ms_step:.3f} ms** | '
+                    f'**{gbs / 1e3:.2f} TB/s = {gbs / peak:.3f} × measured peak** |')
+        return rows
+
+    full = B * d['config']['algorithmic_bytes_per_image']
+    handed = 'focal_loss' not in d['kernels_ms']
+    rows = list(head)
+    rows += block(d['kernels_ms'], handed, d['ms_per_step'], full - sweep if handed else full,
+                  'criterion + decoder, 2 calls, cls read once (hand-over)' if handed else 'criterion + decoder, 2 calls')
+    sep = d.get('separate_sweeps')
+    if handed and sep:
+        rows.append('| *the same loop with `B200DET_HANDOFF=0` (every call sweeps for itself):* | | | | |')
+        rows += block(sep['kernels_ms'], False, sep['ms_per_step'], full, 'criterion + decoder, 2 calls, cls read twice')
     return '\n'.join(rows)
 
 
