@@ -34,7 +34,10 @@ namespace b200det {
 constexpr int kAssignThreads = 128;
 constexpr int kAssignWarps = kAssignThreads / 32;
 constexpr int kTileW = 8, kTileH = 4;   // locations per warp: 8 wide x 4 high
-constexpr int kSparseThreads = 256;
+#ifndef B200DET_SPARSE_THREADS
+#define B200DET_SPARSE_THREADS 256
+#endif
+constexpr int kSparseThreads = B200DET_SPARSE_THREADS;
 
 // Shared-memory carve-up (dynamic): raw rows, then the compacted candidate arrays.
 struct GtSmem {
@@ -438,7 +441,15 @@ __global__ void __launch_bounds__(kAssignThreads)
 // the same float32 op sequence as in scan_candidates; the candidate ranges are conservative supersets
 // (0.5 % slack on the floor, one location of slack per side), so labels are bit-identical.
 // ---------------------------------------------------------------------------------------
-constexpr int kTileThreads = 256;
+#ifndef B200DET_TILE_THREADS
+#define B200DET_TILE_THREADS 256
+#endif
+#ifdef B200DET_TILE_MINB   // resident CTAs per SM to compile for (register cap); default: no cap
+#define B200DET_TILE_BOUNDS __launch_bounds__(B200DET_TILE_THREADS, B200DET_TILE_MINB)
+#else
+#define B200DET_TILE_BOUNDS __launch_bounds__(B200DET_TILE_THREADS)
+#endif
+constexpr int kTileThreads = B200DET_TILE_THREADS;
 constexpr int kTileWarps = kTileThreads / 32;
 #ifndef B200DET_TILE_SIDE
 #define B200DET_TILE_SIDE 32
@@ -460,7 +471,7 @@ __device__ __forceinline__ float shift_f32(int i, float stride) {
     return __fmul_rn(__fadd_rn(__int2float_rn(i), 0.5f), stride);
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void B200DET_TILE_BOUNDS
     retina_assign_tile_kernel(Geo g, BaseAnchors ba, BigTiles bt, IouThresholds thr,
                               const float *__restrict__ annots, int G, int *__restrict__ labels,
                               Queues q, int *__restrict__ npos_partials, int blocks_per_image) {
@@ -868,7 +879,7 @@ __device__ __forceinline__ int split_row(const Geo &g, int i, long long &rrow) {
 }
 
 #ifndef B200DET_SPARSE_MINB
-#define B200DET_SPARSE_MINB 4
+#define B200DET_SPARSE_MINB (1024 / B200DET_SPARSE_THREADS)   // 64 registers
 #endif
 __global__ void __launch_bounds__(kSparseThreads, B200DET_SPARSE_MINB)
     sparse_loss_kernel(SparseArgs a, const float *__restrict__ annots,
@@ -1180,7 +1191,7 @@ int assign_blocks_per_image(const Geo &g) {
 int sparse_blocks(const Geo &g) {
     const long long total = (long long)g.batch * g.off[g.n_levels];
     const long long want = (total + kSparseThreads - 1) / kSparseThreads;
-    const long long cap = 148 * 8;
+    const long long cap = 148 * 8 * (256 / kSparseThreads);   // 2048 threads per SM's worth
     return (int)(want < cap ? want : cap);
 }
 
