@@ -845,17 +845,32 @@ def time_config(name, kind, size, C, B, G, reps, box='GIoU', sigma=1.0, stages=(
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
+    def eval_step():
+        # the reference's evaluation step: both calls on the same head outputs (tools/scripts.py:733-740);
+        # from the second iteration on the criterion's sweep hands the decoder its keys (_handoff.py)
+        with torch.no_grad():
+            d = crit(preds, ann)
+        return d, dec(preds)
+
     pk = hbm_peak()[0]
     out = {'name': name, 'batch': B, 'rows_per_image': N, 'classes': C, 'max_gt': G}
+    # stages are timed one after the other; the separate loss / decode stages come first, so no
+    # decoder has asked for a hand-over yet when the criterion-only loop runs (it sweeps focal-only)
     for key, fn, nbytes in (('loss_fwd', fwd, loss_b), ('loss_fwd_bwd', fwd_bwd, loss_b + bwd_b),
-                            ('decode_nms', dec_fn, dec_b)):
-        if key not in stages:
+                            ('decode_nms', dec_fn, dec_b),
+                            ('eval_step', eval_step, loss_b + dec_b - 4 * N * C)):
+        if key not in stages and not (key == 'eval_step' and 'loss_fwd' in stages and 'decode_nms' in stages):
             continue
         if key == 'loss_fwd_bwd':
             req = [[t.detach().requires_grad_(True) for t in grp] for grp in preds]
         ms = timed(fn)
         out[key] = {'ms': round(ms, 4), 'images_per_s': round(B / ms * 1e3, 1),
                     'frac_of_hbm_peak': round(B * nbytes / (ms * 1e-3) / 1e9 / pk, 4)}
+        if key == 'eval_step':
+            out[key]['note'] = ('criterion(preds, annots) + decoder(preds), cls streamed once (sweep hand-over); '
+                                'fraction = bytes moved (loss_fwd + decode - 4NC) / time / HBM peak')
+    from b200det import _handoff
+    _handoff.reset()
     del preds, req
     torch.cuda.empty_cache()
     if cpu is not None:

@@ -428,7 +428,8 @@ int b200det_decode_from_keys(const b200det_geometry *geo, const b200det_decode_p
  * OPTIONAL extension (not in the reference's call structure): loss forward + decode of one
  * evaluation step with a SINGLE sweep over the classification tensors -- the score / arg-max
  * sweep also accumulates the label-free focal sum.  Same results as b200det_loss_forward followed
- * by b200det_decode; requires num_classes % 4 == 0.  Pass losses = NULL to all-reduce `sums`.
+ * by b200det_decode (any class count: multiples of 4 take the TMA-fed row-group sweep, others the raw-tile
+ * sweep).  Pass losses = NULL to all-reduce `sums`.
  */
 int b200det_eval_step(const b200det_geometry *geo, const b200det_loss_params *loss_params,
                       const b200det_decode_params *decode_params, const float *annotations,
@@ -621,7 +622,7 @@ int b200det_loss_forward_overlap(const b200det_geometry *geo, const b200det_loss
  * classification tensors -- 98 % of the step's HBM traffic -- are read once per step while the caller
  * keeps the reference's two calls.  The host layer (b200det._handoff) decides when that is safe.
  * Same arguments as b200det_loss_forward_overlap plus min_score / keys / classes as
- * b200det_score_argmax.  num_classes % 4 == 0; FCOS needs `ctr` in phase 1 too.
+ * b200det_score_argmax.  FCOS needs `ctr` in phase 1 too.
  */
 int b200det_loss_forward_keys(const b200det_geometry *geo, const b200det_loss_params *params,
                               const float *annotations, int max_gt, const void *const *cls,

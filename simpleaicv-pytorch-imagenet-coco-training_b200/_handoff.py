@@ -16,7 +16,7 @@ How it is kept safe (all host-side logic lives here; no numerics):
 
   * A decoder call that could not use a hand-over leaves a WISH for its (device, stream): "the next
     no-grad criterion call on head outputs of these shapes may produce my keys" (same detector
-    family, num_classes % 4 == 0, the decoder's scratch for that stream exists).
+    family, the decoder's scratch for that stream exists).
   * A no-grad criterion call that finds a matching wish runs b200det_loss_forward_keys, writing keys /
     classes (thresholded with the decoder's min_score_threshold) into the decoder's own scratch, and
     records READY = (the very tensor objects it read, their autograd version counters, the
@@ -64,7 +64,7 @@ def _key(device, stream):
 
 def wish(decoder, device, stream, shapes, num_classes):
     """Called by a decoder that had to sweep itself."""
-    if not ENABLED or num_classes % 4:
+    if not ENABLED:
         return
     key = _key(device, stream)
     old = _wishes.get(key)

@@ -158,7 +158,6 @@ static int eval_step_impl(const b200det_geometry *geo, const b200det_loss_params
     if (!lp || !dp || !annotations || !cls || !labels || !loss_workspace || !sums || !keys ||
         !classes || !out)
         return B200DET_EINVAL;
-    if (g.num_classes % 4) return B200DET_EINVAL;
     const LossWs ws = loss_ws_layout(g);
     if (loss_workspace_bytes < ws.total) return B200DET_EWORKSPACE;
     const bool fork = side && ev_fork && ev_join;

@@ -636,10 +636,73 @@ __global__ void B200DET_FUSED_BOUNDS
     sweep_accumulate_warp((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
 }
 
-// Variant for class counts that are not a multiple of 4 (e.g. Objects365's 365): rows are not
+// Variants for class counts that are not a multiple of 4 (e.g. Objects365's 365): rows are not
 // 16-byte aligned, but a tile of R rows with R % 4 == 0 is, so the tile is still read as one flat
-// stream of 128-bit loads, parked RAW in shared memory, and each row is scanned from there by
-// t2 lanes (consecutive lanes read consecutive floats: conflict-free).
+// stream, parked RAW in shared memory, and each row is scanned from there by t2 lanes (consecutive
+// lanes read consecutive floats: conflict-free).
+//
+// raw_scan_row: one lane's share of one row.  Strict '>' in class order: first maximum (np.argmax).
+// Four independent loads per iteration off a walking pointer: ~5 instructions per element (the plain
+// `for c: row[c]` loop was 20 and made the kernel issue-bound at 0.78 of the HBM peak,
+// profiles/r01_cfg4_sweeps.txt).  FOCAL: the same values also feed the label-free focal sum
+// (focal.cu: focal_all_kernel) -- the focal term does not care which row an element belongs to.
+template <bool FOCAL, bool GAMMA2, bool FULL>
+__device__ __forceinline__ void raw_scan_group(const float *__restrict__ p, int c, int T, int C, float gamma,
+                                               float &best, int &best_c, float &any, float &acc,
+                                               float2 &acc2) {
+    // (a lane's last group may hold 1-3 elements: the missing ones read as -inf for the scan and
+    // contribute exactly 0 to the focal sum)
+    const float ninf = -__int_as_float(0x7f800000);
+    const bool h1 = FULL || c + T < C, h2 = FULL || c + 2 * T < C, h3 = FULL || c + 3 * T < C;
+    const float x0 = p[0], x1 = h1 ? p[T] : ninf, x2 = h2 ? p[2 * T] : ninf, x3 = h3 ? p[3 * T] : ninf;
+    if (x0 > best) best = x0, best_c = c;
+    if (x1 > best) best = x1, best_c = c + T;
+    if (x2 > best) best = x2, best_c = c + 2 * T;
+    if (x3 > best) best = x3, best_c = c + 3 * T;
+    const float m4 = fmax_nan(fmax_nan(x0, x1), fmax_nan(x2, x3));   // NaN if any of them is
+    any = fmax_nan(any, m4);
+    if (FOCAL) {
+        // losses.py:196 lower clamp; the upper one cannot bind on the fast path
+        if (GAMMA2 && fmax_nan(m4, kClampLo) <= kFastMax) {
+            // x = 0 gives xr = 1 - (1 - 0) = 0 and a term of exactly 0: the padding value
+            float2 xr, xs;
+            acc2 = neg_term_fast2_acc(make_float2(fmax_nan(x0, kClampLo), h1 ? fmax_nan(x1, kClampLo) : 0.f),
+                                      acc2, xr, xs);
+            acc2 = neg_term_fast2_acc(make_float2(h2 ? fmax_nan(x2, kClampLo) : 0.f,
+                                                  h3 ? fmax_nan(x3, kClampLo) : 0.f), acc2, xr, xs);
+        } else if (h3) {
+            acc += neg_unit_exact(make_float4(x0, x1, x2, x3), gamma, GAMMA2);
+        } else {
+            acc += neg_term(x0, gamma, GAMMA2);
+            if (h1) acc += neg_term(x1, gamma, GAMMA2);
+            if (h2) acc += neg_term(x2, gamma, GAMMA2);
+        }
+    }
+}
+template <bool FOCAL, bool GAMMA2, int TT /* lanes per row when known at compile time, else 0 */>
+__device__ __forceinline__ void raw_scan_row(const float *__restrict__ p, int j, int t2, int C, float gamma,
+                                             float &best, int &best_c, float &any, float &acc,
+                                             float2 &acc2) {
+    const int T = TT ? TT : t2;   // compile-time T: the four loads become immediate offsets
+    int c = j;
+    for (; c + 3 * T < C; c += 4 * T, p += 4 * T)
+        raw_scan_group<FOCAL, GAMMA2, true>(p, c, T, C, gamma, best, best_c, any, acc, acc2);
+    if (c < C) raw_scan_group<FOCAL, GAMMA2, false>(p, c, T, C, gamma, best, best_c, any, acc, acc2);
+}
+// joins the t2 lanes of a row: first maximum, NaN tracker
+__device__ __forceinline__ void raw_join_row(int t2, float &best, int &best_c, float &any) {
+    for (int o = t2 >> 1; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        any = fmax_nan(any, __shfl_xor_sync(0xffffffffu, any, o));
+        if (ov > best || (ov == best && oc < best_c)) {
+            best = ov;
+            best_c = oc;
+        }
+    }
+    if (any != any) best = any;   // np.argmax stops at the first NaN: the row's score is NaN
+}
+
 __global__ void __launch_bounds__(kArgThreads)
     score_argmax_raw_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes) {
     extern __shared__ __align__(16) unsigned char arg_smem[];
@@ -692,43 +755,18 @@ __global__ void __launch_bounds__(kArgThreads)
     }
 
     const int j = threadIdx.x & (a.t2 - 1);
+    float acc = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
     for (int r = threadIdx.x >> a.t2_shift; r < a.rows_per_block; r += kArgThreads >> a.t2_shift) {
         const bool live = r < n_rows;
         float best = -__int_as_float(0x7f800000);
         int best_c = 0x7fffffff;
         float any = 0.f;   // NaN iff a class score of the row is NaN
         if (live) {
-            // strict '>' in class order: first maximum (np.argmax).  Four independent loads per
-            // iteration off a walking pointer: ~5 instructions per element (the plain
-            // `for c: row[c]` loop was 20 and made this kernel issue-bound at 0.78 of the HBM peak,
-            // profiles/r01_cfg4_sweeps.txt).
-            const int T = a.t2, C = a.C;
-            const float *p = tile + r * C + j;
-            int c = j;
-            for (; c + 3 * T < C; c += 4 * T, p += 4 * T) {
-                const float x0 = p[0], x1 = p[T], x2 = p[2 * T], x3 = p[3 * T];
-                if (x0 > best) best = x0, best_c = c;
-                if (x1 > best) best = x1, best_c = c + T;
-                if (x2 > best) best = x2, best_c = c + 2 * T;
-                if (x3 > best) best = x3, best_c = c + 3 * T;
-                any = fmax_nan(fmax_nan(any, fmax_nan(x0, x1)), fmax_nan(x2, x3));
-            }
-            for (; c < C; c += T, p += T) {
-                const float x = *p;
-                if (x > best) best = x, best_c = c;
-                any = fmax_nan(any, x);
-            }
+            if (a.t2 == 16) raw_scan_row<false, false, 16>(tile + r * a.C + j, j, 16, a.C, 0.f, best, best_c, any, acc, acc2);
+            else raw_scan_row<false, false, 0>(tile + r * a.C + j, j, a.t2, a.C, 0.f, best, best_c, any, acc, acc2);
         }
-        for (int o = a.t2 >> 1; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-            any = fmax_nan(any, __shfl_xor_sync(0xffffffffu, any, o));
-            if (ov > best || (ov == best && oc < best_c)) {
-                best = ov;
-                best_c = oc;
-            }
-        }
-        if (any != any) best = any;   // np.argmax stops at the first NaN: the row's score is NaN
+        raw_join_row(a.t2, best, best_c, any);
         if (live && j == 0) {
             const long long row_g = row0 + r;
             float score = best;
@@ -738,6 +776,104 @@ __global__ void __launch_bounds__(kArgThreads)
             classes[lm] = best_c;
         }
     }
+}
+
+// The FUSED sweep for these class counts (focal sum + decoder keys from one read of cls: the sweep
+// hand-over, b200det/_handoff.py, covers Objects365 too -- BASELINE configs[3]).  With the focal
+// terms a tile costs ~2.5 x the ALU time of the scan alone, and with one tile per CTA (load, wait,
+// compute) the loads of a CTA are idle while it computes: the first version ran at 0.55 of the HBM peak
+// (0.284 ms for 1.02 GB at configs[3]; tools/r02c_run6.sh).  So a CTA walks kRawTiles consecutive
+// tiles through a two-stage ring: the bulk copy of tile i + 1 is in flight while tile i is computed.
+// Every tile is one pass (rows_per_block <= kArgThreads / t2 by construction).
+constexpr int kRawTiles = 8;
+template <bool GAMMA2, int TT /* lanes per row when known at compile time (16), else 0 */>
+__global__ void __launch_bounds__(kArgThreads)
+    fused_raw_ring_kernel(ArgmaxArgs a, uint32_t *__restrict__ keys, int *__restrict__ classes, int stage_floats) {
+    extern __shared__ __align__(16) unsigned char arg_smem[];
+    float *ring = reinterpret_cast<float *>(arg_smem);   // 2 stages of stage_floats (16-byte multiples)
+    __shared__ __align__(8) uint64_t bars[2];
+    pdl_launch_dependents();
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < a.n_levels && (int)blockIdx.x >= a.block_off[i]) l = i;
+    const int R = a.rows_per_block, C = a.C;
+    const int t2 = TT ? TT : a.t2, t2_shift = TT ? 4 : a.t2_shift;
+    static_assert(TT == 0 || TT == 16, "compile-time lane count: 16");
+    const long long row_first = (long long)(blockIdx.x - a.block_off[l]) * (R * kRawTiles);
+    const long long left = a.rows[l] - row_first;
+    const int rows_cta = left < (long long)(R * kRawTiles) ? (int)left : R * kRawTiles;   // 32-bit from here on
+    const int n_tiles = (rows_cta + R - 1) / R;
+    const int tile_floats = R * C;
+    const float *__restrict__ src0 = static_cast<const float *>(a.cls.p[l]) + row_first * C;   // 16-byte aligned
+    const float *__restrict__ ctr0 = static_cast<const float *>(a.ctr.p[l]) + row_first;
+    uint32_t *__restrict__ kout = keys + a.row_base[l] + row_first;
+    int *__restrict__ cout = classes + a.row_base[l] + row_first;
+    const bool has_ctr = a.has_ctr;
+    const float min_score = a.min_score, gamma = a.gamma;
+    const int tid = threadIdx.x;
+    const int j = tid & (t2 - 1), r = tid >> t2_shift;
+    const uint32_t ring_u32 = smem_u32(ring), bar_u32 = smem_u32(&bars[0]);
+
+    // thread 0: bulk copy of tile `it` (n_rows rows) into its stage, if it holds a multiple of 4 floats
+    auto issue = [&](int it, int n_rows) {
+        const int n_floats = n_rows * C;
+        if ((n_floats & 3) == 0) {
+            const uint32_t bar = bar_u32 + (it & 1) * 8, bytes = (uint32_t)n_floats * 4u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage's last readers -> async writes
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(ring_u32 + (uint32_t)((it & 1) * stage_floats) * 4u),
+                "l"(src0 + (size_t)it * tile_floats), "r"(bytes), "r"(bar)
+                : "memory");
+        }
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u32));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u32 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0, min(R, rows_cta));
+    }
+    // FCOS centre-ness: lane 0 of a row keeps its row's value, fetched one tile ahead
+    float ctr_cur = 1.f, ctr_next = 1.f;
+    if (has_ctr && j == 0 && r < rows_cta) ctr_cur = __ldg(ctr0 + r);
+    __syncthreads();   // barriers initialised before anybody waits on them
+
+    float acc = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
+    int rows_after = rows_cta;   // rows of this and the following tiles
+    for (int it = 0; it < n_tiles; ++it, rows_after -= R) {
+        const int n_rows = min(R, rows_after), n_floats = n_rows * C;
+        float *tile = ring + (it & 1) * stage_floats;
+        if (rows_after > R) {   // there is a next tile
+            if (tid == 0) issue(it + 1, min(R, rows_after - R));   // its stage was released by the barrier that ended tile it - 1
+            if (has_ctr && j == 0 && r < rows_after - R) ctr_next = __ldg(ctr0 + (it + 1) * R + r);
+        }
+        if ((n_floats & 3) == 0) {
+            mbar_wait(bar_u32 + (it & 1) * 8, (uint32_t)(it >> 1) & 1u);
+        } else {
+            // a level's last tile when it does not hold a multiple of 4 floats
+            const float *src = src0 + (size_t)it * tile_floats;
+            for (int i = tid; i < n_floats; i += kArgThreads) tile[i] = __ldcs(src + i);
+            __syncthreads();
+        }
+        const bool live = r < n_rows;
+        float best = -__int_as_float(0x7f800000);
+        int best_c = 0x7fffffff;
+        float any = 0.f;
+        if (live) raw_scan_row<true, GAMMA2, TT>(tile + r * C + j, j, t2, C, gamma, best, best_c, any, acc, acc2);
+        raw_join_row(t2, best, best_c, any);
+        if (live && j == 0) {
+            float score = best;
+            if (has_ctr) score = __fsqrt_rn(__fmul_rn(best, ctr_cur));
+            kout[it * R + r] = (score > min_score) ? flip_key(score) : 0u;
+            cout[it * R + r] = best_c;
+        }
+        ctr_cur = ctr_next;
+        __syncthreads();   // every lane has read the stage: it may be refilled (tile it + 2)
+    }
+    sweep_accumulate_warp((1.f - a.alpha) * (acc + (acc2.x + acc2.y)), a.focal_slots);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1581,7 +1717,6 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
     a.alpha = alpha;
     a.gamma = gamma;
     a.focal_slots = focal_slots;
-    if (focal_slots && vec != 4) return B200DET_EINVAL;   // fused sweep: C % 4 == 0 only
     const int units = g.num_classes / vec;
     a.units_per_row = units;
     const int budget = kArgThreads * kArgLoadsVec;   // 128-bit loads per CTA, all in flight
@@ -1669,7 +1804,8 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
         a.row_base[l] = (long long)g.batch * g.off[l];
         a.rows[l] = (long long)g.batch * g.rows[l];
         a.block_off[l] = blocks;
-        blocks += (int)((a.rows[l] + R - 1) / R);
+        const long long rows_per_cta = (long long)R * ((focal_slots && vec != 4) ? kRawTiles : 1);
+        blocks += (int)((a.rows[l] + rows_per_cta - 1) / rows_per_cta);
     }
     for (int l = g.n_levels; l <= kMaxLevels; ++l) a.block_off[l] = blocks;
     const size_t smem = vec == 4 ? (size_t)R * a.pitch * 8 : (size_t)R * a.C * 4 + 16;
@@ -1718,7 +1854,26 @@ int b200det::score_argmax_impl(const b200det_geometry *geo, const void *const *c
         score_argmax_kernel<4, true><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     else if (vec == 4)
         score_argmax_kernel<4, false><<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
-    else
+    else if (focal_slots) {
+        // fused sweep for C % 4 != 0: two-stage ring of raw tiles, kRawTiles tiles per CTA
+        const int stage_floats = (R * a.C + 3) & ~3;
+        const size_t ring_smem = (size_t)2 * stage_floats * 4;
+        static std::atomic<unsigned long long> ring_set{0};   // per device: opt in to > 48 KB
+        int dev = 0;
+        if (ring_smem > 48 * 1024 && cudaGetDevice(&dev) == cudaSuccess && dev < 64 &&
+            !((ring_set.load(std::memory_order_relaxed) >> dev) & 1ull)) {
+            cudaFuncSetAttribute(fused_raw_ring_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaFuncSetAttribute(fused_raw_ring_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaFuncSetAttribute(fused_raw_ring_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaFuncSetAttribute(fused_raw_ring_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ring_set.fetch_or(1ull << dev, std::memory_order_relaxed);
+        }
+        const bool g2 = gamma == 2.f;
+        void (*kern)(ArgmaxArgs, uint32_t *, int *, int) =
+            a.t2 == 16 ? (g2 ? fused_raw_ring_kernel<true, 16> : fused_raw_ring_kernel<false, 16>)
+                       : (g2 ? fused_raw_ring_kernel<true, 0> : fused_raw_ring_kernel<false, 0>);
+        kern<<<blocks, kArgThreads, ring_smem, (cudaStream_t)stream>>>(a, keys, classes, stage_floats);
+    } else
         score_argmax_raw_kernel<<<blocks, kArgThreads, smem, (cudaStream_t)stream>>>(a, keys, classes);
     count_launch();
     return (int)cudaGetLastError();

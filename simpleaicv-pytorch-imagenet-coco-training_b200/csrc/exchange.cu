@@ -350,7 +350,7 @@ int loss_forward_impl(const b200det_geometry *geo, const b200det_loss_params *p,
         g_skip_memset = true;
         // the long HBM-bound sweep first: the host prepares the remaining launches behind it
         if (keys) {
-            if (!classes || g.num_classes % 4 || (p->is_fcos && !ctr)) rc = B200DET_EINVAL;
+            if (!classes || (p->is_fcos && !ctr)) rc = B200DET_EINVAL;
             else
                 rc = score_argmax_impl(geo, cls, p->is_fcos ? ctr : nullptr, keys_min_score, keys, classes,
                                        p->alpha, p->gamma,
@@ -435,7 +435,7 @@ extern "C" int b200det_loss_forward_overlap(const b200det_geometry *geo,
 // sweep of b200det_eval_step (focal sum + first-maximum class / score key per row) instead of the
 // focal-only one.  A decoder call on the same head outputs then only needs b200det_select_decode_nms
 // on these keys -- cls is read once per evaluation step inside the reference's two-call structure
-// (tools/scripts.py:733-740).  num_classes % 4 == 0; FCOS: ctr is needed in phase 1 as well.
+// (tools/scripts.py:733-740).  FCOS: ctr is needed in phase 1 as well.
 extern "C" int b200det_loss_forward_keys(const b200det_geometry *geo, const b200det_loss_params *p,
                                          const float *annotations, int max_gt,
                                          const void *const *cls, const void *const *reg,

@@ -13,7 +13,7 @@ the focal sum, so cls is read once:
     loss_value, (scores, classes, boxes) = step(outs_tuple, annots)
 
 Results are the same as the two separate calls (loss within float rounding of the summation order,
-detections bit-identical).  Requires num_classes % 4 == 0 and no gradients (evaluation only).
+detections bit-identical).  No gradients (evaluation only).
 """
 import ctypes
 
@@ -50,9 +50,6 @@ class EvalStep:
         ctr = _prep_f32([t.detach() for t in preds[2]], 'center_preds') if is_fcos else None
         annotations = _prep_annotations(annotations)
         plan = _plan_for(crit, cls)
-        if int(cls[0].shape[-1]) % 4:
-            raise ValueError('EvalStep needs num_classes % 4 == 0; call criterion and decoder '
-                             'separately')
         device = cls[0].device
         batch, n_rows = plan.batch, plan.n_rows
         m = int(dec.max_object_num)

@@ -60,9 +60,11 @@ def _fcos(batch=3, size=256, seed=6, num_classes=80):
     return dev(preds), ann.cuda()
 
 
-@pytest.mark.parametrize('family', ['retina', 'fcos'])
+@pytest.mark.parametrize('family', ['retina', 'fcos', 'retina21', 'fcos365', 'fcos365_gamma'])
 @pytest.mark.parametrize('fast', [True, False])
 def test_two_calls_share_one_sweep(family, fast, monkeypatch):
+    """class counts that are a multiple of 4 take the TMA-fed row-group sweep, the others (21, and
+    Objects365's 365 = BASELINE configs[3]) the raw-tile fused sweep; gamma != 2 the exact-form terms"""
     if not fast:
         from b200det import _lib
         monkeypatch.setattr(_lib, '_FAST', False)
@@ -70,6 +72,14 @@ def test_two_calls_share_one_sweep(family, fast, monkeypatch):
         preds, ann = _retina()
         crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
         dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    elif family == 'retina21':
+        preds, ann = _retina(num_classes=21)
+        crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+        dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    elif family.startswith('fcos365'):
+        preds, ann = _fcos(batch=2, size=320, num_classes=365)
+        crit = losses.FCOSLoss(strides=synth.STRIDES, gamma=1.5 if family.endswith('gamma') else 2.)
+        dec = decode.FCOSDecoder(strides=synth.STRIDES)
     else:
         preds, ann = _fcos()
         crit = losses.FCOSLoss(strides=synth.STRIDES)
@@ -102,6 +112,24 @@ def test_handover_matches_the_oracle():
     want = O.retina_loss(preds_h, ann_h, **synth.RETINA_KW, box_loss_type='GIoU')
     _same_loss(loss, {k: float(want[k]) for k in ('cls_loss', 'reg_loss')})
     (ws, wc, wb), _ = O.retina_decode(preds_h, **synth.RETINA_KW)
+    _same_detections(det, (ws, wc, wb))
+
+
+def test_handover_matches_the_oracle_odd_class_count():
+    """C = 37 (not a multiple of 4): the raw-tile fused sweep, FCOS with centre-ness, against the oracle"""
+    preds_h = synth.make_tie_free(synth.make_fcos_preds(2, 192, 37, seed=21, sigma=1.5))
+    ann_h = synth.make_annotations(2, 12, 192, 37, seed=22)
+    preds, ann = dev(preds_h), ann_h.cuda()
+    crit = losses.FCOSLoss(strides=synth.STRIDES)
+    dec = decode.FCOSDecoder(strides=synth.STRIDES)
+    for _ in range(2):
+        with torch.no_grad():
+            loss = crit(preds, ann)
+            det = dec(preds)
+    assert _handoff.stats['consumed'] >= 1
+    want = O.fcos_loss(preds_h, ann_h, synth.STRIDES, synth.MI)
+    _same_loss(loss, {k: float(want[k]) for k in ('cls_loss', 'reg_loss', 'center_ness_loss')})
+    (ws, wc, wb), _ = O.fcos_decode(preds_h, synth.STRIDES)
     _same_detections(det, (ws, wc, wb))
 
 

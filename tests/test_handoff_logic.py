@@ -58,10 +58,12 @@ def test_wish_offer_produce_take_roundtrip():
     assert not _handoff.take(dec, DEV, ST, ts, 0.05)   # consumed: a second decoder call sweeps itself
 
 
-def test_class_counts_the_fused_sweep_cannot_take_never_wish():
+def test_every_class_count_may_wish():
+    """r02: class counts that are not a multiple of 4 (Objects365's 365) are covered by the raw-tile
+    fused sweep, so they hand over like the others"""
     dec, ts = _Dec(), _tensors()
     _handoff.wish(dec, DEV, ST, _shapes(ts), 365)
-    assert _handoff.offer(_Crit(), DEV, ST, _shapes(ts)) is None
+    assert _handoff.offer(_Crit(), DEV, ST, _shapes(ts)) is dec
 
 
 @pytest.mark.parametrize('what', ['version', 'object', 'threshold', 'decoder', 'count', 'stream'])

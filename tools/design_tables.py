@@ -60,7 +60,7 @@ def kernel_table(d):
 
 
 def configs_table(d):
-    rows = ['| Config | loss fwd | loss fwd+bwd | decode+NMS | reference on the host CPU (bounded sample) |', '|---|---|---|---|---|']
+    rows = ['| Config | loss fwd | loss fwd+bwd | decode+NMS | eval step: both calls, cls read once | reference on the host CPU (bounded sample) |', '|---|---|---|---|---|---|']
     for c in d.get('configs', []):
         def cell(k):
             if k not in c:
@@ -68,7 +68,7 @@ def configs_table(d):
             v = c[k]
             return f'{v["ms"]:.3f} ms = {v["frac_of_hbm_peak"]:.2f}' if v['frac_of_hbm_peak'] >= 0.3 else f'{v["ms"]:.3f} ms (latency-bound, {v["frac_of_hbm_peak"]:.2f})'
         cpu = c.get('cpu_baseline')
-        rows.append(f'| {c["name"]} | {cell("loss_fwd")} | {cell("loss_fwd_bwd")} | {cell("decode_nms")} | '
+        rows.append(f'| {c["name"]} | {cell("loss_fwd")} | {cell("loss_fwd_bwd")} | {cell("decode_nms")} | {cell("eval_step")} | '
                     + (f'{cpu["value"]:.1f} images/s ({cpu["sample"].split(", stages")[0]}, {cpu["cores"]} cores)' if cpu else '—') + ' |')
     return '\n'.join(rows)
 
