@@ -609,7 +609,7 @@ def run_b200(args, out):
         line['configs'] = run_configs(args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref = load_reference()
-        steps = args.cpu_steps or (12 if ref[0] == 'reference' else 40)
+        steps = args.cpu_steps or 40   # ~11 s of CPU work for the reference classes
         v, dt, threads = time_cpu(ref, 'retina', 2, steps, 1)
         line['cpu_baseline'] = {
             'value': v,

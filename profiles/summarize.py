@@ -98,14 +98,23 @@ if os.path.exists(lpath):
         t = float(r[vi].replace(',', '')) * scale.get(r[ui], 1e-6)
         agg.setdefault(short(r[ki]), []).append(t)
     ours = {k: v for k, v in agg.items() if k in NAMES.values()}
-    step = sum(sum(v) / len(v) for v in ours.values())
+    mean = {k: sum(v) / len(v) for k, v in ours.items()}
+    common = [k for k in ('retina_assign', 'fcos_assign', 'sparse_losses', 'loss_reduce', 'select_decode_nms') if k in mean]
+    steps = {'hand-over step (cls read once: the default)': ['fused_sweep'] + common,
+             'separate sweeps (B200DET_HANDOFF=0)': ['focal_loss', 'score_argmax'] + common}
     with open(os.path.join(ROOT, 'profiles', f'{tag}_launches.txt'), 'w') as f:
-        f.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none, bench.py --batch 256 --steps 3 '
-                f'--warmup 3 (cold-cache, serialised: compare SHARES)\n')
-        f.write(f'{"kernel":24s} {"launches":>8s} {"mean_us":>10s} {"share_of_step":>14s}\n')
-        for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1]) / len(kv[1])):
-            m = sum(v) / len(v)
-            f.write(f'{k:24s} {len(v):8d} {m * 1e6:10.1f} {100 * m / step:13.1f}%\n')
+        f.write('# ncu --metrics gpu__time_duration.sum --clock-control none, bench.py --batch 256 --steps 3 --warmup 3\n'
+                '# (the separate-sweeps loop, then the hand-over loop; per-launch times are cold-cache and serialised:\n'
+                '#  compare the SHARES with bench.py\'s kernels_ms, not the absolute times)\n')
+        for title, names in steps.items():
+            names = [k for k in names if k in mean]
+            if not names or (names[0] not in ('fused_sweep', 'focal_loss')):
+                continue
+            step = sum(mean[k] for k in names)
+            f.write(f'## {title}: {step * 1e6:.1f} us of kernels\n')
+            f.write(f'{"kernel":24s} {"launches":>8s} {"mean_us":>10s} {"share_of_step":>14s}\n')
+            for k in sorted(names, key=lambda k: -mean[k]):
+                f.write(f'{k:24s} {len(ours[k]):8d} {mean[k] * 1e6:10.1f} {100 * mean[k] / step:13.1f}%\n')
         other = {k: v for k, v in agg.items() if k not in NAMES.values()}
         f.write('# other kernels in the same process (input generation with torch, memsets):\n')
         for k, v in sorted(other.items(), key=lambda kv: -sum(kv[1]))[:8]:
