@@ -452,7 +452,9 @@ def run_b200(args, out):
             r = dec(preds)
         return d, r
 
-    profile_every = args.profile_every or (1 if B >= 128 else 4)
+    # per-kernel CUDA events on every 4th step of the timed region: bracketing every launch of every
+    # step costs ~0.02 ms per step (1.846 vs 1.829 ms at batch 256, tools/r02c_run9.sh)
+    profile_every = args.profile_every or 4
     # The two calls share one sweep over cls when the decoder is called on the tensors the criterion
     # just read (b200det/_handoff.py; the library's default).  First the same loop with the hand-over
     # switched off -- every call sweeps for itself, r01 / early-r02 behaviour -- as `separate_sweeps`.

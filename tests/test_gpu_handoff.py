@@ -133,6 +133,36 @@ def test_handover_matches_the_oracle_odd_class_count():
     _same_detections(det, (ws, wc, wb))
 
 
+@pytest.mark.parametrize('shape', ['configs3', 'configs4_shard'])
+def test_handover_equals_separate_calls_at_baseline_shapes(shape):
+    """Size-independent property at the BASELINE sizes (the oracle takes ~1 s per image there): the
+    two calls sharing one sweep give the detections of two independent calls bit for bit and the same
+    losses.  configs[3] = FCOS, Objects365 shape (365 classes: the ring-fed raw-tile sweep), 1024^2,
+    batch 32, <= 200 GT; configs[4] shard = RetinaNet 800^2, 80 classes, 32 images (one of 8 GPUs)."""
+    dev_ = torch.device('cuda')
+    if shape == 'configs3':
+        preds = synth.make_fcos_preds(32, 1024, 365, seed=31, device=dev_)
+        ann = synth.make_annotations(32, 200, 1024, 365, seed=32).to(dev_)
+        crit = losses.FCOSLoss(strides=synth.STRIDES, mi=synth.MI)
+        dec = decode.FCOSDecoder(strides=synth.STRIDES)
+    else:
+        preds = synth.make_retina_preds(32, 800, 80, seed=33, device=dev_)
+        ann = synth.make_annotations(32, 100, 800, 80, seed=34).to(dev_)
+        crit = losses.RetinaLoss(**synth.RETINA_KW, box_loss_type='GIoU')
+        dec = decode.RetinaDecoder(**synth.RETINA_KW)
+    want_loss, want_det = _separate(crit, dec, preds, ann)
+    before = dict(_handoff.stats)
+    for _ in range(3):
+        with torch.no_grad():
+            loss = crit(preds, ann)
+            det = dec(preds)
+        _same_loss(loss, want_loss)
+        _same_detections(det, want_det)
+    assert _handoff.stats['consumed'] - before['consumed'] == 2
+    assert _handoff.stats['stale'] == before['stale']
+    assert (want_det[0] > 0).sum() == 32 * 100   # every image fills its 100 detections at these shapes
+
+
 def test_torch_write_between_the_calls_is_seen():
     """an in-place torch op bumps the version counter: the decoder sweeps for itself"""
     preds, ann = _retina()
