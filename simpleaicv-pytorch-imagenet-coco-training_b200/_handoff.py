@@ -20,8 +20,10 @@ How it is kept safe (all host-side logic lives here; no numerics):
   * A no-grad criterion call that finds a matching wish runs b200det_loss_forward_keys, writing keys /
     classes (thresholded with the decoder's min_score_threshold) into the decoder's own scratch, and
     records READY = (the very tensor objects it read, their autograd version counters, the
-    threshold).  The record holds references to the tensors, so their memory cannot be recycled for
-    other head outputs while it exists.
+    threshold).  The record holds WEAK references: it never extends the life of a batch of head
+    outputs (a validation loop that ends on a criterion call would otherwise pin gigabytes until the
+    next evaluation), and a dead reference can match nothing -- memory recycled for other tensors is
+    reached through other tensor objects, which fail the identity test below.
   * The next decoder call consumes READY only if it is called with the same tensor objects (`is`),
     unchanged version counters, on the same device / stream, with the same threshold; then it runs
     b200det_decode_from_keys.  Anything else: the record is dropped and the decoder sweeps itself.
@@ -99,7 +101,7 @@ def offer(owner, device, stream, shapes):
 def produced(decoder, device, stream, tensors, min_score):
     r = _Ready()
     r.decoder = weakref.ref(decoder)
-    r.tensors = tensors
+    r.tensors = [weakref.ref(t) for t in tensors]
     r.versions = [t._version for t in tensors]
     r.min_score = min_score
     _ready[_key(device, stream)] = r
@@ -116,7 +118,7 @@ def take(decoder, device, stream, tensors, min_score):
         stats['dropped'] += 1
         return False
     for a, b, v in zip(r.tensors, tensors, r.versions):
-        if a is not b or b._version != v:
+        if a() is not b or b._version != v:
             stats['dropped'] += 1
             return False
     w = _wishes.get(_key(device, stream))

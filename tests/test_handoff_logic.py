@@ -112,19 +112,14 @@ def test_unconsumed_handovers_disarm_the_wish():
     assert _handoff.offer(_Crit(), DEV, ST, _shapes(ts)) is dec
 
 
-def test_a_dead_decoder_is_not_served_and_records_keep_tensors_alive():
+def test_a_dead_decoder_is_not_served():
     dec, ts = _Dec(), _tensors()
     _handoff.wish(dec, DEV, ST, _shapes(ts), 80)
     _handoff.offer(_Crit(), DEV, ST, _shapes(ts))
     _handoff.produced(dec, DEV, ST, ts, 0.05)
-    ident = [id(t) for t in ts]
-    del ts
-    gc.collect()
-    # the record holds the tensors: their memory cannot be recycled for other head outputs
-    assert [id(t) for t in _handoff._ready[(0, 1234)].tensors] == ident
     del dec
     gc.collect()
-    assert _handoff.offer(_Crit(), DEV, ST, ()) is None
+    assert _handoff.offer(_Crit(), DEV, ST, _shapes(ts)) is None
 
 
 def test_switch():
@@ -132,3 +127,20 @@ def test_switch():
     _handoff.ENABLED = False
     _handoff.wish(dec, DEV, ST, _shapes(ts), 80)
     assert _handoff.offer(_Crit(), DEV, ST, _shapes(ts)) is None
+
+
+def test_a_pending_handover_does_not_keep_the_head_outputs_alive():
+    """the record holds weak references: dropping the last user reference frees the tensors, and the
+    dead record matches nothing"""
+    import gc
+    import weakref
+    dec, ts = _Dec(), _tensors()
+    _handoff.wish(dec, DEV, ST, _shapes(ts), 80)
+    _handoff.offer(_Crit(), DEV, ST, _shapes(ts))
+    _handoff.produced(dec, DEV, ST, ts, 0.05)
+    probe = weakref.ref(ts[0])
+    fresh = _tensors()
+    del ts
+    gc.collect()
+    assert probe() is None
+    assert not _handoff.take(dec, DEV, ST, fresh, 0.05)
