@@ -27,6 +27,7 @@
 #include <atomic>
 #include "common.cuh"
 #include "dual.cuh"
+#include <algorithm>
 #include "focal_terms.cuh"
 
 namespace b200det {
@@ -456,6 +457,10 @@ constexpr int kTileWarps = kTileThreads / 32;
 #endif
 constexpr int kTileSide = B200DET_TILE_SIDE;   // largest tile side in locations
 constexpr int kTileItems = 1024;   // (GT box, anchor shape) work items per round
+constexpr int kTileSideMin = 16;          // smallest tile side the host may choose (sizes the workspace)
+constexpr int kTileSideSmallBatch = 24;   // tile side for batches <= kTileSmallBatch (more, smaller CTAs)
+constexpr int kTileSmallBatch = 16;       // measured (tools/r02c_run10.sh): 16 images 0.229 -> 0.210 ms per
+                                          // step, 32 images 0.311 vs 0.312 (side 24) / 0.318 (side 16), 64 worse
 
 struct BigTiles {
     int tile_off[kMaxLevels + 1];        // tiles of one image before level l
@@ -1129,7 +1134,8 @@ static void set_anchor_extents(TileTab *t, const Geo &g, const BaseAnchors &ba) 
     }
 }
 
-static BigTiles make_big_tiles(const Geo &g) {
+// side: largest tile side in locations, <= kTileSide (the kernel's static arrays are sized for it)
+static BigTiles make_big_tiles(const Geo &g, int side = kTileSide) {
     BigTiles t;
     int off = 0;
     t.max_anchors = 0;
@@ -1139,7 +1145,7 @@ static BigTiles make_big_tiles(const Geo &g) {
         for (int k = 0; k < 4; ++k) t.ext[l][k] = 0.f;
         if (l < g.n_levels) {
             // balanced tiles of at most kTileSide x kTileSide locations (100 -> 4 x 25, 50 -> 2 x 25)
-            const int nx = (g.W[l] + kTileSide - 1) / kTileSide, ny = (g.H[l] + kTileSide - 1) / kTileSide;
+            const int nx = (g.W[l] + side - 1) / side, ny = (g.H[l] + side - 1) / side;
             t.nx[l] = nx;
             t.tw[l] = (g.W[l] + nx - 1) / nx;
             t.th[l] = (g.H[l] + ny - 1) / ny;
@@ -1185,7 +1191,9 @@ int assign_blocks_per_image(const Geo &g) {
     // the slots it does not use)
     const TileTab t = make_tiles(g);
     const int anchor_centric = (t.tile_off[g.n_levels] + kAssignWarps - 1) / kAssignWarps;
-    const int tiles = make_big_tiles(g).tile_off[g.n_levels];
+    // one partial-count slot per CTA of whichever kernel / tile side runs
+    const int tiles = std::max(make_big_tiles(g).tile_off[g.n_levels],
+                               make_big_tiles(g, kTileSideMin).tile_off[g.n_levels]);
     return anchor_centric > tiles ? anchor_centric : tiles;
 }
 int sparse_blocks(const Geo &g) {
@@ -1276,7 +1284,14 @@ extern "C" int b200det_retina_assign(const b200det_geometry *geo, const float *a
     // production scan (labels + queues only): the GT-centric tile kernel
     static const bool no_tiles = getenv("B200DET_ASSIGN_ANCHOR_CENTRIC") != nullptr;   // A/B knob
     if (!matched && !no_tiles) {
-        BigTiles bt = make_big_tiles(g);
+        // Small batches: smaller tiles.  A CTA is a chain of short phases (stage + compact the GT rows,
+        // queue the (box, shape) items, scatter, labels: ~12 us), so at a few dozen images the kernel is
+        // bound by how many CTAs run at once -- 2 per SM with 32 x 32 tiles (74 KB of keys each) -- not
+        // by its instruction count (B200DET_TILE_SIDE_SMALL / B200DET_TILE_SMALL_BATCH: A/B knobs)
+        static const int side_small = getenv("B200DET_TILE_SIDE_SMALL") ? atoi(getenv("B200DET_TILE_SIDE_SMALL")) : kTileSideSmallBatch;
+        static const int small_batch = getenv("B200DET_TILE_SMALL_BATCH") ? atoi(getenv("B200DET_TILE_SMALL_BATCH")) : kTileSmallBatch;
+        const int side = (g.batch <= small_batch && side_small >= kTileSideMin && side_small <= kTileSide) ? side_small : kTileSide;
+        BigTiles bt = make_big_tiles(g, side);
         for (int l = 0; l < g.n_levels; ++l)
             for (int k = 0; k < 4; ++k) bt.ext[l][k] = tt.ext[l][k];
         const size_t tile_smem = ((gt_smem_bytes(max_gt) + 15) & ~(size_t)15) + (size_t)bt.max_anchors * 8;
