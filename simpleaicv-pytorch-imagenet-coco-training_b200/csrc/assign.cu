@@ -459,8 +459,10 @@ constexpr int kTileSide = B200DET_TILE_SIDE;   // largest tile side in locations
 constexpr int kTileItems = 1024;   // (GT box, anchor shape) work items per round
 constexpr int kTileSideMin = 16;          // smallest tile side the host may choose (sizes the workspace)
 constexpr int kTileSideSmallBatch = 24;   // tile side for batches <= kTileSmallBatch (more, smaller CTAs)
-constexpr int kTileSmallBatch = 16;       // measured (tools/r02c_run10.sh): 16 images 0.229 -> 0.210 ms per
-                                          // step, 32 images 0.311 vs 0.312 (side 24) / 0.318 (side 16), 64 worse
+constexpr int kTileSmallBatch = 4;        // measured (tools/r02c_run10.sh, r02c_run13.sh): criterion-only calls
+                                          // 0.0495 -> 0.0422 ms at 1 image, 0.072 -> 0.063 at 4, but 0.066 -> 0.070
+                                          // at 8 and 0.110 -> 0.127 at 16 (BASELINE configs[1]); beside the FUSED
+                                          // sweep the small tiles also win at 16 images (0.229 -> 0.210 ms per step)
 
 struct BigTiles {
     int tile_off[kMaxLevels + 1];        // tiles of one image before level l
