@@ -14,7 +14,8 @@ The caller keeps the reference's two calls; nothing is skipped, cls is read once
 
 How it is kept safe (all host-side logic lives here; no numerics):
 
-  * A decoder call that could not use a hand-over leaves a WISH for its (device, stream): "the next
+  * A decoder call that could not use a hand-over and whose own sweep succeeded (so the shapes and the
+    class count are ones the sweeps support) leaves a WISH for its (device, stream): "the next
     no-grad criterion call on head outputs of these shapes may produce my keys" (same detector
     family, the decoder's scratch for that stream exists).
   * A no-grad criterion call that finds a matching wish runs b200det_loss_forward_keys, writing keys /

@@ -178,16 +178,20 @@ class _DecoderBase:
 
     def _handed_over(self, cls_preds, reg_preds, center_preds, device, st):
         """True when the criterion's sweep already left this call's keys in the scratch
-        (b200det._handoff); otherwise asks the next criterion call for them."""
+        (b200det._handoff)."""
         if not (_handoff.ENABLED and _ZERO_COPY):
             return False
         tensors = list(cls_preds) + (list(center_preds) if center_preds is not None else []) + \
             list(reg_preds)
-        if _handoff.take(self, device, st, tensors, float(self._params.min_score)):
-            return True
-        _handoff.wish(self, device, st, tuple([t.shape for t in cls_preds]),
-                      int(cls_preds[0].shape[-1]))
-        return False
+        return _handoff.take(self, device, st, tensors, float(self._params.min_score))
+
+    def _wish(self, cls_preds, device, st):
+        """After a decode that swept for itself AND succeeded (so the class count / shapes are ones the
+        sweeps support -- the fused sweep has the decoder's limits): ask the next criterion call on
+        head outputs of these shapes to produce the keys."""
+        if _handoff.ENABLED and _ZERO_COPY:
+            _handoff.wish(self, device, st, tuple([t.shape for t in cls_preds]),
+                          int(cls_preds[0].shape[-1]))
 
     @staticmethod
     def _stale(out, index):
@@ -232,6 +236,8 @@ class _DecoderBase:
                 return None
             if isinstance(res, int):
                 _lib.check(res, 'b200det_decode')
+            if not handed:
+                self._wish(cls_preds, device, st)
             result = self._to_host(res, batch, int(self.max_object_num), device)
             if not handed or not self._stale(res, 6 * batch * int(self.max_object_num)):
                 return result
@@ -321,6 +327,7 @@ class _DecoderBase:
                                        counts.data_ptr() if details else None,
                                        keys_ptr + rows_bytes, ws_bytes, st),
                     'b200det_decode')
+                self._wish(cls_preds, device, st)
             result = self._to_host(out, batch, m, device)
             if not handed or not self._stale(out, 6 * batch * m):
                 break
