@@ -571,7 +571,7 @@ def run_b200(args, out):
         'host_cpus_per_rank': R.cpus,
         'roofline': {
             'bound': 'hbm',
-            'kernel': 'fused_sweep (fused_rows_kernel: focal sum + arg-max keys from one read of cls; '
+            'kernel': 'fused_sweep (fused_rows_tma_kernel: focal sum + arg-max keys from one read of cls; '
                       'assignment + sparse losses beside it on the helper stream)' if fused_sweep else dom,
             'achieved': achieved,
             'peak': peak,
