@@ -1,5 +1,7 @@
 # r02 (third session): A/B of the fused sweep's register cap (3 CTAs x 72 registers leave room for one
 # 40-register assignment CTA per SM beside the sweep; 64 registers: four sweep CTAs)
+# variants/lib_r72.so, lib_r64.so: decode.cu rebuilt with -DB200DET_FUSED_MAXNREG=72 / 64 and linked with the other
+# objects of csrc/_obj (variants/ is scratch: built for this run, not kept)
 mkdir -p gpurun_out
 LIB=simpleaicv-pytorch-imagenet-coco-training_b200/libb200det.so
 for v in default r72 r64; do

@@ -1,6 +1,8 @@
 # r02 (third session): A/B of helper-stream kernels shaped to fit BESIDE three resident sweep CTAs
 # (fused sweep: 3 x 256 threads x 80 registers = 61440 of 65536 registers per SM; leftover 4096 =
 # 128 threads x 32 registers = 64 threads x 64 registers)
+# variants/: assign.cu rebuilt with -DB200DET_TILE_THREADS=128 (t128), + -DB200DET_TILE_MINB=16 (t128r32),
+# + -DB200DET_SPARSE_THREADS=64 (t128r32_s64), linked with the other objects of csrc/_obj (scratch, not kept)
 mkdir -p gpurun_out
 LIB=simpleaicv-pytorch-imagenet-coco-training_b200/libb200det.so
 for v in default t128 t128r32 t128r32_s64; do
