@@ -163,6 +163,32 @@ def test_handover_equals_separate_calls_at_baseline_shapes(shape):
     assert (want_det[0] > 0).sum() == 32 * 100   # every image fills its 100 detections at these shapes
 
 
+def test_retinaface_pair_hands_over_and_matches_the_reference_golden():
+    """SURVEY 8f-2 through the hand-over: RetinaFaceLoss then RetinaFaceDecoder on the same head outputs
+    (one class: the raw-tile fused sweep with one lane per row) against the vectors of the reference's own
+    face_detection classes."""
+    import golden_util as G
+    from b200det.face_detection import losses as face_losses, decode as face_decode
+    face = G.load('retinaface_small.npz')
+    preds_h, ann_h = G.retina_inputs(face)
+    preds, ann = dev(preds_h), ann_h.cuda()
+    sizes, strides = [[8, 16, 32], [32, 64, 128], [128, 256, 512]], [8, 16, 32]
+    crit = face_losses.RetinaFaceLoss(anchor_sizes=sizes, strides=strides, box_loss_type='CIoU')
+    dec = face_decode.RetinaFaceDecoder(anchor_sizes=sizes, strides=strides, nms_type='python_nms')
+    before = dict(_handoff.stats)
+    for _ in range(3):
+        with torch.no_grad():
+            loss = crit(preds, ann)
+            s, c, b = dec(preds)
+        want = face['loss_CIoU']
+        for got, w in zip((float(loss['cls_loss']), float(loss['reg_loss'])), want):
+            assert abs(got - float(w)) <= LOSS_RTOL * max(abs(float(w)), 1e-6)
+        G.assert_bit_equal(s, face['dec_python_nms_scores'], 'scores')
+        G.assert_bit_equal(c, face['dec_python_nms_classes'], 'classes')
+        G.assert_bit_equal(b, face['dec_python_nms_boxes'], 'boxes')
+    assert _handoff.stats['consumed'] - before['consumed'] == 2
+
+
 def test_torch_write_between_the_calls_is_seen():
     """an in-place torch op bumps the version counter: the decoder sweeps for itself"""
     preds, ann = _retina()
